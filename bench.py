@@ -1,0 +1,544 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers mapped per second on synthetic inputs of the BASELINE.json shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2] [--impl ours|reference]
+
+One "step" = one pass of the hot path (ASCII reads -> 2-bit -> rolling k-mers -> index probe -> per-node
+uint32 counts) over one batch of synthetic reads.  At N=1 the default workload is BASELINE.json's
+configs[1]: k=31, 100 M-entry index (modulo 452 930 477, 80 M nodes), 50 M x 150 bp reads = 6.0 G k-mers
+per step.  For N>1 (torchrun, one rank per GPU) every rank holds a replica of the index and maps its own
+50 M reads (weak scaling); the private count arrays are summed by one NCCL all-reduce inside every step.
+
+Printed JSON (rank 0, one line):
+  value          whole-job G k-mers/s with the reads already resident in HBM (CUDA events, max over ranks)
+  e2e            the same through the public API with HOST buffers: pinned host -> H2D -> kernels -> counts
+                 D2H, every step (host wall clock between device synchronisations, max over ranks)
+  roofline       fused kernel only: algorithmic bytes (L/(L-k+1) + 32 + 8h per k-mer) / its
+                 CUDA-event duration, against the measured HBM copy peak of MEASURED_PEAKS.json
+  cpu_baseline   the reference's CPU path (compiled mapper.pyx from oracle/_ref when present, else the C
+                 port; hashing restated in C) on all host cores over a bounded sample of the same workload
+  --impl reference   times only that CPU path (rank 0 alone under torchrun).
+
+Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "kmers_mapped_per_sec"
+UNIT = "GK/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "config1": dict(k=31, genome=10_000_000, entries=1_000_000, nodes=800_000, modulo=2_000_003,
+                    reads=100_000, read_len=150, seed=101),
+    # configs[1]: human-scale short-read genotyping shape on 1 B200 -- the configuration the metric is quoted on
+    "config2": dict(k=31, genome=1_000_000_000, entries=100_000_000, nodes=80_000_000, modulo=452_930_477,
+                    reads=50_000_000, read_len=150, seed=201),
+    # configs[2]: multi-GB table; 200 M reads sharded over the GPUs of the job (25 M per GPU at 8)
+    "config3": dict(k=31, genome=2_000_000_000, entries=500_000_000, nodes=400_000_000, modulo=1_000_000_007,
+                    reads=25_000_000, read_len=150, seed=301),
+    # configs[3]: small k, higher hit rate, Zipf nodes (atomic contention)
+    "config4_k21": dict(k=21, genome=1_000_000_000, entries=100_000_000, nodes=80_000_000, modulo=452_930_477,
+                        reads=50_000_000, read_len=150, seed=401, zipf=True),
+    "config4_k15": dict(k=15, genome=1_000_000_000, entries=100_000_000, nodes=80_000_000, modulo=452_930_477,
+                        reads=50_000_000, read_len=150, seed=402, zipf=True),
+    # configs[4]: long reads, 5 % N, mixed case
+    "config5": dict(k=31, genome=1_000_000_000, entries=100_000_000, nodes=80_000_000, modulo=452_930_477,
+                    reads=750_000, read_len=10_000, seed=502, n_rate=0.05, lower_rate=0.5),
+}
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    p.add_argument("--scale", type=float, default=1.0, help="shrink genome/index/reads (smoke runs only)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    p.add_argument("--opt", action="append", default=[], help="library option name=value (tuning)")
+    # internal: the CPU baseline runs in a CUDA-free child process
+    p.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
+    p.add_argument("--cpu-threads", type=int, default=0, help=argparse.SUPPRESS)
+    return p.parse_args(argv)
+
+
+def workload(name, scale):
+    w = dict(WORKLOADS[name])
+    if scale != 1.0:
+        for key in ("genome", "entries", "nodes", "reads"):
+            w[key] = max(int(w[key] * scale), 1000)
+        w["modulo"] = max(int(w["modulo"] * scale) | 1, 1009)
+    return w
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def known_traffic(name):
+    """DRAM bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(name)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        self.gpu_index = gpu_index
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU path (the reference arm / cpu_baseline).  Runs in a child process that never touches CUDA.
+# ---------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(data_dir, k):
+    from oracle import c_oracle, ref_loader
+    from oracle.oracle import OracleIndex
+    # copy-on-write mapping: shared page cache, but "writable" as the reference's memoryview casts demand
+    ld = lambda n: np.load(os.path.join(data_dir, n + ".npy"), mmap_mode="c")  # noqa: E731
+    _W["index"] = OracleIndex.__new__(OracleIndex)
+    idx = _W["index"]
+    idx._hashes_to_index, idx._n_kmers, idx._nodes = ld("hashes_to_index"), ld("n_kmers"), ld("nodes")
+    idx._kmers, idx._frequencies = ld("kmers"), ld("frequencies")
+    idx._modulo = int(np.load(os.path.join(data_dir, "modulo.npy")))
+    _W["max_node"] = int(np.load(os.path.join(data_dir, "max_node.npy")))
+    _W["bases"], _W["offsets"] = ld("bases"), ld("offsets")
+    _W["k"] = k
+    _W["ref"] = ref_loader.load_reference_mapper()
+    _W["c"] = c_oracle
+    _W["acc"] = None
+
+
+def _cpu_chunk(rng):
+    """One chunk of reads, the body of map_cpu (command_line_interface.py:32-56): N->A + hash (restated in C),
+    then the lookup -- the reference's own compiled Cython function when oracle/_ref exists."""
+    r0, r1 = rng
+    off = np.asarray(_W["offsets"][r0:r1 + 1])
+    bases = np.asarray(_W["bases"][off[0]:off[-1]])
+    hashes = _W["c"].kmer_hashes(bases, off - off[0], _W["k"], n_to_a=True)
+    if _W["ref"] is not None:
+        res = _W["ref"].map_kmers_to_graph_index(_W["index"], _W["max_node"], hashes)   # fresh array per call (mapper.pyx:37)
+    else:
+        res = _W["c"].map_kmers_to_graph_index(_W["index"], _W["max_node"], hashes)
+    if _W["acc"] is None:
+        _W["acc"] = res
+    else:
+        _W["acc"] += res            # the additive reduce (command_line_interface.py:124-130), worker-local
+    return hashes.shape[0]
+
+
+def cpu_worker_main(args):
+    """Child process: time `steps` passes over the sample after `warmup` passes; print one JSON line."""
+    import multiprocessing as mp
+    data_dir = args.cpu_worker
+    meta = json.load(open(os.path.join(data_dir, "meta.json")))
+    k, n_reads, read_len = meta["k"], meta["n_reads"], meta["read_len"]
+    threads = args.cpu_threads or os.cpu_count() or 1
+    n_counts = meta["n_counts"]
+    try:
+        ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+        threads = max(1, min(threads, int(0.4 * ram / (2 * 4 * n_counts + 1))))
+    except Exception:
+        pass
+    reads_per_chunk = max(1, 2_500_000 // max(read_len, 1))   # --chunk-size default 2 500 000 bytes (cli:169)
+    chunks = [(s, min(s + reads_per_chunk, n_reads)) for s in range(0, n_reads, reads_per_chunk)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(threads, initializer=_cpu_init, initargs=(data_dir, k)) as pool:
+        times, n_kmers = [], 0
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            n_kmers = sum(pool.imap_unordered(_cpu_chunk, chunks, chunksize=1))
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    from oracle import ref_loader
+    kind = "reference" if ref_loader.load_reference_mapper() is not None else "port"
+    print(json.dumps({"n_kmers": n_kmers, "seconds": times, "threads": threads, "kind": kind,
+                      "chunks": len(chunks)}))
+
+
+def run_cpu_child(data_dir, steps, warmup, threads=0, timeout=1500):
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", data_dir, "--steps", str(steps), "--warmup", str(warmup),
+           "--cpu-threads", str(threads)]
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    for v in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(v, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if out.returncode != 0:
+        raise RuntimeError("cpu worker failed: " + out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def write_cpu_sample(data_dir, host_index, max_node, bases, offsets, n_reads, w):
+    os.makedirs(data_dir, exist_ok=True)
+    for name in ("hashes_to_index", "n_kmers", "nodes", "kmers", "frequencies"):
+        np.save(os.path.join(data_dir, name + ".npy"), np.ascontiguousarray(getattr(host_index, "_" + name)))
+    np.save(os.path.join(data_dir, "modulo.npy"), np.int64(host_index._modulo))
+    np.save(os.path.join(data_dir, "max_node.npy"), np.int64(max_node))
+    np.save(os.path.join(data_dir, "offsets.npy"), np.ascontiguousarray(offsets[:n_reads + 1]))
+    np.save(os.path.join(data_dir, "bases.npy"), np.ascontiguousarray(bases[:int(offsets[n_reads])]))
+    json.dump(dict(k=w["k"], n_reads=int(n_reads), read_len=w["read_len"], n_counts=int(max_node) + 1),
+              open(os.path.join(data_dir, "meta.json"), "w"))
+
+
+def cpu_baseline_record(res, sample_desc):
+    sec = float(np.median(res["seconds"]))
+    return {"value": res["n_kmers"] / sec / 1e9, "unit": UNIT, "cores": res["threads"], "kind": res["kind"],
+            "sample": sample_desc + "; %d chunks of 2.5 MB per pass, median of %d passes (%.2f s each); lookup = %s, "
+            "N->A + hashing restated in C (bionumpy absent), worker-local additive reduce"
+            % (res["chunks"], len(res["seconds"]), sec,
+               "reference mapper.pyx compiled unmodified (oracle/_ref)" if res["kind"] == "reference" else "C port (oracle/kmer_oracle.c)")}
+
+
+# ---------------------------------------------------------------------------------------------
+# data
+# ---------------------------------------------------------------------------------------------
+def generate(w, rank, device):
+    """Index tensors (same on every rank: a replica) and this rank's reads, on `device`."""
+    from kmer_mapper_b200 import synthetic as S
+    genome = S.t_make_genome(w["genome"], w["seed"], device=device)
+    idx = S.t_make_index(genome, w["entries"], w["k"], w["nodes"], w["modulo"], w["seed"] + 1000,
+                         zipf_nodes=bool(w.get("zipf")))
+    bases, offsets = S.t_make_reads(genome, w["reads"], w["read_len"], w["seed"] + 1 + 7919 * rank,
+                                    n_rate=w.get("n_rate", 0.0), lower_rate=w.get("lower_rate", 0.0),
+                                    slice_reads=max(1, (1 << 27) // w["read_len"]))
+    del genome
+    return S.TensorIndex(idx), bases, offsets
+
+
+# ---------------------------------------------------------------------------------------------
+# main arms
+# ---------------------------------------------------------------------------------------------
+def main_reference(args):
+    """The reference's CPU path on all host cores, same config/metric/unit; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    w = workload(args.workload, args.scale)
+    device = "cuda" if torch.cuda.is_available() else "cpu"
+    tindex, bases, offsets = generate(w, 0, device)
+    host_index = tindex.to_host()
+    max_node = host_index.max_node_id()
+    cores = os.cpu_count() or 1
+    sample_reads = args.cpu_sample_reads or min(w["reads"], max(cores * 20_000 * 150 // w["read_len"], 1000))
+    hb = bases[:int(offsets[sample_reads].item())].cpu().numpy()
+    ho = offsets[:sample_reads + 1].cpu().numpy()
+    del tindex, bases, offsets
+    if device == "cuda":
+        torch.cuda.empty_cache()
+    data_dir = tempfile.mkdtemp(prefix="kmb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        write_cpu_sample(data_dir, host_index, max_node, hb, ho, sample_reads, w)
+        del host_index
+        res = run_cpu_child(data_dir, args.steps, args.warmup)
+    finally:
+        shutil.rmtree(data_dir, ignore_errors=True)
+    sec = float(np.median(res["seconds"]))
+    value = res["n_kmers"] / sec / 1e9
+    desc = "first %d reads of %s (%d k-mers per step)" % (sample_reads, args.workload, res["n_kmers"])
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "impl": "reference",
+            "config": dict(workload=args.workload, k=w["k"], index_entries=w["entries"], modulo=w["modulo"],
+                           nodes=w["nodes"], reads_per_step=sample_reads, read_len=w["read_len"], scale=args.scale,
+                           host_threads=res["threads"]),
+            "cpu_baseline": cpu_baseline_record(res, desc),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kmer_mapper_b200 import _lib, distributed
+    from kmer_mapper_b200.device import DeviceIndex, Mapper
+
+    _lib.require_device()
+    rank, world, local_rank = distributed.init_process_group("nccl")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        _lib.set_option(name, int(val))
+    _lib.set_option("time_kernels", 1)
+    w = workload(args.workload, args.scale)
+    k, L = w["k"], w["read_len"]
+    t_setup = time.perf_counter()
+    tindex, bases, offsets = generate(w, rank, device)
+    n_reads = w["reads"]
+    n_bases = int(bases.shape[0])
+    max_node = tindex.max_node_id()
+    n_counts = max_node + 1
+
+    # ---- CPU baseline sample (rank 0, N == 1 only), written before the raw index tensors are dropped
+    cpu_dir = None
+    do_cpu = (not args.no_cpu_baseline) and world == 1 and rank == 0
+    sample_reads = 0
+    if do_cpu:
+        cores = os.cpu_count() or 1
+        sample_reads = args.cpu_sample_reads or min(n_reads, max(cores * 20_000 * 150 // L, 1000))
+        cpu_dir = tempfile.mkdtemp(prefix="kmb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        host_index = tindex.to_host()
+        write_cpu_sample(cpu_dir, host_index, max_node, bases[:int(offsets[sample_reads].item())].cpu().numpy(),
+                         offsets[:sample_reads + 1].cpu().numpy(), sample_reads, w)
+        del host_index
+
+    di = DeviceIndex.from_index(tindex, device=local_rank)
+    del tindex
+    torch.cuda.empty_cache()
+
+    stream = torch.cuda.Stream(device=device)
+    counts = torch.zeros(n_counts, dtype=torch.int32, device=device)
+    mapper = Mapper(di, n_counts, counts_tensor=counts)
+    mapper.set_stream(stream)
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step_resident():
+        mapper.reset()
+        mapper.map_reads(bases, offsets, k)
+        if world > 1:
+            distributed.all_reduce_counts(counts)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_resident()
+        torch.cuda.synchronize()
+        mapper.kernel_time()            # drop warm-up records
+        n_kmers_step, n_counted_step = mapper.stats()
+        barrier()
+        clocks = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                              os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+        if rank == 0:
+            clocks.start()
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - launches0
+        kernel_ms, kernel_n = mapper.kernel_time()
+    clock_rec = clocks.stop() if rank == 0 else None
+    mapper.sync()                        # raises on an invalid base
+
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_kmers = n_kmers_step * world   # weak scaling: every rank maps the same number of windows
+    value = total_kmers * args.steps / (ms_max / 1e3) / 1e9
+
+    # ---- checks at full size (size-independent properties)
+    checks = {}
+    full_counts = counts.clone()
+    if world == 1:
+        s = int(full_counts.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+        checks["sum_counts_equals_entries_counted"] = (s == n_counted_step)
+    checks["kmers_per_step"] = n_kmers_step
+    checks["expected_kmers_per_step"] = n_reads * max(L - k + 1, 0)
+    assert n_kmers_step == n_reads * max(L - k + 1, 0), (n_kmers_step, n_reads, L, k)
+
+    # ---- e2e: host buffers through the public API, H2D and D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hb = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
+        ho = torch.empty(n_reads + 1, dtype=torch.int64, pin_memory=True)
+        hc = torch.empty(n_counts, dtype=torch.int32, pin_memory=True)
+        hb.copy_(bases)
+        ho.copy_(offsets)
+        torch.cuda.synchronize()
+        hb_np, ho_np, hc_np = hb.numpy(), ho.numpy(), hc.numpy().view(np.uint32)
+
+        def step_e2e():
+            mapper.reset()
+            mapper.map_reads(hb_np, ho_np, k)            # pinned host -> staged H2D (copy stream) -> kernels
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    distributed.all_reduce_counts(counts)
+            mapper.counts(out=hc_np)                       # result D2H, synchronises
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_kmers * args.steps / float(tt.item()) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(4 * n_counts),
+               "ms_per_step": float(tt.item()) * 1e3 / args.steps, "timing": "host wall clock between device synchronisations"}
+        if world == 1:
+            checks["e2e_counts_equal_resident_counts"] = bool(np.array_equal(hc_np, full_counts.cpu().numpy().view(np.uint32)))
+        del hb, ho, hc
+
+    # ---- roofline of the fused kernel
+    h = n_counted_step / max(n_kmers_step, 1)
+    bytes_per_kmer = L / max(L - k + 1, 1) + 32.0 + 8.0 * h
+    peak, peak_src = measured_peak()
+    kernel_avg_ms = kernel_ms / max(kernel_n, 1)
+    kernels_per_step = kernel_n / max(args.steps, 1)
+    achieved = bytes_per_kmer * n_kmers_step / max(kernels_per_step, 1) / (kernel_avg_ms / 1e3) / 1e9 if kernel_n else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": known_traffic(args.workload),
+                "kernel": "kmb_map_reads_kernel", "kernel_ms": kernel_avg_ms, "kernel_share_of_step": kernel_ms / ms if ms else None,
+                "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h, "peak_source": peak_src,
+                "filter_bytes": di.filter_bytes}
+
+    # ---- CPU baseline + parity on the sample
+    cpu_rec = None
+    if do_cpu:
+        try:
+            res = run_cpu_child(cpu_dir, steps=2, warmup=1)
+            desc = "first %d reads of %s (%d k-mers per pass)" % (sample_reads, args.workload, res["n_kmers"])
+            cpu_rec = cpu_baseline_record(res, desc)
+            # parity: the GPU counts of the same sample == the oracle's (C port, pinned against the compiled reference)
+            from oracle import c_oracle
+            from oracle.oracle import OracleIndex
+            ld = lambda n: np.load(os.path.join(cpu_dir, n + ".npy"), mmap_mode="r")  # noqa: E731
+            oi = OracleIndex.__new__(OracleIndex)
+            oi._hashes_to_index, oi._n_kmers, oi._nodes, oi._kmers, oi._frequencies = (
+                ld("hashes_to_index"), ld("n_kmers"), ld("nodes"), ld("kmers"), ld("frequencies"))
+            oi._modulo = w["modulo"]
+            sb, so = np.load(os.path.join(cpu_dir, "bases.npy")), np.load(os.path.join(cpu_dir, "offsets.npy"))
+            want, n_want = c_oracle.map_reads(oi, max_node, sb, so, k, n_threads=os.cpu_count() or 1)
+            mapper.reset()
+            mapper.map_reads(sb, so, k)
+            got = mapper.counts()
+            checks["sample_counts_bit_exact_vs_oracle"] = bool(np.array_equal(got, want))
+            checks["sample_kmers"] = int(n_want)
+        finally:
+            shutil.rmtree(cpu_dir, ignore_errors=True)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic",
+                "config": dict(workload=args.workload, k=k, index_entries=w["entries"], modulo=w["modulo"], nodes=w["nodes"],
+                               reads_per_gpu_per_step=n_reads, read_len=L, kmers_per_step=total_kmers, scale=args.scale,
+                               parallelism="reads sharded over %d GPU(s), index replicated, one uint32 all-reduce per step" % world,
+                               l2="inputs larger than L2 (reads %.1f GB, directory %.1f GB per step); no flush"
+                                  % (n_bases / 1e9, w["modulo"] * 8 / 1e9),
+                               index_device_bytes=di.device_bytes, setup_seconds=round(setup_s, 1),
+                               options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter", "aggregate_atomics",
+                                                                        "probe_variant", "map_reads_blocks_per_sm")}),
+                "clocks": clock_rec, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_rec, "checks": checks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    bad = [k_ for k_, v in checks.items() if v is False]
+    if bad:
+        print("PARITY CHECK FAILED: %s" % bad, file=sys.stderr)
+        sys.exit(3)
+
+
+def main():
+    args = parse_args()
+    if args.cpu_worker:
+        return cpu_worker_main(args)
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

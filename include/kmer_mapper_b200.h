@@ -1,0 +1,165 @@
+/* kmer_mapper_b200 -- C ABI of the B200-native k-mer mapping path.
+ *
+ * This is the drop-in boundary for kmer_mapper's read -> k-mer -> index lookup -> per-node count
+ * path.  Every entry point below replaces one reference interface (cited as file:line under
+ * ivargr/kmer_mapper v0.0.37) and is what a ctypes/cffi binding on the reference side would bind;
+ * INTEGRATION.md shows that binding.  Plain pointers and sizes only: no torch, numpy or C++ types.
+ *
+ * Conventions
+ *   - Every function returns an int status: KMB_OK (0) or a negative KMB_ERR_* class.  Nothing
+ *     throws across the boundary; kmb_last_error() returns a thread-local message for the last
+ *     failure on the calling thread.
+ *   - "buf" pointers may be HOST or DEVICE memory of the handle's GPU; the library asks the CUDA
+ *     driver which (cudaPointerGetAttributes).  Host buffers are copied with asynchronous
+ *     host-to-device copies on a side stream, double buffered against the kernels; device buffers
+ *     are used in place (they must be 16-byte aligned).
+ *   - One handle per GPU, not re-entrant: one host thread drives a handle at a time.  All device
+ *     allocations are owned by the handle that made them.  The caller keeps ownership of every
+ *     buffer it passes in.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     KMB_ERR_CUDA.
+ */
+#ifndef KMER_MAPPER_B200_H
+#define KMER_MAPPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMB_OK 0
+#define KMB_ERR_BAD_ARG (-1)       /* null pointer, bad k, misaligned device buffer, size mismatch ... */
+#define KMB_ERR_INVALID_BASE (-2)  /* a byte outside ACGTacgt/N in the reads; see kmb_mapper_bad_offset */
+#define KMB_ERR_CUDA (-3)          /* CUDA runtime error (message in kmb_last_error) */
+#define KMB_ERR_BAD_INDEX (-4)     /* index arrays inconsistent: bucket out of range, negative node ... */
+#define KMB_ERR_NOMEM (-5)
+
+#define KMB_FLAG_REVCOMP 1u        /* also look up the reverse complement of every window
+                                      (command_line_interface.py:74,180-182, GPU route's -r) */
+#define KMB_FLAG_NO_N_TO_A 2u      /* do NOT apply the CPU route's N->A policy
+                                      (command_line_interface.py:40-41): 'N' becomes an invalid byte */
+
+typedef struct kmb_index kmb_index;   /* device-resident, re-laid-out k-mer index (one GPU) */
+typedef struct kmb_mapper kmb_mapper; /* a count buffer + streams + staging bound to one index */
+
+/* ---- library / device ---------------------------------------------------------------------- */
+
+const char *kmb_last_error(void);
+const char *kmb_version(void);
+int kmb_device_count(int *n_devices);
+
+/* ---- index: replaces the six attributes mapper.pyx:22-29 reads from a KmerIndex -------------
+ * hashes_to_index int32[modulo], n_kmers int32[modulo], nodes int32[n_entries],
+ * kmers uint64[n_entries], frequencies uint16[n_entries], modulo scalar.
+ * The arrays are copied to `device`, validated once (the reference runs with boundscheck off,
+ * mapper.pyx:15-18: every bucket must lie inside [0, n_entries], nodes must be >= 0) and re-laid
+ * out on the device into a one-sector bucket directory plus packed 16-byte entries. */
+int kmb_index_create(int device,
+                     const int32_t *hashes_to_index, const int32_t *n_kmers, uint64_t modulo,
+                     const int32_t *nodes, const uint64_t *kmers, const uint16_t *frequencies,
+                     uint64_t n_entries, kmb_index **out);
+int kmb_index_destroy(kmb_index *index);
+/* max_node_id = nodes.max() (KmerIndex.max_node_id(), command_line_interface.py:51,79,117) */
+int kmb_index_info(const kmb_index *index, int64_t *max_node_id, uint64_t *n_entries,
+                   uint64_t *modulo, uint64_t *device_bytes);
+/* Size of the L2-resident bucket-occupancy filter (probe level 0), 0 when not in use. */
+int kmb_index_filter_bytes(const kmb_index *index, uint64_t *bytes);
+
+/* ---- mapper: replaces map_kmers_to_graph_index (mapper.pyx:19-72), the per-chunk worker map_cpu
+ * (command_line_interface.py:32-56) and cucounter's count() as driven by GpuCounter
+ * (gpu_counter.py:23-24).  Holds node_counts uint32[n_counts], n_counts = max_node_id+1
+ * (mapper.pyx:37), cumulative across calls like the reference's additive map-reduce
+ * (command_line_interface.py:124-130); sums wrap mod 2^32.
+ * counts_device: NULL -> the mapper allocates and zeroes its own buffer; otherwise a caller-owned
+ * DEVICE buffer of n_counts uint32 (e.g. a torch tensor that will be NCCL-all-reduced), used as is.
+ * max_index_lookup_frequency: entries with frequency > this are skipped (mapper.pyx:19,64). */
+int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *counts_device,
+                      int max_index_lookup_frequency, kmb_mapper **out);
+int kmb_mapper_destroy(kmb_mapper *mapper);
+/* Run the mapper's kernels on a caller stream (a cudaStream_t, e.g. torch's current stream);
+ * NULL restores the mapper's own stream. */
+int kmb_mapper_set_stream(kmb_mapper *mapper, void *cuda_stream);
+
+/* mapper.pyx:19 map_kmers_to_graph_index(index, max_node_id, kmers): add the counts of n uint64
+ * k-mers (host or device buffer) to the mapper's node counts. */
+int kmb_mapper_map_kmers(kmb_mapper *mapper, const uint64_t *kmers, uint64_t n, uint32_t flags, int k);
+
+/* command_line_interface.py:32-56 map_cpu body, fused: N->A (:41), 2-bit encode + every in-read
+ * window hashed as sum_j code[p+j]*4^j (util.py:71-75), lookup + count (mapper.pyx:53-69).
+ * bases   uint8[n_bases]    ASCII bases of all reads back to back (no separators)
+ * offsets int64[n_reads+1]  read r = bases[offsets[r] : offsets[r+1]]; offsets[0] == 0,
+ *                           offsets[n_reads] == n_bases, non-decreasing
+ * Both buffers on the host, or both on the device. 0 < k < 32. */
+int kmb_mapper_map_reads(kmb_mapper *mapper, const uint8_t *bases, uint64_t n_bases,
+                         const int64_t *offsets, uint64_t n_reads, int k, uint32_t flags);
+
+/* Wait for all queued work of the mapper; returns KMB_ERR_INVALID_BASE if any kernel met an
+ * invalid byte since the last reset (counts are then undefined until kmb_mapper_reset). */
+int kmb_mapper_sync(kmb_mapper *mapper);
+/* Flat offset (within the call that failed) of the first invalid byte, or -1. */
+int kmb_mapper_bad_offset(kmb_mapper *mapper, int64_t *offset);
+/* Copy the n_counts node counts to a host (or device) buffer; implies kmb_mapper_sync. */
+int kmb_mapper_read_counts(kmb_mapper *mapper, uint32_t *out, uint64_t n_counts);
+/* Zero the counts, the statistics and the error state. */
+int kmb_mapper_reset(kmb_mapper *mapper);
+/* Device pointer of the count buffer (for an in-place NCCL all-reduce by the host framework). */
+int kmb_mapper_counts_device(kmb_mapper *mapper, uint32_t **counts_device, uint64_t *n_counts);
+/* Windows looked up and index entries counted since the last reset (implies kmb_mapper_sync). */
+int kmb_mapper_stats(kmb_mapper *mapper, uint64_t *n_kmers_mapped, uint64_t *n_entries_counted);
+
+/* ---- membership: replaces in_graph_index / in_graph_index_no_memory_maps (mapper.pyx:81,137) --
+ * out[i] = 1 iff some entry of bucket kmers[i] % modulo has key kmers[i]; frequency ignored. */
+int kmb_in_graph_index(kmb_index *index, const uint64_t *kmers, uint64_t n, uint8_t *out);
+
+/* ---- hashing: replaces get_kmer_hashes_from_chunk_sequence (util.py:71-75) --------------------
+ * Writes the hash of every in-read window, read-major then position order, to out (host or device,
+ * capacity out_capacity); *n_out = number written = sum_r max(0, L_r - k + 1).
+ * flags: KMB_FLAG_NO_N_TO_A as above (the bare util.py function has no N policy; the CPU route
+ * applies it before calling, command_line_interface.py:41-42). */
+int kmb_hash_reads(int device, const uint8_t *bases, uint64_t n_bases, const int64_t *offsets,
+                   uint64_t n_reads, int k, uint32_t flags, uint64_t *out, uint64_t out_capacity,
+                   uint64_t *n_out, int64_t *bad_offset);
+
+/* ---- per-key counter: replaces cucounter.Counter as seen from gpu_counter.py:16,24,33 ----------
+ * A counter over unique keys is a mapper whose index maps key i -> "node" i (built by the host
+ * shim), so count() is kmb_mapper_map_kmers and Counter.__getitem__ (gpu_counter.py:33) is this
+ * lookup: out[i] = counts[node of the first entry whose key equals keys[i]], 0 when absent. */
+int kmb_mapper_lookup_counts(kmb_mapper *mapper, const uint64_t *keys, uint64_t n, uint32_t *out);
+
+/* ---- legacy 2-bit codec: replaces encodings.py:25-112 on the device -------------------------- */
+int kmb_codec_actg_from_bytes(int device, const uint8_t *seq, uint64_t n, uint8_t *out);   /* :51-59 */
+int kmb_codec_simple_from_bytes(int device, const uint8_t *seq, uint64_t n, uint8_t *out); /* :96-102 */
+int kmb_codec_to_bytes(int device, const uint8_t *packed, uint64_t n, uint8_t *out);       /* :70-75 */
+int kmb_codec_complement(int device, const uint8_t *in, uint64_t n_bytes, uint8_t *out);   /* :44-48 */
+int kmb_codec_twobit_swap(int device, const void *in, uint64_t n_words, int word_bytes, void *out); /* :104-112 */
+
+/* ---- pinned host memory for the chunk reader (command_line_interface.py:102-111 replacement) -- */
+int kmb_host_alloc(void **ptr, size_t bytes);
+int kmb_host_free(void *ptr);
+
+/* ---- measurement helpers (bench.py): the random-gather micro-roofline of SURVEY.md 8(d) -------
+ * Issues n_loads uniform random loads of load_bytes (8, 16 or 32) from a table of table_bytes,
+ * `unroll` independent loads in flight per thread; returns the CUDA-event time in ms. */
+int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loads, int load_bytes, int unroll,
+                     int threads_per_block, int blocks_per_sm, float *ms);
+
+/* Sum of the device durations (ms) of the mapping kernels launched on this mapper since the last
+ * call -- the fused reads kernel / the k-mer kernel only, not the mask or memset launches -- when
+ * option "time_kernels" is 1 (CUDA events on the mapper's stream).  Implies a stream synchronize. */
+int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kernels);
+
+/* Tuning knobs (process-wide, read at launch / index-creation time): name in
+ * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "aggregate_atomics",
+ *  "gathers_in_flight", "use_filter", "filter_l2_budget_bytes", "l2_persist", "time_kernels",
+ *  "chunk_bytes"}. */
+int kmb_set_option(const char *name, int64_t value);
+int kmb_get_option(const char *name, int64_t *value);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+int kmb_launch_count(uint64_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMER_MAPPER_B200_H */

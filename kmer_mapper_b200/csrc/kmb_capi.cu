@@ -1,0 +1,1109 @@
+// kmb_capi.cu -- the C ABI of include/kmer_mapper_b200.h: handles, streams, staging and launches.
+//
+// Nothing in this file computes on the CPU.  Host code here only validates arguments, moves bytes
+// (pinned/pageable host memory -> device staging on a copy stream, double buffered against the
+// compute stream) and launches the kernels of kmb_kernels.cuh.  Without a CUDA device every compute
+// entry point returns KMB_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "../../include/kmer_mapper_b200.h"
+#include "kmb_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int kmb_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define KMB_CUDA(call)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            cudaGetLastError();                                                                              \
+            return kmb_fail(e__ == cudaErrorMemoryAllocation ? KMB_ERR_NOMEM : KMB_ERR_CUDA, "%s: %s (%s:%d)", \
+                            #call, cudaGetErrorString(e__), __FILE__, __LINE__);                             \
+        }                                                                                                    \
+    } while (0)
+
+#define KMB_TRY(call)              \
+    do {                           \
+        int rc__ = (call);         \
+        if (rc__ != KMB_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// options and launch accounting
+// ------------------------------------------------------------------------------------------------
+struct KmbOptions {
+    int64_t map_reads_blocks_per_sm = 0;  // 0 = whatever the occupancy calculator allows
+    int64_t map_kmers_blocks_per_sm = 0;
+    int64_t probe_variant = 1;            // 0 = one query per thread, 1 = staged probe with warp stack
+    int64_t aggregate_atomics = 0;        // merge same-node hits of a warp step before the RED
+    int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
+    int64_t gathers_in_flight = 8;        // U: 4, 8 or 16 independent gathers per thread
+    int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
+    int64_t filter_l2_budget_bytes = 80ll << 20;
+    int64_t l2_persist = 1;               // set a persisting-L2 access window over the filter
+    int64_t time_kernels = 0;             // bracket every mapping kernel with CUDA events (kmb_mapper_kernel_time)
+};
+static KmbOptions g_opt;
+static std::atomic<unsigned long long> g_launches{0};
+
+extern "C" int kmb_set_option(const char *name, int64_t value) {
+    if (!name) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_set_option: null name");
+#define OPT(n)                    \
+    if (!strcmp(name, #n)) {      \
+        g_opt.n = value;          \
+        return KMB_OK;            \
+    }
+    OPT(map_reads_blocks_per_sm)
+    OPT(map_kmers_blocks_per_sm)
+    OPT(probe_variant)
+    OPT(aggregate_atomics)
+    OPT(gathers_in_flight)
+    OPT(use_filter)
+    OPT(filter_l2_budget_bytes)
+    OPT(l2_persist)
+    OPT(time_kernels)
+#undef OPT
+    if (!strcmp(name, "chunk_bytes")) {
+        if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
+        g_opt.chunk_bytes = (value + 255) & ~255ll;
+        return KMB_OK;
+    }
+    return kmb_fail(KMB_ERR_BAD_ARG, "kmb_set_option: unknown option '%s'", name);
+}
+
+extern "C" int kmb_get_option(const char *name, int64_t *value) {
+    if (!name || !value) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_get_option: null argument");
+#define OPT(n)                    \
+    if (!strcmp(name, #n)) {      \
+        *value = g_opt.n;         \
+        return KMB_OK;            \
+    }
+    OPT(map_reads_blocks_per_sm)
+    OPT(map_kmers_blocks_per_sm)
+    OPT(probe_variant)
+    OPT(aggregate_atomics)
+    OPT(gathers_in_flight)
+    OPT(use_filter)
+    OPT(filter_l2_budget_bytes)
+    OPT(l2_persist)
+    OPT(time_kernels)
+    OPT(chunk_bytes)
+#undef OPT
+    return kmb_fail(KMB_ERR_BAD_ARG, "kmb_get_option: unknown option '%s'", name);
+}
+
+extern "C" int kmb_launch_count(uint64_t *n) {
+    if (!n) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_launch_count: null");
+    *n = g_launches.load();
+    return KMB_OK;
+}
+
+extern "C" const char *kmb_last_error(void) { return g_err; }
+extern "C" const char *kmb_version(void) { return "kmer_mapper_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int kmb_device_count(int *n_devices) {
+    if (!n_devices) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_device_count: null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *n_devices = 0;
+        return kmb_fail(KMB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n_devices = n;
+    return KMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+struct DevInfo {
+    int sms = 0;
+    int l2_bytes = 0;
+    int max_persist_l2 = 0;
+};
+static int dev_info(int device, DevInfo *d) {
+    KMB_CUDA(cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, device));
+    KMB_CUDA(cudaDeviceGetAttribute(&d->l2_bytes, cudaDevAttrL2CacheSize, device));
+    KMB_CUDA(cudaDeviceGetAttribute(&d->max_persist_l2, cudaDevAttrMaxPersistingL2CacheSize, device));
+    return KMB_OK;
+}
+
+// Is p device memory (usable by kernels of `device`)?  Plain malloc / numpy memory is "unregistered".
+static int ptr_on_device(const void *p, int device, bool *on_device) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *on_device = false;
+        return KMB_OK;
+    }
+    if (a.type == cudaMemoryTypeDevice) {
+        if (a.device != device)
+            return kmb_fail(KMB_ERR_BAD_ARG, "device buffer lives on GPU %d, handle is on GPU %d", a.device, device);
+        *on_device = true;
+    } else if (a.type == cudaMemoryTypeManaged) {
+        *on_device = true;
+    } else {
+        *on_device = false;
+    }
+    return KMB_OK;
+}
+
+struct DeviceGuard {  // every entry point runs on the handle's GPU and restores the caller's
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+        ok = cudaSetDevice(device) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define KMB_ON_DEVICE(dev)  \
+    DeviceGuard guard__(dev); \
+    if (!guard__.ok) return kmb_fail(KMB_ERR_CUDA, "cudaSetDevice(%d) failed: no such CUDA device", dev)
+
+template <class T>
+struct DevBuf {  // RAII scratch allocation
+    T *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n) {
+        KMB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        return KMB_OK;
+    }
+    T *release() {
+        T *r = p;
+        p = nullptr;
+        return r;
+    }
+};
+
+// Bring `n` elements to the device if they are on the host; `out` = usable device pointer.
+template <class T>
+static int to_device(const T *src, size_t n, int device, DevBuf<T> &tmp, const T **out, cudaStream_t s) {
+    bool dev;
+    KMB_TRY(ptr_on_device(src, device, &dev));
+    if (dev) {
+        *out = src;
+        return KMB_OK;
+    }
+    KMB_TRY(tmp.alloc(n));
+    if (n) KMB_CUDA(cudaMemcpyAsync(tmp.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    *out = tmp.p;
+    return KMB_OK;
+}
+
+static int grid_for(size_t work_items, int block, int sms, int per_sm = 8) {
+    size_t need = (work_items + block - 1) / block;
+    size_t cap = (size_t)sms * per_sm;
+    return (int)std::max<size_t>(1, std::min(need, cap));
+}
+
+// ------------------------------------------------------------------------------------------------
+// index
+// ------------------------------------------------------------------------------------------------
+struct kmb_index {
+    int device = 0;
+    uint64_t modulo = 0, n_entries = 0;
+    uint64_t *dir = nullptr;
+    KmbEntry *entries = nullptr;
+    int32_t *n_overflow = nullptr;  // only kept when some bucket has >= 31 entries
+    uint32_t *filter = nullptr;
+    size_t filter_bytes = 0;
+    bool filter_on = false;
+    int64_t max_node = -1;
+    uint64_t device_bytes = 0;
+    KmbMod mod;
+    DevInfo info;
+};
+
+extern "C" int kmb_index_destroy(kmb_index *ix) {
+    if (!ix) return KMB_OK;
+    DeviceGuard g(ix->device);
+    cudaFree(ix->dir);
+    cudaFree(ix->entries);
+    cudaFree(ix->n_overflow);
+    cudaFree(ix->filter);
+    delete ix;
+    return KMB_OK;
+}
+
+extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, const int32_t *n_kmers, uint64_t modulo,
+                                const int32_t *nodes, const uint64_t *kmers, const uint16_t *frequencies,
+                                uint64_t n_entries, kmb_index **out) {
+    if (!out) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_create: out is null");
+    *out = nullptr;
+    if (!hashes_to_index || !n_kmers) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_create: null bucket arrays");
+    if (n_entries && (!nodes || !kmers || !frequencies))
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_create: null entry arrays");
+    if (modulo == 0 || modulo >= (1ull << 32))
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_create: modulo %llu outside [1, 2^32)", (unsigned long long)modulo);
+    if (n_entries >= (1ull << 31))
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_create: n_entries %llu does not fit the int32 bucket positions",
+                        (unsigned long long)n_entries);
+    KMB_ON_DEVICE(device);
+    kmb_index *ix = new (std::nothrow) kmb_index;
+    if (!ix) return kmb_fail(KMB_ERR_NOMEM, "out of host memory");
+    struct Cleanup {
+        kmb_index *ix;
+        ~Cleanup() {
+            if (ix) kmb_index_destroy(ix);
+        }
+    } cleanup{ix};
+    ix->device = device;
+    ix->modulo = modulo;
+    ix->n_entries = n_entries;
+    ix->mod = kmb_mod_make(modulo);
+    KMB_TRY(dev_info(device, &ix->info));
+
+    cudaStream_t s = 0;  // index construction is a one-off: legacy default stream, synchronous
+    DevBuf<int32_t> t_h2i, t_nk, t_nodes;
+    DevBuf<uint64_t> t_kmers;
+    DevBuf<uint16_t> t_freq;
+    const int32_t *d_h2i, *d_nk, *d_nodes;
+    const uint64_t *d_kmers;
+    const uint16_t *d_freq;
+    KMB_TRY(to_device(hashes_to_index, (size_t)modulo, device, t_h2i, &d_h2i, s));
+    KMB_TRY(to_device(n_kmers, (size_t)modulo, device, t_nk, &d_nk, s));
+    KMB_TRY(to_device(nodes, (size_t)n_entries, device, t_nodes, &d_nodes, s));
+    KMB_TRY(to_device(kmers, (size_t)n_entries, device, t_kmers, &d_kmers, s));
+    KMB_TRY(to_device(frequencies, (size_t)n_entries, device, t_freq, &d_freq, s));
+
+    ix->filter_bytes = (size_t)((modulo + 31) / 32) * 4;
+    KMB_CUDA(cudaMalloc(&ix->dir, (size_t)modulo * 8));
+    KMB_CUDA(cudaMalloc(&ix->entries, std::max<size_t>((size_t)n_entries, 1) * sizeof(KmbEntry)));
+    KMB_CUDA(cudaMalloc(&ix->filter, ix->filter_bytes));
+    DevBuf<KmbStatus> d_status;
+    KMB_TRY(d_status.alloc(1));
+    KmbStatus hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.first_bad_offset = ~0ull;
+    hs.max_node = -1;
+    KMB_CUDA(cudaMemcpyAsync(d_status.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+
+    const int sms = ix->info.sms;
+    if (n_entries) {
+        kmb_pack_entries<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, n_entries, ix->entries,
+                                                                     d_status.p);
+        g_launches++;
+    }
+    kmb_build_directory<<<grid_for(modulo, 256, sms), 256, 0, s>>>(d_h2i, d_nk, d_kmers, modulo, n_entries, ix->mod,
+                                                                  ix->dir, ix->filter, d_status.p);
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
+    if (hs.index_flags & 1u)
+        return kmb_fail(KMB_ERR_BAD_INDEX,
+                        "index: a bucket (hashes_to_index[h], n_kmers[h]) lies outside [0, n_entries=%llu] or has a "
+                        "negative size (the reference would read out of bounds, mapper.pyx:15-18)",
+                        (unsigned long long)n_entries);
+    if (hs.index_flags & 2u)
+        return kmb_fail(KMB_ERR_BAD_INDEX, "index: negative node id (the reference would write out of bounds)");
+    ix->max_node = hs.max_node;
+    if (hs.index_flags & 4u) {
+        // keep the exact sizes of the >= 31-entry buckets
+        if (t_nk.p) {
+            ix->n_overflow = t_nk.release();
+        } else {
+            KMB_CUDA(cudaMalloc(&ix->n_overflow, (size_t)modulo * 4));
+            KMB_CUDA(cudaMemcpy(ix->n_overflow, d_nk, (size_t)modulo * 4, cudaMemcpyDeviceToDevice));
+        }
+    }
+    bool want_filter = g_opt.use_filter == 1 ||
+                       (g_opt.use_filter < 0 && (int64_t)ix->filter_bytes <= g_opt.filter_l2_budget_bytes &&
+                        n_entries < modulo);  // a table with load factor >= 1 has no empty buckets to skip
+    ix->filter_on = want_filter;
+    if (!want_filter) {
+        cudaFree(ix->filter);
+        ix->filter = nullptr;
+        ix->filter_bytes = 0;
+    }
+    ix->device_bytes = modulo * 8 + std::max<uint64_t>(n_entries, 1) * sizeof(KmbEntry) + ix->filter_bytes +
+                       (ix->n_overflow ? modulo * 4 : 0);
+    cleanup.ix = nullptr;
+    *out = ix;
+    return KMB_OK;
+}
+
+extern "C" int kmb_index_info(const kmb_index *ix, int64_t *max_node_id, uint64_t *n_entries, uint64_t *modulo,
+                              uint64_t *device_bytes) {
+    if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_info: null index");
+    if (max_node_id) *max_node_id = ix->max_node;
+    if (n_entries) *n_entries = ix->n_entries;
+    if (modulo) *modulo = ix->modulo;
+    if (device_bytes) *device_bytes = ix->device_bytes;
+    return KMB_OK;
+}
+
+// 1 when the bucket-occupancy filter (probe level 0) is in use for this index
+extern "C" int kmb_index_filter_bytes(const kmb_index *ix, uint64_t *bytes) {
+    if (!ix || !bytes) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_filter_bytes: null argument");
+    *bytes = ix->filter_on ? ix->filter_bytes : 0;
+    return KMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mapper
+// ------------------------------------------------------------------------------------------------
+struct StageSlot {
+    uint8_t *data = nullptr;  // bases (or k-mers) of one chunk
+    int64_t *offsets = nullptr;
+    uint32_t *mask = nullptr;
+    size_t data_cap = 0, off_cap = 0, mask_cap = 0;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    bool used = false;
+};
+
+struct kmb_mapper {
+    kmb_index *index = nullptr;
+    uint64_t n_counts = 0;
+    uint32_t *counts = nullptr;
+    bool own_counts = false;
+    int32_t max_freq = 1000;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    KmbStatus *d_status = nullptr;
+    KmbStatus *h_status = nullptr;  // pinned
+    StageSlot slot[2];
+    uint32_t *dmask = nullptr;  // read-boundary mask for in-place device input
+    size_t dmask_cap = 0;
+    int next_slot = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // event pairs around mapping kernels
+    size_t timed_used = 0;
+};
+
+static void slot_free(StageSlot &s) {
+    cudaFree(s.data);
+    cudaFree(s.offsets);
+    cudaFree(s.mask);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+    s = StageSlot();
+}
+
+extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
+    if (!m) return KMB_OK;
+    DeviceGuard g(m->index->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+    slot_free(m->slot[0]);
+    slot_free(m->slot[1]);
+    for (auto &pr : m->timed) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    cudaFree(m->dmask);
+    if (m->own_counts) cudaFree(m->counts);
+    cudaFree(m->d_status);
+    if (m->h_status) cudaFreeHost(m->h_status);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    cudaGetLastError();
+    delete m;
+    return KMB_OK;
+}
+
+static int status_reset(kmb_mapper *m) {
+    KmbStatus hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.first_bad_offset = ~0ull;
+    hs.max_node = -1;
+    *m->h_status = hs;
+    KMB_CUDA(cudaMemcpyAsync(m->d_status, m->h_status, sizeof(hs), cudaMemcpyHostToDevice, m->stream));
+    KMB_CUDA(cudaStreamSynchronize(m->stream));
+    return KMB_OK;
+}
+
+static int set_l2_window(kmb_mapper *m) {
+    // Hint: keep the filter in the persisting part of L2 for kernels on this stream.  Purely a
+    // performance hint; failure is not an error.
+    kmb_index *ix = m->index;
+    if (!ix->filter_on || !g_opt.l2_persist || ix->info.max_persist_l2 <= 0) return KMB_OK;
+    size_t want = std::min<size_t>(ix->filter_bytes, (size_t)ix->info.max_persist_l2);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+        cudaGetLastError();
+        return KMB_OK;
+    }
+    int max_win = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ix->device);
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = ix->filter;
+    v.accessPolicyWindow.num_bytes = std::min<size_t>(ix->filter_bytes, (size_t)std::max(max_win, 0));
+    v.accessPolicyWindow.hitRatio = std::min(1.0f, (float)want / (float)std::max<size_t>(v.accessPolicyWindow.num_bytes, 1));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(m->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *counts_device,
+                                 int max_index_lookup_frequency, kmb_mapper **out) {
+    if (!out) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_create: out is null");
+    *out = nullptr;
+    if (!index) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_create: null index");
+    if ((int64_t)n_counts <= index->max_node)
+        return kmb_fail(KMB_ERR_BAD_ARG,
+                        "kmb_mapper_create: n_counts=%llu but the index holds node id %lld (max_node_id+1 counters are "
+                        "needed; the reference would write out of bounds, mapper.pyx:37,68)",
+                        (unsigned long long)n_counts, (long long)index->max_node);
+    KMB_ON_DEVICE(index->device);
+    kmb_mapper *m = new (std::nothrow) kmb_mapper;
+    if (!m) return kmb_fail(KMB_ERR_NOMEM, "out of host memory");
+    m->index = index;
+    struct Cleanup {
+        kmb_mapper *m;
+        ~Cleanup() {
+            if (m) kmb_mapper_destroy(m);
+        }
+    } cleanup{m};
+    m->n_counts = n_counts;
+    m->max_freq = max_index_lookup_frequency;  // a C int like the reference's (mapper.pyx:19,64)
+    KMB_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    KMB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    m->stream = m->own_stream;
+    if (counts_device) {
+        bool dev;
+        KMB_TRY(ptr_on_device(counts_device, index->device, &dev));
+        if (!dev) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_create: counts_device is not device memory");
+        m->counts = counts_device;
+    } else {
+        KMB_CUDA(cudaMalloc(&m->counts, std::max<uint64_t>(n_counts, 1) * 4));
+        m->own_counts = true;
+        KMB_CUDA(cudaMemsetAsync(m->counts, 0, n_counts * 4, m->stream));
+    }
+    KMB_CUDA(cudaMalloc(&m->d_status, sizeof(KmbStatus)));
+    KMB_CUDA(cudaMallocHost(&m->h_status, sizeof(KmbStatus)));
+    KMB_TRY(status_reset(m));
+    for (int i = 0; i < 2; i++) {
+        KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].copied, cudaEventDisableTiming));
+        KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].consumed, cudaEventDisableTiming));
+    }
+    set_l2_window(m);
+    cleanup.m = nullptr;
+    *out = m;
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_set_stream(kmb_mapper *m, void *cuda_stream) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_set_stream: null mapper");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_CUDA(cudaStreamSynchronize(m->stream));
+    m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+    set_l2_window(m);
+    return KMB_OK;
+}
+
+static KmbProbe make_probe(const kmb_mapper *m) {
+    const kmb_index *ix = m->index;
+    KmbProbe P;
+    P.dir = ix->dir;
+    P.entries = ix->entries;
+    P.n_overflow = ix->n_overflow;
+    P.filter = ix->filter_on ? ix->filter : nullptr;
+    P.counts = m->counts;
+    P.mod = ix->mod;
+    P.max_freq = m->max_freq;
+    return P;
+}
+
+static int pick_u() {
+    int64_t u = g_opt.gathers_in_flight;
+    return u <= 4 ? 4 : (u <= 8 ? 8 : 16);
+}
+
+// ---- kernel dispatch (template instantiation table) ------------------------------------------------
+typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, int, bool, KmbProbe, KmbStatus *);
+typedef void (*MapKmersFn)(const uint64_t *, uint64_t, int, KmbProbe, KmbStatus *);
+
+template <int U>
+static MapReadsFn map_reads_fn_u(bool filt, bool agg, bool rc) {
+    if (filt) {
+        if (agg) return rc ? kmb_map_reads_kernel<U, true, true, true> : kmb_map_reads_kernel<U, true, true, false>;
+        return rc ? kmb_map_reads_kernel<U, true, false, true> : kmb_map_reads_kernel<U, true, false, false>;
+    }
+    if (agg) return rc ? kmb_map_reads_kernel<U, false, true, true> : kmb_map_reads_kernel<U, false, true, false>;
+    return rc ? kmb_map_reads_kernel<U, false, false, true> : kmb_map_reads_kernel<U, false, false, false>;
+}
+static MapReadsFn map_reads_fn(int u, bool filt, bool agg, bool rc) {
+    return u == 4 ? map_reads_fn_u<4>(filt, agg, rc) : (u == 8 ? map_reads_fn_u<8>(filt, agg, rc) : map_reads_fn_u<16>(filt, agg, rc));
+}
+template <int U>
+static MapKmersFn map_kmers_fn_u(bool filt, bool agg, bool rc) {
+    if (filt) {
+        if (agg) return rc ? kmb_map_kmers_kernel<U, true, true, true> : kmb_map_kmers_kernel<U, true, true, false>;
+        return rc ? kmb_map_kmers_kernel<U, true, false, true> : kmb_map_kmers_kernel<U, true, false, false>;
+    }
+    if (agg) return rc ? kmb_map_kmers_kernel<U, false, true, true> : kmb_map_kmers_kernel<U, false, true, false>;
+    return rc ? kmb_map_kmers_kernel<U, false, false, true> : kmb_map_kmers_kernel<U, false, false, false>;
+}
+static MapKmersFn map_kmers_fn(int u, bool filt, bool agg, bool rc) {
+    return u == 4 ? map_kmers_fn_u<4>(filt, agg, rc) : (u == 8 ? map_kmers_fn_u<8>(filt, agg, rc) : map_kmers_fn_u<16>(filt, agg, rc));
+}
+
+static int resident_blocks(const void *fn, int64_t opt, int *out) {
+    int b = 0;
+    KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, KMB_TILE_THREADS, 0));
+    if (b < 1) b = 1;
+    if (opt > 0) b = (int)std::min<int64_t>(opt, 32);
+    *out = b;
+    return KMB_OK;
+}
+
+static int timed_begin(kmb_mapper *m) {
+    if (!g_opt.time_kernels) return KMB_OK;
+    if (m->timed_used == m->timed.size()) {
+        cudaEvent_t a, b;
+        KMB_CUDA(cudaEventCreate(&a));
+        KMB_CUDA(cudaEventCreate(&b));
+        m->timed.emplace_back(a, b);
+    }
+    KMB_CUDA(cudaEventRecord(m->timed[m->timed_used].first, m->stream));
+    return KMB_OK;
+}
+static int timed_end(kmb_mapper *m) {
+    if (!g_opt.time_kernels) return KMB_OK;
+    KMB_CUDA(cudaEventRecord(m->timed[m->timed_used].second, m->stream));
+    m->timed_used++;
+    return KMB_OK;
+}
+
+// launch the read-boundary mask + the fused kernel over one device-resident batch
+static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_bases, uint64_t base0,
+                            const int64_t *d_offsets, uint64_t n_reads, uint32_t *d_mask, int k, uint32_t flags) {
+    if (n_bases == 0) return KMB_OK;
+    const kmb_index *ix = m->index;
+    const size_t mask_words = (size_t)(n_bases / 32 + 1);
+    KMB_CUDA(cudaMemsetAsync(d_mask, 0, mask_words * 4, m->stream));
+    if (n_reads) {
+        kmb_mark_read_ends<<<grid_for(n_reads, 256, ix->info.sms), 256, 0, m->stream>>>(d_offsets, n_reads, (int64_t)base0,
+                                                                                      k, d_mask);
+        g_launches++;
+    }
+    KmbProbe P = make_probe(m);
+    MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, g_opt.aggregate_atomics != 0, (flags & KMB_FLAG_REVCOMP) != 0);
+    int per_sm;
+    KMB_TRY(resident_blocks((const void *)fn, g_opt.map_reads_blocks_per_sm, &per_sm));
+    uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
+    int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
+    KMB_TRY(timed_begin(m));
+    fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_bases, n_bases, base0, d_mask, k, !(flags & KMB_FLAG_NO_N_TO_A), P,
+                                                m->d_status);
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    KMB_TRY(timed_end(m));
+    return KMB_OK;
+}
+
+static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, uint32_t flags, int k) {
+    if (n == 0) return KMB_OK;
+    const kmb_index *ix = m->index;
+    KmbProbe P = make_probe(m);
+    bool rc = (flags & KMB_FLAG_REVCOMP) != 0;
+    KMB_TRY(timed_begin(m));
+    if (g_opt.probe_variant == 0) {
+        int grid = grid_for(n, 256, ix->info.sms, 16);
+        if (rc) kmb_map_kmers_simple_kernel<true><<<grid, 256, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
+        else kmb_map_kmers_simple_kernel<false><<<grid, 256, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
+    } else {
+        int u = pick_u();
+        MapKmersFn fn = map_kmers_fn(u, P.filter != nullptr, g_opt.aggregate_atomics != 0, rc);
+        int per_sm;
+        KMB_TRY(resident_blocks((const void *)fn, g_opt.map_kmers_blocks_per_sm, &per_sm));
+        uint64_t n_blocks = (n + (uint64_t)KMB_TILE_THREADS * u - 1) / ((uint64_t)KMB_TILE_THREADS * u);
+        int grid = (int)std::min<uint64_t>(n_blocks, (uint64_t)ix->info.sms * per_sm);
+        fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
+    }
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    KMB_TRY(timed_end(m));
+    return KMB_OK;
+}
+
+static int slot_reserve(StageSlot &s, size_t data_bytes, size_t n_offsets, size_t mask_words) {
+    if (data_bytes > s.data_cap) {
+        cudaFree(s.data);
+        s.data = nullptr;
+        s.data_cap = 0;
+        size_t cap = (data_bytes + 255) & ~(size_t)255;
+        KMB_CUDA(cudaMalloc(&s.data, cap));
+        s.data_cap = cap;
+    }
+    if (n_offsets > s.off_cap) {
+        cudaFree(s.offsets);
+        s.offsets = nullptr;
+        s.off_cap = 0;
+        size_t cap = n_offsets + n_offsets / 4 + 64;
+        KMB_CUDA(cudaMalloc(&s.offsets, cap * 8));
+        s.off_cap = cap;
+    }
+    if (mask_words > s.mask_cap) {
+        cudaFree(s.mask);
+        s.mask = nullptr;
+        s.mask_cap = 0;
+        size_t cap = mask_words + mask_words / 4 + 64;
+        KMB_CUDA(cudaMalloc(&s.mask, cap * 4));
+        s.mask_cap = cap;
+    }
+    return KMB_OK;
+}
+
+static int check_k(int k) {
+    if (k <= 0 || k >= 32) return kmb_fail(KMB_ERR_BAD_ARG, "k=%d outside 1..31", k);
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_t n_bases, const int64_t *offsets,
+                                    uint64_t n_reads, int k, uint32_t flags) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: null mapper");
+    KMB_TRY(check_k(k));
+    if (n_bases == 0 || n_reads == 0) return KMB_OK;
+    if (!bases || !offsets) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: null buffer");
+    KMB_ON_DEVICE(m->index->device);
+    bool dev_b, dev_o;
+    KMB_TRY(ptr_on_device(bases, m->index->device, &dev_b));
+    KMB_TRY(ptr_on_device(offsets, m->index->device, &dev_o));
+    if (dev_b != dev_o)
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: bases and offsets must both be host or both be device buffers");
+    if (dev_b) {
+        if (((uintptr_t)bases & 15u) != 0)
+            return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: device bases buffer must be 16-byte aligned");
+        size_t words = (size_t)(n_bases / 32 + 1);
+        if (words > m->dmask_cap) {
+            KMB_CUDA(cudaStreamSynchronize(m->stream));
+            cudaFree(m->dmask);
+            m->dmask = nullptr;
+            m->dmask_cap = 0;
+            KMB_CUDA(cudaMalloc(&m->dmask, (words + words / 8 + 64) * 4));
+            m->dmask_cap = words + words / 8 + 64;
+        }
+        return launch_map_reads(m, bases, n_bases, 0, offsets, n_reads, m->dmask, k, flags);
+    }
+    // ---- host input: whole reads per chunk, double-buffered H2D on the copy stream
+    if (offsets[0] != 0 || (uint64_t)offsets[n_reads] != n_bases)
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: offsets[0] must be 0 and offsets[n_reads] must equal n_bases");
+    const uint64_t chunk = (uint64_t)g_opt.chunk_bytes;
+    uint64_t r0 = 0;
+    while (r0 < n_reads) {
+        // largest r1 with offsets[r1] - offsets[r0] <= chunk (at least one read)
+        const int64_t *lo = offsets + r0 + 1, *hi = offsets + n_reads + 1;
+        const int64_t *it = std::upper_bound(lo, hi, (int64_t)(offsets[r0] + chunk));
+        uint64_t r1 = (uint64_t)(it - offsets) - 1;
+        if (r1 <= r0) r1 = r0 + 1;
+        if (offsets[r1] < offsets[r0]) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: offsets must be non-decreasing");
+        const uint64_t b0 = (uint64_t)offsets[r0], nb = (uint64_t)offsets[r1] - b0, nr = r1 - r0;
+        if (nb) {
+            StageSlot &s = m->slot[m->next_slot];
+            m->next_slot ^= 1;
+            if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));  // also makes re-allocation safe
+            KMB_TRY(slot_reserve(s, nb + 16, nr + 1, nb / 32 + 1));
+            KMB_CUDA(cudaMemcpyAsync(s.data, bases + b0, nb, cudaMemcpyHostToDevice, m->copy_stream));
+            KMB_CUDA(cudaMemcpyAsync(s.offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, m->copy_stream));
+            KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
+            KMB_CUDA(cudaStreamWaitEvent(m->stream, s.copied, 0));
+            KMB_TRY(launch_map_reads(m, s.data, nb, b0, s.offsets, nr, s.mask, k, flags));
+            KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
+            s.used = true;
+        }
+        r0 = r1;
+    }
+    // the caller may reuse its host buffers as soon as we return
+    KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_map_kmers(kmb_mapper *m, const uint64_t *kmers, uint64_t n, uint32_t flags, int k) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_kmers: null mapper");
+    if (flags & KMB_FLAG_REVCOMP) KMB_TRY(check_k(k));
+    if (n == 0) return KMB_OK;
+    if (!kmers) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_kmers: null buffer");
+    KMB_ON_DEVICE(m->index->device);
+    bool dev;
+    KMB_TRY(ptr_on_device(kmers, m->index->device, &dev));
+    if (dev) {
+        if (((uintptr_t)kmers & 7u) != 0) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_kmers: misaligned device buffer");
+        return launch_map_kmers(m, kmers, n, flags, k);
+    }
+    const uint64_t per = std::max<uint64_t>((uint64_t)g_opt.chunk_bytes / 8, 1);
+    for (uint64_t i0 = 0; i0 < n; i0 += per) {
+        uint64_t cnt = std::min(per, n - i0);
+        StageSlot &s = m->slot[m->next_slot];
+        m->next_slot ^= 1;
+        if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
+        KMB_TRY(slot_reserve(s, cnt * 8, 0, 0));
+        KMB_CUDA(cudaMemcpyAsync(s.data, kmers + i0, cnt * 8, cudaMemcpyHostToDevice, m->copy_stream));
+        KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
+        KMB_CUDA(cudaStreamWaitEvent(m->stream, s.copied, 0));
+        KMB_TRY(launch_map_kmers(m, reinterpret_cast<const uint64_t *>(s.data), cnt, flags, k));
+        KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
+        s.used = true;
+    }
+    KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+    return KMB_OK;
+}
+
+static int fetch_status(kmb_mapper *m) {
+    KMB_CUDA(cudaMemcpyAsync(m->h_status, m->d_status, sizeof(KmbStatus), cudaMemcpyDeviceToHost, m->stream));
+    KMB_CUDA(cudaStreamSynchronize(m->stream));
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_sync(kmb_mapper *m) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_sync: null mapper");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(fetch_status(m));
+    if (m->h_status->first_bad_offset != ~0ull)
+        return kmb_fail(KMB_ERR_INVALID_BASE, "invalid base byte at flat offset %llu (only ACGTacgt and N are accepted)",
+                        m->h_status->first_bad_offset);
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_bad_offset(kmb_mapper *m, int64_t *offset) {
+    if (!m || !offset) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_bad_offset: null argument");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(fetch_status(m));
+    *offset = m->h_status->first_bad_offset == ~0ull ? -1 : (int64_t)m->h_status->first_bad_offset;
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_read_counts(kmb_mapper *m, uint32_t *out, uint64_t n_counts) {
+    if (!m || (!out && n_counts)) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_read_counts: null argument");
+    if (n_counts > m->n_counts) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_read_counts: n_counts larger than the mapper's");
+    int rc = kmb_mapper_sync(m);
+    if (rc != KMB_OK) return rc;
+    KMB_ON_DEVICE(m->index->device);
+    if (n_counts) {
+        KMB_CUDA(cudaMemcpyAsync(out, m->counts, n_counts * 4, cudaMemcpyDefault, m->stream));
+        KMB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_reset(kmb_mapper *m) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_reset: null mapper");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_CUDA(cudaMemsetAsync(m->counts, 0, m->n_counts * 4, m->stream));
+    return status_reset(m);
+}
+
+extern "C" int kmb_mapper_counts_device(kmb_mapper *m, uint32_t **counts_device, uint64_t *n_counts) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_counts_device: null mapper");
+    if (counts_device) *counts_device = m->counts;
+    if (n_counts) *n_counts = m->n_counts;
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_stats(kmb_mapper *m, uint64_t *n_kmers_mapped, uint64_t *n_entries_counted) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_stats: null mapper");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(fetch_status(m));
+    if (n_kmers_mapped) *n_kmers_mapped = m->h_status->n_kmers_mapped;
+    if (n_entries_counted) *n_entries_counted = m->h_status->n_entries_counted;
+    return KMB_OK;
+}
+
+// Sum of the device durations of the mapping kernels (the fused reads kernel / the k-mer kernel, not
+// the mask or memset launches) recorded since the last call, with option "time_kernels" = 1.
+extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t *n_kernels) {
+    if (!m || !ms_total) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_kernel_time: null argument");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_CUDA(cudaStreamSynchronize(m->stream));
+    double total = 0;
+    for (size_t i = 0; i < m->timed_used; i++) {
+        float ms = 0;
+        KMB_CUDA(cudaEventElapsedTime(&ms, m->timed[i].first, m->timed[i].second));
+        total += ms;
+    }
+    *ms_total = total;
+    if (n_kernels) *n_kernels = m->timed_used;
+    m->timed_used = 0;
+    return KMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// membership and per-key lookup
+// ------------------------------------------------------------------------------------------------
+static KmbProbe index_probe(const kmb_index *ix, uint32_t *counts) {
+    KmbProbe P;
+    P.dir = ix->dir;
+    P.entries = ix->entries;
+    P.n_overflow = ix->n_overflow;
+    P.filter = ix->filter_on ? ix->filter : nullptr;
+    P.counts = counts;
+    P.mod = ix->mod;
+    P.max_freq = 0;
+    return P;
+}
+
+template <int MODE, class OutT>
+static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uint64_t *keys, uint64_t n, OutT *out) {
+    if (n == 0) return KMB_OK;
+    if (!keys || !out) return kmb_fail(KMB_ERR_BAD_ARG, "lookup: null buffer");
+    DevBuf<uint64_t> t_keys;
+    const uint64_t *d_keys;
+    KMB_TRY(to_device(keys, (size_t)n, ix->device, t_keys, &d_keys, s));
+    bool out_dev;
+    KMB_TRY(ptr_on_device(out, ix->device, &out_dev));
+    DevBuf<OutT> t_out;
+    OutT *d_out = out;
+    if (!out_dev) {
+        KMB_TRY(t_out.alloc((size_t)n));
+        d_out = t_out.p;
+    }
+    KmbProbe P = index_probe(ix, counts);
+    kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(d_keys, n, P, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),
+                                                                              (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    if (!out_dev) KMB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(OutT), cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
+    return KMB_OK;
+}
+
+extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t n, uint8_t *out) {
+    if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_in_graph_index: null index");
+    KMB_ON_DEVICE(ix->device);
+    return run_lookup<0, uint8_t>(ix, nullptr, 0, kmers, n, out);
+}
+
+extern "C" int kmb_mapper_lookup_counts(kmb_mapper *m, const uint64_t *keys, uint64_t n, uint32_t *out) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_lookup_counts: null mapper");
+    KMB_ON_DEVICE(m->index->device);
+    return run_lookup<1, uint32_t>(m->index, m->counts, m->stream, keys, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// hashing (util.py:71-75)
+// ------------------------------------------------------------------------------------------------
+extern "C" int kmb_hash_reads(int device, const uint8_t *bases, uint64_t n_bases, const int64_t *offsets, uint64_t n_reads,
+                              int k, uint32_t flags, uint64_t *out, uint64_t out_capacity, uint64_t *n_out,
+                              int64_t *bad_offset) {
+    KMB_TRY(check_k(k));
+    if (n_out) *n_out = 0;
+    if (bad_offset) *bad_offset = -1;
+    if (n_bases == 0 || n_reads == 0) return KMB_OK;
+    if (!bases || !offsets) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_hash_reads: null buffer");
+    if (out_capacity && !out) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_hash_reads: null output with non-zero capacity");
+    KMB_ON_DEVICE(device);
+    DevInfo info;
+    KMB_TRY(dev_info(device, &info));
+    cudaStream_t s = 0;
+    DevBuf<uint8_t> t_bases;
+    DevBuf<int64_t> t_off;
+    const uint8_t *d_bases;
+    const int64_t *d_off;
+    bool dev_b;
+    KMB_TRY(ptr_on_device(bases, device, &dev_b));
+    if (dev_b) {
+        if (((uintptr_t)bases & 15u) != 0) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_hash_reads: device bases buffer must be 16-byte aligned");
+        d_bases = bases;
+    } else {
+        KMB_TRY(t_bases.alloc((size_t)n_bases + 16));
+        KMB_CUDA(cudaMemcpyAsync(t_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, s));
+        d_bases = t_bases.p;
+    }
+    KMB_TRY(to_device(offsets, (size_t)n_reads + 1, device, t_off, &d_off, s));
+    const size_t mask_words = (size_t)(n_bases / 32 + 1);
+    const uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
+    DevBuf<uint32_t> d_mask;
+    DevBuf<unsigned long long> d_tiles;
+    DevBuf<KmbStatus> d_status;
+    KMB_TRY(d_mask.alloc(mask_words));
+    KMB_TRY(d_tiles.alloc((size_t)n_tiles + 1));
+    KMB_TRY(d_status.alloc(1));
+    KmbStatus hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.first_bad_offset = ~0ull;
+    KMB_CUDA(cudaMemcpyAsync(d_status.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+    KMB_CUDA(cudaMemsetAsync(d_mask.p, 0, mask_words * 4, s));
+    kmb_mark_read_ends<<<grid_for(n_reads, 256, info.sms), 256, 0, s>>>(d_off, n_reads, 0, k, d_mask.p);
+    kmb_hash_count_kernel<<<(unsigned)n_tiles, KMB_TILE_THREADS, 0, s>>>(d_mask.p, n_bases, k, d_tiles.p);
+    kmb_hash_scan_kernel<<<1, 1024, 0, s>>>(d_tiles.p, n_tiles, d_tiles.p + n_tiles);
+    g_launches += 3;
+    KMB_CUDA(cudaGetLastError());
+    unsigned long long total = 0;
+    KMB_CUDA(cudaMemcpyAsync(&total, d_tiles.p + n_tiles, 8, cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
+    if (n_out) *n_out = total;
+    // emit (also the pass that validates the bytes); with out_capacity == 0 this only validates
+    bool out_dev = true;
+    if (out_capacity) KMB_TRY(ptr_on_device(out, device, &out_dev));
+    uint64_t cap = std::min<uint64_t>(out_capacity, total);
+    DevBuf<uint64_t> t_out;
+    uint64_t *d_out = out;
+    if (!out_dev) {
+        KMB_TRY(t_out.alloc((size_t)cap));
+        d_out = t_out.p;
+    }
+    kmb_hash_emit_kernel<<<(unsigned)n_tiles, KMB_TILE_THREADS, 0, s>>>(d_bases, n_bases, d_mask.p, k, !(flags & KMB_FLAG_NO_N_TO_A),
+                                                                       d_tiles.p, d_out, cap, d_status.p);
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    if (!out_dev && cap) KMB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)cap * 8, cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
+    if (hs.first_bad_offset != ~0ull) {
+        if (bad_offset) *bad_offset = (int64_t)hs.first_bad_offset;
+        return kmb_fail(KMB_ERR_INVALID_BASE, "invalid base byte at flat offset %llu (only ACGTacgt%s are accepted)",
+                        hs.first_bad_offset, (flags & KMB_FLAG_NO_N_TO_A) ? "" : " and N");
+    }
+    if (out_capacity < total)
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_hash_reads: output capacity %llu < %llu hashes", (unsigned long long)out_capacity, total);
+    return KMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// legacy codec (encodings.py)
+// ------------------------------------------------------------------------------------------------
+template <class Launch>
+static int run_codec(int device, const void *in, size_t in_bytes, void *out, size_t out_bytes, Launch launch) {
+    if (in_bytes == 0 || out_bytes == 0) return KMB_OK;
+    if (!in || !out) return kmb_fail(KMB_ERR_BAD_ARG, "codec: null buffer");
+    KMB_ON_DEVICE(device);
+    DevInfo info;
+    KMB_TRY(dev_info(device, &info));
+    cudaStream_t s = 0;
+    DevBuf<uint8_t> t_in, t_out;
+    const uint8_t *d_in;
+    KMB_TRY(to_device((const uint8_t *)in, in_bytes, device, t_in, &d_in, s));
+    bool out_dev;
+    KMB_TRY(ptr_on_device(out, device, &out_dev));
+    uint8_t *d_out = (uint8_t *)out;
+    if (!out_dev) {
+        KMB_TRY(t_out.alloc(out_bytes));
+        d_out = t_out.p;
+    }
+    if ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 7u) return kmb_fail(KMB_ERR_BAD_ARG, "codec: device buffers must be 8-byte aligned");
+    launch(d_in, d_out, info.sms, s);
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    if (!out_dev) KMB_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
+    return KMB_OK;
+}
+
+extern "C" int kmb_codec_actg_from_bytes(int device, const uint8_t *seq, uint64_t n, uint8_t *out) {
+    if (n % 4) return kmb_fail(KMB_ERR_BAD_ARG, "from_bytes: sequence length %llu is not a multiple of 4 (encodings.py:53)", (unsigned long long)n);
+    return run_codec(device, seq, n, out, n / 4, [&](const uint8_t *i, uint8_t *o, int sms, cudaStream_t s) {
+        kmb_codec_actg_from_bytes_kernel<<<grid_for(n / 4, 256, sms), 256, 0, s>>>(i, n / 4, o);
+    });
+}
+extern "C" int kmb_codec_simple_from_bytes(int device, const uint8_t *seq, uint64_t n, uint8_t *out) {
+    if (n % 4) return kmb_fail(KMB_ERR_BAD_ARG, "from_bytes: sequence length %llu is not a multiple of 4 (encodings.py:99)", (unsigned long long)n);
+    return run_codec(device, seq, n, out, n / 4, [&](const uint8_t *i, uint8_t *o, int sms, cudaStream_t s) {
+        kmb_codec_simple_from_bytes_kernel<<<grid_for(n / 4, 256, sms), 256, 0, s>>>(i, n / 4, o);
+    });
+}
+extern "C" int kmb_codec_to_bytes(int device, const uint8_t *packed, uint64_t n, uint8_t *out) {
+    return run_codec(device, packed, n, out, n * 4, [&](const uint8_t *i, uint8_t *o, int sms, cudaStream_t s) {
+        kmb_codec_to_bytes_kernel<<<grid_for(n, 256, sms), 256, 0, s>>>(i, n, o);
+    });
+}
+extern "C" int kmb_codec_complement(int device, const uint8_t *in, uint64_t n_bytes, uint8_t *out) {
+    return run_codec(device, in, n_bytes, out, n_bytes, [&](const uint8_t *i, uint8_t *o, int sms, cudaStream_t s) {
+        kmb_codec_complement_kernel<<<grid_for(n_bytes, 256, sms), 256, 0, s>>>(i, n_bytes, o);
+    });
+}
+extern "C" int kmb_codec_twobit_swap(int device, const void *in, uint64_t n_words, int word_bytes, void *out) {
+    if (word_bytes != 1 && word_bytes != 2 && word_bytes != 4 && word_bytes != 8)
+        return kmb_fail(KMB_ERR_BAD_ARG, "twobit_swap: word size %d not in {1,2,4,8}", word_bytes);
+    size_t bytes = (size_t)n_words * word_bytes;
+    return run_codec(device, in, bytes, out, bytes, [&](const uint8_t *i, uint8_t *o, int sms, cudaStream_t s) {
+        int grid = grid_for(n_words, 256, sms);
+        switch (word_bytes) {
+            case 1: kmb_codec_twobit_swap_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t *)i, n_words, (uint8_t *)o); break;
+            case 2: kmb_codec_twobit_swap_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t *)i, n_words, (uint16_t *)o); break;
+            case 4: kmb_codec_twobit_swap_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t *)i, n_words, (uint32_t *)o); break;
+            default: kmb_codec_twobit_swap_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t *)i, n_words, (uint64_t *)o); break;
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// pinned host memory
+// ------------------------------------------------------------------------------------------------
+extern "C" int kmb_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_host_alloc: null");
+    *ptr = nullptr;
+    KMB_CUDA(cudaMallocHost(ptr, std::max<size_t>(bytes, 1)));
+    return KMB_OK;
+}
+extern "C" int kmb_host_free(void *ptr) {
+    if (ptr) KMB_CUDA(cudaFreeHost(ptr));
+    return KMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather micro-roofline
+// ------------------------------------------------------------------------------------------------
+typedef void (*GatherFn)(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *);
+template <int W>
+static GatherFn gather_fn_w(int unroll) {
+    switch (unroll) {
+        case 1: return kmb_gather_bench_kernel<W, 1>;
+        case 2: return kmb_gather_bench_kernel<W, 2>;
+        case 4: return kmb_gather_bench_kernel<W, 4>;
+        case 8: return kmb_gather_bench_kernel<W, 8>;
+        case 16: return kmb_gather_bench_kernel<W, 16>;
+        default: return nullptr;
+    }
+}
+
+extern "C" int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loads, int load_bytes, int unroll,
+                                int threads_per_block, int blocks_per_sm, float *ms) {
+    if (!ms) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_bench_gather: null ms");
+    GatherFn fn = load_bytes == 8 ? gather_fn_w<8>(unroll) : load_bytes == 16 ? gather_fn_w<16>(unroll) : load_bytes == 32 ? gather_fn_w<32>(unroll) : nullptr;
+    if (!fn) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_bench_gather: load_bytes in {8,16,32}, unroll in {1,2,4,8,16}");
+    if (table_bytes < 32 || threads_per_block < 32 || threads_per_block > 1024 || blocks_per_sm < 1)
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_bench_gather: bad launch shape");
+    KMB_ON_DEVICE(device);
+    DevInfo info;
+    KMB_TRY(dev_info(device, &info));
+    DevBuf<uint8_t> table;
+    DevBuf<uint64_t> sink;
+    KMB_TRY(table.alloc((size_t)table_bytes));
+    KMB_TRY(sink.alloc(1));
+    KMB_CUDA(cudaMemset(table.p, 1, (size_t)table_bytes));
+    cudaEvent_t e0, e1;
+    KMB_CUDA(cudaEventCreate(&e0));
+    KMB_CUDA(cudaEventCreate(&e1));
+    int grid = info.sms * blocks_per_sm;
+    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads / 8 + 1, 1, sink.p);  // warm-up
+    KMB_CUDA(cudaEventRecord(e0));
+    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads, 2, sink.p);
+    KMB_CUDA(cudaEventRecord(e1));
+    g_launches += 2;
+    KMB_CUDA(cudaEventSynchronize(e1));
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return KMB_OK;
+}

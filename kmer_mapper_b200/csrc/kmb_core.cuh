@@ -1,0 +1,155 @@
+// kmb_core.cuh -- bit-level primitives shared by every kernel of the k-mer mapping path.
+//
+// All functions here are pure and __host__ __device__ so that tests/test_core_host.py can compile
+// this header with g++ and check the arithmetic (exact u64 % modulo, SWAR 2-bit encoding, window
+// extraction, directory word packing) against Python integers without a GPU.  The host build is a
+// unit-test harness for these primitives only; no mapping path exists on the CPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KMB_HD __host__ __device__ __forceinline__
+#else
+#define KMB_HD inline
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Exact n / d and n % d for a runtime 64-bit divisor (reference: `kmers[i] % modulo`,
+// mapper.pyx:54).  Barrett: m = floor((2^64-1)/d); q' = mulhi(n, m) is floor(n/d) or one less
+// (n/d - n*m/2^64 < 1 for every n < 2^64, d >= 1), so a single correction step is exact.
+// ---------------------------------------------------------------------------------------------
+struct KmbMod {
+    uint64_t d;
+    uint64_t m;
+};
+
+KMB_HD uint64_t kmb_umulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+KMB_HD KmbMod kmb_mod_make(uint64_t d) {
+    KmbMod r;
+    r.d = d;
+    r.m = ~0ull / d;
+    return r;
+}
+
+KMB_HD void kmb_divmod(uint64_t n, const KmbMod md, uint64_t &q, uint64_t &r) {
+    uint64_t qe = kmb_umulhi64(n, md.m);
+    uint64_t re = n - qe * md.d;
+    if (re >= md.d) {
+        re -= md.d;
+        qe += 1;
+    }
+    q = qe;
+    r = re;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bucket directory word (one per bucket h = kmer % modulo), 8 bytes:
+//   bits  0..30  pos  first entry of the bucket          (hashes_to_index[h], mapper.pyx:56)
+//   bits 31..35  n    bucket size, 31 = "31 or more, read the overflow table"  (n_kmers[h], :55)
+//   bits 36..63  fp   low 28 bits of (key / modulo) of the bucket's FIRST entry
+// An all-zero word is an empty bucket.  With n == 1 a query whose quotient fingerprint differs
+// cannot match (same bucket + same quotient <=> same key), so it is answered from the directory
+// sector alone; a fingerprint collision (2^-28) only costs a wasted entry fetch, never a result.
+// ---------------------------------------------------------------------------------------------
+#define KMB_DIR_POS_BITS 31
+#define KMB_DIR_N_BITS 5
+#define KMB_DIR_N_OVERFLOW 31u
+#define KMB_DIR_FP_BITS 28
+#define KMB_DIR_FP_MASK ((1u << KMB_DIR_FP_BITS) - 1u)
+
+KMB_HD uint64_t kmb_dir_pack(uint32_t pos, uint32_t n, uint32_t fp) {
+    uint32_t nn = n >= KMB_DIR_N_OVERFLOW ? KMB_DIR_N_OVERFLOW : n;
+    return (uint64_t)pos | ((uint64_t)nn << KMB_DIR_POS_BITS) |
+           ((uint64_t)(fp & KMB_DIR_FP_MASK) << (KMB_DIR_POS_BITS + KMB_DIR_N_BITS));
+}
+KMB_HD uint32_t kmb_dir_pos(uint64_t w) { return (uint32_t)w & 0x7FFFFFFFu; }
+KMB_HD uint32_t kmb_dir_n(uint64_t w) { return (uint32_t)(w >> KMB_DIR_POS_BITS) & 31u; }
+KMB_HD uint32_t kmb_dir_fp(uint64_t w) { return (uint32_t)(w >> (KMB_DIR_POS_BITS + KMB_DIR_N_BITS)); }
+
+// true when the directory word alone proves that no entry can match a query with fingerprint fpq
+KMB_HD bool kmb_dir_rejects(uint64_t w, uint32_t fpq) {
+    uint32_t n = kmb_dir_n(w);
+    return n == 0u || (n == 1u && kmb_dir_fp(w) != (fpq & KMB_DIR_FP_MASK));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-bit encoding of ASCII bases, 4 bytes at a time in one 32-bit register (SWAR).
+// Codes follow bionumpy's DNAEncoding as used by util.py:72-73: A/a,C/c,G/g,T/t -> 0,1,2,3.
+// Upper-case 'N' -> code 0 ('A') when n_to_a (command_line_interface.py:40-41); every other byte
+// (including lower-case 'n') is flagged invalid: bit 7 of its byte lane in *invalid.
+// Returns the 4 codes packed into 8 bits, first base in bits 1:0 (hash = sum code[j] * 4^j,
+// tests/test_hashing.py:13-26).
+// ---------------------------------------------------------------------------------------------
+KMB_HD uint32_t kmb_zero_bytes(uint32_t x) {  // 0x80 in every byte lane of x that is 0x00
+    uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);
+}
+
+KMB_HD uint32_t kmb_encode4(uint32_t w, bool n_to_a, uint32_t &invalid) {
+    uint32_t cf = w & 0xDFDFDFDFu;  // fold case
+    uint32_t isN = n_to_a ? kmb_zero_bytes(w ^ 0x4E4E4E4Eu) : 0u;
+    uint32_t ok = kmb_zero_bytes(cf ^ 0x41414141u) | kmb_zero_bytes(cf ^ 0x43434343u) |
+                  kmb_zero_bytes(cf ^ 0x47474747u) | kmb_zero_bytes(cf ^ 0x54545454u) | isN;
+    invalid = ok ^ 0x80808080u;
+    uint32_t x = (cf >> 1) & 0x03030303u;  // A0 C1 G3 T2
+    x ^= (x >> 1) & 0x01010101u;           // A0 C1 G2 T3
+    x &= ~((isN >> 7) * 3u);               // N -> 0
+    uint32_t t = (x | (x >> 6)) & 0x000F000Fu;
+    return (t | (t >> 12)) & 0xFFu;
+}
+
+// 16 bases (four little-endian 32-bit words of ASCII) -> 32 bits of 2-bit codes, base 0 lowest.
+KMB_HD uint32_t kmb_encode16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, bool n_to_a,
+                             uint32_t &invalid_lanes) {
+    uint32_t i0, i1, i2, i3;
+    uint32_t p = kmb_encode4(w0, n_to_a, i0) | (kmb_encode4(w1, n_to_a, i1) << 8) |
+                 (kmb_encode4(w2, n_to_a, i2) << 16) | (kmb_encode4(w3, n_to_a, i3) << 24);
+    // one bit per base: bit j set <=> base j invalid
+    uint32_t m = 0;
+    m |= ((i0 >> 7) & 1u) | ((i0 >> 14) & 2u) | ((i0 >> 21) & 4u) | ((i0 >> 28) & 8u);
+    m |= (((i1 >> 7) & 1u) | ((i1 >> 14) & 2u) | ((i1 >> 21) & 4u) | ((i1 >> 28) & 8u)) << 4;
+    m |= (((i2 >> 7) & 1u) | ((i2 >> 14) & 2u) | ((i2 >> 21) & 4u) | ((i2 >> 28) & 8u)) << 8;
+    m |= (((i3 >> 7) & 1u) | ((i3 >> 14) & 2u) | ((i3 >> 21) & 4u) | ((i3 >> 28) & 8u)) << 12;
+    invalid_lanes = m;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Window extraction: lo/hi are two consecutive 64-bit words of the packed 2-bit stream
+// (32 bases each, base 0 in the lowest bits); the k-mer starting at base i (0..31) of lo is
+// bits [2i, 2i+2k) of the 128-bit value hi:lo.  This IS the reference hash: first base lowest.
+// ---------------------------------------------------------------------------------------------
+KMB_HD uint64_t kmb_kmer_mask(int k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull); }
+
+KMB_HD uint64_t kmb_window(uint64_t lo, uint64_t hi, int i, uint64_t kmask) {
+    int s = 2 * i;
+    uint64_t v = (lo >> s) | ((hi << 1) << (63 - s));
+    return v & kmask;
+}
+
+// Reverse complement of a k-mer hash in the A,C,G,T=0..3 / first-base-lowest convention:
+// complement = 3 - code = bitwise NOT of the 2-bit group; order reversed.
+KMB_HD uint64_t kmb_revcomp(uint64_t x, int k) {
+    x = ~x;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    x = (x >> 32) | (x << 32);
+    return x >> (64 - 2 * k);
+}
+
+// 64-bit mix (splitmix64 finaliser) for the synthetic-address generator of the gather benchmark.
+KMB_HD uint64_t kmb_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}

@@ -1,0 +1,24 @@
+// Host build of kmb_core.cuh for unit tests (g++, no CUDA): exposes the pure bit-level primitives
+// the kernels are made of so that tests/test_core_host.py can check them against Python integers.
+// This is a test harness for arithmetic only -- it contains no mapping path.
+#include "../../kmer_mapper_b200/csrc/kmb_core.cuh"
+
+extern "C" {
+void h_divmod(const uint64_t *n, int64_t cnt, uint64_t d, uint64_t *q, uint64_t *r) {
+    KmbMod m = kmb_mod_make(d);
+    for (int64_t i = 0; i < cnt; i++) kmb_divmod(n[i], m, q[i], r[i]);
+}
+// encode 16 ASCII bytes: returns packed 32-bit code word, *invalid = per-base invalid bit mask
+uint32_t h_encode16(const uint8_t *b, int n_to_a, uint32_t *invalid) {
+    uint32_t w[4];
+    for (int a = 0; a < 4; a++) w[a] = (uint32_t)b[4 * a] | ((uint32_t)b[4 * a + 1] << 8) | ((uint32_t)b[4 * a + 2] << 16) | ((uint32_t)b[4 * a + 3] << 24);
+    return kmb_encode16(w[0], w[1], w[2], w[3], n_to_a != 0, *invalid);
+}
+uint64_t h_window(uint64_t lo, uint64_t hi, int i, int k) { return kmb_window(lo, hi, i, kmb_kmer_mask(k)); }
+uint64_t h_revcomp(uint64_t x, int k) { return kmb_revcomp(x, k); }
+uint64_t h_dir_pack(uint32_t pos, uint32_t n, uint32_t fp) { return kmb_dir_pack(pos, n, fp); }
+uint32_t h_dir_pos(uint64_t w) { return kmb_dir_pos(w); }
+uint32_t h_dir_n(uint64_t w) { return kmb_dir_n(w); }
+uint32_t h_dir_fp(uint64_t w) { return kmb_dir_fp(w); }
+int h_dir_rejects(uint64_t w, uint32_t fpq) { return kmb_dir_rejects(w, fpq) ? 1 : 0; }
+}

@@ -1,0 +1,134 @@
+"""Bit-level primitives of the kernels (kmb_core.cuh), compiled for the host with g++ and checked
+against Python integers: exact u64 % modulo (Barrett), SWAR 2-bit encoding, window extraction,
+reverse complement, directory word packing.  CPU-only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_harness", "kmb_core_host.cpp")
+OUT = os.path.join(HERE, "host_harness", "libkmb_core_host.so")
+HDR = os.path.join(os.path.dirname(HERE), "kmer_mapper_b200", "csrc", "kmb_core.cuh")
+
+
+@pytest.fixture(scope="module")
+def core():
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", SRC, "-o", OUT])
+    lib = C.CDLL(OUT)
+    lib.h_window.restype = C.c_uint64
+    lib.h_window.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+    lib.h_revcomp.restype = C.c_uint64
+    lib.h_revcomp.argtypes = [C.c_uint64, C.c_int]
+    lib.h_dir_pack.restype = C.c_uint64
+    lib.h_dir_pack.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    for f in (lib.h_dir_pos, lib.h_dir_n, lib.h_dir_fp):
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_uint64]
+    lib.h_dir_rejects.argtypes = [C.c_uint64, C.c_uint32]
+    lib.h_encode16.restype = C.c_uint32
+    return lib
+
+
+def test_barrett_divmod_is_exact(core):
+    rng = np.random.default_rng(1)
+    edge = np.array([0, 1, 2, 2 ** 32 - 1, 2 ** 32, 2 ** 62 - 1, 2 ** 62, 2 ** 63, 2 ** 64 - 1, 2 ** 64 - 2], dtype=np.uint64)
+    for d in [1, 2, 3, 21, 97, 2003, 65537, 2_000_003, 452_930_477, 1_000_000_007, 2 ** 31 - 1, 2 ** 32 - 1,
+              2 ** 32 - 5, 4_000_000_007 % (2 ** 32)]:
+        n = np.concatenate([edge, rng.integers(0, 2 ** 64, size=20000, dtype=np.uint64),
+                            rng.integers(0, 4 ** 31, size=20000, dtype=np.uint64),
+                            # multiples of d and their neighbours: where a one-off quotient would show
+                            (rng.integers(0, (2 ** 64 - 1) // d, size=5000, dtype=np.uint64) * np.uint64(d)),
+                            (rng.integers(1, (2 ** 64 - 1) // d, size=5000, dtype=np.uint64) * np.uint64(d)) - np.uint64(1)])
+        q = np.zeros_like(n)
+        r = np.zeros_like(n)
+        core.h_divmod(n.ctypes.data_as(C.c_void_p), C.c_int64(n.shape[0]), C.c_uint64(d), q.ctypes.data_as(C.c_void_p),
+                      r.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(r, n % np.uint64(d)), d
+        assert np.array_equal(q, n // np.uint64(d)), d
+
+
+def _encode_ref(b, n_to_a):
+    codes, inv = 0, 0
+    for j, ch in enumerate(b):
+        c = {65: 0, 97: 0, 67: 1, 99: 1, 71: 2, 103: 2, 84: 3, 116: 3}.get(ch)
+        if c is None and n_to_a and ch == 78:
+            c = 0
+        if c is None:
+            inv |= 1 << j
+            c = None
+        codes |= (c or 0) << (2 * j)
+    return codes, inv
+
+
+def test_swar_encode_all_bytes(core):
+    # every byte value in every lane position, both N policies
+    for n_to_a in (0, 1):
+        for lane in range(16):
+            for v in range(256):
+                b = bytearray(b"ACGTacgtACGTacgt")
+                b[lane] = v
+                inv = C.c_uint32(0)
+                got = core.h_encode16(bytes(b), n_to_a, C.byref(inv))
+                want, winv = _encode_ref(b, n_to_a)
+                assert inv.value == winv, (n_to_a, lane, v)
+                # codes of invalid lanes are unspecified; compare the valid ones
+                mask = 0
+                for j in range(16):
+                    if not (winv >> j) & 1:
+                        mask |= 3 << (2 * j)
+                assert (got & mask) == (want & mask), (n_to_a, lane, v)
+    rng = np.random.default_rng(2)
+    for _ in range(2000):
+        b = bytes(rng.choice(np.frombuffer(b"ACGTacgtNn", np.uint8), size=16))
+        inv = C.c_uint32(0)
+        got = core.h_encode16(b, 1, C.byref(inv))
+        want, winv = _encode_ref(b, 1)
+        assert inv.value == winv
+        if winv == 0:
+            assert got == want
+
+
+def test_window_extraction_is_the_reference_hash(core):
+    # tests/test_hashing.py:13-26 convention: first base of the window in the lowest bits
+    rng = np.random.default_rng(3)
+    codes = rng.integers(0, 4, size=64)
+    lo = sum(int(c) << (2 * j) for j, c in enumerate(codes[:32]))
+    hi = sum(int(c) << (2 * j) for j, c in enumerate(codes[32:]))
+    for k in (1, 2, 15, 16, 17, 21, 30, 31):
+        for i in range(32):
+            want = sum(int(codes[i + j]) << (2 * j) for j in range(k))
+            assert core.h_window(lo, hi, i, k) == want, (k, i)
+
+
+def test_revcomp(core):
+    rng = np.random.default_rng(4)
+    for k in (1, 3, 15, 21, 31):
+        for _ in range(200):
+            codes = rng.integers(0, 4, size=k)
+            x = sum(int(c) << (2 * j) for j, c in enumerate(codes))
+            rc = [3 - int(c) for c in codes[::-1]]
+            want = sum(c << (2 * j) for j, c in enumerate(rc))
+            assert core.h_revcomp(x, k) == want
+            assert core.h_revcomp(want, k) == x
+
+
+def test_directory_word(core):
+    rng = np.random.default_rng(5)
+    assert core.h_dir_pack(0, 0, 0) == 0 and core.h_dir_rejects(0, 123) == 1
+    for _ in range(2000):
+        pos = int(rng.integers(0, 2 ** 31))
+        n = int(rng.integers(1, 100))
+        fp = int(rng.integers(0, 2 ** 32))
+        w = core.h_dir_pack(pos, n, fp)
+        assert w != 0
+        assert core.h_dir_pos(w) == pos
+        assert core.h_dir_n(w) == min(n, 31)
+        assert core.h_dir_fp(w) == fp & (2 ** 28 - 1)
+        other = int(rng.integers(0, 2 ** 32))
+        same_fp = (other & (2 ** 28 - 1)) == (fp & (2 ** 28 - 1))
+        assert core.h_dir_rejects(w, fp) == 0                      # a possible match is never rejected
+        assert core.h_dir_rejects(w, other) == (1 if (n == 1 and not same_fp) else 0)
