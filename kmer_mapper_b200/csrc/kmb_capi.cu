@@ -60,6 +60,8 @@ struct KmbOptions {
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
     int64_t filter_l2_budget_bytes = 80ll << 20;
     int64_t l2_persist = 1;               // set a persisting-L2 access window over the filter
+    int64_t l2_fetch_granularity = 0;     // 0 = leave the device default; else 32/64/128 (cudaLimitMaxL2FetchGranularity)
+    int64_t bench_grid_blocks = 0;        // kmb_bench_gather: total CTAs (0 = SMs x blocks_per_sm)
     int64_t time_kernels = 0;             // bracket every mapping kernel with CUDA events (kmb_mapper_kernel_time)
 };
 static KmbOptions g_opt;
@@ -81,6 +83,8 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(filter_l2_budget_bytes)
     OPT(l2_persist)
     OPT(time_kernels)
+    OPT(l2_fetch_granularity)
+    OPT(bench_grid_blocks)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -106,6 +110,8 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(filter_l2_budget_bytes)
     OPT(l2_persist)
     OPT(time_kernels)
+    OPT(l2_fetch_granularity)
+    OPT(bench_grid_blocks)
     OPT(chunk_bytes)
 #undef OPT
     return kmb_fail(KMB_ERR_BAD_ARG, "kmb_get_option: unknown option '%s'", name);
@@ -442,6 +448,9 @@ static int status_reset(kmb_mapper *m) {
 }
 
 static int set_l2_window(kmb_mapper *m) {
+    if (g_opt.l2_fetch_granularity > 0 &&
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g_opt.l2_fetch_granularity) != cudaSuccess)
+        cudaGetLastError();
     // Hint: keep the filter in the persisting part of L2 for kernels on this stream.  Purely a
     // performance hint; failure is not an error.
     kmb_index *ix = m->index;
@@ -1086,6 +1095,7 @@ extern "C" int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loa
     KMB_ON_DEVICE(device);
     DevInfo info;
     KMB_TRY(dev_info(device, &info));
+    if (g_opt.l2_fetch_granularity > 0) KMB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g_opt.l2_fetch_granularity));
     DevBuf<uint8_t> table;
     DevBuf<uint64_t> sink;
     KMB_TRY(table.alloc((size_t)table_bytes));
@@ -1094,7 +1104,7 @@ extern "C" int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loa
     cudaEvent_t e0, e1;
     KMB_CUDA(cudaEventCreate(&e0));
     KMB_CUDA(cudaEventCreate(&e1));
-    int grid = info.sms * blocks_per_sm;
+    int grid = g_opt.bench_grid_blocks > 0 ? (int)g_opt.bench_grid_blocks : info.sms * blocks_per_sm;
     fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads / 8 + 1, 1, sink.p);  // warm-up
     KMB_CUDA(cudaEventRecord(e0));
     fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads, 2, sink.p);

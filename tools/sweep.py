@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Tuning sweep on one GPU: build one workload, time the resident fused path under every option set.
+    python tools/sweep.py [--workload config2] [--scale 1.0] [--steps 3]"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from kmer_mapper_b200 import _lib  # noqa: E402
+from kmer_mapper_b200.device import DeviceIndex, Mapper  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=0)
+    ap.add_argument("--grid", default="default")
+    a = ap.parse_args()
+    w = bench.workload(a.workload, a.scale)
+    if a.reads:
+        w["reads"] = a.reads
+    tindex, bases, offsets = bench.generate(w, 0, torch.device("cuda", 0))
+    n_counts = tindex.max_node_id() + 1
+    ref_counts = None
+    grids = {
+        "default": dict(use_filter=[1, 0], gathers_in_flight=[4, 8, 16], aggregate_atomics=[0], map_reads_blocks_per_sm=[0]),
+        "occupancy": dict(use_filter=[1], gathers_in_flight=[8, 16], aggregate_atomics=[0], map_reads_blocks_per_sm=[1, 2, 3, 4, 6, 8]),
+        "agg": dict(use_filter=[1], gathers_in_flight=[8], aggregate_atomics=[0, 1], map_reads_blocks_per_sm=[0]),
+        "persist": dict(use_filter=[1], gathers_in_flight=[8], aggregate_atomics=[0], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
+    }[a.grid]
+    names = list(grids)
+    last_filter = None
+    di = None
+    for combo in itertools.product(*[grids[n] for n in names]):
+        opts = dict(zip(names, combo))
+        for n, v in opts.items():
+            _lib.set_option(n, v)
+        if di is None or opts.get("use_filter") != last_filter:
+            if hasattr(tindex, "_kmb_device_index"):
+                del tindex._kmb_device_index
+            di = None
+            torch.cuda.empty_cache()
+            di = DeviceIndex.from_index(tindex, device=0)
+            last_filter = opts.get("use_filter")
+        _lib.set_option("time_kernels", 1)
+        m = Mapper(di, n_counts)
+        for _ in range(2):
+            m.reset()
+            m.map_reads(bases, offsets, w["k"])
+        m.kernel_time()
+        for _ in range(a.steps):
+            m.reset()
+            m.map_reads(bases, offsets, w["k"])
+        ms, n = m.kernel_time()
+        nk, nc = m.stats()
+        c = m.counts()
+        if ref_counts is None:
+            ref_counts = c
+        same = bool((c == ref_counts).all())
+        m.close()
+        print(json.dumps(dict(opts=opts, kernel_ms=ms / n, GKps=nk / (ms / n) / 1e6, filter_bytes=di.filter_bytes,
+                              counts_equal_first=same)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
