@@ -383,6 +383,7 @@ def main_ours(args):
     def step_resident():
         mapper.reset()
         mapper.map_reads(bases, offsets, k)
+        mapper.flush()                  # slot counters -> node counts (queued on the same stream)
         if world > 1:
             distributed.all_reduce_counts(counts)
 
@@ -444,6 +445,7 @@ def main_ours(args):
         def step_e2e():
             mapper.reset()
             mapper.map_reads(hb_np, ho_np, k)            # pinned host -> staged H2D (copy stream) -> kernels
+            mapper.flush()
             if world > 1:
                 with torch.cuda.stream(stream):
                     distributed.all_reduce_counts(counts)
@@ -517,8 +519,10 @@ def main_ours(args):
                                l2="inputs larger than L2 (reads %.1f GB, directory %.1f GB per step); no flush"
                                   % (n_bases / 1e9, w["modulo"] * 8 / 1e9),
                                index_device_bytes=di.device_bytes, setup_seconds=round(setup_s, 1),
-                               options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter", "aggregate_atomics",
-                                                                        "probe_variant", "map_reads_blocks_per_sm")}),
+                               index_layout=dict(buckets_per_line=di.buckets_per_line, main_lines=di.n_main_lines,
+                                                 overflow_lines=di.n_overflow_lines, filter_bytes=di.filter_bytes),
+                               options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter",
+                                                                        "map_reads_blocks_per_sm")}),
                 "clocks": clock_rec, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_rec, "checks": checks}
         print(json.dumps(line))

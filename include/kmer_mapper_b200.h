@@ -64,8 +64,13 @@ int kmb_index_destroy(kmb_index *index);
 /* max_node_id = nodes.max() (KmerIndex.max_node_id(), command_line_interface.py:51,79,117) */
 int kmb_index_info(const kmb_index *index, int64_t *max_node_id, uint64_t *n_entries,
                    uint64_t *modulo, uint64_t *device_bytes);
-/* Size of the L2-resident bucket-occupancy filter (probe level 0), 0 when not in use. */
+/* Size of the L2-resident bucket filter (probe level 0), 0 when not in use. */
 int kmb_index_filter_bytes(const kmb_index *index, uint64_t *bytes);
+/* Geometry of the 128-byte-line table: buckets per line, main lines, overflow lines and the number
+ * of live entries (entries that lie inside the bucket range of their own key -- the only ones the
+ * reference's scan can ever match). */
+int kmb_index_layout(const kmb_index *index, uint32_t *buckets_per_line, uint64_t *n_main_lines,
+                     uint64_t *n_overflow_lines, uint64_t *n_live_entries);
 
 /* ---- mapper: replaces map_kmers_to_graph_index (mapper.pyx:19-72), the per-chunk worker map_cpu
  * (command_line_interface.py:32-56) and cucounter's count() as driven by GpuCounter
@@ -95,7 +100,13 @@ int kmb_mapper_map_kmers(kmb_mapper *mapper, const uint64_t *kmers, uint64_t n, 
 int kmb_mapper_map_reads(kmb_mapper *mapper, const uint8_t *bases, uint64_t n_bases,
                          const int64_t *offsets, uint64_t n_reads, int k, uint32_t flags);
 
-/* Wait for all queued work of the mapper; returns KMB_ERR_INVALID_BASE if any kernel met an
+/* Hits are first accumulated in per-entry counters that share a 128-byte line with the entry's key;
+ * the flush applies the frequency cut-off (mapper.pyx:64) and adds them onto the node counts
+ * (mapper.pyx:68).  kmb_mapper_flush queues that pass on the mapper's stream without waiting (use it
+ * before handing the count buffer to an all-reduce on the same stream); sync, read_counts, stats and
+ * lookup_counts flush implicitly. */
+int kmb_mapper_flush(kmb_mapper *mapper);
+/* Wait for all queued work of the mapper (flushing first); returns KMB_ERR_INVALID_BASE if any kernel met an
  * invalid byte since the last reset (counts are then undefined until kmb_mapper_reset). */
 int kmb_mapper_sync(kmb_mapper *mapper);
 /* Flat offset (within the call that failed) of the first invalid byte, or -1. */
@@ -151,8 +162,8 @@ int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loads, int loa
 int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kernels);
 
 /* Tuning knobs (process-wide, read at launch / index-creation time): name in
- * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "aggregate_atomics",
- *  "gathers_in_flight", "use_filter", "filter_l2_budget_bytes", "l2_persist", "time_kernels",
+ * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
+ *  "use_filter", "filter_l2_budget_bytes", "l2_persist", "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "chunk_bytes"}. */
 int kmb_set_option(const char *name, int64_t value);
 int kmb_get_option(const char *name, int64_t *value);

@@ -50,11 +50,13 @@ SIGNATURES = {
     "kmb_index_destroy": (C.c_int, [_vp]),
     "kmb_index_info": (C.c_int, [_vp, C.POINTER(C.c_int64), _u64p, _u64p, _u64p]),
     "kmb_index_filter_bytes": (C.c_int, [_vp, _u64p]),
+    "kmb_index_layout": (C.c_int, [_vp, _u32p, _u64p, _u64p, _u64p]),
     "kmb_mapper_create": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, C.POINTER(_vp)]),
     "kmb_mapper_destroy": (C.c_int, [_vp]),
     "kmb_mapper_set_stream": (C.c_int, [_vp, _vp]),
     "kmb_mapper_map_kmers": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_int]),
     "kmb_mapper_map_reads": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int, C.c_uint32]),
+    "kmb_mapper_flush": (C.c_int, [_vp]),
     "kmb_mapper_sync": (C.c_int, [_vp]),
     "kmb_mapper_bad_offset": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "kmb_mapper_read_counts": (C.c_int, [_vp, _vp, C.c_uint64]),

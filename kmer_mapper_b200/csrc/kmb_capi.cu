@@ -53,8 +53,7 @@ static int kmb_fail(int code, const char *fmt, ...) {
 struct KmbOptions {
     int64_t map_reads_blocks_per_sm = 0;  // 0 = whatever the occupancy calculator allows
     int64_t map_kmers_blocks_per_sm = 0;
-    int64_t probe_variant = 1;            // 0 = one query per thread, 1 = staged probe with warp stack
-    int64_t aggregate_atomics = 0;        // merge same-node hits of a warp step before the RED
+    int64_t probe_variant = 1;            // map_kmers: 0 = one query per thread, 1 = staged probe with warp stack
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
     int64_t gathers_in_flight = 8;        // U: 4, 8 or 16 independent gathers per thread
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
@@ -77,7 +76,6 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(map_reads_blocks_per_sm)
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
-    OPT(aggregate_atomics)
     OPT(gathers_in_flight)
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
@@ -104,7 +102,6 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(map_reads_blocks_per_sm)
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
-    OPT(aggregate_atomics)
     OPT(gathers_in_flight)
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
@@ -237,13 +234,17 @@ static int grid_for(size_t work_items, int block, int sms, int per_sm = 8) {
 // ------------------------------------------------------------------------------------------------
 struct kmb_index {
     int device = 0;
-    uint64_t modulo = 0, n_entries = 0;
-    uint64_t *dir = nullptr;
-    KmbEntry *entries = nullptr;
-    int32_t *n_overflow = nullptr;  // only kept when some bucket has >= 31 entries
+    uint64_t modulo = 0, n_entries = 0, n_live = 0;
+    uint32_t line_shift = 0;            // g: 2^g buckets per 128-byte line
+    uint64_t n_main = 0, n_lines = 0;   // main lines, main + overflow lines
+    uint32_t *lines = nullptr;          // master copy (keys + the counters of the mapper that borrows it)
+    uint32_t *cold_node = nullptr;      // node of (line, slot)
+    uint16_t *cold_freq = nullptr;      // frequency of (line, slot)
     uint32_t *filter = nullptr;
     size_t filter_bytes = 0;
     bool filter_on = false;
+    bool lines_in_use = false;          // a mapper is counting into the master copy
+    bool lines_dirty = false;           // master counters may be non-zero
     int64_t max_node = -1;
     uint64_t device_bytes = 0;
     KmbMod mod;
@@ -253,12 +254,20 @@ struct kmb_index {
 extern "C" int kmb_index_destroy(kmb_index *ix) {
     if (!ix) return KMB_OK;
     DeviceGuard g(ix->device);
-    cudaFree(ix->dir);
-    cudaFree(ix->entries);
-    cudaFree(ix->n_overflow);
+    cudaFree(ix->lines);
+    cudaFree(ix->cold_node);
+    cudaFree(ix->cold_freq);
     cudaFree(ix->filter);
+    cudaGetLastError();
     delete ix;
     return KMB_OK;
+}
+
+// buckets per line: the largest power of two that keeps the mean line occupancy <= 4.5 of 10 slots
+static uint32_t choose_line_shift(uint64_t modulo, uint64_t n_entries) {
+    uint32_t g = 0;
+    while (g < 16 && (double)(2ull << g) * (double)n_entries <= 4.5 * (double)modulo && (2ull << g) <= modulo) g++;
+    return g;
 }
 
 extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, const int32_t *n_kmers, uint64_t modulo,
@@ -287,6 +296,8 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     ix->modulo = modulo;
     ix->n_entries = n_entries;
     ix->mod = kmb_mod_make(modulo);
+    ix->line_shift = choose_line_shift(modulo, n_entries);
+    ix->n_main = ((modulo - 1) >> ix->line_shift) + 1;
     KMB_TRY(dev_info(device, &ix->info));
 
     cudaStream_t s = 0;  // index construction is a one-off: legacy default stream, synchronous
@@ -303,9 +314,11 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     KMB_TRY(to_device(frequencies, (size_t)n_entries, device, t_freq, &d_freq, s));
 
     ix->filter_bytes = (size_t)((modulo + 31) / 32) * 4;
-    KMB_CUDA(cudaMalloc(&ix->dir, (size_t)modulo * 8));
-    KMB_CUDA(cudaMalloc(&ix->entries, std::max<size_t>((size_t)n_entries, 1) * sizeof(KmbEntry)));
     KMB_CUDA(cudaMalloc(&ix->filter, ix->filter_bytes));
+    KMB_CUDA(cudaMemsetAsync(ix->filter, 0, ix->filter_bytes, s));
+    DevBuf<uint32_t> line_fill;
+    KMB_TRY(line_fill.alloc((size_t)ix->n_main));
+    KMB_CUDA(cudaMemsetAsync(line_fill.p, 0, (size_t)ix->n_main * 4, s));
     DevBuf<KmbStatus> d_status;
     KMB_TRY(d_status.alloc(1));
     KmbStatus hs;
@@ -315,13 +328,8 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     KMB_CUDA(cudaMemcpyAsync(d_status.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
 
     const int sms = ix->info.sms;
-    if (n_entries) {
-        kmb_pack_entries<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, n_entries, ix->entries,
-                                                                     d_status.p);
-        g_launches++;
-    }
-    kmb_build_directory<<<grid_for(modulo, 256, sms), 256, 0, s>>>(d_h2i, d_nk, d_kmers, modulo, n_entries, ix->mod,
-                                                                  ix->dir, ix->filter, d_status.p);
+    // 1. the directory must stay inside the entry arrays (the reference runs with boundscheck off)
+    kmb_v2_check_buckets<<<grid_for(modulo, 256, sms), 256, 0, s>>>(d_h2i, d_nk, modulo, n_entries, d_status.p);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
@@ -331,29 +339,52 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
                         "index: a bucket (hashes_to_index[h], n_kmers[h]) lies outside [0, n_entries=%llu] or has a "
                         "negative size (the reference would read out of bounds, mapper.pyx:15-18)",
                         (unsigned long long)n_entries);
+    // 2. per-line counts + filter bits, 3. overflow lines needed
+    if (n_entries) {
+        kmb_v2_count<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_h2i, d_nk, n_entries, ix->mod,
+                                                                 ix->line_shift, line_fill.p, ix->filter, d_status.p);
+        g_launches++;
+    }
+    kmb_v2_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, d_status.p);
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
     if (hs.index_flags & 2u)
         return kmb_fail(KMB_ERR_BAD_INDEX, "index: negative node id (the reference would write out of bounds)");
     ix->max_node = hs.max_node;
-    if (hs.index_flags & 4u) {
-        // keep the exact sizes of the >= 31-entry buckets
-        if (t_nk.p) {
-            ix->n_overflow = t_nk.release();
-        } else {
-            KMB_CUDA(cudaMalloc(&ix->n_overflow, (size_t)modulo * 4));
-            KMB_CUDA(cudaMemcpy(ix->n_overflow, d_nk, (size_t)modulo * 4, cudaMemcpyDeviceToDevice));
-        }
+    ix->n_live = hs.n_live_entries;
+    ix->n_lines = ix->n_main + hs.pool_lines;
+    if (ix->n_lines >= (1ull << 32)) return kmb_fail(KMB_ERR_BAD_INDEX, "index: too many lines");
+    // 4. lines + cold arrays, headers, scatter
+    KMB_CUDA(cudaMalloc(&ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
+    KMB_CUDA(cudaMalloc(&ix->cold_node, (size_t)ix->n_lines * KMB_LINE_SLOTS * 4));
+    KMB_CUDA(cudaMalloc(&ix->cold_freq, (size_t)ix->n_lines * KMB_LINE_SLOTS * 2));
+    KMB_CUDA(cudaMemsetAsync(ix->lines, 0, (size_t)ix->n_lines * KMB_LINE_BYTES, s));
+    KMB_CUDA(cudaMemsetAsync(ix->cold_node, 0, (size_t)ix->n_lines * KMB_LINE_SLOTS * 4, s));
+    KMB_CUDA(cudaMemsetAsync(ix->cold_freq, 0, (size_t)ix->n_lines * KMB_LINE_SLOTS * 2, s));
+    KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
+    kmb_v2_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, d_status.p);
+    g_launches++;
+    if (n_entries) {
+        kmb_v2_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
+                                                                   ix->line_shift, line_fill.p, ix->lines, ix->cold_node,
+                                                                   ix->cold_freq);
+        g_launches++;
     }
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaStreamSynchronize(s));
+
     bool want_filter = g_opt.use_filter == 1 ||
                        (g_opt.use_filter < 0 && (int64_t)ix->filter_bytes <= g_opt.filter_l2_budget_bytes &&
-                        n_entries < modulo);  // a table with load factor >= 1 has no empty buckets to skip
+                        n_entries < 2 * modulo);  // a table this dense sets nearly every filter bit
     ix->filter_on = want_filter;
     if (!want_filter) {
         cudaFree(ix->filter);
         ix->filter = nullptr;
         ix->filter_bytes = 0;
     }
-    ix->device_bytes = modulo * 8 + std::max<uint64_t>(n_entries, 1) * sizeof(KmbEntry) + ix->filter_bytes +
-                       (ix->n_overflow ? modulo * 4 : 0);
+    ix->device_bytes = ix->n_lines * (KMB_LINE_BYTES + KMB_LINE_SLOTS * 6) + ix->filter_bytes;
     cleanup.ix = nullptr;
     *out = ix;
     return KMB_OK;
@@ -369,10 +400,20 @@ extern "C" int kmb_index_info(const kmb_index *ix, int64_t *max_node_id, uint64_
     return KMB_OK;
 }
 
-// 1 when the bucket-occupancy filter (probe level 0) is in use for this index
 extern "C" int kmb_index_filter_bytes(const kmb_index *ix, uint64_t *bytes) {
     if (!ix || !bytes) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_filter_bytes: null argument");
     *bytes = ix->filter_on ? ix->filter_bytes : 0;
+    return KMB_OK;
+}
+
+// Geometry of the line table: buckets per line, main lines, overflow lines, live entries.
+extern "C" int kmb_index_layout(const kmb_index *ix, uint32_t *buckets_per_line, uint64_t *n_main_lines,
+                                uint64_t *n_overflow_lines, uint64_t *n_live_entries) {
+    if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_layout: null index");
+    if (buckets_per_line) *buckets_per_line = 1u << ix->line_shift;
+    if (n_main_lines) *n_main_lines = ix->n_main;
+    if (n_overflow_lines) *n_overflow_lines = ix->n_lines - ix->n_main;
+    if (n_live_entries) *n_live_entries = ix->n_live;
     return KMB_OK;
 }
 
@@ -393,6 +434,9 @@ struct kmb_mapper {
     uint64_t n_counts = 0;
     uint32_t *counts = nullptr;
     bool own_counts = false;
+    uint32_t *lines = nullptr;   // the index's master copy, or a private clone when that is taken
+    bool own_lines = false;
+    bool dirty = false;          // slot counters may be non-zero (hits not yet flushed onto nodes)
     int32_t max_freq = 1000;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     KmbStatus *d_status = nullptr;
@@ -426,6 +470,12 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
         cudaEventDestroy(pr.second);
     }
     cudaFree(m->dmask);
+    if (m->own_lines) {
+        cudaFree(m->lines);
+    } else if (m->lines) {
+        m->index->lines_in_use = false;
+        m->index->lines_dirty = m->index->lines_dirty || m->dirty;
+    }
     if (m->own_counts) cudaFree(m->counts);
     cudaFree(m->d_status);
     if (m->h_status) cudaFreeHost(m->h_status);
@@ -445,6 +495,36 @@ static int status_reset(kmb_mapper *m) {
     KMB_CUDA(cudaMemcpyAsync(m->d_status, m->h_status, sizeof(hs), cudaMemcpyHostToDevice, m->stream));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
     return KMB_OK;
+}
+
+template <bool CLEAR_ONLY>
+static int launch_flush(kmb_mapper *m) {
+    const kmb_index *ix = m->index;
+    kmb_flush_kernel<CLEAR_ONLY><<<grid_for(ix->n_lines, 256, ix->info.sms), 256, 0, m->stream>>>(
+        m->lines, ix->n_lines, ix->cold_node, ix->cold_freq, m->max_freq, m->counts, m->d_status);
+    g_launches++;
+    KMB_CUDA(cudaGetLastError());
+    m->dirty = false;
+    return KMB_OK;
+}
+
+// The slot counters live inside the lines, so a mapper needs a line table of its own: the first
+// mapper of an index borrows the index's master copy, further concurrent mappers get a clone.
+static int attach_lines(kmb_mapper *m) {
+    kmb_index *ix = m->index;
+    if (!ix->lines_in_use) {
+        m->lines = ix->lines;
+        ix->lines_in_use = true;
+        if (ix->lines_dirty) {
+            KMB_TRY(launch_flush<true>(m));
+            ix->lines_dirty = false;
+        }
+        return KMB_OK;
+    }
+    KMB_CUDA(cudaMalloc(&m->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
+    m->own_lines = true;
+    KMB_CUDA(cudaMemcpyAsync(m->lines, ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES, cudaMemcpyDeviceToDevice, m->stream));
+    return launch_flush<true>(m);
 }
 
 static int set_l2_window(kmb_mapper *m) {
@@ -511,6 +591,7 @@ extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *
     KMB_CUDA(cudaMalloc(&m->d_status, sizeof(KmbStatus)));
     KMB_CUDA(cudaMallocHost(&m->h_status, sizeof(KmbStatus)));
     KMB_TRY(status_reset(m));
+    KMB_TRY(attach_lines(m));
     for (int i = 0; i < 2; i++) {
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].copied, cudaEventDisableTiming));
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].consumed, cudaEventDisableTiming));
@@ -533,13 +614,10 @@ extern "C" int kmb_mapper_set_stream(kmb_mapper *m, void *cuda_stream) {
 static KmbProbe make_probe(const kmb_mapper *m) {
     const kmb_index *ix = m->index;
     KmbProbe P;
-    P.dir = ix->dir;
-    P.entries = ix->entries;
-    P.n_overflow = ix->n_overflow;
+    P.lines = m->lines;
     P.filter = ix->filter_on ? ix->filter : nullptr;
-    P.counts = m->counts;
     P.mod = ix->mod;
-    P.max_freq = m->max_freq;
+    P.line_shift = ix->line_shift;
     return P;
 }
 
@@ -553,28 +631,20 @@ typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *
 typedef void (*MapKmersFn)(const uint64_t *, uint64_t, int, KmbProbe, KmbStatus *);
 
 template <int U>
-static MapReadsFn map_reads_fn_u(bool filt, bool agg, bool rc) {
-    if (filt) {
-        if (agg) return rc ? kmb_map_reads_kernel<U, true, true, true> : kmb_map_reads_kernel<U, true, true, false>;
-        return rc ? kmb_map_reads_kernel<U, true, false, true> : kmb_map_reads_kernel<U, true, false, false>;
-    }
-    if (agg) return rc ? kmb_map_reads_kernel<U, false, true, true> : kmb_map_reads_kernel<U, false, true, false>;
-    return rc ? kmb_map_reads_kernel<U, false, false, true> : kmb_map_reads_kernel<U, false, false, false>;
+static MapReadsFn map_reads_fn_u(bool filt, bool rc) {
+    if (filt) return rc ? kmb_map_reads_kernel<U, true, true> : kmb_map_reads_kernel<U, true, false>;
+    return rc ? kmb_map_reads_kernel<U, false, true> : kmb_map_reads_kernel<U, false, false>;
 }
-static MapReadsFn map_reads_fn(int u, bool filt, bool agg, bool rc) {
-    return u == 4 ? map_reads_fn_u<4>(filt, agg, rc) : (u == 8 ? map_reads_fn_u<8>(filt, agg, rc) : map_reads_fn_u<16>(filt, agg, rc));
+static MapReadsFn map_reads_fn(int u, bool filt, bool rc) {
+    return u == 4 ? map_reads_fn_u<4>(filt, rc) : (u == 8 ? map_reads_fn_u<8>(filt, rc) : map_reads_fn_u<16>(filt, rc));
 }
 template <int U>
-static MapKmersFn map_kmers_fn_u(bool filt, bool agg, bool rc) {
-    if (filt) {
-        if (agg) return rc ? kmb_map_kmers_kernel<U, true, true, true> : kmb_map_kmers_kernel<U, true, true, false>;
-        return rc ? kmb_map_kmers_kernel<U, true, false, true> : kmb_map_kmers_kernel<U, true, false, false>;
-    }
-    if (agg) return rc ? kmb_map_kmers_kernel<U, false, true, true> : kmb_map_kmers_kernel<U, false, true, false>;
-    return rc ? kmb_map_kmers_kernel<U, false, false, true> : kmb_map_kmers_kernel<U, false, false, false>;
+static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
+    if (filt) return rc ? kmb_map_kmers_kernel<U, true, true> : kmb_map_kmers_kernel<U, true, false>;
+    return rc ? kmb_map_kmers_kernel<U, false, true> : kmb_map_kmers_kernel<U, false, false>;
 }
-static MapKmersFn map_kmers_fn(int u, bool filt, bool agg, bool rc) {
-    return u == 4 ? map_kmers_fn_u<4>(filt, agg, rc) : (u == 8 ? map_kmers_fn_u<8>(filt, agg, rc) : map_kmers_fn_u<16>(filt, agg, rc));
+static MapKmersFn map_kmers_fn(int u, bool filt, bool rc) {
+    return u == 4 ? map_kmers_fn_u<4>(filt, rc) : (u == 8 ? map_kmers_fn_u<8>(filt, rc) : map_kmers_fn_u<16>(filt, rc));
 }
 
 static int resident_blocks(const void *fn, int64_t opt, int *out) {
@@ -617,11 +687,12 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
         g_launches++;
     }
     KmbProbe P = make_probe(m);
-    MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, g_opt.aggregate_atomics != 0, (flags & KMB_FLAG_REVCOMP) != 0);
+    MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
     int per_sm;
     KMB_TRY(resident_blocks((const void *)fn, g_opt.map_reads_blocks_per_sm, &per_sm));
     uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
+    m->dirty = true;
     KMB_TRY(timed_begin(m));
     fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_bases, n_bases, base0, d_mask, k, !(flags & KMB_FLAG_NO_N_TO_A), P,
                                                 m->d_status);
@@ -636,6 +707,7 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
     const kmb_index *ix = m->index;
     KmbProbe P = make_probe(m);
     bool rc = (flags & KMB_FLAG_REVCOMP) != 0;
+    m->dirty = true;
     KMB_TRY(timed_begin(m));
     if (g_opt.probe_variant == 0) {
         int grid = grid_for(n, 256, ix->info.sms, 16);
@@ -643,7 +715,7 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
         else kmb_map_kmers_simple_kernel<false><<<grid, 256, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
     } else {
         int u = pick_u();
-        MapKmersFn fn = map_kmers_fn(u, P.filter != nullptr, g_opt.aggregate_atomics != 0, rc);
+        MapKmersFn fn = map_kmers_fn(u, P.filter != nullptr, rc);
         int per_sm;
         KMB_TRY(resident_blocks((const void *)fn, g_opt.map_kmers_blocks_per_sm, &per_sm));
         uint64_t n_blocks = (n + (uint64_t)KMB_TILE_THREADS * u - 1) / ((uint64_t)KMB_TILE_THREADS * u);
@@ -779,6 +851,7 @@ extern "C" int kmb_mapper_map_kmers(kmb_mapper *m, const uint64_t *kmers, uint64
 }
 
 static int fetch_status(kmb_mapper *m) {
+    if (m->dirty) KMB_TRY(launch_flush<false>(m));
     KMB_CUDA(cudaMemcpyAsync(m->h_status, m->d_status, sizeof(KmbStatus), cudaMemcpyDeviceToHost, m->stream));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
     return KMB_OK;
@@ -818,8 +891,17 @@ extern "C" int kmb_mapper_read_counts(kmb_mapper *m, uint32_t *out, uint64_t n_c
 extern "C" int kmb_mapper_reset(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_reset: null mapper");
     KMB_ON_DEVICE(m->index->device);
+    if (m->dirty) KMB_TRY(launch_flush<true>(m));
     KMB_CUDA(cudaMemsetAsync(m->counts, 0, m->n_counts * 4, m->stream));
     return status_reset(m);
+}
+
+// Queue the flush of the slot counters onto the node counts (asynchronous, on the mapper's stream).
+extern "C" int kmb_mapper_flush(kmb_mapper *m) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_flush: null mapper");
+    KMB_ON_DEVICE(m->index->device);
+    if (m->dirty) KMB_TRY(launch_flush<false>(m));
+    return KMB_OK;
 }
 
 extern "C" int kmb_mapper_counts_device(kmb_mapper *m, uint32_t **counts_device, uint64_t *n_counts) {
@@ -859,20 +941,9 @@ extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t 
 // ------------------------------------------------------------------------------------------------
 // membership and per-key lookup
 // ------------------------------------------------------------------------------------------------
-static KmbProbe index_probe(const kmb_index *ix, uint32_t *counts) {
-    KmbProbe P;
-    P.dir = ix->dir;
-    P.entries = ix->entries;
-    P.n_overflow = ix->n_overflow;
-    P.filter = ix->filter_on ? ix->filter : nullptr;
-    P.counts = counts;
-    P.mod = ix->mod;
-    P.max_freq = 0;
-    return P;
-}
-
 template <int MODE, class OutT>
-static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uint64_t *keys, uint64_t n, OutT *out) {
+static int run_lookup(kmb_index *ix, const uint32_t *lines, const uint32_t *counts, cudaStream_t s, const uint64_t *keys,
+                      uint64_t n, OutT *out) {
     if (n == 0) return KMB_OK;
     if (!keys || !out) return kmb_fail(KMB_ERR_BAD_ARG, "lookup: null buffer");
     DevBuf<uint64_t> t_keys;
@@ -886,9 +957,14 @@ static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uin
         KMB_TRY(t_out.alloc((size_t)n));
         d_out = t_out.p;
     }
-    KmbProbe P = index_probe(ix, counts);
-    kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(d_keys, n, P, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),
-                                                                              (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
+    KmbProbe P;
+    P.lines = const_cast<uint32_t *>(lines);  // keys are only read
+    P.filter = ix->filter_on ? ix->filter : nullptr;
+    P.mod = ix->mod;
+    P.line_shift = ix->line_shift;
+    kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(
+        d_keys, n, P, ix->cold_node, counts, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),
+        (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     if (!out_dev) KMB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(OutT), cudaMemcpyDeviceToHost, s));
@@ -899,13 +975,14 @@ static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uin
 extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t n, uint8_t *out) {
     if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_in_graph_index: null index");
     KMB_ON_DEVICE(ix->device);
-    return run_lookup<0, uint8_t>(ix, nullptr, 0, kmers, n, out);
+    return run_lookup<0, uint8_t>(ix, ix->lines, nullptr, 0, kmers, n, out);
 }
 
 extern "C" int kmb_mapper_lookup_counts(kmb_mapper *m, const uint64_t *keys, uint64_t n, uint32_t *out) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_lookup_counts: null mapper");
     KMB_ON_DEVICE(m->index->device);
-    return run_lookup<1, uint32_t>(m->index, m->counts, m->stream, keys, n, out);
+    if (m->dirty) KMB_TRY(launch_flush<false>(m));
+    return run_lookup<1, uint32_t>(m->index, m->lines, m->counts, m->stream, keys, n, out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -50,33 +50,45 @@ KMB_HD void kmb_divmod(uint64_t n, const KmbMod md, uint64_t &q, uint64_t &r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bucket directory word (one per bucket h = kmer % modulo), 8 bytes:
-//   bits  0..30  pos  first entry of the bucket          (hashes_to_index[h], mapper.pyx:56)
-//   bits 31..35  n    bucket size, 31 = "31 or more, read the overflow table"  (n_kmers[h], :55)
-//   bits 36..63  fp   low 28 bits of (key / modulo) of the bucket's FIRST entry
-// An all-zero word is an empty bucket.  With n == 1 a query whose quotient fingerprint differs
-// cannot match (same bucket + same quotient <=> same key), so it is answered from the directory
-// sector alone; a fingerprint collision (2^-28) only costs a wasted entry fetch, never a result.
+// Index layout v2: the 128-byte line.
+//
+// Measured on B200 (profiles/README.md): a random global load that misses L2 always costs one full
+// 128-byte line of HBM traffic, so the layout is built around lines, not sectors.  G = 2^g
+// consecutive buckets (h = key % modulo, mapper.pyx:54) share one line; the line holds up to ten
+// of their entries -- the 8-byte key and, in the same line, its 4-byte hit counter -- so that the
+// one line fetched for a query answers it completely and the count (mapper.pyx:68) is a reduction
+// into a line that is already in L2.  32-bit word map of a line:
+//   w0        n_total   entries in the chain that starts at this (main) line
+//   w1        ovf_base  line index of the first overflow line (only if n_total > 10)
+//   w2..w21   key j at (w[2+2j], w[3+2j]) = (lo, hi), j = 0..9
+//   w22..w31  counter j
+// Sector s (words 8s..8s+7) therefore holds key pairs p = 0..3 <-> slot j = 4s + p - 1; sector 3 is
+// counters only.  Entries beyond ten go to overflow lines ovf_base + (s-10)/10 with the same slot map.
+// node and frequency of a slot live in cold side arrays (line*10 + j), read only by the flush pass.
 // ---------------------------------------------------------------------------------------------
-#define KMB_DIR_POS_BITS 31
-#define KMB_DIR_N_BITS 5
-#define KMB_DIR_N_OVERFLOW 31u
-#define KMB_DIR_FP_BITS 28
-#define KMB_DIR_FP_MASK ((1u << KMB_DIR_FP_BITS) - 1u)
+#define KMB_LINE_BYTES 128
+#define KMB_LINE_WORDS 32
+#define KMB_LINE_SLOTS 10
+#define KMB_LINE_KEY_WORD0 2
+#define KMB_LINE_CNT_WORD0 22
 
-KMB_HD uint64_t kmb_dir_pack(uint32_t pos, uint32_t n, uint32_t fp) {
-    uint32_t nn = n >= KMB_DIR_N_OVERFLOW ? KMB_DIR_N_OVERFLOW : n;
-    return (uint64_t)pos | ((uint64_t)nn << KMB_DIR_POS_BITS) |
-           ((uint64_t)(fp & KMB_DIR_FP_MASK) << (KMB_DIR_POS_BITS + KMB_DIR_N_BITS));
+// chain position s (0-based among the entries of a main line) -> (line index, slot)
+KMB_HD uint64_t kmb_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) {
+    return s < KMB_LINE_SLOTS ? main_line : (uint64_t)ovf_base + (s - KMB_LINE_SLOTS) / KMB_LINE_SLOTS;
 }
-KMB_HD uint32_t kmb_dir_pos(uint64_t w) { return (uint32_t)w & 0x7FFFFFFFu; }
-KMB_HD uint32_t kmb_dir_n(uint64_t w) { return (uint32_t)(w >> KMB_DIR_POS_BITS) & 31u; }
-KMB_HD uint32_t kmb_dir_fp(uint64_t w) { return (uint32_t)(w >> (KMB_DIR_POS_BITS + KMB_DIR_N_BITS)); }
+KMB_HD uint32_t kmb_chain_slot(uint32_t s) { return s % KMB_LINE_SLOTS; }
+KMB_HD uint32_t kmb_chain_extra_lines(uint32_t n_total) {
+    return n_total > KMB_LINE_SLOTS ? (n_total - 1) / KMB_LINE_SLOTS : 0u;
+}
 
-// true when the directory word alone proves that no entry can match a query with fingerprint fpq
-KMB_HD bool kmb_dir_rejects(uint64_t w, uint32_t fpq) {
-    uint32_t n = kmb_dir_n(w);
-    return n == 0u || (n == 1u && kmb_dir_fp(w) != (fpq & KMB_DIR_FP_MASK));
+// Occupancy filter (probe level 0): one 32-bit word per 32 consecutive buckets; every live entry
+// sets TWO bits of the word h >> 5: its bucket's bit (h & 31) and a bit chosen by the quotient
+// q = key / modulo, which is independent of h.  A query passes iff both of its bits are set: a
+// two-probe Bloom filter blocked into the word one 4-byte load brings (false-pass rate ~13 % at the
+// reference's load factor 0.22 instead of ~20 % for the occupancy bit alone).
+KMB_HD uint32_t kmb_filter_mask(uint32_t h, uint64_t q) {
+    uint32_t b2 = ((uint32_t)q * 0x9E3779B1u) >> 27;
+    return (1u << (h & 31u)) | (1u << b2);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,19 +1,21 @@
 // kmb_kernels.cuh -- hand-written sm_100a kernels of the k-mer mapping path.
 //
-//   K5  kmb_pack_entries / kmb_build_directory / kmb_scan_nodes   index re-layout (once per index)
+//   K5  kmb_v2_check_buckets / _count / _plan / _scatter   index re-layout into 128-byte lines (once per index)
 //   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
-//   K1-4 kmb_map_reads_kernel     fused encode + window + directory probe + count  (production path)
+//   K1-4 kmb_map_reads_kernel     fused encode + window + filter + line probe + count  (production path)
 //   K3-4 kmb_map_kmers_kernel     probe + count on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
+//   K4b kmb_flush_kernel          per-slot hit counters -> per-node counts (frequency cut-off applied here)
 //   K6  kmb_in_graph_kernel       membership mask (mapper.pyx:81)
 //   K2  kmb_hash_count/_scan/_emit  flat hash array (util.py:71-75 drop-in)
 //   E1  kmb_codec_* kernels       legacy 2-bit codec (encodings.py)
-//   B   kmb_gather_bench_kernel   random-sector gather micro-roofline
+//   B   kmb_gather_bench_kernel   random-line gather micro-roofline
 //
 // Nothing here is a dense contraction, so no tensor-core / TMEM / TMA-tile machinery is used: the
-// path is bound by random 32-byte-sector gathers from HBM (directory) plus a thin coalesced stream
-// of bases.  What matters: one sector per query in the common case, many independent
-// gathers in flight per thread, warp-compacted second-level work so hits do not serialise the
-// warp, no-return reductions (RED) for the counters, persistent grid sized to the SM count.
+// path is bound by random 128-byte-line fetches from HBM plus one L2 hit per k-mer (the filter)
+// and a thin coalesced stream of bases.  What matters: as few line fetches per k-mer
+// as possible (L2-resident filter), every fetched line answers its query completely (keys and
+// counters share the line), warp-compacted second-level work so hits do not serialise the warp,
+// no-return reductions (RED) into lines that are already in L2, persistent grid sized to the SMs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,27 +29,20 @@
 #define KMB_QUEUE_SLOTS 64                                    // per-warp candidate stack (>= 32 + 32)
 
 struct KmbStatus {
-    unsigned long long first_bad_offset;  // min flat offset of an invalid byte, ~0 if none
-    unsigned long long n_kmers_mapped;    // windows looked up
-    unsigned long long n_entries_counted; // index entries that received a +1 (mapper.pyx:68)
-    unsigned int index_flags;             // bit0 bucket out of range, bit1 negative node, bit2 overflow bucket seen
+    unsigned long long first_bad_offset;   // min flat offset of an invalid byte, ~0 if none
+    unsigned long long n_kmers_mapped;     // windows looked up
+    unsigned long long n_entries_counted;  // +1s applied to node counts (mapper.pyx:68), known after a flush
+    unsigned long long n_live_entries;     // index build: entries reachable through their own bucket
+    unsigned int index_flags;              // bit0 bucket out of range, bit1 negative node
+    unsigned int pool_lines;               // index build: overflow lines needed / handed out
     int max_node;
 };
 
-struct KmbEntry {  // 16 bytes, one LDG.128
-    uint64_t key;
-    uint32_t node;
-    uint32_t freq;
-};
-
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
-    const uint64_t *__restrict__ dir;
-    const KmbEntry *__restrict__ entries;
-    const int32_t *__restrict__ n_overflow;  // original n_kmers[], only read for n == 31 buckets
-    const uint32_t *__restrict__ filter;     // bit h set <=> bucket h is not empty (L2-resident), or nullptr
-    uint32_t *counts;
+    uint32_t *lines;                         // 128-byte lines (keys immutable, counters reduced into)
+    const uint32_t *__restrict__ filter;     // 2 bits per live entry in word h >> 5, or nullptr
     KmbMod mod;
-    int32_t max_freq;  // C int like the reference's cut-off (mapper.pyx:19,64); negative = nothing counts
+    uint32_t line_shift;                     // g: line = h >> g
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -95,76 +90,114 @@ __device__ __forceinline__ uint4 kmb_ldg_v4_hint(const void *p, uint64_t pol) {
                  : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ KmbEntry kmb_load_entry(const KmbEntry *p, uint64_t pol) {
-    uint4 v = kmb_ldg_v4_hint(p, pol);
-    KmbEntry e;
-    e.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
-    e.node = v.z;
-    e.freq = v.w;
-    return e;
+// one 32-byte sector of a line; the counters in it are concurrently reduced into, so no .nc path
+__device__ __forceinline__ void kmb_ld_sector(const uint32_t *p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ uint2 kmb_ld_u64_volatile(const uint32_t *p) {
+    uint2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
 }
 
 // ================================================================================================
-// K5: index re-layout
+// K5: index re-layout.  The reference's structure is "scan n_kmers[h] entries from
+// hashes_to_index[h], compare keys" (mapper.pyx:55-62).  Entry l can only ever match a query of
+// bucket hl = kmers[l] % modulo, and only if l lies inside that bucket's range: such entries are
+// "live", and the set of live entries defines the lookup result for ANY directory, well-formed or
+// not (overlapping ranges, entries filed under a foreign bucket).  Live entries are scattered into
+// the line of their own bucket; order inside a line is irrelevant for counting.
 // ================================================================================================
-__global__ void kmb_pack_entries(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
-                                 const uint16_t *__restrict__ freqs, uint64_t n, KmbEntry *__restrict__ out,
-                                 KmbStatus *status) {
+__global__ void kmb_v2_check_buckets(const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
+                                     uint64_t modulo, uint64_t n_entries, KmbStatus *status) {
+    unsigned flags = 0;
+    for (uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; h < modulo; h += (uint64_t)gridDim.x * blockDim.x) {
+        int n = n_kmers[h];
+        int pos = hashes_to_index[h];
+        if (n < 0 || (n > 0 && (pos < 0 || (uint64_t)pos + (uint64_t)n > n_entries))) flags |= 1u;
+    }
+    if (flags) atomicOr(&status->index_flags, flags);
+}
+
+__device__ __forceinline__ bool kmb_entry_live(const int32_t *__restrict__ hashes_to_index,
+                                               const int32_t *__restrict__ n_kmers, uint64_t l, uint64_t h) {
+    int64_t pos = hashes_to_index[h], n = n_kmers[h];
+    return n > 0 && (int64_t)l >= pos && (int64_t)l < pos + n;
+}
+
+// pass 1: per-line entry counts, filter bits, node statistics
+__global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
+                             const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
+                             uint64_t n_entries, KmbMod mod, uint32_t line_shift, uint32_t *__restrict__ line_fill,
+                             uint32_t *__restrict__ filter, KmbStatus *status) {
     int local_max = -1;
     bool neg = false;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        int node = nodes[i];
-        uint4 v;
-        uint64_t key = kmers[i];
-        v.x = (uint32_t)key;
-        v.y = (uint32_t)(key >> 32);
-        v.z = (uint32_t)node;
-        v.w = (uint32_t)freqs[i];
-        reinterpret_cast<uint4 *>(out)[i] = v;
+    unsigned long long live_n = 0;
+    for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_entries; l += (uint64_t)gridDim.x * blockDim.x) {
+        int node = nodes[l];
         neg |= node < 0;
         local_max = max(local_max, node);
+        uint64_t q, h;
+        kmb_divmod(kmers[l], mod, q, h);
+        if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
+        live_n++;
+        atomicAdd(&line_fill[h >> line_shift], 1u);
+        atomicOr(&filter[h >> 5], kmb_filter_mask((uint32_t)h, q));
     }
-    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(KMB_FULL_MASK, local_max, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        local_max = max(local_max, __shfl_xor_sync(KMB_FULL_MASK, local_max, o));
+        live_n += __shfl_xor_sync(KMB_FULL_MASK, live_n, o);
+    }
     unsigned any_neg = __ballot_sync(KMB_FULL_MASK, neg);
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&status->max_node, local_max);
+        if (live_n) atomicAdd(&status->n_live_entries, live_n);
         if (any_neg) atomicOr(&status->index_flags, 2u);
     }
 }
 
-__global__ void kmb_build_directory(const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
-                                    const uint64_t *__restrict__ kmers, uint64_t modulo, uint64_t n_entries,
-                                    KmbMod mod, uint64_t *__restrict__ dir, uint32_t *__restrict__ filter,
-                                    KmbStatus *status) {
-    // every warp walks aligned groups of 32 consecutive buckets so that one ballot is one filter word
-    unsigned flags = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t h0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x - lane); h0 < modulo; h0 += stride) {
-        const uint64_t h = h0 + lane;
-        uint64_t w = 0;
-        if (h < modulo) {
-            int n = n_kmers[h];
-            int pos = hashes_to_index[h];
-            if (n > 0) {
-                if (pos < 0 || (uint64_t)pos + (uint64_t)n > n_entries) {
-                    flags |= 1u;
-                } else {
-                    uint64_t q, r;
-                    kmb_divmod(kmers[pos], mod, q, r);
-                    w = kmb_dir_pack((uint32_t)pos, (uint32_t)n, (uint32_t)q);
-                    if (n >= (int)KMB_DIR_N_OVERFLOW) flags |= 4u;
-                }
-            } else if (n < 0) {
-                flags |= 1u;
-            }
-            dir[h] = w;
+// pass 2 (ASSIGN = false): total overflow lines needed; (ASSIGN = true): hand them out, write the
+// headers and reset line_fill for the scatter
+template <bool ASSIGN>
+__global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, uint32_t *__restrict__ lines,
+                            KmbStatus *status) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_main; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t c = line_fill[i];
+        uint32_t extra = kmb_chain_extra_lines(c);
+        if (!ASSIGN) {
+            if (extra) atomicAdd(&status->pool_lines, extra);
+        } else {
+            uint32_t base = 0;
+            if (extra) base = (uint32_t)n_main + atomicAdd(&status->pool_lines, extra);
+            *reinterpret_cast<uint2 *>(lines + i * KMB_LINE_WORDS) = make_uint2(c, base);
+            line_fill[i] = 0;
         }
-        // NB: a non-empty bucket always has a non-zero word (n field >= 1)
-        unsigned occ = __ballot_sync(KMB_FULL_MASK, w != 0ull);
-        if (lane == 0) filter[h0 >> 5] = occ;
     }
-    if (flags) atomicOr(&status->index_flags, flags);
+}
+
+// pass 3: place every live entry; slot order inside a chain is whatever the atomics give
+__global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
+                               const uint16_t *__restrict__ freqs, const int32_t *__restrict__ hashes_to_index,
+                               const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, uint32_t line_shift,
+                               uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines,
+                               uint32_t *__restrict__ cold_node, uint16_t *__restrict__ cold_freq) {
+    for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_entries; l += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = kmers[l];
+        uint64_t q, h;
+        kmb_divmod(key, mod, q, h);
+        if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
+        uint64_t main_line = h >> line_shift;
+        uint32_t s = atomicAdd(&line_fill[main_line], 1u);
+        uint32_t ovf_base = lines[main_line * KMB_LINE_WORDS + 1];
+        uint64_t line = kmb_chain_line(main_line, ovf_base, s);
+        uint32_t j = kmb_chain_slot(s);
+        *reinterpret_cast<uint2 *>(lines + line * KMB_LINE_WORDS + KMB_LINE_KEY_WORD0 + 2 * j) =
+            make_uint2((uint32_t)key, (uint32_t)(key >> 32));
+        cold_node[line * KMB_LINE_SLOTS + j] = (uint32_t)nodes[l];
+        cold_freq[line * KMB_LINE_SLOTS + j] = freqs[l];
+    }
 }
 
 // ================================================================================================
@@ -195,18 +228,17 @@ __global__ void kmb_mark_read_ends(const int64_t *__restrict__ offsets, uint64_t
 // ================================================================================================
 // The probe, shared by every mapping kernel.
 //
-// Level 0 (optional, FILT): one bit per bucket, "bucket h is not empty".  modulo/8 bytes -- 57 MB for
-//   the reference's default modulo 452 930 477 -- so it stays resident in the 126 MB L2 while the
-//   3.6 GB directory cannot.  At the reference's load factor (~0.22 entries per bucket) four out of
-//   five queries end here without touching HBM.
-// Level 1: one 8-byte directory word per surviving query (one HBM sector): position, size and a
-//   28-bit quotient fingerprint of the bucket's first entry -> single-entry buckets whose key
-//   differs are rejected without reading the entry.
-// Level 2: surviving candidates are compacted onto a per-warp stack in shared memory and drained 32
-//   at a time, one candidate per lane, so the entry walk (mapper.pyx:58-69: every equal key counts,
-//   no break; frequency filter :64) runs with full lanes instead of one divergent lane per hit.
-//   One no-return reduction (RED) per counted entry; with AGG the lanes that hit the same node in
-//   the same step are merged first (__match_any_sync) so hot nodes cost one RED per warp step.
+// Level 0 (FILT): two bits of one filter word per query (kmb_filter_mask).  modulo/8 bytes -- 57 MB
+//   for the reference's default modulo 452 930 477 -- so it stays resident in the 126 MB L2.  At
+//   the reference's load factor (~0.22 entries per bucket) ~87 % of the absent k-mers end here
+//   without touching HBM.
+// Level 1: survivors are compacted onto a per-warp stack in shared memory and drained 32 at a
+//   time: four lanes per candidate fetch its 128-byte line (three 32-byte sector loads = ONE
+//   L1TEX wavefront and one HBM line), compare the keys of their sector, and every lane that finds
+//   an equal key (mapper.pyx:58-62, no break) issues one no-return reduction on that slot's
+//   counter -- in the line that has just been brought into L2.  Chains of overflow lines are walked
+//   the same way.  The frequency cut-off (mapper.pyx:64) and the scatter onto nodes (:68) happen in
+//   the flush pass, once per slot instead of once per hit.
 // ================================================================================================
 struct KmbPol {
     uint64_t first;  // L2 evict-first: use-once gathers and streams
@@ -219,102 +251,95 @@ __device__ __forceinline__ KmbPol kmb_make_policies() {
     return p;
 }
 
-template <bool AGG>
-__device__ __forceinline__ void kmb_drain(const KmbProbe &P, const KmbPol &pol, const uint64_t *q_kmer,
-                                          const uint64_t *q_dir, int base, int cnt, int lane, unsigned &counted) {
-    bool active = lane < cnt;
-    uint64_t km = 0, dw = 0;
-    if (active) {
-        km = q_kmer[base + lane];
-        dw = q_dir[base + lane];
-    }
-    uint32_t n = kmb_dir_n(dw);
-    uint32_t pos = kmb_dir_pos(dw);
-    if (n == KMB_DIR_N_OVERFLOW) {
-        uint64_t q, h;
-        kmb_divmod(km, P.mod, q, h);
-        n = (uint32_t)P.n_overflow[h];
-    }
-    for (uint32_t j = 0;; ++j) {
-        bool more = active && j < n;
-        if (!__any_sync(KMB_FULL_MASK, more)) break;
-        bool hit = false;
-        uint32_t node = 0;
-        if (more) {
-            KmbEntry e = kmb_load_entry(P.entries + pos + j, pol.first);
-            hit = (e.key == km) && ((int32_t)e.freq <= P.max_freq);
-            node = e.node;
+// Drain up to 32 queued candidates (km, h).  Called by all 32 lanes.
+__device__ __forceinline__ void kmb_drain(const KmbProbe &P, const uint64_t *q_kmer, const uint32_t *q_h, int base,
+                                          int cnt, int lane) {
+    const int sub = lane & 3;    // sector of the line this lane looks at (3 = counters only: idle)
+    const int grp = lane >> 2;   // candidate within the round
+#pragma unroll 1
+    for (int r0 = 0; r0 < cnt; r0 += 8) {
+        const int c = r0 + grp;
+        const bool have = c < cnt;
+        uint64_t km = 0;
+        uint64_t line = 0;
+        if (have) {
+            km = q_kmer[base + c];
+            line = (uint64_t)(q_h[base + c] >> P.line_shift);
         }
-        counted += hit ? 1u : 0u;
-        if (AGG) {
-            unsigned hm = __ballot_sync(KMB_FULL_MASK, hit);
-            if (hit) {
-                unsigned peers = __match_any_sync(hm, node);
-                if (lane == __ffs(peers) - 1) atomicAdd(P.counts + node, (uint32_t)__popc(peers));
+        const uint32_t klo = (uint32_t)km, khi = (uint32_t)(km >> 32);
+        uint32_t n_total = 0, ovf_base = 0;
+        uint32_t t = 0;  // chain line number
+        bool more = have;
+        while (__any_sync(KMB_FULL_MASK, more)) {
+            uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t *lp = P.lines + line * KMB_LINE_WORDS;
+            if (more && sub < 3) kmb_ld_sector(lp + 8 * sub, r);
+            if (t == 0) {  // header of the main line sits in sector 0 (lane sub == 0 of the group)
+                n_total = __shfl_sync(KMB_FULL_MASK, r[0], lane & ~3);
+                ovf_base = __shfl_sync(KMB_FULL_MASK, r[1], lane & ~3);
             }
-        } else {
-            if (hit) atomicAdd(P.counts + node, 1u);
+            if (more && sub < 3) {
+                const uint32_t n_here = min((uint32_t)KMB_LINE_SLOTS, n_total - t * KMB_LINE_SLOTS);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int j = 4 * sub + p - 1;
+                    if (j >= 0 && (uint32_t)j < n_here && r[2 * p] == klo && r[2 * p + 1] == khi)
+                        atomicAdd(lp + KMB_LINE_CNT_WORD0 + j, 1u);
+                }
+            }
+            t++;
+            more = more && (t * KMB_LINE_SLOTS < n_total);
+            line = (uint64_t)ovf_base + (t - 1);
         }
     }
 }
 
 // Push this lane's candidate (if any) on the warp's stack; drain when 32 are waiting.
 // Must be called by all 32 lanes (cand=false for lanes without one).
-template <bool AGG>
-__device__ __forceinline__ void kmb_push_candidate(const KmbProbe &P, const KmbPol &pol, uint64_t *q_kmer,
-                                                   uint64_t *q_dir, int &qcount, bool cand, uint64_t km, uint64_t dw,
-                                                   int lane, unsigned &counted) {
+__device__ __forceinline__ void kmb_push_candidate(const KmbProbe &P, uint64_t *q_kmer, uint32_t *q_h, int &qcount,
+                                                   bool cand, uint64_t km, uint32_t h, int lane) {
     unsigned bal = __ballot_sync(KMB_FULL_MASK, cand);
     if (bal == 0u) return;
     if (cand) {
         int slot = qcount + __popc(bal & ((1u << lane) - 1u));
         q_kmer[slot] = km;
-        q_dir[slot] = dw;
+        q_h[slot] = h;
     }
     qcount += __popc(bal);
     if (qcount >= 32) {
         __syncwarp();
         qcount -= 32;
-        kmb_drain<AGG>(P, pol, q_kmer, q_dir, qcount, 32, lane, counted);
+        kmb_drain(P, q_kmer, q_h, qcount, 32, lane);
         __syncwarp();
     }
 }
 
-// Levels 0 and 1 for U queries of this lane, all gathers of a level in flight together.
-// kf(u) yields query u (cheap to recompute, so it is not kept in registers); bit u of vbits says
-// whether query u exists.
-template <int U, bool FILT, bool AGG, class KF>
+// Level 0 for U queries of this lane, all filter loads in flight together.  kf(u) yields query u
+// (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u exists.
+template <int U, bool FILT, class KF>
 __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, const KF &kf, uint32_t vbits,
-                                                uint64_t *q_kmer, uint64_t *q_dir, int &qcount, int lane,
-                                                unsigned &counted) {
-    uint64_t dw[U];
-    uint32_t fq[U];
-    if (FILT) {
-        uint32_t hh[U], fw[U];
+                                                uint64_t *q_kmer, uint32_t *q_h, int &qcount, int lane) {
+    uint32_t hh[U];
+    uint32_t need[U];  // filter bits the query needs; 0 = no query
+    uint32_t fw[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            uint64_t q, h;
-            kmb_divmod(kf(u), P.mod, q, h);
-            fq[u] = (uint32_t)q;
-            hh[u] = (uint32_t)h;
-            fw[u] = ((vbits >> u) & 1u) ? kmb_ldg_u32_hint(P.filter + (hh[u] >> 5), pol.last) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            dw[u] = ((fw[u] >> (hh[u] & 31u)) & 1u) ? kmb_ldg_u64_hint(P.dir + hh[u], pol.first) : 0ull;
-    } else {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            uint64_t q, h;
-            kmb_divmod(kf(u), P.mod, q, h);
-            fq[u] = (uint32_t)q;
-            dw[u] = ((vbits >> u) & 1u) ? kmb_ldg_u64_hint(P.dir + h, pol.first) : 0ull;
+    for (int u = 0; u < U; u++) {
+        uint64_t q, h;
+        kmb_divmod(kf(u), P.mod, q, h);
+        hh[u] = (uint32_t)h;
+        const bool valid = (vbits >> u) & 1u;
+        if (FILT) {
+            need[u] = valid ? kmb_filter_mask((uint32_t)h, q) : 0u;
+            fw[u] = valid ? kmb_ldg_u32_hint(P.filter + (hh[u] >> 5), pol.last) : 0u;
+        } else {
+            need[u] = valid ? 1u : 0u;
+            fw[u] = 1u;
         }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        bool cand = !kmb_dir_rejects(dw[u], fq[u]);
-        kmb_push_candidate<AGG>(P, pol, q_kmer, q_dir, qcount, cand, kf(u), dw[u], lane, counted);
+        bool cand = need[u] != 0u && (fw[u] & need[u]) == need[u];
+        kmb_push_candidate(P, q_kmer, q_h, qcount, cand, kf(u), hh[u], lane);
     }
 }
 
@@ -334,7 +359,7 @@ struct KmbArrayFn {
 };
 
 // ================================================================================================
-// K1-4 fused: raw ASCII bases in, node counts out.  Each base is read from HBM exactly once.
+// K1-4 fused: raw ASCII bases in, slot counters out.  Each base is read from HBM exactly once.
 //
 // Persistent CTAs of 256 threads walk tiles of 8192 window-start positions.  Per tile:
 //   1. 16-byte vector loads of 8192+32 bases (coalesced, evict-first), SWAR-encoded in registers to
@@ -342,7 +367,7 @@ struct KmbArrayFn {
 //   2. each thread owns 32 consecutive positions: two 64-bit shared loads give it every window
 //      (window i = bits [2i, 2i+2k) -- the reference's first-base-lowest hash, util.py:71-75);
 //      one 32-bit word of the read-boundary mask says which of its 32 starts are real windows;
-//   3. in batches of U positions: exact kmer % modulo (Barrett), then the three probe levels above.
+//   3. in batches of U positions: exact kmer % modulo (Barrett), then the probe levels above.
 // base0 = flat offset of bases[0] inside the caller's buffer (chunked host input), only used to
 // report the position of an invalid byte.
 // ================================================================================================
@@ -376,21 +401,20 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
     return valid;
 }
 
-template <int U, bool FILT, bool AGG, bool REVCOMP>
+template <int U, bool FILT, bool REVCOMP>
 __global__ void __launch_bounds__(KMB_TILE_THREADS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
                      const uint32_t *__restrict__ mask, int k, bool n_to_a, KmbProbe P, KmbStatus *status) {
     __shared__ __align__(16) uint32_t s_pack[KMB_TILE_POS / 16 + 8];  // 512 words + halo
     __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
-    __shared__ uint64_t s_qd[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
+    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint64_t *q_kmer = s_qk[warp];
-    uint64_t *q_dir = s_qd[warp];
+    uint32_t *q_h = s_qh[warp];
     int qcount = 0;
-    unsigned counted = 0;
     const KmbPol pol = kmb_make_policies();
     const uint64_t kmask = kmb_kmer_mask(k);
     const uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
@@ -423,40 +447,35 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             const uint32_t vb = (valid >> b0) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
             if (!__any_sync(KMB_FULL_MASK, vb != 0u)) continue;
             KmbWindowFn fw = {lo, hi, kmask, b0};
-            kmb_probe_batch<U, FILT, AGG>(P, pol, fw, vb, q_kmer, q_dir, qcount, lane, counted);
+            kmb_probe_batch<U, FILT>(P, pol, fw, vb, q_kmer, q_h, qcount, lane);
             if (REVCOMP) {
                 KmbRcWindowFn rc = {lo, hi, kmask, b0, k};
-                kmb_probe_batch<U, FILT, AGG>(P, pol, rc, vb, q_kmer, q_dir, qcount, lane, counted);
+                kmb_probe_batch<U, FILT>(P, pol, rc, vb, q_kmer, q_h, qcount, lane);
             }
         }
     }
     __syncwarp();
-    if (qcount > 0) kmb_drain<AGG>(P, pol, q_kmer, q_dir, 0, qcount, lane, counted);
+    if (qcount > 0) kmb_drain(P, q_kmer, q_h, 0, qcount, lane);
     // statistics: one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) {
-        mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
-        counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
     if (lane == 0 && mapped) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * mapped : mapped);
-    if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
 }
 
 // ================================================================================================
 // K3-4 on ready-made k-mers (drop-in for map_kmers_to_graph_index, mapper.pyx:19-72).
-// Coalesced 8-byte loads, U gathers in flight per thread, same probe.
+// Coalesced 8-byte loads, U filter loads in flight per thread, same probe.
 // ================================================================================================
-template <int U, bool FILT, bool AGG, bool REVCOMP>
+template <int U, bool FILT, bool REVCOMP>
 __global__ void __launch_bounds__(KMB_TILE_THREADS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
     __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
-    __shared__ uint64_t s_qd[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
+    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint64_t *q_kmer = s_qk[warp];
-    uint64_t *q_dir = s_qd[warp];
+    uint32_t *q_h = s_qh[warp];
     int qcount = 0;
-    unsigned counted = 0;
     const KmbPol pol = kmb_make_policies();
     const uint64_t per_block = (uint64_t)KMB_TILE_THREADS * U;
     const uint64_t n_blocks = (n + per_block - 1) / per_block;
@@ -472,87 +491,124 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
             vb |= in ? (1u << u) : 0u;
         }
         KmbArrayFn fa = {km};
-        kmb_probe_batch<U, FILT, AGG>(P, pol, fa, vb, q_kmer, q_dir, qcount, lane, counted);
+        kmb_probe_batch<U, FILT>(P, pol, fa, vb, q_kmer, q_h, qcount, lane);
         if (REVCOMP) {
 #pragma unroll
             for (int u = 0; u < U; u++) km[u] = kmb_revcomp(km[u], k);
-            kmb_probe_batch<U, FILT, AGG>(P, pol, fa, vb, q_kmer, q_dir, qcount, lane, counted);
+            kmb_probe_batch<U, FILT>(P, pol, fa, vb, q_kmer, q_h, qcount, lane);
         }
     }
     __syncwarp();
-    if (qcount > 0) kmb_drain<AGG>(P, pol, q_kmer, q_dir, 0, qcount, lane, counted);
-    for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
-    if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
+    if (qcount > 0) kmb_drain(P, q_kmer, q_h, 0, qcount, lane);
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * n : (unsigned long long)n);
 }
 
-// One-query-per-thread probe without the warp stack: the cross-check variant
-// (kmb_set_option("probe_variant", 0)) and the baseline the staged probe is measured against.
-__device__ __forceinline__ bool kmb_probe_one(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t &pos,
-                                              uint32_t &nn) {
+// ------------------------------------------------------------------------------------------------
+// One-query-per-thread walk of a chain: the cross-check variant of the mapping kernels
+// (kmb_set_option("probe_variant", 0)), the membership kernel and the per-key lookup.
+// Calls on_match(line, slot) for every slot whose key equals km; stops early if it returns true.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void kmb_walk_one(const KmbProbe &P, const KmbPol &pol, uint64_t km, F on_match) {
     uint64_t q, h;
     kmb_divmod(km, P.mod, q, h);
     if (P.filter != nullptr) {
+        uint32_t need = kmb_filter_mask((uint32_t)h, q);
         uint32_t w = kmb_ldg_u32_hint(P.filter + (h >> 5), pol.last);
-        if (!((w >> (h & 31u)) & 1u)) return false;
+        if ((w & need) != need) return;
     }
-    uint64_t dw = kmb_ldg_u64_hint(P.dir + h, pol.first);
-    if (kmb_dir_rejects(dw, (uint32_t)q)) return false;
-    nn = kmb_dir_n(dw);
-    pos = kmb_dir_pos(dw);
-    if (nn == KMB_DIR_N_OVERFLOW) nn = (uint32_t)P.n_overflow[h];
-    return true;
+    const uint64_t main_line = h >> P.line_shift;
+    const uint2 hdr = kmb_ld_u64_volatile(P.lines + main_line * KMB_LINE_WORDS);
+    const uint32_t n_total = hdr.x, ovf_base = hdr.y;
+    for (uint32_t s = 0; s < n_total; s++) {
+        const uint64_t line = kmb_chain_line(main_line, ovf_base, s);
+        const uint32_t j = kmb_chain_slot(s);
+        const uint2 key = kmb_ld_u64_volatile(P.lines + line * KMB_LINE_WORDS + KMB_LINE_KEY_WORD0 + 2 * j);
+        if (key.x == (uint32_t)km && key.y == (uint32_t)(km >> 32))
+            if (on_match(line, j)) return;
+    }
 }
 
 template <bool REVCOMP>
 __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P,
                                             KmbStatus *status) {
     const KmbPol pol = kmb_make_policies();
-    unsigned long long counted = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t km = kmers[i];
 #pragma unroll
         for (int strand = 0; strand < (REVCOMP ? 2 : 1); strand++) {
             if (strand == 1) km = kmb_revcomp(km, k);
-            uint32_t pos, nn;
-            if (!kmb_probe_one(P, pol, km, pos, nn)) continue;
-            for (uint32_t j = 0; j < nn; j++) {
-                KmbEntry e = kmb_load_entry(P.entries + pos + j, pol.first);
-                if (e.key == km && (int32_t)e.freq <= P.max_freq) {
-                    atomicAdd(P.counts + e.node, 1u);
-                    counted++;
-                }
-            }
+            kmb_walk_one(P, pol, km, [&](uint64_t line, uint32_t j) {
+                atomicAdd(P.lines + line * KMB_LINE_WORDS + KMB_LINE_CNT_WORD0 + j, 1u);
+                return false;
+            });
         }
     }
-    if (counted) atomicAdd(&status->n_entries_counted, counted);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * n : (unsigned long long)n);
 }
 
 // ================================================================================================
-// K6 membership (mapper.pyx:81-130): first key match wins, frequency ignored.
-// MODE 0: out_u8[i] = hit.  MODE 1: out_u32[i] = counts[node of first match] (Counter.__getitem__).
+// K4b flush: slot counters -> node counts.  For every slot with a non-zero counter c whose
+// frequency passes the cut-off (mapper.pyx:64): node_counts[node] += c (mod 2^32, mapper.pyx:68),
+// then the counter is zeroed.  One thread per line; the cold (node, frequency) arrays are only
+// touched for slots that were hit.  CLEAR_ONLY zeroes without counting (mapper reset).
 // ================================================================================================
-template <int MODE>
-__global__ void kmb_in_graph_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KmbProbe P, uint8_t *out8,
-                                    uint32_t *out32) {
-    const KmbPol pol = kmb_make_policies();
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t km = kmers[i];
-        bool hit = false;
-        uint32_t node = 0, pos, nn;
-        if (kmb_probe_one(P, pol, km, pos, nn)) {
-            for (uint32_t j = 0; j < nn; j++) {
-                KmbEntry e = kmb_load_entry(P.entries + pos + j, pol.first);
-                if (e.key == km) {
-                    hit = true;
-                    node = e.node;
-                    break;
+template <bool CLEAR_ONLY>
+__global__ void kmb_flush_kernel(uint32_t *__restrict__ lines, uint64_t n_lines, const uint32_t *__restrict__ cold_node,
+                                 const uint16_t *__restrict__ cold_freq, int32_t max_freq, uint32_t *__restrict__ counts,
+                                 KmbStatus *status) {
+    unsigned long long counted = 0;
+    for (uint64_t line = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; line < n_lines;
+         line += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t *cp = lines + line * KMB_LINE_WORDS + KMB_LINE_CNT_WORD0;  // 10 counters: 8-byte + 2 x 16-byte
+        uint32_t c[KMB_LINE_SLOTS];
+        uint2 a = *reinterpret_cast<const uint2 *>(cp);
+        uint4 b = *reinterpret_cast<const uint4 *>(cp + 2);
+        uint4 d = *reinterpret_cast<const uint4 *>(cp + 6);
+        c[0] = a.x, c[1] = a.y, c[2] = b.x, c[3] = b.y, c[4] = b.z, c[5] = b.w, c[6] = d.x, c[7] = d.y, c[8] = d.z, c[9] = d.w;
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < KMB_LINE_SLOTS; j++) any |= c[j];
+        if (!any) continue;
+        if (!CLEAR_ONLY) {
+#pragma unroll
+            for (int j = 0; j < KMB_LINE_SLOTS; j++) {
+                if (c[j] && (int32_t)cold_freq[line * KMB_LINE_SLOTS + j] <= max_freq) {
+                    atomicAdd(counts + cold_node[line * KMB_LINE_SLOTS + j], c[j]);
+                    counted += c[j];
                 }
             }
         }
+        *reinterpret_cast<uint2 *>(cp) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint4 *>(cp + 2) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(cp + 6) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (!CLEAR_ONLY) {
+        for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
+        if ((threadIdx.x & 31) == 0 && counted) atomicAdd(&status->n_entries_counted, counted);
+    }
+}
+
+// ================================================================================================
+// K6 membership (mapper.pyx:81-130): any key match, frequency ignored.
+// MODE 0: out_u8[i] = hit.  MODE 1: out_u32[i] = counts[node of a matching slot] (Counter.__getitem__;
+// the counter's keys are unique, so "a" matching slot is "the" slot).
+// ================================================================================================
+template <int MODE>
+__global__ void kmb_in_graph_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KmbProbe P,
+                                    const uint32_t *__restrict__ cold_node, const uint32_t *__restrict__ counts,
+                                    uint8_t *out8, uint32_t *out32) {
+    const KmbPol pol = kmb_make_policies();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool hit = false;
+        uint32_t node = 0;
+        kmb_walk_one(P, pol, kmers[i], [&](uint64_t line, uint32_t j) {
+            hit = true;
+            if (MODE == 1) node = cold_node[line * KMB_LINE_SLOTS + j];
+            return true;
+        });
         if (MODE == 0) out8[i] = hit ? 1 : 0;
-        else out32[i] = hit ? P.counts[node] : 0u;
+        else out32[i] = hit ? counts[node] : 0u;
     }
 }
 

@@ -83,6 +83,10 @@ class DeviceIndex:
         fb = C.c_uint64()
         check(lib().kmb_index_filter_bytes(h, C.byref(fb)))
         self.filter_bytes = fb.value
+        bpl, nm, no, nl = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().kmb_index_layout(h, C.byref(bpl), C.byref(nm), C.byref(no), C.byref(nl)))
+        self.buckets_per_line, self.n_main_lines, self.n_overflow_lines, self.n_live_entries = (
+            bpl.value, nm.value, no.value, nl.value)
 
     @classmethod
     def from_index(cls, index, device=None) -> "DeviceIndex":
@@ -164,6 +168,10 @@ class Mapper:
         flags = (FLAG_REVCOMP if revcomp else 0) | (0 if n_to_a else FLAG_NO_N_TO_A)
         _order_after_torch(bases, offsets, same_stream=self._stream)
         check(lib().kmb_mapper_map_reads(self._h, pb, nb, po, no - 1, int(k), flags))
+
+    def flush(self):
+        """Queue the slot-counter -> node-count pass on the mapper's stream (no host wait)."""
+        check(lib().kmb_mapper_flush(self._h))
 
     def sync(self):
         rc = lib().kmb_mapper_sync(self._h)

@@ -16,9 +16,8 @@ uint32_t h_encode16(const uint8_t *b, int n_to_a, uint32_t *invalid) {
 }
 uint64_t h_window(uint64_t lo, uint64_t hi, int i, int k) { return kmb_window(lo, hi, i, kmb_kmer_mask(k)); }
 uint64_t h_revcomp(uint64_t x, int k) { return kmb_revcomp(x, k); }
-uint64_t h_dir_pack(uint32_t pos, uint32_t n, uint32_t fp) { return kmb_dir_pack(pos, n, fp); }
-uint32_t h_dir_pos(uint64_t w) { return kmb_dir_pos(w); }
-uint32_t h_dir_n(uint64_t w) { return kmb_dir_n(w); }
-uint32_t h_dir_fp(uint64_t w) { return kmb_dir_fp(w); }
-int h_dir_rejects(uint64_t w, uint32_t fpq) { return kmb_dir_rejects(w, fpq) ? 1 : 0; }
+uint64_t h_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) { return kmb_chain_line(main_line, ovf_base, s); }
+uint32_t h_chain_slot(uint32_t s) { return kmb_chain_slot(s); }
+uint32_t h_chain_extra_lines(uint32_t n) { return kmb_chain_extra_lines(n); }
+uint32_t h_filter_mask(uint32_t h, uint64_t q) { return kmb_filter_mask(h, q); }
 }

@@ -44,7 +44,7 @@ def test_library_is_sm100a_only(kmb):
 
 
 def test_options_round_trip(kmb):
-    for name in ("map_reads_blocks_per_sm", "probe_variant", "aggregate_atomics", "gathers_in_flight", "use_filter"):
+    for name in ("map_reads_blocks_per_sm", "probe_variant", "gathers_in_flight", "use_filter"):
         old = kmb.get_option(name)
         kmb.set_option(name, 3)
         assert kmb.get_option(name) == 3

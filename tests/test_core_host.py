@@ -23,12 +23,12 @@ def core():
     lib.h_window.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int]
     lib.h_revcomp.restype = C.c_uint64
     lib.h_revcomp.argtypes = [C.c_uint64, C.c_int]
-    lib.h_dir_pack.restype = C.c_uint64
-    lib.h_dir_pack.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
-    for f in (lib.h_dir_pos, lib.h_dir_n, lib.h_dir_fp):
-        f.restype = C.c_uint32
-        f.argtypes = [C.c_uint64]
-    lib.h_dir_rejects.argtypes = [C.c_uint64, C.c_uint32]
+    lib.h_chain_line.restype = C.c_uint64
+    lib.h_chain_line.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+    lib.h_chain_slot.restype = C.c_uint32
+    lib.h_chain_extra_lines.restype = C.c_uint32
+    lib.h_filter_mask.restype = C.c_uint32
+    lib.h_filter_mask.argtypes = [C.c_uint32, C.c_uint64]
     lib.h_encode16.restype = C.c_uint32
     return lib
 
@@ -116,19 +116,25 @@ def test_revcomp(core):
             assert core.h_revcomp(want, k) == x
 
 
-def test_directory_word(core):
-    rng = np.random.default_rng(5)
-    assert core.h_dir_pack(0, 0, 0) == 0 and core.h_dir_rejects(0, 123) == 1
+def test_line_chain_geometry_and_filter_mask(core):
+    # ten slots per 128-byte line; entry s of a chain lives in the main line (s < 10) or in overflow line
+    # ovf_base + (s-10)//10; every (line, slot) pair is used exactly once
+    for n_total in (0, 1, 9, 10, 11, 20, 21, 1234):
+        extra = core.h_chain_extra_lines(n_total)
+        assert extra == max(0, -(-n_total // 10) - 1)
+        seen = set()
+        for s in range(n_total):
+            line = core.h_chain_line(77, 1000, s)
+            slot = core.h_chain_slot(s)
+            assert 0 <= slot < 10
+            assert line == 77 if s < 10 else 1000 <= line < 1000 + extra
+            seen.add((line, slot))
+        assert len(seen) == n_total
+    rng = np.random.default_rng(6)
     for _ in range(2000):
-        pos = int(rng.integers(0, 2 ** 31))
-        n = int(rng.integers(1, 100))
-        fp = int(rng.integers(0, 2 ** 32))
-        w = core.h_dir_pack(pos, n, fp)
-        assert w != 0
-        assert core.h_dir_pos(w) == pos
-        assert core.h_dir_n(w) == min(n, 31)
-        assert core.h_dir_fp(w) == fp & (2 ** 28 - 1)
-        other = int(rng.integers(0, 2 ** 32))
-        same_fp = (other & (2 ** 28 - 1)) == (fp & (2 ** 28 - 1))
-        assert core.h_dir_rejects(w, fp) == 0                      # a possible match is never rejected
-        assert core.h_dir_rejects(w, other) == (1 if (n == 1 and not same_fp) else 0)
+        h = int(rng.integers(0, 2 ** 32))
+        q = int(rng.integers(0, 2 ** 40))
+        m = core.h_filter_mask(h, q)
+        assert m & (1 << (h & 31))
+        assert bin(m).count("1") in (1, 2)
+        assert m == core.h_filter_mask(h + 32 * 5, q)        # depends on h only through h & 31

@@ -18,18 +18,17 @@ def kmb():
     from kmer_mapper_b200 import _lib
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
-    for name, v in (("probe_variant", 1), ("use_filter", -1), ("aggregate_atomics", 0), ("gathers_in_flight", 8),
-                    ("chunk_bytes", 64 << 20)):
+    for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 8), ("chunk_bytes", 64 << 20)):
         _lib.set_option(name, v)
 
 
-VARIANTS = [dict(probe_variant=1, use_filter=1, aggregate_atomics=0, gathers_in_flight=8),
-            dict(probe_variant=1, use_filter=0, aggregate_atomics=0, gathers_in_flight=8),
-            dict(probe_variant=1, use_filter=1, aggregate_atomics=1, gathers_in_flight=4),
-            dict(probe_variant=1, use_filter=0, aggregate_atomics=1, gathers_in_flight=16),
-            dict(probe_variant=1, use_filter=1, aggregate_atomics=0, gathers_in_flight=16),
-            dict(probe_variant=0, use_filter=1, aggregate_atomics=0, gathers_in_flight=8),
-            dict(probe_variant=0, use_filter=0, aggregate_atomics=0, gathers_in_flight=8)]
+VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=8),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=8),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=16),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=16),
+            dict(probe_variant=0, use_filter=1, gathers_in_flight=8),
+            dict(probe_variant=0, use_filter=0, gathers_in_flight=8)]
 
 
 def _fresh(index):
@@ -157,6 +156,33 @@ def test_map_kmers_device_buffers_and_accumulation(kmb, golden_lookup):
     m.reset()
     assert m.counts().sum() == 0 and m.stats() == (0, 0)
     m.close()
+
+
+def test_two_mappers_on_one_index_and_overflow_chains(kmb):
+    """The slot counters live inside the index lines: a second concurrent mapper must get its own copy,
+    and a bucket with far more than ten entries must be walked through its whole chain."""
+    from kmer_mapper_b200.device import DeviceIndex, Mapper
+    rng = np.random.default_rng(21)
+    keys = rng.integers(0, 4 ** 12, size=4000, dtype=np.uint64)
+    keys = np.concatenate([keys, np.full(777, keys[3], np.uint64), np.full(35, keys[9], np.uint64)])
+    nodes = rng.integers(0, 3000, size=keys.shape[0])
+    idx = oracle.index_from_flat_kmers(keys, nodes, 211)          # ~23 entries per bucket: chains everywhere
+    di = DeviceIndex.from_index(_fresh(idx))
+    assert di.n_overflow_lines > 0 and di.n_live_entries == keys.shape[0]
+    q1 = np.concatenate([rng.choice(keys, 30000), rng.integers(0, 4 ** 12, size=30000, dtype=np.uint64)])
+    q2 = rng.choice(keys, 10000)
+    a, b = Mapper(di, 3000, 1000), Mapper(di, 3000, 5)
+    a.map_kmers(q1)
+    b.map_kmers(q2)
+    a.map_kmers(q2)
+    assert np.array_equal(b.counts(), c_oracle.map_kmers_to_graph_index(idx, 2999, q2, 5))
+    assert np.array_equal(a.counts(), c_oracle.map_kmers_to_graph_index(idx, 2999, np.concatenate([q1, q2]), 1000))
+    a.close()
+    b.close()
+    c = Mapper(di, 3000, 1000)                                     # the master copy is clean again
+    c.map_kmers(q2)
+    assert np.array_equal(c.counts(), c_oracle.map_kmers_to_graph_index(idx, 2999, q2, 1000))
+    c.close()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -30,10 +30,9 @@ def main():
     n_counts = tindex.max_node_id() + 1
     ref_counts = None
     grids = {
-        "default": dict(use_filter=[1, 0], gathers_in_flight=[4, 8, 16], aggregate_atomics=[0], map_reads_blocks_per_sm=[0]),
-        "occupancy": dict(use_filter=[1], gathers_in_flight=[8, 16], aggregate_atomics=[0], map_reads_blocks_per_sm=[1, 2, 3, 4, 6, 8]),
-        "agg": dict(use_filter=[1], gathers_in_flight=[8], aggregate_atomics=[0, 1], map_reads_blocks_per_sm=[0]),
-        "persist": dict(use_filter=[1], gathers_in_flight=[8], aggregate_atomics=[0], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
+        "default": dict(use_filter=[1, 0], gathers_in_flight=[4, 8, 16], map_reads_blocks_per_sm=[0]),
+        "occupancy": dict(use_filter=[1], gathers_in_flight=[4, 8, 16], map_reads_blocks_per_sm=[1, 2, 3, 4, 5, 6]),
+        "persist": dict(use_filter=[1], gathers_in_flight=[8], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
     }[a.grid]
     names = list(grids)
     last_filter = None
@@ -55,9 +54,15 @@ def main():
             m.reset()
             m.map_reads(bases, offsets, w["k"])
         m.kernel_time()
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
         for _ in range(a.steps):
             m.reset()
             m.map_reads(bases, offsets, w["k"])
+            m.flush()
+        m.sync()
+        step_ms = (time.perf_counter() - t0) * 1e3 / a.steps
         ms, n = m.kernel_time()
         nk, nc = m.stats()
         c = m.counts()
@@ -65,7 +70,8 @@ def main():
             ref_counts = c
         same = bool((c == ref_counts).all())
         m.close()
-        print(json.dumps(dict(opts=opts, kernel_ms=ms / n, GKps=nk / (ms / n) / 1e6, filter_bytes=di.filter_bytes,
+        print(json.dumps(dict(opts=opts, kernel_ms=ms / n, kernel_GKps=nk / (ms / n) / 1e6, step_ms=step_ms, step_GKps=nk / step_ms / 1e6,
+                              filter_bytes=di.filter_bytes, overflow_lines=di.n_overflow_lines,
                               counts_equal_first=same)), flush=True)
 
 
