@@ -55,11 +55,17 @@ struct KmbOptions {
     int64_t map_kmers_blocks_per_sm = 0;
     int64_t probe_variant = 1;            // map_kmers: 0 = one query per thread, 1 = staged probe with warp stack
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
-    int64_t gathers_in_flight = 8;        // U: 4, 8 or 16 independent gathers per thread
+    int64_t gathers_in_flight = 4;        // U: 2, 4 or 8 independent filter loads per thread
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
     int64_t filter_l2_budget_bytes = 80ll << 20;
+    int64_t policy_filter = 2;            // L2 priority hints: 0 normal, 1 evict-first, 2 evict-last
+    int64_t policy_line = 0;
+    int64_t policy_red = 0;
+    int64_t ablate = 0;                   // measurement only (results become wrong): 1 no RED, 2 no line loads, 4 no filter loads, 8 no key loads
+    int64_t prefetch_lines = 0;           // prefetch a candidate's line into L2 at queue time
     int64_t l2_persist = 1;               // set a persisting-L2 access window over the filter
     int64_t l2_fetch_granularity = 0;     // 0 = leave the device default; else 32/64/128 (cudaLimitMaxL2FetchGranularity)
+    int64_t bench_load_mode = 0;          // kmb_bench_gather, 8-byte loads: 0 .nc, 1-3 L2::64B/128B/256B, 4 plain, 5 .cv
     int64_t bench_grid_blocks = 0;        // kmb_bench_gather: total CTAs (0 = SMs x blocks_per_sm)
     int64_t time_kernels = 0;             // bracket every mapping kernel with CUDA events (kmb_mapper_kernel_time)
 };
@@ -80,9 +86,15 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
     OPT(l2_persist)
+    OPT(prefetch_lines)
+    OPT(ablate)
+    OPT(policy_filter)
+    OPT(policy_line)
+    OPT(policy_red)
     OPT(time_kernels)
     OPT(l2_fetch_granularity)
     OPT(bench_grid_blocks)
+    OPT(bench_load_mode)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -106,9 +118,15 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
     OPT(l2_persist)
+    OPT(prefetch_lines)
+    OPT(ablate)
+    OPT(policy_filter)
+    OPT(policy_line)
+    OPT(policy_red)
     OPT(time_kernels)
     OPT(l2_fetch_granularity)
     OPT(bench_grid_blocks)
+    OPT(bench_load_mode)
     OPT(chunk_bytes)
 #undef OPT
     return kmb_fail(KMB_ERR_BAD_ARG, "kmb_get_option: unknown option '%s'", name);
@@ -238,8 +256,7 @@ struct kmb_index {
     uint32_t line_shift = 0;            // g: 2^g buckets per 128-byte line
     uint64_t n_main = 0, n_lines = 0;   // main lines, main + overflow lines
     uint32_t *lines = nullptr;          // master copy (keys + the counters of the mapper that borrows it)
-    uint32_t *cold_node = nullptr;      // node of (line, slot)
-    uint16_t *cold_freq = nullptr;      // frequency of (line, slot)
+    uint2 *cold = nullptr;              // (node, frequency) of (line, slot)
     uint32_t *filter = nullptr;
     size_t filter_bytes = 0;
     bool filter_on = false;
@@ -255,18 +272,17 @@ extern "C" int kmb_index_destroy(kmb_index *ix) {
     if (!ix) return KMB_OK;
     DeviceGuard g(ix->device);
     cudaFree(ix->lines);
-    cudaFree(ix->cold_node);
-    cudaFree(ix->cold_freq);
+    cudaFree(ix->cold);
     cudaFree(ix->filter);
     cudaGetLastError();
     delete ix;
     return KMB_OK;
 }
 
-// buckets per line: the largest power of two that keeps the mean line occupancy <= 4.5 of 10 slots
+// buckets per line: the largest power of two that keeps the mean sector occupancy <= 0.5 of 2 slots
 static uint32_t choose_line_shift(uint64_t modulo, uint64_t n_entries) {
     uint32_t g = 0;
-    while (g < 16 && (double)(2ull << g) * (double)n_entries <= 4.5 * (double)modulo && (2ull << g) <= modulo) g++;
+    while (g < 16 && (double)(2ull << g) * (double)n_entries <= 0.5 * (double)modulo && (2ull << g) <= modulo) g++;
     return g;
 }
 
@@ -355,21 +371,18 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     ix->max_node = hs.max_node;
     ix->n_live = hs.n_live_entries;
     ix->n_lines = ix->n_main + hs.pool_lines;
-    if (ix->n_lines >= (1ull << 32)) return kmb_fail(KMB_ERR_BAD_INDEX, "index: too many lines");
+    if (ix->n_lines * KMB_LINE_WORDS >= (1ull << 35)) return kmb_fail(KMB_ERR_BAD_INDEX, "index: too many sectors");
     // 4. lines + cold arrays, headers, scatter
     KMB_CUDA(cudaMalloc(&ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
-    KMB_CUDA(cudaMalloc(&ix->cold_node, (size_t)ix->n_lines * KMB_LINE_SLOTS * 4));
-    KMB_CUDA(cudaMalloc(&ix->cold_freq, (size_t)ix->n_lines * KMB_LINE_SLOTS * 2));
+    KMB_CUDA(cudaMalloc(&ix->cold, (size_t)ix->n_lines * KMB_LINE_SLOTS * sizeof(uint2)));
     KMB_CUDA(cudaMemsetAsync(ix->lines, 0, (size_t)ix->n_lines * KMB_LINE_BYTES, s));
-    KMB_CUDA(cudaMemsetAsync(ix->cold_node, 0, (size_t)ix->n_lines * KMB_LINE_SLOTS * 4, s));
-    KMB_CUDA(cudaMemsetAsync(ix->cold_freq, 0, (size_t)ix->n_lines * KMB_LINE_SLOTS * 2, s));
+    KMB_CUDA(cudaMemsetAsync(ix->cold, 0, (size_t)ix->n_lines * KMB_LINE_SLOTS * sizeof(uint2), s));
     KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
     kmb_v2_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, d_status.p);
     g_launches++;
     if (n_entries) {
         kmb_v2_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
-                                                                   ix->line_shift, line_fill.p, ix->lines, ix->cold_node,
-                                                                   ix->cold_freq);
+                                                                   ix->line_shift, line_fill.p, ix->lines, ix->cold);
         g_launches++;
     }
     KMB_CUDA(cudaGetLastError());
@@ -384,7 +397,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
         ix->filter = nullptr;
         ix->filter_bytes = 0;
     }
-    ix->device_bytes = ix->n_lines * (KMB_LINE_BYTES + KMB_LINE_SLOTS * 6) + ix->filter_bytes;
+    ix->device_bytes = ix->n_lines * (KMB_LINE_BYTES + KMB_LINE_SLOTS * sizeof(uint2)) + ix->filter_bytes;
     cleanup.ix = nullptr;
     *out = ix;
     return KMB_OK;
@@ -501,7 +514,7 @@ template <bool CLEAR_ONLY>
 static int launch_flush(kmb_mapper *m) {
     const kmb_index *ix = m->index;
     kmb_flush_kernel<CLEAR_ONLY><<<grid_for(ix->n_lines, 256, ix->info.sms), 256, 0, m->stream>>>(
-        m->lines, ix->n_lines, ix->cold_node, ix->cold_freq, m->max_freq, m->counts, m->d_status);
+        m->lines, ix->n_lines, ix->cold, m->max_freq, m->counts, m->d_status);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     m->dirty = false;
@@ -534,7 +547,11 @@ static int set_l2_window(kmb_mapper *m) {
     // Hint: keep the filter in the persisting part of L2 for kernels on this stream.  Purely a
     // performance hint; failure is not an error.
     kmb_index *ix = m->index;
-    if (!ix->filter_on || !g_opt.l2_persist || ix->info.max_persist_l2 <= 0) return KMB_OK;
+    if (!g_opt.l2_persist) {
+        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+        return KMB_OK;
+    }
+    if (!ix->filter_on || ix->info.max_persist_l2 <= 0) return KMB_OK;
     size_t want = std::min<size_t>(ix->filter_bytes, (size_t)ix->info.max_persist_l2);
     if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
         cudaGetLastError();
@@ -618,12 +635,14 @@ static KmbProbe make_probe(const kmb_mapper *m) {
     P.filter = ix->filter_on ? ix->filter : nullptr;
     P.mod = ix->mod;
     P.line_shift = ix->line_shift;
+    P.prefetch = g_opt.prefetch_lines ? 1u : 0u;
+    P.policies = (uint32_t)((g_opt.policy_filter & 3) | ((g_opt.policy_line & 3) << 2) | ((g_opt.policy_red & 3) << 4) | ((g_opt.ablate & 15) << 8));
     return P;
 }
 
 static int pick_u() {
     int64_t u = g_opt.gathers_in_flight;
-    return u <= 4 ? 4 : (u <= 8 ? 8 : 16);
+    return u <= 2 ? 2 : (u <= 4 ? 4 : 8);
 }
 
 // ---- kernel dispatch (template instantiation table) ------------------------------------------------
@@ -636,7 +655,7 @@ static MapReadsFn map_reads_fn_u(bool filt, bool rc) {
     return rc ? kmb_map_reads_kernel<U, false, true> : kmb_map_reads_kernel<U, false, false>;
 }
 static MapReadsFn map_reads_fn(int u, bool filt, bool rc) {
-    return u == 4 ? map_reads_fn_u<4>(filt, rc) : (u == 8 ? map_reads_fn_u<8>(filt, rc) : map_reads_fn_u<16>(filt, rc));
+    return u == 2 ? map_reads_fn_u<2>(filt, rc) : (u == 4 ? map_reads_fn_u<4>(filt, rc) : map_reads_fn_u<8>(filt, rc));
 }
 template <int U>
 static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
@@ -644,7 +663,7 @@ static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
     return rc ? kmb_map_kmers_kernel<U, false, true> : kmb_map_kmers_kernel<U, false, false>;
 }
 static MapKmersFn map_kmers_fn(int u, bool filt, bool rc) {
-    return u == 4 ? map_kmers_fn_u<4>(filt, rc) : (u == 8 ? map_kmers_fn_u<8>(filt, rc) : map_kmers_fn_u<16>(filt, rc));
+    return u == 2 ? map_kmers_fn_u<2>(filt, rc) : (u == 4 ? map_kmers_fn_u<4>(filt, rc) : map_kmers_fn_u<8>(filt, rc));
 }
 
 static int resident_blocks(const void *fn, int64_t opt, int *out) {
@@ -962,8 +981,10 @@ static int run_lookup(kmb_index *ix, const uint32_t *lines, const uint32_t *coun
     P.filter = ix->filter_on ? ix->filter : nullptr;
     P.mod = ix->mod;
     P.line_shift = ix->line_shift;
+    P.prefetch = 0;
+    P.policies = 2u;
     kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(
-        d_keys, n, P, ix->cold_node, counts, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),
+        d_keys, n, P, ix->cold, counts, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),
         (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
     g_launches++;
     KMB_CUDA(cudaGetLastError());
@@ -1149,7 +1170,7 @@ extern "C" int kmb_host_free(void *ptr) {
 // ------------------------------------------------------------------------------------------------
 // gather micro-roofline
 // ------------------------------------------------------------------------------------------------
-typedef void (*GatherFn)(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *);
+typedef void (*GatherFn)(const uint8_t *, uint64_t, uint64_t, uint64_t, uint64_t *, int);
 template <int W>
 static GatherFn gather_fn_w(int unroll) {
     switch (unroll) {
@@ -1182,9 +1203,9 @@ extern "C" int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loa
     KMB_CUDA(cudaEventCreate(&e0));
     KMB_CUDA(cudaEventCreate(&e1));
     int grid = g_opt.bench_grid_blocks > 0 ? (int)g_opt.bench_grid_blocks : info.sms * blocks_per_sm;
-    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads / 8 + 1, 1, sink.p);  // warm-up
+    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads / 8 + 1, 1, sink.p, (int)g_opt.bench_load_mode);  // warm-up
     KMB_CUDA(cudaEventRecord(e0));
-    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads, 2, sink.p);
+    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads, 2, sink.p, (int)g_opt.bench_load_mode);
     KMB_CUDA(cudaEventRecord(e1));
     g_launches += 2;
     KMB_CUDA(cudaEventSynchronize(e1));

@@ -40,6 +40,14 @@ KMB_HD KmbMod kmb_mod_make(uint64_t d) {
 
 KMB_HD void kmb_divmod(uint64_t n, const KmbMod md, uint64_t &q, uint64_t &r) {
     uint64_t qe = kmb_umulhi64(n, md.m);
+    if (md.d < 0x80000000ull) {
+        // n - qe*d lies in [0, 2d) and 2d < 2^32, so the low 32 bits of the difference are the difference
+        uint32_t re = (uint32_t)n - (uint32_t)qe * (uint32_t)md.d;
+        bool fix = re >= (uint32_t)md.d;
+        r = fix ? re - (uint32_t)md.d : re;
+        q = qe + (fix ? 1u : 0u);
+        return;
+    }
     uint64_t re = n - qe * md.d;
     if (re >= md.d) {
         re -= md.d;
@@ -50,29 +58,30 @@ KMB_HD void kmb_divmod(uint64_t n, const KmbMod md, uint64_t &q, uint64_t &r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Index layout v2: the 128-byte line.
+// Index layout: the 32-byte sector line.
 //
-// Measured on B200 (profiles/README.md): a random global load that misses L2 always costs one full
-// 128-byte line of HBM traffic, so the layout is built around lines, not sectors.  G = 2^g
-// consecutive buckets (h = key % modulo, mapper.pyx:54) share one line; the line holds up to ten
-// of their entries -- the 8-byte key and, in the same line, its 4-byte hit counter -- so that the
-// one line fetched for a query answers it completely and the count (mapper.pyx:68) is a reduction
-// into a line that is already in L2.  32-bit word map of a line:
-//   w0        n_total   entries in the chain that starts at this (main) line
-//   w1        ovf_base  line index of the first overflow line (only if n_total > 10)
-//   w2..w21   key j at (w[2+2j], w[3+2j]) = (lo, hi), j = 0..9
-//   w22..w31  counter j
-// Sector s (words 8s..8s+7) therefore holds key pairs p = 0..3 <-> slot j = 4s + p - 1; sector 3 is
-// counters only.  Entries beyond ten go to overflow lines ovf_base + (s-10)/10 with the same slot map.
-// node and frequency of a slot live in cold side arrays (line*10 + j), read only by the flush pass.
+// Measured on B200 (profiles/README.md): (1) a random global load that misses L2 costs one full
+// 128-byte line of HBM traffic whatever its width; (2) the L2 holds ~75 MB, of which the filter
+// takes 57 MB, so a fetched line survives only a few microseconds -- a second, later access to it
+// (a separate key read, a late RED) goes back to HBM more often than not.  Hence ONE 32-byte
+// sector answers a query completely and takes the count immediately:
+//   w0      n_total   entries in the chain that starts at this (main) sector
+//   w1      ovf_base  index of the first overflow sector (only if n_total > 2)
+//   w2..w5  key 0, key 1  (lo, hi)
+//   w6, w7  hit counter 0, 1
+// G = 2^g consecutive buckets (h = key % modulo, mapper.pyx:54) share a sector, with G chosen so
+// that a sector holds 0.25-0.5 entries on average (99 % of the non-empty ones need no chain);
+// entries beyond two go to overflow sectors ovf_base + (s-2)/2 with the same slot map.  node and
+// frequency of a slot live in a cold side array (sector*2 + j), read only by the flush pass.
+// HBM capacity (180 GB) is what pays for this: 7.2 GB of sectors for the 100 M-entry index.
 // ---------------------------------------------------------------------------------------------
-#define KMB_LINE_BYTES 128
-#define KMB_LINE_WORDS 32
-#define KMB_LINE_SLOTS 10
+#define KMB_LINE_BYTES 32
+#define KMB_LINE_WORDS 8
+#define KMB_LINE_SLOTS 2
 #define KMB_LINE_KEY_WORD0 2
-#define KMB_LINE_CNT_WORD0 22
+#define KMB_LINE_CNT_WORD0 6
 
-// chain position s (0-based among the entries of a main line) -> (line index, slot)
+// chain position s (0-based among the entries of a main sector) -> (sector index, slot)
 KMB_HD uint64_t kmb_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) {
     return s < KMB_LINE_SLOTS ? main_line : (uint64_t)ovf_base + (s - KMB_LINE_SLOTS) / KMB_LINE_SLOTS;
 }

@@ -1,6 +1,6 @@
 // kmb_kernels.cuh -- hand-written sm_100a kernels of the k-mer mapping path.
 //
-//   K5  kmb_v2_check_buckets / _count / _plan / _scatter   index re-layout into 128-byte lines (once per index)
+//   K5  kmb_v2_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sector lines (once per index)
 //   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
 //   K1-4 kmb_map_reads_kernel     fused encode + window + filter + line probe + count  (production path)
 //   K3-4 kmb_map_kmers_kernel     probe + count on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
@@ -11,11 +11,12 @@
 //   B   kmb_gather_bench_kernel   random-line gather micro-roofline
 //
 // Nothing here is a dense contraction, so no tensor-core / TMEM / TMA-tile machinery is used: the
-// path is bound by random 128-byte-line fetches from HBM plus one L2 hit per k-mer (the filter)
-// and a thin coalesced stream of bases.  What matters: as few line fetches per k-mer
-// as possible (L2-resident filter), every fetched line answers its query completely (keys and
-// counters share the line), warp-compacted second-level work so hits do not serialise the warp,
-// no-return reductions (RED) into lines that are already in L2, persistent grid sized to the SMs.
+// path is bound by random line fetches from HBM plus one L2 hit per k-mer (the filter) and a thin
+// coalesced stream of bases.  What matters: as few fetches per k-mer as possible
+// (L2-resident filter), one 32-byte sector answers its query completely and takes the count at
+// once (keys and counters share the sector), warp-compacted second-level work so hits do not
+// serialise the warp, the fetch latency overlapped with the next batch's arithmetic, no-return
+// reductions (RED) while the sector is still in L2, persistent grid sized to the SMs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,7 +27,8 @@
 #define KMB_TILE_THREADS 256
 #define KMB_POS_PER_THREAD 32
 #define KMB_TILE_POS (KMB_TILE_THREADS * KMB_POS_PER_THREAD)  // 8192 window starts per tile
-#define KMB_QUEUE_SLOTS 64                                    // per-warp candidate stack (>= 32 + 32)
+#define KMB_WTILE_POS (32 * KMB_POS_PER_THREAD)                // 1024 window starts per warp tile
+#define KMB_QUEUE_SLOTS(U) (32 * ((U) + 1))                   // per-warp candidate stack: < 32 left over + 32 U new
 
 struct KmbStatus {
     unsigned long long first_bad_offset;   // min flat offset of an invalid byte, ~0 if none
@@ -43,6 +45,8 @@ struct KmbProbe {  // everything a probe needs, passed by value to the kernels
     const uint32_t *__restrict__ filter;     // 2 bits per live entry in word h >> 5, or nullptr
     KmbMod mod;
     uint32_t line_shift;                     // g: line = h >> g
+    uint32_t prefetch;                       // 1: prefetch a candidate's line into L2 when it is queued
+    uint32_t policies;                       // L2 priority of: filter (bits 0-1), line loads (2-3), counter REDs (4-5)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -60,6 +64,15 @@ __device__ __forceinline__ uint64_t kmb_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+__device__ __forceinline__ uint64_t kmb_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 0 = normal, 1 = evict-first, 2 = evict-last
+__device__ __forceinline__ uint64_t kmb_policy_select(uint32_t which) {
+    return which == 1u ? kmb_policy_evict_first() : (which == 2u ? kmb_policy_evict_last() : kmb_policy_evict_normal());
 }
 __device__ __forceinline__ uint64_t kmb_ldg_u64_nc(const uint64_t *p) {
     uint64_t v;
@@ -90,11 +103,18 @@ __device__ __forceinline__ uint4 kmb_ldg_v4_hint(const void *p, uint64_t pol) {
                  : "l"(p), "l"(pol));
     return v;
 }
-// one 32-byte sector of a line; the counters in it are concurrently reduced into, so no .nc path
-__device__ __forceinline__ void kmb_ld_sector(const uint32_t *p, uint32_t (&r)[8]) {
-    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+// One 32-byte sector of a line.  Plain (coherent) path: counters of the same line are concurrently
+// reduced into.  Normal L2 priority on purpose: the key read and the RED that follow a hit must still
+// find the line in L2 -- marked evict-first it was gone 60 % of the time (profiles/README.md).
+// L2::64B: a miss then fetches 64 bytes from HBM instead of the default 128 (measured: 1.98 vs 3.91
+// DRAM sectors per random load, profiles/README.md).
+__device__ __forceinline__ void kmb_ld_sector(const uint32_t *p, uint32_t (&r)[8], uint64_t pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void kmb_red_add(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint2 kmb_ld_u64_volatile(const uint32_t *p) {
     uint2 v;
@@ -182,7 +202,7 @@ __global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t
                                const uint16_t *__restrict__ freqs, const int32_t *__restrict__ hashes_to_index,
                                const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, uint32_t line_shift,
                                uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines,
-                               uint32_t *__restrict__ cold_node, uint16_t *__restrict__ cold_freq) {
+                               uint2 *__restrict__ cold) {
     for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_entries; l += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = kmers[l];
         uint64_t q, h;
@@ -195,8 +215,7 @@ __global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t
         uint32_t j = kmb_chain_slot(s);
         *reinterpret_cast<uint2 *>(lines + line * KMB_LINE_WORDS + KMB_LINE_KEY_WORD0 + 2 * j) =
             make_uint2((uint32_t)key, (uint32_t)(key >> 32));
-        cold_node[line * KMB_LINE_SLOTS + j] = (uint32_t)nodes[l];
-        cold_freq[line * KMB_LINE_SLOTS + j] = freqs[l];
+        cold[line * KMB_LINE_SLOTS + j] = make_uint2((uint32_t)nodes[l], (uint32_t)freqs[l]);
     }
 }
 
@@ -233,92 +252,130 @@ __global__ void kmb_mark_read_ends(const int64_t *__restrict__ offsets, uint64_t
 //   the reference's load factor (~0.22 entries per bucket) ~87 % of the absent k-mers end here
 //   without touching HBM.
 // Level 1: survivors are compacted onto a per-warp stack in shared memory and drained 32 at a
-//   time: four lanes per candidate fetch its 128-byte line (three 32-byte sector loads = ONE
-//   L1TEX wavefront and one HBM line), compare the keys of their sector, and every lane that finds
-//   an equal key (mapper.pyx:58-62, no break) issues one no-return reduction on that slot's
-//   counter -- in the line that has just been brought into L2.  Chains of overflow lines are walked
-//   the same way.  The frequency cut-off (mapper.pyx:64) and the scatter onto nodes (:68) happen in
+//   time, one per lane (32 independent HBM line fetches in flight per warp): sector 0 of the
+//   candidate's line carries the chain header and eight one-byte tags; a key is read (from L2, the
+//   line has just arrived) only where the tag matches, and every equal key (mapper.pyx:58-62, no
+//   break) gets one no-return reduction on its slot counter -- in that same line.  Chains of
+//   overflow lines are walked the same way.  The frequency cut-off (mapper.pyx:64) and the scatter onto nodes (:68) happen in
 //   the flush pass, once per slot instead of once per hit.
 // ================================================================================================
 struct KmbPol {
-    uint64_t first;  // L2 evict-first: use-once gathers and streams
-    uint64_t last;   // L2 evict-last: the filter
+    uint64_t first;   // L2 evict-first: the read stream (use once)
+    uint64_t filter;  // the filter words (default evict-last: the structure meant to live in L2)
+    uint64_t line;    // index lines (default normal: the key read and the RED must still find them)
+    uint64_t red;     // counter reductions
 };
-__device__ __forceinline__ KmbPol kmb_make_policies() {
+__device__ __forceinline__ KmbPol kmb_make_policies(uint32_t bits) {
     KmbPol p;
     p.first = kmb_policy_evict_first();
-    p.last = kmb_policy_evict_last();
+    p.filter = kmb_policy_select(bits & 3u);
+    p.line = kmb_policy_select((bits >> 2) & 3u);
+    p.red = kmb_policy_select((bits >> 4) & 3u);
     return p;
 }
 
-// Drain up to 32 queued candidates (km, h).  Called by all 32 lanes.
-__device__ __forceinline__ void kmb_drain(const KmbProbe &P, const uint64_t *q_kmer, const uint32_t *q_h, int base,
-                                          int cnt, int lane) {
-    const int sub = lane & 3;    // sector of the line this lane looks at (3 = counters only: idle)
-    const int grp = lane >> 2;   // candidate within the round
-#pragma unroll 1
-    for (int r0 = 0; r0 < cnt; r0 += 8) {
-        const int c = r0 + grp;
-        const bool have = c < cnt;
-        uint64_t km = 0;
-        uint64_t line = 0;
-        if (have) {
-            km = q_kmer[base + c];
-            line = (uint64_t)(q_h[base + c] >> P.line_shift);
-        }
-        const uint32_t klo = (uint32_t)km, khi = (uint32_t)(km >> 32);
-        uint32_t n_total = 0, ovf_base = 0;
-        uint32_t t = 0;  // chain line number
-        bool more = have;
-        while (__any_sync(KMB_FULL_MASK, more)) {
-            uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            uint32_t *lp = P.lines + line * KMB_LINE_WORDS;
-            if (more && sub < 3) kmb_ld_sector(lp + 8 * sub, r);
-            if (t == 0) {  // header of the main line sits in sector 0 (lane sub == 0 of the group)
-                n_total = __shfl_sync(KMB_FULL_MASK, r[0], lane & ~3);
-                ovf_base = __shfl_sync(KMB_FULL_MASK, r[1], lane & ~3);
-            }
-            if (more && sub < 3) {
-                const uint32_t n_here = min((uint32_t)KMB_LINE_SLOTS, n_total - t * KMB_LINE_SLOTS);
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const int j = 4 * sub + p - 1;
-                    if (j >= 0 && (uint32_t)j < n_here && r[2 * p] == klo && r[2 * p + 1] == khi)
-                        atomicAdd(lp + KMB_LINE_CNT_WORD0 + j, 1u);
-                }
-            }
-            t++;
-            more = more && (t * KMB_LINE_SLOTS < n_total);
-            line = (uint64_t)ovf_base + (t - 1);
-        }
+// Compare the (up to two) keys of a loaded sector with km and count the matches (mapper.pyx:58-68:
+// every equal key counts, no break).  n_here = valid slots of this sector.
+template <class F>
+__device__ __forceinline__ bool kmb_match_sector(const uint32_t (&r)[8], uint32_t n_here, uint64_t km, uint32_t *lp,
+                                                 uint64_t line, F on_match) {
+    const uint32_t klo = (uint32_t)km, khi = (uint32_t)(km >> 32);
+    if (n_here >= 1u && r[KMB_LINE_KEY_WORD0] == klo && r[KMB_LINE_KEY_WORD0 + 1] == khi)
+        if (on_match(lp, line, 0u)) return true;
+    if (n_here >= 2u && r[KMB_LINE_KEY_WORD0 + 2] == klo && r[KMB_LINE_KEY_WORD0 + 3] == khi)
+        if (on_match(lp, line, 1u)) return true;
+    return false;
+}
+
+// Walk the overflow sectors of a chain (entries 2 .. n_total-1), synchronously.  Rare.
+template <class F>
+__device__ __forceinline__ void kmb_walk_overflow(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t n_total,
+                                                  uint32_t ovf_base, F on_match) {
+    for (uint32_t done = KMB_LINE_SLOTS, t = 0; done < n_total; done += KMB_LINE_SLOTS, t++) {
+        const uint64_t line = (uint64_t)ovf_base + t;
+        uint32_t *lp = P.lines + line * KMB_LINE_WORDS;
+        uint32_t r[8];
+        kmb_ld_sector(lp, r, pol.line);
+        if (kmb_match_sector(r, min((uint32_t)KMB_LINE_SLOTS, n_total - done), km, lp, line, on_match)) return;
     }
 }
 
-// Push this lane's candidate (if any) on the warp's stack; drain when 32 are waiting.
-// Must be called by all 32 lanes (cand=false for lanes without one).
-__device__ __forceinline__ void kmb_push_candidate(const KmbProbe &P, uint64_t *q_kmer, uint32_t *q_h, int &qcount,
-                                                   bool cand, uint64_t km, uint32_t h, int lane) {
+// Synchronous probe of the whole chain that owns bucket h (cross-check variant, membership, lookup).
+template <class F>
+__device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t h, F on_match) {
+    const uint64_t line = (uint64_t)(h >> P.line_shift);
+    uint32_t *lp = P.lines + line * KMB_LINE_WORDS;
+    uint32_t r[8];
+    kmb_ld_sector(lp, r, pol.line);
+    const uint32_t n_total = r[0];
+    if (kmb_match_sector(r, min((uint32_t)KMB_LINE_SLOTS, n_total), km, lp, line, on_match)) return;
+    if (n_total > KMB_LINE_SLOTS) kmb_walk_overflow(P, pol, km, n_total, r[1], on_match);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split drain.  A warp that has 32 candidates issues their 32 sector loads (one HBM line fetch each)
+// and goes back to work: the Barrett reductions and filter loads of the next batch of windows run
+// while the sectors are on their way, and only then are the keys compared and the counters reduced
+// into -- about a microsecond after the fill, while the sector is still in L2.  (Deferring the
+// second half by a whole drain period, ~10 us per warp, was measured: by then 60 % of the sectors had
+// left the L2 again and the RED had to fetch them a second time.)
+// ------------------------------------------------------------------------------------------------
+struct KmbPipe {
+    uint32_t r[8];  // the candidate's main sector, in flight between issue and consume
+    uint64_t km;
+    uint32_t line;
+    bool valid;
+};
+__device__ __forceinline__ void kmb_pipe_init(KmbPipe &pp) {
+    pp.valid = false;
+    pp.km = 0;
+    pp.line = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) pp.r[i] = 0;
+}
+__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const uint64_t *q_kmer,
+                                               const uint32_t *q_h, int base, int cnt, int lane) {
+    if (lane < cnt && !(P.policies & 0x200u)) {
+        pp.km = q_kmer[base + lane];
+        pp.line = q_h[base + lane] >> P.line_shift;
+        kmb_ld_sector(P.lines + (uint64_t)pp.line * KMB_LINE_WORDS, pp.r, pol.line);
+        pp.valid = true;
+    }
+}
+__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp) {
+    if (!pp.valid) return;
+    pp.valid = false;
+    const uint64_t pr = pol.red;
+    const bool no_red = (P.policies & 0x100u) != 0u;
+    auto count = [pr, no_red](uint32_t *lp, uint64_t, uint32_t j) {
+        if (!no_red) kmb_red_add(lp + KMB_LINE_CNT_WORD0 + j, 1u, pr);
+        return false;
+    };
+    const uint32_t n_total = pp.r[0];
+    uint32_t *lp = P.lines + (uint64_t)pp.line * KMB_LINE_WORDS;
+    kmb_match_sector(pp.r, min((uint32_t)KMB_LINE_SLOTS, n_total), pp.km, lp, pp.line, count);
+    if (n_total > KMB_LINE_SLOTS) kmb_walk_overflow(P, pol, pp.km, n_total, pp.r[1], count);
+}
+
+// Push this lane's candidate (if any) on the warp's stack.  Called by all 32 lanes.
+__device__ __forceinline__ void kmb_push_candidate(uint64_t *q_kmer, uint32_t *q_h, int &qcount, bool cand, uint64_t km,
+                                                   uint32_t h, int lane) {
     unsigned bal = __ballot_sync(KMB_FULL_MASK, cand);
-    if (bal == 0u) return;
     if (cand) {
         int slot = qcount + __popc(bal & ((1u << lane) - 1u));
         q_kmer[slot] = km;
         q_h[slot] = h;
     }
     qcount += __popc(bal);
-    if (qcount >= 32) {
-        __syncwarp();
-        qcount -= 32;
-        kmb_drain(P, q_kmer, q_h, qcount, 32, lane);
-        __syncwarp();
-    }
 }
 
-// Level 0 for U queries of this lane, all filter loads in flight together.  kf(u) yields query u
-// (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u exists.
+// Level 0 for U queries of this lane (all filter loads in flight together), with the consume half
+// of the previous drain placed between the issue of those loads and their first use.  kf(u) yields
+// query u (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u
+// exists.  The stack holds < 32 entries on entry and on exit, so KMB_QUEUE_SLOTS >= 32 * (U + 1).
 template <int U, bool FILT, class KF>
-__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, const KF &kf, uint32_t vbits,
-                                                uint64_t *q_kmer, uint32_t *q_h, int &qcount, int lane) {
+__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KF &kf,
+                                                uint32_t vbits, uint64_t *q_kmer, uint32_t *q_h, int &qcount, int lane) {
     uint32_t hh[U];
     uint32_t need[U];  // filter bits the query needs; 0 = no query
     uint32_t fw[U];
@@ -330,17 +387,35 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
         const bool valid = (vbits >> u) & 1u;
         if (FILT) {
             need[u] = valid ? kmb_filter_mask((uint32_t)h, q) : 0u;
-            fw[u] = valid ? kmb_ldg_u32_hint(P.filter + (hh[u] >> 5), pol.last) : 0u;
+            fw[u] = (valid && !(P.policies & 0x400u)) ? kmb_ldg_u32_hint(P.filter + (hh[u] >> 5), pol.filter) : 0u;
         } else {
             need[u] = valid ? 1u : 0u;
             fw[u] = 1u;
         }
     }
+    kmb_pipe_consume(P, pol, pp);  // the sectors issued by the previous call have had this long to arrive
 #pragma unroll
     for (int u = 0; u < U; u++) {
         bool cand = need[u] != 0u && (fw[u] & need[u]) == need[u];
-        kmb_push_candidate(P, q_kmer, q_h, qcount, cand, kf(u), hh[u], lane);
+        kmb_push_candidate(q_kmer, q_h, qcount, cand, kf(u), hh[u], lane);
     }
+    __syncwarp();
+#pragma unroll 1
+    while (qcount >= 32) {
+        kmb_pipe_consume(P, pol, pp);
+        qcount -= 32;
+        kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, 32, lane);
+    }
+    __syncwarp();
+}
+
+// End of kernel: retire the outstanding batch, then the partial one.
+__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const uint64_t *q_kmer,
+                                                const uint32_t *q_h, int qcount, int lane) {
+    __syncwarp();
+    kmb_pipe_consume(P, pol, pp);
+    kmb_pipe_issue(P, pol, pp, q_kmer, q_h, 0, qcount, lane);
+    kmb_pipe_consume(P, pol, pp);
 }
 
 struct KmbWindowFn {  // forward window b0+u of the 64 bases in hi:lo
@@ -405,40 +480,46 @@ template <int U, bool FILT, bool REVCOMP>
 __global__ void __launch_bounds__(KMB_TILE_THREADS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
                      const uint32_t *__restrict__ mask, int k, bool n_to_a, KmbProbe P, KmbStatus *status) {
-    __shared__ __align__(16) uint32_t s_pack[KMB_TILE_POS / 16 + 8];  // 512 words + halo
-    __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
-    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
+    // Everything is per warp (tile of 1024 window starts, packed stream, candidate stack): no CTA barrier,
+    // so a warp that is walking a long chain never holds the other seven back.
+    __shared__ __align__(16) uint32_t s_pack[KMB_TILE_THREADS / 32][KMB_WTILE_POS / 16 + 4];  // 64 words + halo
+    __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
+    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *pack = s_pack[warp];
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
     int qcount = 0;
-    const KmbPol pol = kmb_make_policies();
+    KmbPipe pp;
+    kmb_pipe_init(pp);
+    const KmbPol pol = kmb_make_policies(P.policies);
     const uint64_t kmask = kmb_kmer_mask(k);
-    const uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
+    const uint64_t n_tiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
     const uint64_t n_vec_full = n_bases / 16;  // vectors entirely inside the buffer
+    const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_TILE_THREADS / 32);
     unsigned long long mapped = 0;
 
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * KMB_TILE_POS;
-        __syncthreads();  // previous tile's readers are done with s_pack
-        // ---- 1. load + encode: vectors v = t0/16 + i, i in [0, 514)
-        for (int i = tid; i < KMB_TILE_POS / 16 + 2; i += KMB_TILE_THREADS) {
+    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_TILE_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
+        const uint64_t t0 = tile * KMB_WTILE_POS;
+        __syncwarp();  // the previous tile's readers are done with pack
+        // ---- 1. load + encode: vectors v = t0/16 + i, i in [0, 66)
+#pragma unroll
+        for (int i = lane; i < KMB_WTILE_POS / 16 + 2; i += 32) {
             uint64_t v = t0 / 16 + (uint64_t)i;
             uint4 w = kmb_load_bases16(bases, v, n_vec_full, n_bases, pol.first);
             uint32_t inv;
-            s_pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
+            pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
             if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + v * 16 + (uint64_t)(__ffs(inv) - 1)));
         }
-        __syncthreads();
-        // ---- 2. this thread's 32 positions
-        const uint64_t p0 = t0 + (uint64_t)tid * KMB_POS_PER_THREAD;
+        __syncwarp();
+        // ---- 2. this lane's 32 positions
+        const uint64_t p0 = t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
         const uint32_t valid = kmb_valid_starts(mask, p0, n_bases, k);
         mapped += __popc(valid);
-        const uint2 a = *reinterpret_cast<const uint2 *>(&s_pack[2 * tid]);
-        const uint2 b = *reinterpret_cast<const uint2 *>(&s_pack[2 * tid + 2]);
+        const uint2 a = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
+        const uint2 b = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
         const uint64_t lo = (uint64_t)a.x | ((uint64_t)a.y << 32);
         const uint64_t hi = (uint64_t)b.x | ((uint64_t)b.y << 32);
         // ---- 3. probe in batches of U
@@ -447,15 +528,14 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             const uint32_t vb = (valid >> b0) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
             if (!__any_sync(KMB_FULL_MASK, vb != 0u)) continue;
             KmbWindowFn fw = {lo, hi, kmask, b0};
-            kmb_probe_batch<U, FILT>(P, pol, fw, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT>(P, pol, pp, fw, vb, q_kmer, q_h, qcount, lane);
             if (REVCOMP) {
                 KmbRcWindowFn rc = {lo, hi, kmask, b0, k};
-                kmb_probe_batch<U, FILT>(P, pol, rc, vb, q_kmer, q_h, qcount, lane);
+                kmb_probe_batch<U, FILT>(P, pol, pp, rc, vb, q_kmer, q_h, qcount, lane);
             }
         }
     }
-    __syncwarp();
-    if (qcount > 0) kmb_drain(P, q_kmer, q_h, 0, qcount, lane);
+    kmb_pipe_finish(P, pol, pp, q_kmer, q_h, qcount, lane);
     // statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
     if (lane == 0 && mapped) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * mapped : mapped);
@@ -468,45 +548,46 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 template <int U, bool FILT, bool REVCOMP>
 __global__ void __launch_bounds__(KMB_TILE_THREADS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
-    __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
-    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS];
+    __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
+    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
     int qcount = 0;
-    const KmbPol pol = kmb_make_policies();
+    KmbPipe pp;
+    kmb_pipe_init(pp);
+    const KmbPol pol = kmb_make_policies(P.policies);
     const uint64_t per_block = (uint64_t)KMB_TILE_THREADS * U;
     const uint64_t n_blocks = (n + per_block - 1) / per_block;
     for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        uint64_t base = blk * per_block + (uint64_t)tid;
+        // warp w of the CTA owns 32*U consecutive k-mers; lane l takes elements l, l+32, ... (coalesced)
+        uint64_t base = blk * per_block + (uint64_t)warp * (32 * U) + (uint64_t)lane;
         uint64_t km[U];
         uint32_t vb = 0;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            uint64_t i = base + (uint64_t)u * KMB_TILE_THREADS;
+            uint64_t i = base + (uint64_t)u * 32;
             bool in = i < n;
             km[u] = in ? kmb_ldg_u64_hint(kmers + i, pol.first) : 0ull;
             vb |= in ? (1u << u) : 0u;
         }
         KmbArrayFn fa = {km};
-        kmb_probe_batch<U, FILT>(P, pol, fa, vb, q_kmer, q_h, qcount, lane);
+        kmb_probe_batch<U, FILT>(P, pol, pp, fa, vb, q_kmer, q_h, qcount, lane);
         if (REVCOMP) {
 #pragma unroll
             for (int u = 0; u < U; u++) km[u] = kmb_revcomp(km[u], k);
-            kmb_probe_batch<U, FILT>(P, pol, fa, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT>(P, pol, pp, fa, vb, q_kmer, q_h, qcount, lane);
         }
     }
-    __syncwarp();
-    if (qcount > 0) kmb_drain(P, q_kmer, q_h, 0, qcount, lane);
+    kmb_pipe_finish(P, pol, pp, q_kmer, q_h, qcount, lane);
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * n : (unsigned long long)n);
 }
 
 // ------------------------------------------------------------------------------------------------
-// One-query-per-thread walk of a chain: the cross-check variant of the mapping kernels
+// One query per thread without the warp stack: the cross-check variant of the mapping kernels
 // (kmb_set_option("probe_variant", 0)), the membership kernel and the per-key lookup.
-// Calls on_match(line, slot) for every slot whose key equals km; stops early if it returns true.
 // ------------------------------------------------------------------------------------------------
 template <class F>
 __device__ __forceinline__ void kmb_walk_one(const KmbProbe &P, const KmbPol &pol, uint64_t km, F on_match) {
@@ -514,32 +595,23 @@ __device__ __forceinline__ void kmb_walk_one(const KmbProbe &P, const KmbPol &po
     kmb_divmod(km, P.mod, q, h);
     if (P.filter != nullptr) {
         uint32_t need = kmb_filter_mask((uint32_t)h, q);
-        uint32_t w = kmb_ldg_u32_hint(P.filter + (h >> 5), pol.last);
+        uint32_t w = kmb_ldg_u32_hint(P.filter + (h >> 5), pol.filter);
         if ((w & need) != need) return;
     }
-    const uint64_t main_line = h >> P.line_shift;
-    const uint2 hdr = kmb_ld_u64_volatile(P.lines + main_line * KMB_LINE_WORDS);
-    const uint32_t n_total = hdr.x, ovf_base = hdr.y;
-    for (uint32_t s = 0; s < n_total; s++) {
-        const uint64_t line = kmb_chain_line(main_line, ovf_base, s);
-        const uint32_t j = kmb_chain_slot(s);
-        const uint2 key = kmb_ld_u64_volatile(P.lines + line * KMB_LINE_WORDS + KMB_LINE_KEY_WORD0 + 2 * j);
-        if (key.x == (uint32_t)km && key.y == (uint32_t)(km >> 32))
-            if (on_match(line, j)) return;
-    }
+    kmb_probe_line(P, pol, km, (uint32_t)h, on_match);
 }
 
 template <bool REVCOMP>
 __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P,
                                             KmbStatus *status) {
-    const KmbPol pol = kmb_make_policies();
+    const KmbPol pol = kmb_make_policies(P.policies);
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t km = kmers[i];
 #pragma unroll
         for (int strand = 0; strand < (REVCOMP ? 2 : 1); strand++) {
             if (strand == 1) km = kmb_revcomp(km, k);
-            kmb_walk_one(P, pol, km, [&](uint64_t line, uint32_t j) {
-                atomicAdd(P.lines + line * KMB_LINE_WORDS + KMB_LINE_CNT_WORD0 + j, 1u);
+            kmb_walk_one(P, pol, km, [](uint32_t *lp, uint64_t, uint32_t j) {
+                atomicAdd(lp + KMB_LINE_CNT_WORD0 + j, 1u);
                 return false;
             });
         }
@@ -550,38 +622,30 @@ __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, 
 // ================================================================================================
 // K4b flush: slot counters -> node counts.  For every slot with a non-zero counter c whose
 // frequency passes the cut-off (mapper.pyx:64): node_counts[node] += c (mod 2^32, mapper.pyx:68),
-// then the counter is zeroed.  One thread per line; the cold (node, frequency) arrays are only
-// touched for slots that were hit.  CLEAR_ONLY zeroes without counting (mapper reset).
+// then the counter is zeroed.  One thread per sector (coalesced 8-byte counter reads at a 32-byte
+// stride); the cold (node, frequency) array is only touched for sectors that were hit.  CLEAR_ONLY zeroes without counting (mapper reset).
 // ================================================================================================
 template <bool CLEAR_ONLY>
-__global__ void kmb_flush_kernel(uint32_t *__restrict__ lines, uint64_t n_lines, const uint32_t *__restrict__ cold_node,
-                                 const uint16_t *__restrict__ cold_freq, int32_t max_freq, uint32_t *__restrict__ counts,
-                                 KmbStatus *status) {
+__global__ void kmb_flush_kernel(uint32_t *__restrict__ lines, uint64_t n_lines, const uint2 *__restrict__ cold,
+                                 int32_t max_freq, uint32_t *__restrict__ counts, KmbStatus *status) {
     unsigned long long counted = 0;
     for (uint64_t line = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; line < n_lines;
          line += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t *cp = lines + line * KMB_LINE_WORDS + KMB_LINE_CNT_WORD0;  // 10 counters: 8-byte + 2 x 16-byte
-        uint32_t c[KMB_LINE_SLOTS];
-        uint2 a = *reinterpret_cast<const uint2 *>(cp);
-        uint4 b = *reinterpret_cast<const uint4 *>(cp + 2);
-        uint4 d = *reinterpret_cast<const uint4 *>(cp + 6);
-        c[0] = a.x, c[1] = a.y, c[2] = b.x, c[3] = b.y, c[4] = b.z, c[5] = b.w, c[6] = d.x, c[7] = d.y, c[8] = d.z, c[9] = d.w;
-        uint32_t any = 0;
-#pragma unroll
-        for (int j = 0; j < KMB_LINE_SLOTS; j++) any |= c[j];
-        if (!any) continue;
+        uint2 *cp = reinterpret_cast<uint2 *>(lines + line * KMB_LINE_WORDS + KMB_LINE_CNT_WORD0);
+        const uint2 c = *cp;
+        if (!(c.x | c.y)) continue;
         if (!CLEAR_ONLY) {
-#pragma unroll
-            for (int j = 0; j < KMB_LINE_SLOTS; j++) {
-                if (c[j] && (int32_t)cold_freq[line * KMB_LINE_SLOTS + j] <= max_freq) {
-                    atomicAdd(counts + cold_node[line * KMB_LINE_SLOTS + j], c[j]);
-                    counted += c[j];
-                }
+            const uint4 nf = *reinterpret_cast<const uint4 *>(cold + line * KMB_LINE_SLOTS);  // (node0, freq0, node1, freq1)
+            if (c.x && (int32_t)nf.y <= max_freq) {
+                atomicAdd(counts + nf.x, c.x);
+                counted += c.x;
+            }
+            if (c.y && (int32_t)nf.w <= max_freq) {
+                atomicAdd(counts + nf.z, c.y);
+                counted += c.y;
             }
         }
-        *reinterpret_cast<uint2 *>(cp) = make_uint2(0u, 0u);
-        *reinterpret_cast<uint4 *>(cp + 2) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4 *>(cp + 6) = make_uint4(0u, 0u, 0u, 0u);
+        *cp = make_uint2(0u, 0u);
     }
     if (!CLEAR_ONLY) {
         for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
@@ -596,15 +660,15 @@ __global__ void kmb_flush_kernel(uint32_t *__restrict__ lines, uint64_t n_lines,
 // ================================================================================================
 template <int MODE>
 __global__ void kmb_in_graph_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KmbProbe P,
-                                    const uint32_t *__restrict__ cold_node, const uint32_t *__restrict__ counts,
+                                    const uint2 *__restrict__ cold, const uint32_t *__restrict__ counts,
                                     uint8_t *out8, uint32_t *out32) {
-    const KmbPol pol = kmb_make_policies();
+    const KmbPol pol = kmb_make_policies(P.policies);
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         bool hit = false;
         uint32_t node = 0;
-        kmb_walk_one(P, pol, kmers[i], [&](uint64_t line, uint32_t j) {
+        kmb_walk_one(P, pol, kmers[i], [&](uint32_t *, uint64_t line, uint32_t j) {
             hit = true;
-            if (MODE == 1) node = cold_node[line * KMB_LINE_SLOTS + j];
+            if (MODE == 1) node = cold[line * KMB_LINE_SLOTS + j].x;
             return true;
         });
         if (MODE == 0) out8[i] = hit ? 1 : 0;
@@ -780,9 +844,24 @@ __global__ void kmb_codec_twobit_swap_kernel(const T *__restrict__ in, uint64_t 
 // uniformly random W-aligned... (32-byte-sector-aligned) addresses; the XOR of everything loaded is
 // written once so the loads cannot be elided.
 // ================================================================================================
+// 8-byte load variants for the fetch-granularity experiment: mode 0 plain .nc, 1/2/3 = L2::64B/128B/256B
+// prefetch-size qualifier, 4 = plain coherent ld.global, 5 = ld.global.cv (volatile-like, "don't cache")
+__device__ __forceinline__ uint64_t kmb_ldg_u64_mode(const uint64_t *p, int mode) {
+    uint64_t v;
+    switch (mode) {
+        case 1: asm volatile("ld.global.nc.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p)); break;
+        case 2: asm volatile("ld.global.nc.L1::no_allocate.L2::128B.u64 %0, [%1];" : "=l"(v) : "l"(p)); break;
+        case 3: asm volatile("ld.global.nc.L1::no_allocate.L2::256B.u64 %0, [%1];" : "=l"(v) : "l"(p)); break;
+        case 4: asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p)); break;
+        case 5: asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"(p)); break;
+        default: asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p)); break;
+    }
+    return v;
+}
+
 template <int W, int UNROLL>
 __global__ void kmb_gather_bench_kernel(const uint8_t *__restrict__ table, uint64_t n_sectors, uint64_t n_loads,
-                                        uint64_t seed, uint64_t *sink) {
+                                        uint64_t seed, uint64_t *sink, int mode) {
     uint64_t acc = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_loads; i += stride * UNROLL) {
@@ -794,7 +873,7 @@ __global__ void kmb_gather_bench_kernel(const uint8_t *__restrict__ table, uint6
             uint64_t sector = kmb_umulhi64(r, n_sectors);
             const uint8_t *p = table + sector * 32;
             if (W == 8) {
-                v[u] = kmb_ldg_u64_nc(reinterpret_cast<const uint64_t *>(p));
+                v[u] = kmb_ldg_u64_mode(reinterpret_cast<const uint64_t *>(p), mode);
             } else if (W == 16) {
                 uint4 t = kmb_ldg_v4_nc(p);
                 v[u] = (uint64_t)t.x ^ ((uint64_t)t.y << 32) ^ t.z ^ ((uint64_t)t.w << 32);

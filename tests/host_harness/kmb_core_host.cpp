@@ -20,4 +20,5 @@ uint64_t h_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) { retur
 uint32_t h_chain_slot(uint32_t s) { return kmb_chain_slot(s); }
 uint32_t h_chain_extra_lines(uint32_t n) { return kmb_chain_extra_lines(n); }
 uint32_t h_filter_mask(uint32_t h, uint64_t q) { return kmb_filter_mask(h, q); }
+
 }

@@ -116,18 +116,18 @@ def test_revcomp(core):
             assert core.h_revcomp(want, k) == x
 
 
-def test_line_chain_geometry_and_filter_mask(core):
-    # ten slots per 128-byte line; entry s of a chain lives in the main line (s < 10) or in overflow line
-    # ovf_base + (s-10)//10; every (line, slot) pair is used exactly once
-    for n_total in (0, 1, 9, 10, 11, 20, 21, 1234):
+def test_sector_chain_geometry_and_filter_mask(core):
+    # two slots per 32-byte sector; entry s of a chain lives in the main sector (s < 2) or in overflow sector
+    # ovf_base + (s-2)//2; every (sector, slot) pair is used exactly once
+    for n_total in (0, 1, 2, 3, 4, 5, 17, 1234):
         extra = core.h_chain_extra_lines(n_total)
-        assert extra == max(0, -(-n_total // 10) - 1)
+        assert extra == max(0, -(-n_total // 2) - 1)
         seen = set()
         for s in range(n_total):
             line = core.h_chain_line(77, 1000, s)
             slot = core.h_chain_slot(s)
-            assert 0 <= slot < 10
-            assert line == 77 if s < 10 else 1000 <= line < 1000 + extra
+            assert 0 <= slot < 2
+            assert line == 77 if s < 2 else 1000 <= line < 1000 + extra
             seen.add((line, slot))
         assert len(seen) == n_total
     rng = np.random.default_rng(6)

@@ -25,8 +25,8 @@ def kmb():
 VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=8),
             dict(probe_variant=1, use_filter=0, gathers_in_flight=8),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
-            dict(probe_variant=1, use_filter=0, gathers_in_flight=16),
-            dict(probe_variant=1, use_filter=1, gathers_in_flight=16),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=2),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=2),
             dict(probe_variant=0, use_filter=1, gathers_in_flight=8),
             dict(probe_variant=0, use_filter=0, gathers_in_flight=8)]
 
