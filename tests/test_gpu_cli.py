@@ -1,0 +1,71 @@
+"""End to end through the reference-shaped CLI on the GPU: files in, <out>.npy out, compared with the oracle
+run on an independently parsed copy of the same files."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world(tmp_path_factory):
+    from kmer_mapper_b200 import _lib, synthetic
+    _lib.require_device()
+    d = tmp_path_factory.mktemp("cli")
+    k = 31
+    g = synthetic.make_genome(300_000, 11)
+    idx = synthetic.make_index(g, 40_000, k, 30_000, 200_003, 12, n_hot_nodes=1100)
+    idx.to_file(str(d / "index.npz"))
+    bases, offsets = synthetic.make_reads(g, 6_000, 150, seed=13, n_rate=0.01, lower_rate=0.3, ragged=True)
+    synthetic.write_fasta(str(d / "reads.fa"), bases, offsets, line_width=70)
+    synthetic.write_fastq(str(d / "reads.fq.gz"), bases, offsets, members=4)
+    want, n_kmers = c_oracle.map_reads(idx, idx.max_node_id(), bases, offsets, k, n_threads=4)
+    assert want.sum() > 1000
+    return dict(dir=d, idx=idx, want=want, k=k, bases=bases, offsets=offsets)
+
+
+@pytest.mark.parametrize("reads,chunk", [("reads.fa", 2_500_000), ("reads.fa", 20_000), ("reads.fq.gz", 50_000)])
+def test_cli_map_writes_reference_shaped_output(world, reads, chunk):
+    from kmer_mapper_b200.command_line_interface import run_argument_parser
+    d = world["dir"]
+    out = str(d / ("out_%s_%d" % (reads.replace(".", "_"), chunk)))
+    run_argument_parser(["map", "-i", str(d / "index.npz"), "-f", str(d / reads), "-o", out, "-k", str(world["k"]),
+                         "-c", str(chunk), "-t", "3"])
+    got = np.load(out + ".npy")                    # np.save appends .npy (command_line_interface.py:149)
+    assert got.dtype == np.uint32 and got.shape == (world["idx"].max_node_id() + 1,)
+    assert np.array_equal(got, world["want"])
+
+
+def test_map_bnp_programmatic_call_returns_counts(world):
+    # KAGE-style call: a Namespace carrying a loaded index object and output_file=None (cli:146-147, util.py:40-44)
+    from kmer_mapper_b200.command_line_interface import map_bnp
+    from kmer_mapper_b200.kmer_index import KmerIndex
+    d = world["dir"]
+    idx = KmerIndex.from_file(str(d / "index.npz"))
+    args = argparse.Namespace(kmer_index=idx, index_bundle=None, reads=str(d / "reads.fq.gz"), kmer_size=world["k"],
+                              n_threads=1, chunk_size=1_000_000, output_file=None, debug=None, max_hits_per_kmer=1000,
+                              gpu=True, gpu_hash_map_size=0, map_reverse_complements=False, func=map_bnp)
+    got = map_bnp(args)
+    assert np.array_equal(got, world["want"])
+    # the CPU route refuses reverse complements (cli:107); the GPU route accepts the flag
+    args = argparse.Namespace(**{**vars(args), "gpu": False, "map_reverse_complements": True, "func": map_bnp})
+    with pytest.raises(AssertionError):
+        map_bnp(args)
+
+
+def test_map_gpu_signature_and_invalid_reads(world, tmp_path):
+    from kmer_mapper_b200._lib import InvalidBaseError
+    from kmer_mapper_b200.command_line_interface import map_gpu
+    from kmer_mapper_b200.reader import open_reads
+    d = world["dir"]
+    chunks = open_reads(str(d / "reads.fa")).read_chunks(min_chunk_size=100_000)
+    got = map_gpu(world["idx"], chunks, world["k"], 0, False)
+    assert np.array_equal(got, world["want"])
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">r1\nACGTACGTACGTACGTACGTACGTACGTACGTACGTRACGT\n")
+    with pytest.raises(InvalidBaseError):
+        map_gpu(world["idx"], open_reads(str(bad)).read_chunks(1000), world["k"], 0, False)
