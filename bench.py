@@ -302,7 +302,7 @@ def main_reference(args):
     host_index = tindex.to_host()
     max_node = host_index.max_node_id()
     cores = os.cpu_count() or 1
-    sample_reads = args.cpu_sample_reads or min(w["reads"], max(cores * 20_000 * 150 // w["read_len"], 1000))
+    sample_reads = args.cpu_sample_reads or min(w["reads"], max(cores * 100_000 * 150 // w["read_len"], 1000))
     hb = bases[:int(offsets[sample_reads].item())].cpu().numpy()
     ho = offsets[:sample_reads + 1].cpu().numpy()
     del tindex, bases, offsets
@@ -359,7 +359,7 @@ def main_ours(args):
     sample_reads = 0
     if do_cpu:
         cores = os.cpu_count() or 1
-        sample_reads = args.cpu_sample_reads or min(n_reads, max(cores * 20_000 * 150 // L, 1000))
+        sample_reads = args.cpu_sample_reads or min(n_reads, max(cores * 100_000 * 150 // L, 1000))
         cpu_dir = tempfile.mkdtemp(prefix="kmb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         host_index = tindex.to_host()
         write_cpu_sample(cpu_dir, host_index, max_node, bases[:int(offsets[sample_reads].item())].cpu().numpy(),

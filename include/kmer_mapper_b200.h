@@ -163,7 +163,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
 
 /* Tuning knobs (process-wide, read at launch / index-creation time): name in
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
- *  "use_filter", "filter_l2_budget_bytes", "l2_persist", "prefetch_lines", "ablate", "policy_filter", "policy_line", "policy_red",
+ *  "use_filter", "filter_l2_budget_bytes", "filter_shift", "l2_persist", "ablate", "policy_filter", "policy_line", "policy_red",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes"}. */
 int kmb_set_option(const char *name, int64_t value);

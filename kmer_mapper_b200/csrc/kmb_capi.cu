@@ -57,12 +57,12 @@ struct KmbOptions {
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
     int64_t gathers_in_flight = 4;        // U: 2, 4 or 8 independent filter loads per thread
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
-    int64_t filter_l2_budget_bytes = 80ll << 20;
+    int64_t filter_l2_budget_bytes = 64ll << 20;  // the L2 keeps ~72 MB of randomly accessed data (profiles/README.md)
+    int64_t filter_shift = -1;            // buckets per filter bit = 2^shift; -1 = smallest that fits the budget
     int64_t policy_filter = 2;            // L2 priority hints: 0 normal, 1 evict-first, 2 evict-last
     int64_t policy_line = 0;
     int64_t policy_red = 0;
     int64_t ablate = 0;                   // measurement only (results become wrong): 1 no RED, 2 no line loads, 4 no filter loads, 8 no key loads
-    int64_t prefetch_lines = 0;           // prefetch a candidate's line into L2 at queue time
     int64_t l2_persist = 1;               // set a persisting-L2 access window over the filter
     int64_t l2_fetch_granularity = 0;     // 0 = leave the device default; else 32/64/128 (cudaLimitMaxL2FetchGranularity)
     int64_t bench_load_mode = 0;          // kmb_bench_gather, 8-byte loads: 0 .nc, 1-3 L2::64B/128B/256B, 4 plain, 5 .cv
@@ -85,8 +85,8 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(gathers_in_flight)
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
+    OPT(filter_shift)
     OPT(l2_persist)
-    OPT(prefetch_lines)
     OPT(ablate)
     OPT(policy_filter)
     OPT(policy_line)
@@ -117,8 +117,8 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(gathers_in_flight)
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
+    OPT(filter_shift)
     OPT(l2_persist)
-    OPT(prefetch_lines)
     OPT(ablate)
     OPT(policy_filter)
     OPT(policy_line)
@@ -259,6 +259,7 @@ struct kmb_index {
     uint2 *cold = nullptr;              // (node, frequency) of (line, slot)
     uint32_t *filter = nullptr;
     size_t filter_bytes = 0;
+    uint32_t filter_cfg = 0;            // kmb_filter_mask configuration
     bool filter_on = false;
     bool lines_in_use = false;          // a mapper is counting into the master copy
     bool lines_dirty = false;           // master counters may be non-zero
@@ -329,7 +330,18 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     KMB_TRY(to_device(kmers, (size_t)n_entries, device, t_kmers, &d_kmers, s));
     KMB_TRY(to_device(frequencies, (size_t)n_entries, device, t_freq, &d_freq, s));
 
-    ix->filter_bytes = (size_t)((modulo + 31) / 32) * 4;
+    // Filter geometry: one bit per 2^fs buckets, fs the smallest shift that fits the L2 budget; a second
+    // probe bit only while the filter has >= 2.5 bits per key; no filter at all below 0.62 bits per key
+    // (more than 80 % of the absent k-mers would pass).
+    uint32_t fs = 0;
+    if (g_opt.filter_shift >= 0) {
+        fs = (uint32_t)std::min<int64_t>(g_opt.filter_shift, 31);
+    } else {
+        while (fs < 31 && (int64_t)((((modulo - 1) >> fs) + 32) / 32 * 4) > g_opt.filter_l2_budget_bytes) fs++;
+    }
+    const double bits_per_key = (double)(((modulo - 1) >> fs) + 1) / (double)std::max<uint64_t>(n_entries, 1);
+    ix->filter_cfg = fs | (bits_per_key >= 2.5 ? KMB_FILTER_TWO : 0u);
+    ix->filter_bytes = (size_t)((((modulo - 1) >> fs) + 32) / 32) * 4;
     KMB_CUDA(cudaMalloc(&ix->filter, ix->filter_bytes));
     KMB_CUDA(cudaMemsetAsync(ix->filter, 0, ix->filter_bytes, s));
     DevBuf<uint32_t> line_fill;
@@ -358,7 +370,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     // 2. per-line counts + filter bits, 3. overflow lines needed
     if (n_entries) {
         kmb_v2_count<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_h2i, d_nk, n_entries, ix->mod,
-                                                                 ix->line_shift, line_fill.p, ix->filter, d_status.p);
+                                                                 ix->line_shift, line_fill.p, ix->filter, ix->filter_cfg, d_status.p);
         g_launches++;
     }
     kmb_v2_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, d_status.p);
@@ -388,9 +400,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaStreamSynchronize(s));
 
-    bool want_filter = g_opt.use_filter == 1 ||
-                       (g_opt.use_filter < 0 && (int64_t)ix->filter_bytes <= g_opt.filter_l2_budget_bytes &&
-                        n_entries < 2 * modulo);  // a table this dense sets nearly every filter bit
+    bool want_filter = g_opt.use_filter == 1 || (g_opt.use_filter < 0 && bits_per_key >= 0.62);
     ix->filter_on = want_filter;
     if (!want_filter) {
         cudaFree(ix->filter);
@@ -633,9 +643,9 @@ static KmbProbe make_probe(const kmb_mapper *m) {
     KmbProbe P;
     P.lines = m->lines;
     P.filter = ix->filter_on ? ix->filter : nullptr;
+    P.filter_cfg = ix->filter_cfg;
     P.mod = ix->mod;
     P.line_shift = ix->line_shift;
-    P.prefetch = g_opt.prefetch_lines ? 1u : 0u;
     P.policies = (uint32_t)((g_opt.policy_filter & 3) | ((g_opt.policy_line & 3) << 2) | ((g_opt.policy_red & 3) << 4) | ((g_opt.ablate & 15) << 8));
     return P;
 }
@@ -979,9 +989,9 @@ static int run_lookup(kmb_index *ix, const uint32_t *lines, const uint32_t *coun
     KmbProbe P;
     P.lines = const_cast<uint32_t *>(lines);  // keys are only read
     P.filter = ix->filter_on ? ix->filter : nullptr;
+    P.filter_cfg = ix->filter_cfg;
     P.mod = ix->mod;
     P.line_shift = ix->line_shift;
-    P.prefetch = 0;
     P.policies = 2u;
     kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(
         d_keys, n, P, ix->cold, counts, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),

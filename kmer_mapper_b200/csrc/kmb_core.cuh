@@ -90,14 +90,20 @@ KMB_HD uint32_t kmb_chain_extra_lines(uint32_t n_total) {
     return n_total > KMB_LINE_SLOTS ? (n_total - 1) / KMB_LINE_SLOTS : 0u;
 }
 
-// Occupancy filter (probe level 0): one 32-bit word per 32 consecutive buckets; every live entry
-// sets TWO bits of the word h >> 5: its bucket's bit (h & 31) and a bit chosen by the quotient
-// q = key / modulo, which is independent of h.  A query passes iff both of its bits are set: a
-// two-probe Bloom filter blocked into the word one 4-byte load brings (false-pass rate ~13 % at the
-// reference's load factor 0.22 instead of ~20 % for the occupancy bit alone).
-KMB_HD uint32_t kmb_filter_mask(uint32_t h, uint64_t q) {
-    uint32_t b2 = ((uint32_t)q * 0x9E3779B1u) >> 27;
-    return (1u << (h & 31u)) | (1u << b2);
+// Filter (probe level 0): one bit per 2^fs consecutive buckets, 32 of them per word.  Every live
+// entry sets the bit of its bucket group hb = h >> fs and -- when the table is sparse enough for a
+// second probe to pay (>= 2.5 filter bits per key) -- a second bit of the same word chosen by the
+// quotient q = key / modulo, which is independent of h.  A query passes iff all of its bits are set:
+// a Bloom filter blocked into the word one 4-byte load brings.  At the reference's load factor
+// (0.22 entries per bucket, fs = 0, two probes) ~13 % of the absent k-mers pass; fs grows until the
+// filter fits the L2 budget (config 3: fs = 1, one probe, 63 % pass).
+// cfg: bits 0-4 = fs, bit 8 = two probes.
+#define KMB_FILTER_TWO 0x100u
+KMB_HD uint32_t kmb_filter_word(uint32_t h, uint32_t cfg) { return (h >> (cfg & 31u)) >> 5; }
+KMB_HD uint32_t kmb_filter_mask(uint32_t h, uint64_t q, uint32_t cfg) {
+    uint32_t m = 1u << ((h >> (cfg & 31u)) & 31u);
+    if (cfg & KMB_FILTER_TWO) m |= 1u << (((uint32_t)q * 0x9E3779B1u) >> 27);
+    return m;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -42,10 +42,10 @@ struct KmbStatus {
 
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
     uint32_t *lines;                         // 128-byte lines (keys immutable, counters reduced into)
-    const uint32_t *__restrict__ filter;     // 2 bits per live entry in word h >> 5, or nullptr
+    const uint32_t *__restrict__ filter;     // blocked Bloom filter over the buckets (kmb_filter_mask), or nullptr
+    uint32_t filter_cfg;                     // bits 0-4 buckets-per-bit shift, bit 8 two probes
     KmbMod mod;
     uint32_t line_shift;                     // g: line = h >> g
-    uint32_t prefetch;                       // 1: prefetch a candidate's line into L2 when it is queued
     uint32_t policies;                       // L2 priority of: filter (bits 0-1), line loads (2-3), counter REDs (4-5)
 };
 
@@ -151,7 +151,7 @@ __device__ __forceinline__ bool kmb_entry_live(const int32_t *__restrict__ hashe
 __global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                              const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
                              uint64_t n_entries, KmbMod mod, uint32_t line_shift, uint32_t *__restrict__ line_fill,
-                             uint32_t *__restrict__ filter, KmbStatus *status) {
+                             uint32_t *__restrict__ filter, uint32_t filter_cfg, KmbStatus *status) {
     int local_max = -1;
     bool neg = false;
     unsigned long long live_n = 0;
@@ -164,7 +164,7 @@ __global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *
         if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
         live_n++;
         atomicAdd(&line_fill[h >> line_shift], 1u);
-        atomicOr(&filter[h >> 5], kmb_filter_mask((uint32_t)h, q));
+        atomicOr(&filter[kmb_filter_word((uint32_t)h, filter_cfg)], kmb_filter_mask((uint32_t)h, q, filter_cfg));
     }
     for (int o = 16; o > 0; o >>= 1) {
         local_max = max(local_max, __shfl_xor_sync(KMB_FULL_MASK, local_max, o));
@@ -247,8 +247,8 @@ __global__ void kmb_mark_read_ends(const int64_t *__restrict__ offsets, uint64_t
 // ================================================================================================
 // The probe, shared by every mapping kernel.
 //
-// Level 0 (FILT): two bits of one filter word per query (kmb_filter_mask).  modulo/8 bytes -- 57 MB
-//   for the reference's default modulo 452 930 477 -- so it stays resident in the 126 MB L2.  At
+// Level 0 (FILT): one or two bits of one filter word per query (kmb_filter_mask).  modulo/8 bytes
+//   -- 57 MB for the reference's default modulo 452 930 477 -- so it stays resident in the L2.  At
 //   the reference's load factor (~0.22 entries per bucket) ~87 % of the absent k-mers end here
 //   without touching HBM.
 // Level 1: survivors are compacted onto a per-warp stack in shared memory and drained 32 at a
@@ -386,8 +386,8 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
         hh[u] = (uint32_t)h;
         const bool valid = (vbits >> u) & 1u;
         if (FILT) {
-            need[u] = valid ? kmb_filter_mask((uint32_t)h, q) : 0u;
-            fw[u] = (valid && !(P.policies & 0x400u)) ? kmb_ldg_u32_hint(P.filter + (hh[u] >> 5), pol.filter) : 0u;
+            need[u] = valid ? kmb_filter_mask((uint32_t)h, q, P.filter_cfg) : 0u;
+            fw[u] = (valid && !(P.policies & 0x400u)) ? kmb_ldg_u32_hint(P.filter + kmb_filter_word(hh[u], P.filter_cfg), pol.filter) : 0u;
         } else {
             need[u] = valid ? 1u : 0u;
             fw[u] = 1u;
@@ -594,8 +594,8 @@ __device__ __forceinline__ void kmb_walk_one(const KmbProbe &P, const KmbPol &po
     uint64_t q, h;
     kmb_divmod(km, P.mod, q, h);
     if (P.filter != nullptr) {
-        uint32_t need = kmb_filter_mask((uint32_t)h, q);
-        uint32_t w = kmb_ldg_u32_hint(P.filter + (h >> 5), pol.filter);
+        uint32_t need = kmb_filter_mask((uint32_t)h, q, P.filter_cfg);
+        uint32_t w = kmb_ldg_u32_hint(P.filter + kmb_filter_word((uint32_t)h, P.filter_cfg), pol.filter);
         if ((w & need) != need) return;
     }
     kmb_probe_line(P, pol, km, (uint32_t)h, on_match);

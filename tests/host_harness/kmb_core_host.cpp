@@ -19,6 +19,7 @@ uint64_t h_revcomp(uint64_t x, int k) { return kmb_revcomp(x, k); }
 uint64_t h_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) { return kmb_chain_line(main_line, ovf_base, s); }
 uint32_t h_chain_slot(uint32_t s) { return kmb_chain_slot(s); }
 uint32_t h_chain_extra_lines(uint32_t n) { return kmb_chain_extra_lines(n); }
-uint32_t h_filter_mask(uint32_t h, uint64_t q) { return kmb_filter_mask(h, q); }
+uint32_t h_filter_mask(uint32_t h, uint64_t q, uint32_t cfg) { return kmb_filter_mask(h, q, cfg); }
+uint32_t h_filter_word(uint32_t h, uint32_t cfg) { return kmb_filter_word(h, cfg); }
 
 }

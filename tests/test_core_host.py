@@ -28,7 +28,9 @@ def core():
     lib.h_chain_slot.restype = C.c_uint32
     lib.h_chain_extra_lines.restype = C.c_uint32
     lib.h_filter_mask.restype = C.c_uint32
-    lib.h_filter_mask.argtypes = [C.c_uint32, C.c_uint64]
+    lib.h_filter_mask.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
+    lib.h_filter_word.restype = C.c_uint32
+    lib.h_filter_word.argtypes = [C.c_uint32, C.c_uint32]
     lib.h_encode16.restype = C.c_uint32
     return lib
 
@@ -134,7 +136,11 @@ def test_sector_chain_geometry_and_filter_mask(core):
     for _ in range(2000):
         h = int(rng.integers(0, 2 ** 32))
         q = int(rng.integers(0, 2 ** 40))
-        m = core.h_filter_mask(h, q)
+        m = core.h_filter_mask(h, q, 0x100)
         assert m & (1 << (h & 31))
         assert bin(m).count("1") in (1, 2)
-        assert m == core.h_filter_mask(h + 32 * 5, q)        # depends on h only through h & 31
+        assert m == core.h_filter_mask((h + 32 * 5) & 0xFFFFFFFF, q, 0x100)        # depends on h only through h & 31
+        fs = int(rng.integers(0, 6))
+        m1 = core.h_filter_mask(h, q, fs)                        # one probe, 2^fs buckets per bit
+        assert m1 == 1 << ((h >> fs) & 31) and core.h_filter_word(h, fs) == (h >> fs) >> 5
+        assert core.h_filter_mask(h, q, fs | 0x100) & m1

@@ -18,7 +18,8 @@ def kmb():
     from kmer_mapper_b200 import _lib
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
-    for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 8), ("chunk_bytes", 64 << 20)):
+    for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_shift", -1),
+                    ("chunk_bytes", 64 << 20)):
         _lib.set_option(name, v)
 
 
@@ -27,6 +28,7 @@ VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=8),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
             dict(probe_variant=1, use_filter=0, gathers_in_flight=2),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=2),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, filter_shift=3),
             dict(probe_variant=0, use_filter=1, gathers_in_flight=8),
             dict(probe_variant=0, use_filter=0, gathers_in_flight=8)]
 
@@ -39,6 +41,7 @@ def _fresh(index):
 
 
 def _set(kmb, variant):
+    kmb.set_option("filter_shift", -1)
     for k, v in variant.items():
         kmb.set_option(k, v)
 
@@ -96,7 +99,7 @@ def test_gpu_counter_matches_restated_semantics(kmb):
         assert got.shape == want.shape and np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", VARIANTS[:5], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
+@pytest.mark.parametrize("variant", VARIANTS[:6], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
 def test_lookup_random_indexes_vs_oracle(kmb, variant):
     from kmer_mapper_b200.mapper import in_graph_index, map_kmers_to_graph_index
     _set(kmb, variant)
@@ -247,7 +250,7 @@ def _small_world(k, seed, n_entries=60_000, modulo=262_147, zipf=False, hot=1200
     return g, idx
 
 
-@pytest.mark.parametrize("variant", VARIANTS[:5], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
+@pytest.mark.parametrize("variant", VARIANTS[:6], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
 @pytest.mark.parametrize("k", [31, 21, 15, 5])
 def test_map_reads_vs_oracle(kmb, k, variant):
     import torch
