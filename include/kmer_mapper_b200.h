@@ -146,6 +146,19 @@ int kmb_codec_to_bytes(int device, const uint8_t *packed, uint64_t n, uint8_t *o
 int kmb_codec_complement(int device, const uint8_t *in, uint64_t n_bytes, uint8_t *out);   /* :44-48 */
 int kmb_codec_twobit_swap(int device, const void *in, uint64_t n_words, int word_bytes, void *out); /* :104-112 */
 
+/* ---- chunked read parsing: replaces bnp.open(path).read_chunks(min_chunk_size) -> chunk.sequence
+ * (command_line_interface.py:102-111).  Host-side, multi-threaded; no GPU involved.
+ * text[0, n_text) is a piece of a FASTA (format 0; multi-line allowed) or FASTQ (format 1; 4-line
+ * records) file that starts at a record boundary.  Every COMPLETE record is parsed (all of them when
+ * final_chunk): bases of the reads back to back into bases[], offsets[0..n_reads] (offsets[0] = 0);
+ * *consumed = bytes of text used, the caller carries the rest over to the next chunk.  With
+ * bases == NULL only the counts are returned.  Returns KMB_ERR_BAD_ARG for malformed records
+ * (FASTQ record not starting with '@' / third line not '+', FASTA data before the first '>'),
+ * KMB_ERR_NOMEM when an output capacity is too small. */
+int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format, int final_chunk, int n_threads,
+                    uint8_t *bases, uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity,
+                    uint64_t *n_reads, uint64_t *n_bases, uint64_t *consumed);
+
 /* ---- pinned host memory for the chunk reader (command_line_interface.py:102-111 replacement) -- */
 int kmb_host_alloc(void **ptr, size_t bytes);
 int kmb_host_free(void *ptr);

@@ -12,11 +12,11 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.path.join(PKG, "libkmer_mapper_b200.so")
-SOURCES = [os.path.join(CSRC, "kmb_capi.cu")]
+SOURCES = [os.path.join(CSRC, "kmb_capi.cu"), os.path.join(CSRC, "kmb_reader.cpp")]
 HEADERS = [os.path.join(CSRC, "kmb_kernels.cuh"), os.path.join(CSRC, "kmb_core.cuh"),
            os.path.join(os.path.dirname(PKG), "include", "kmer_mapper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def up_to_date() -> bool:

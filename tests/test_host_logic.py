@@ -122,6 +122,39 @@ def test_reader_matches_independent_parser(tmp_path, suffix, writer):
             assert n_chunks > 10
 
 
+@pytest.mark.parametrize("fmt", ["fastq", "fasta"])
+def test_reader_parallel_pieces_resynchronise_on_hostile_text(tmp_path, fmt):
+    """Chunks above 1 MB are cut into per-thread pieces at record boundaries found by resynchronisation; make
+    that hard: quality lines that start with '@' or '+' and contain '>' , FASTA wrapped at odd widths."""
+    rng = np.random.default_rng(9)
+    g = synthetic.make_genome(100_000, 5)
+    bases, offsets = synthetic.make_reads(g, 25_000, 160, seed=6, ragged=True)
+    want = [bytes(bases[offsets[r]:offsets[r + 1]]) for r in range(25_000)]
+    path = str(tmp_path / ("hostile." + ("fq" if fmt == "fastq" else "fa")))
+    qual_alphabet = np.frombuffer(b"@+>I#", np.uint8)
+    with open(path, "wb") as f:
+        for r, seq in enumerate(want):
+            if fmt == "fastq":
+                q = bytes(rng.choice(qual_alphabet, size=len(seq)))
+                f.write(b"@read%d +x\n%s\n+\n%s\n" % (r, seq, q))
+            else:
+                w = int(rng.integers(1, 90))
+                f.write(b">read%d\n" % r)
+                for i in range(0, len(seq), w):
+                    f.write(seq[i:i + w] + b"\n")
+    assert os.path.getsize(path) > 2_000_000
+    for chunk_size in (1_100_000, 1_700_000, 50_000_000):
+        for n_threads in (1, 3, 16):
+            got = []
+            for chunk in open_reads(path, pinned=False, n_threads=n_threads).read_chunks(min_chunk_size=chunk_size):
+                s = chunk.sequence
+                assert s.offsets[0] == 0 and s.offsets[-1] == s.bases.shape[0]
+                lens = np.diff(s.offsets)
+                assert (lens >= 0).all()
+                got += [bytes(s[i]) for i in range(len(s))]
+            assert got == want, (chunk_size, n_threads)
+
+
 def test_reader_edge_cases(tmp_path):
     p = str(tmp_path / "e.fa")
     open(p, "wb").write(b">r1 desc\r\nACGT\r\nAC\r\n>r2\n\n>r3\nGGGTTT\n>r4\nA")     # CRLF, empty read, no final newline
