@@ -484,6 +484,26 @@ def main_ours(args):
                 "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h, "peak_source": peak_src,
                 "filter_bytes": di.filter_bytes}
 
+    # ---- the random-gather micro-roofline of SURVEY.md 8(d), measured live on this GPU: uniform random 8-byte
+    # loads over a table of the sector table's footprint (capped at 8 GB); the north_star's denominator
+    if rank == 0:
+        try:
+            import ctypes
+            ms_g = ctypes.c_float(0)
+            table_bytes = int(min(di.device_bytes, 8 << 30))
+            n_loads = 1 << 28
+            _lib.check(_lib.lib().kmb_bench_gather(local_rank, table_bytes, n_loads, 8, 8, 256, 8, ctypes.byref(ms_g)))
+            gathers_per_s = n_loads / (ms_g.value / 1e3)
+            kernel_kmers_per_s = n_kmers_step / max(kernels_per_step, 1) / (kernel_avg_ms / 1e3)
+            roofline["gather_roofline"] = {
+                "random_8B_loads_per_s": gathers_per_s, "table_bytes": table_bytes,
+                "kernel_kmers_per_s": kernel_kmers_per_s,
+                "fraction_of_gather_roofline": kernel_kmers_per_s / gathers_per_s,
+                "note": "k-mers mapped per second by the fused kernel / random HBM gathers per second the chip sustains; "
+                        "above 1 because the L2-resident filter answers most k-mers without a gather"}
+        except Exception as e:  # measurement helper only
+            roofline["gather_roofline"] = {"error": str(e)}
+
     # ---- CPU baseline + parity on the sample
     cpu_rec = None
     if do_cpu:
