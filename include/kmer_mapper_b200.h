@@ -66,7 +66,7 @@ int kmb_index_info(const kmb_index *index, int64_t *max_node_id, uint64_t *n_ent
                    uint64_t *modulo, uint64_t *device_bytes);
 /* Size of the L2-resident bucket filter (probe level 0), 0 when not in use. */
 int kmb_index_filter_bytes(const kmb_index *index, uint64_t *bytes);
-/* Geometry of the 128-byte-line table: buckets per line, main lines, overflow lines and the number
+/* Geometry of the sector table: buckets per sector, main sectors, overflow sectors and the number
  * of live entries (entries that lie inside the bucket range of their own key -- the only ones the
  * reference's scan can ever match). */
 int kmb_index_layout(const kmb_index *index, uint32_t *buckets_per_line, uint64_t *n_main_lines,
@@ -100,11 +100,11 @@ int kmb_mapper_map_kmers(kmb_mapper *mapper, const uint64_t *kmers, uint64_t n, 
 int kmb_mapper_map_reads(kmb_mapper *mapper, const uint8_t *bases, uint64_t n_bases,
                          const int64_t *offsets, uint64_t n_reads, int k, uint32_t flags);
 
-/* Hits are first accumulated in per-entry counters that share a 128-byte line with the entry's key;
- * the flush applies the frequency cut-off (mapper.pyx:64) and adds them onto the node counts
- * (mapper.pyx:68).  kmb_mapper_flush queues that pass on the mapper's stream without waiting (use it
- * before handing the count buffer to an all-reduce on the same stream); sync, read_counts, stats and
- * lookup_counts flush implicitly. */
+/* Hits (node ids that passed the frequency cut-off, mapper.pyx:64) are first appended to device-side
+ * logs binned by node range; the flush plays the logs into the node counts (mapper.pyx:68) one
+ * L2-sized window at a time.  kmb_mapper_flush queues that pass on the mapper's stream without waiting
+ * (use it before handing the count buffer to an all-reduce on the same stream); sync, read_counts,
+ * stats and lookup_counts flush implicitly. */
 int kmb_mapper_flush(kmb_mapper *mapper);
 /* Wait for all queued work of the mapper (flushing first); returns KMB_ERR_INVALID_BASE if any kernel met an
  * invalid byte since the last reset (counts are then undefined until kmb_mapper_reset). */
@@ -176,7 +176,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
 
 /* Tuning knobs (process-wide, read at launch / index-creation time): name in
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
- *  "use_filter", "filter_l2_budget_bytes", "filter_shift", "l2_persist", "ablate", "policy_filter", "policy_line", "policy_red",
+ *  "use_filter", "filter_l2_budget_bytes", "filter_shift", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries_per_bin",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes"}. */
 int kmb_set_option(const char *name, int64_t value);

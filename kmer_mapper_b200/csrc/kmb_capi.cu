@@ -55,13 +55,13 @@ struct KmbOptions {
     int64_t map_kmers_blocks_per_sm = 0;
     int64_t probe_variant = 1;            // map_kmers: 0 = one query per thread, 1 = staged probe with warp stack
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
-    int64_t gathers_in_flight = 4;        // U: 2, 4 or 8 independent filter loads per thread
+    int64_t gathers_in_flight = 4;        // U: 2 or 4 independent filter loads per thread
+    int64_t log_max_entries_per_bin = 256ll << 20;  // upper bound of one hit log (x 8 bins x 4 bytes)
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
     int64_t filter_l2_budget_bytes = 64ll << 20;  // the L2 keeps ~72 MB of randomly accessed data (profiles/README.md)
     int64_t filter_shift = -1;            // buckets per filter bit = 2^shift; -1 = smallest that fits the budget
     int64_t policy_filter = 2;            // L2 priority hints: 0 normal, 1 evict-first, 2 evict-last
     int64_t policy_line = 0;
-    int64_t policy_red = 0;
     int64_t ablate = 0;                   // measurement only (results become wrong): 1 no RED, 2 no line loads, 4 no filter loads, 8 no key loads
     int64_t l2_persist = 1;               // set a persisting-L2 access window over the filter
     int64_t l2_fetch_granularity = 0;     // 0 = leave the device default; else 32/64/128 (cudaLimitMaxL2FetchGranularity)
@@ -83,6 +83,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
     OPT(gathers_in_flight)
+    OPT(log_max_entries_per_bin)
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
     OPT(filter_shift)
@@ -90,7 +91,6 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(ablate)
     OPT(policy_filter)
     OPT(policy_line)
-    OPT(policy_red)
     OPT(time_kernels)
     OPT(l2_fetch_granularity)
     OPT(bench_grid_blocks)
@@ -115,6 +115,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
     OPT(gathers_in_flight)
+    OPT(log_max_entries_per_bin)
     OPT(use_filter)
     OPT(filter_l2_budget_bytes)
     OPT(filter_shift)
@@ -122,7 +123,6 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(ablate)
     OPT(policy_filter)
     OPT(policy_line)
-    OPT(policy_red)
     OPT(time_kernels)
     OPT(l2_fetch_granularity)
     OPT(bench_grid_blocks)
@@ -255,14 +255,11 @@ struct kmb_index {
     uint64_t modulo = 0, n_entries = 0, n_live = 0;
     uint32_t line_shift = 0;            // g: 2^g buckets per 128-byte line
     uint64_t n_main = 0, n_lines = 0;   // main lines, main + overflow lines
-    uint32_t *lines = nullptr;          // master copy (keys + the counters of the mapper that borrows it)
-    uint2 *cold = nullptr;              // (node, frequency) of (line, slot)
+    uint32_t *lines = nullptr;          // 32-byte sectors (header, frequencies, keys, nodes), read-only after the build
     uint32_t *filter = nullptr;
     size_t filter_bytes = 0;
     uint32_t filter_cfg = 0;            // kmb_filter_mask configuration
     bool filter_on = false;
-    bool lines_in_use = false;          // a mapper is counting into the master copy
-    bool lines_dirty = false;           // master counters may be non-zero
     int64_t max_node = -1;
     uint64_t device_bytes = 0;
     KmbMod mod;
@@ -273,7 +270,6 @@ extern "C" int kmb_index_destroy(kmb_index *ix) {
     if (!ix) return KMB_OK;
     DeviceGuard g(ix->device);
     cudaFree(ix->lines);
-    cudaFree(ix->cold);
     cudaFree(ix->filter);
     cudaGetLastError();
     delete ix;
@@ -383,18 +379,16 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     ix->max_node = hs.max_node;
     ix->n_live = hs.n_live_entries;
     ix->n_lines = ix->n_main + hs.pool_lines;
-    if (ix->n_lines * KMB_LINE_WORDS >= (1ull << 35)) return kmb_fail(KMB_ERR_BAD_INDEX, "index: too many sectors");
+    if (ix->n_lines >= (1ull << 31)) return kmb_fail(KMB_ERR_BAD_INDEX, "index: too many sectors (%llu) for the 31-bit chain links", (unsigned long long)ix->n_lines);
     // 4. lines + cold arrays, headers, scatter
     KMB_CUDA(cudaMalloc(&ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
-    KMB_CUDA(cudaMalloc(&ix->cold, (size_t)ix->n_lines * KMB_LINE_SLOTS * sizeof(uint2)));
     KMB_CUDA(cudaMemsetAsync(ix->lines, 0, (size_t)ix->n_lines * KMB_LINE_BYTES, s));
-    KMB_CUDA(cudaMemsetAsync(ix->cold, 0, (size_t)ix->n_lines * KMB_LINE_SLOTS * sizeof(uint2), s));
     KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
     kmb_v2_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, d_status.p);
     g_launches++;
     if (n_entries) {
         kmb_v2_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
-                                                                   ix->line_shift, line_fill.p, ix->lines, ix->cold);
+                                                                   ix->line_shift, line_fill.p, ix->lines);
         g_launches++;
     }
     KMB_CUDA(cudaGetLastError());
@@ -407,7 +401,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
         ix->filter = nullptr;
         ix->filter_bytes = 0;
     }
-    ix->device_bytes = ix->n_lines * (KMB_LINE_BYTES + KMB_LINE_SLOTS * sizeof(uint2)) + ix->filter_bytes;
+    ix->device_bytes = ix->n_lines * KMB_LINE_BYTES + ix->filter_bytes;
     cleanup.ix = nullptr;
     *out = ix;
     return KMB_OK;
@@ -457,9 +451,9 @@ struct kmb_mapper {
     uint64_t n_counts = 0;
     uint32_t *counts = nullptr;
     bool own_counts = false;
-    uint32_t *lines = nullptr;   // the index's master copy, or a private clone when that is taken
-    bool own_lines = false;
-    bool dirty = false;          // slot counters may be non-zero (hits not yet flushed onto nodes)
+    KmbLog log = {nullptr, nullptr, 0, 0};  // hit logs (grown on demand) + their cursors
+    bool dirty = false;            // the logs may hold hits that are not yet in the node counts
+    uint64_t queries_since_flush = 0;
     int32_t max_freq = 1000;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     KmbStatus *d_status = nullptr;
@@ -493,12 +487,8 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
         cudaEventDestroy(pr.second);
     }
     cudaFree(m->dmask);
-    if (m->own_lines) {
-        cudaFree(m->lines);
-    } else if (m->lines) {
-        m->index->lines_in_use = false;
-        m->index->lines_dirty = m->index->lines_dirty || m->dirty;
-    }
+    cudaFree(m->log.entries);
+    cudaFree(m->log.cursor);
     if (m->own_counts) cudaFree(m->counts);
     cudaFree(m->d_status);
     if (m->h_status) cudaFreeHost(m->h_status);
@@ -520,34 +510,51 @@ static int status_reset(kmb_mapper *m) {
     return KMB_OK;
 }
 
-template <bool CLEAR_ONLY>
+// Play the hit logs into the node counts (asynchronous on the mapper's stream) and empty them.
 static int launch_flush(kmb_mapper *m) {
     const kmb_index *ix = m->index;
-    kmb_flush_kernel<CLEAR_ONLY><<<grid_for(ix->n_lines, 256, ix->info.sms), 256, 0, m->stream>>>(
-        m->lines, ix->n_lines, ix->cold, m->max_freq, m->counts, m->d_status);
-    g_launches++;
-    KMB_CUDA(cudaGetLastError());
+    if (m->log.entries) {
+        for (int b = 0; b < KMB_LOG_BINS; b++) {
+            kmb_log_apply_kernel<<<ix->info.sms * 8, 256, 0, m->stream>>>(m->log, b, m->counts);
+            g_launches++;
+        }
+        kmb_log_reset_kernel<<<1, 32, 0, m->stream>>>(m->log);
+        g_launches++;
+        KMB_CUDA(cudaGetLastError());
+    }
     m->dirty = false;
+    m->queries_since_flush = 0;
     return KMB_OK;
 }
 
-// The slot counters live inside the lines, so a mapper needs a line table of its own: the first
-// mapper of an index borrows the index's master copy, further concurrent mappers get a clone.
-static int attach_lines(kmb_mapper *m) {
-    kmb_index *ix = m->index;
-    if (!ix->lines_in_use) {
-        m->lines = ix->lines;
-        ix->lines_in_use = true;
-        if (ix->lines_dirty) {
-            KMB_TRY(launch_flush<true>(m));
-            ix->lines_dirty = false;
-        }
-        return KMB_OK;
+// Size the logs for a launch of n_queries look-ups: capacity for one hit per four queries in total
+// (twice the hit rate of the benchmark shapes), between 2^20 and log_max_entries_per_bin per bin.  A log
+// that runs full is not an error: the kernels then reduce directly onto the counts.
+static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
+    uint64_t want = std::max<uint64_t>(n_queries / 4 / KMB_LOG_BINS, 1ull << 20);
+    want = std::min<uint64_t>(want, (uint64_t)std::max<int64_t>(g_opt.log_max_entries_per_bin, 1 << 10));
+    if (!m->log.cursor) {
+        KMB_CUDA(cudaMalloc(&m->log.cursor, 2 * KMB_LOG_BINS * sizeof(unsigned long long)));
+        uint32_t shift = 0;
+        while (((m->n_counts ? m->n_counts - 1 : 0) >> shift) >= KMB_LOG_BINS) shift++;
+        m->log.bin_shift = shift;
     }
-    KMB_CUDA(cudaMalloc(&m->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
-    m->own_lines = true;
-    KMB_CUDA(cudaMemcpyAsync(m->lines, ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES, cudaMemcpyDeviceToDevice, m->stream));
-    return launch_flush<true>(m);
+    if (want > m->log.cap) {
+        if (m->dirty) KMB_TRY(launch_flush(m));
+        KMB_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(m->log.entries);
+        m->log.entries = nullptr;
+        m->log.cap = 0;
+        KMB_CUDA(cudaMalloc(&m->log.entries, (size_t)want * KMB_LOG_BINS * sizeof(uint32_t)));
+        m->log.cap = want;
+        kmb_log_reset_kernel<<<1, 32, 0, m->stream>>>(m->log);
+        g_launches++;
+        KMB_CUDA(cudaGetLastError());
+    } else if (m->dirty && m->queries_since_flush + n_queries > 4 * KMB_LOG_BINS * m->log.cap) {
+        KMB_TRY(launch_flush(m));  // make room before the logs overflow into direct reductions
+    }
+    m->queries_since_flush += n_queries;
+    return KMB_OK;
 }
 
 static int set_l2_window(kmb_mapper *m) {
@@ -618,7 +625,6 @@ extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *
     KMB_CUDA(cudaMalloc(&m->d_status, sizeof(KmbStatus)));
     KMB_CUDA(cudaMallocHost(&m->h_status, sizeof(KmbStatus)));
     KMB_TRY(status_reset(m));
-    KMB_TRY(attach_lines(m));
     for (int i = 0; i < 2; i++) {
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].copied, cudaEventDisableTiming));
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].consumed, cudaEventDisableTiming));
@@ -641,18 +647,21 @@ extern "C" int kmb_mapper_set_stream(kmb_mapper *m, void *cuda_stream) {
 static KmbProbe make_probe(const kmb_mapper *m) {
     const kmb_index *ix = m->index;
     KmbProbe P;
-    P.lines = m->lines;
+    P.lines = ix->lines;
     P.filter = ix->filter_on ? ix->filter : nullptr;
     P.filter_cfg = ix->filter_cfg;
     P.mod = ix->mod;
     P.line_shift = ix->line_shift;
-    P.policies = (uint32_t)((g_opt.policy_filter & 3) | ((g_opt.policy_line & 3) << 2) | ((g_opt.policy_red & 3) << 4) | ((g_opt.ablate & 15) << 8));
+    P.policies = (uint32_t)((g_opt.policy_filter & 3) | ((g_opt.policy_line & 3) << 2) | ((g_opt.ablate & 15) << 8));
+    P.max_freq = m->max_freq;
+    P.counts = m->counts;
+    P.log = m->log;
     return P;
 }
 
 static int pick_u() {
     int64_t u = g_opt.gathers_in_flight;
-    return u <= 2 ? 2 : (u <= 4 ? 4 : 8);
+    return u <= 2 ? 2 : 4;
 }
 
 // ---- kernel dispatch (template instantiation table) ------------------------------------------------
@@ -665,7 +674,7 @@ static MapReadsFn map_reads_fn_u(bool filt, bool rc) {
     return rc ? kmb_map_reads_kernel<U, false, true> : kmb_map_reads_kernel<U, false, false>;
 }
 static MapReadsFn map_reads_fn(int u, bool filt, bool rc) {
-    return u == 2 ? map_reads_fn_u<2>(filt, rc) : (u == 4 ? map_reads_fn_u<4>(filt, rc) : map_reads_fn_u<8>(filt, rc));
+    return u == 2 ? map_reads_fn_u<2>(filt, rc) : map_reads_fn_u<4>(filt, rc);
 }
 template <int U>
 static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
@@ -673,7 +682,7 @@ static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
     return rc ? kmb_map_kmers_kernel<U, false, true> : kmb_map_kmers_kernel<U, false, false>;
 }
 static MapKmersFn map_kmers_fn(int u, bool filt, bool rc) {
-    return u == 2 ? map_kmers_fn_u<2>(filt, rc) : (u == 4 ? map_kmers_fn_u<4>(filt, rc) : map_kmers_fn_u<8>(filt, rc));
+    return u == 2 ? map_kmers_fn_u<2>(filt, rc) : map_kmers_fn_u<4>(filt, rc);
 }
 
 static int resident_blocks(const void *fn, int64_t opt, int *out) {
@@ -715,6 +724,8 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
                                                                                       k, d_mask);
         g_launches++;
     }
+    // every window, both strands when asked: the number of look-ups this launch can make
+    KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases));
     KmbProbe P = make_probe(m);
     MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
     int per_sm;
@@ -734,8 +745,9 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
 static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, uint32_t flags, int k) {
     if (n == 0) return KMB_OK;
     const kmb_index *ix = m->index;
-    KmbProbe P = make_probe(m);
     bool rc = (flags & KMB_FLAG_REVCOMP) != 0;
+    KMB_TRY(ensure_log(m, (rc ? 2 : 1) * n));
+    KmbProbe P = make_probe(m);
     m->dirty = true;
     KMB_TRY(timed_begin(m));
     if (g_opt.probe_variant == 0) {
@@ -880,7 +892,7 @@ extern "C" int kmb_mapper_map_kmers(kmb_mapper *m, const uint64_t *kmers, uint64
 }
 
 static int fetch_status(kmb_mapper *m) {
-    if (m->dirty) KMB_TRY(launch_flush<false>(m));
+    if (m->dirty) KMB_TRY(launch_flush(m));
     KMB_CUDA(cudaMemcpyAsync(m->h_status, m->d_status, sizeof(KmbStatus), cudaMemcpyDeviceToHost, m->stream));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
     return KMB_OK;
@@ -920,7 +932,12 @@ extern "C" int kmb_mapper_read_counts(kmb_mapper *m, uint32_t *out, uint64_t n_c
 extern "C" int kmb_mapper_reset(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_reset: null mapper");
     KMB_ON_DEVICE(m->index->device);
-    if (m->dirty) KMB_TRY(launch_flush<true>(m));
+    if (m->log.entries) {
+        kmb_log_reset_kernel<<<1, 32, 0, m->stream>>>(m->log);
+        g_launches++;
+    }
+    m->dirty = false;
+    m->queries_since_flush = 0;
     KMB_CUDA(cudaMemsetAsync(m->counts, 0, m->n_counts * 4, m->stream));
     return status_reset(m);
 }
@@ -929,7 +946,7 @@ extern "C" int kmb_mapper_reset(kmb_mapper *m) {
 extern "C" int kmb_mapper_flush(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_flush: null mapper");
     KMB_ON_DEVICE(m->index->device);
-    if (m->dirty) KMB_TRY(launch_flush<false>(m));
+    if (m->dirty) KMB_TRY(launch_flush(m));
     return KMB_OK;
 }
 
@@ -971,8 +988,7 @@ extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t 
 // membership and per-key lookup
 // ------------------------------------------------------------------------------------------------
 template <int MODE, class OutT>
-static int run_lookup(kmb_index *ix, const uint32_t *lines, const uint32_t *counts, cudaStream_t s, const uint64_t *keys,
-                      uint64_t n, OutT *out) {
+static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uint64_t *keys, uint64_t n, OutT *out) {
     if (n == 0) return KMB_OK;
     if (!keys || !out) return kmb_fail(KMB_ERR_BAD_ARG, "lookup: null buffer");
     DevBuf<uint64_t> t_keys;
@@ -987,15 +1003,16 @@ static int run_lookup(kmb_index *ix, const uint32_t *lines, const uint32_t *coun
         d_out = t_out.p;
     }
     KmbProbe P;
-    P.lines = const_cast<uint32_t *>(lines);  // keys are only read
+    memset(&P, 0, sizeof(P));
+    P.lines = ix->lines;
     P.filter = ix->filter_on ? ix->filter : nullptr;
     P.filter_cfg = ix->filter_cfg;
     P.mod = ix->mod;
     P.line_shift = ix->line_shift;
     P.policies = 2u;
+    P.counts = counts;
     kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(
-        d_keys, n, P, ix->cold, counts, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr),
-        (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
+        d_keys, n, P, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr), (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     if (!out_dev) KMB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(OutT), cudaMemcpyDeviceToHost, s));
@@ -1006,14 +1023,14 @@ static int run_lookup(kmb_index *ix, const uint32_t *lines, const uint32_t *coun
 extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t n, uint8_t *out) {
     if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_in_graph_index: null index");
     KMB_ON_DEVICE(ix->device);
-    return run_lookup<0, uint8_t>(ix, ix->lines, nullptr, 0, kmers, n, out);
+    return run_lookup<0, uint8_t>(ix, nullptr, 0, kmers, n, out);
 }
 
 extern "C" int kmb_mapper_lookup_counts(kmb_mapper *m, const uint64_t *keys, uint64_t n, uint32_t *out) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_lookup_counts: null mapper");
     KMB_ON_DEVICE(m->index->device);
-    if (m->dirty) KMB_TRY(launch_flush<false>(m));
-    return run_lookup<1, uint32_t>(m->index, m->lines, m->counts, m->stream, keys, n, out);
+    if (m->dirty) KMB_TRY(launch_flush(m));
+    return run_lookup<1, uint32_t>(m->index, m->counts, m->stream, keys, n, out);
 }
 
 // ------------------------------------------------------------------------------------------------

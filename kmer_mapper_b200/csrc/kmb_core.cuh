@@ -58,28 +58,30 @@ KMB_HD void kmb_divmod(uint64_t n, const KmbMod md, uint64_t &q, uint64_t &r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Index layout: the 32-byte sector line.
+// Index layout: the 32-byte sector.
 //
-// Measured on B200 (profiles/README.md): (1) a random global load that misses L2 costs one full
-// 128-byte line of HBM traffic whatever its width; (2) the L2 holds ~75 MB, of which the filter
-// takes 57 MB, so a fetched line survives only a few microseconds -- a second, later access to it
-// (a separate key read, a late RED) goes back to HBM more often than not.  Hence ONE 32-byte
-// sector answers a query completely and takes the count immediately:
-//   w0      n_total   entries in the chain that starts at this (main) sector
-//   w1      ovf_base  index of the first overflow sector (only if n_total > 2)
+// Measured on B200 (profiles/README.md): (1) a random global load that misses L2 is one DRAM
+// transaction whatever its width, and the chip sustains 38.2 G of them per second; (2) every dirty
+// sector costs a second transaction when it is written back; (3) the L2 holds ~72 MB, of which the
+// filter takes 57 MB, so a fetched line is gone again after a few microseconds.  Hence ONE
+// read-only 32-byte sector answers a query completely -- keys, nodes and frequencies -- and hits
+// are not counted in place but appended to a log (see kmb_kernels.cuh):
+//   w0      header: n (0..2 entries, chain ends here) or KMB_HDR_CHAIN | index of the next sector
+//   w1      frequency 0 | frequency 1 << 16
 //   w2..w5  key 0, key 1  (lo, hi)
-//   w6, w7  hit counter 0, 1
+//   w6, w7  node 0, node 1
 // G = 2^g consecutive buckets (h = key % modulo, mapper.pyx:54) share a sector, with G chosen so
 // that a sector holds 0.25-0.5 entries on average (99 % of the non-empty ones need no chain);
-// entries beyond two go to overflow sectors ovf_base + (s-2)/2 with the same slot map.  node and
-// frequency of a slot live in a cold side array (sector*2 + j), read only by the flush pass.
+// entries beyond two go to overflow sectors ovf_base + (s-2)/2, linked through their headers.
 // HBM capacity (180 GB) is what pays for this: 7.2 GB of sectors for the 100 M-entry index.
 // ---------------------------------------------------------------------------------------------
 #define KMB_LINE_BYTES 32
 #define KMB_LINE_WORDS 8
 #define KMB_LINE_SLOTS 2
+#define KMB_LINE_FREQ_WORD 1
 #define KMB_LINE_KEY_WORD0 2
-#define KMB_LINE_CNT_WORD0 6
+#define KMB_LINE_NODE_WORD0 6
+#define KMB_HDR_CHAIN 0x80000000u
 
 // chain position s (0-based among the entries of a main sector) -> (sector index, slot)
 KMB_HD uint64_t kmb_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) {
@@ -88,6 +90,19 @@ KMB_HD uint64_t kmb_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s
 KMB_HD uint32_t kmb_chain_slot(uint32_t s) { return s % KMB_LINE_SLOTS; }
 KMB_HD uint32_t kmb_chain_extra_lines(uint32_t n_total) {
     return n_total > KMB_LINE_SLOTS ? (n_total - 1) / KMB_LINE_SLOTS : 0u;
+}
+// header of a sector that still has `remaining` entries to hold (itself included)
+KMB_HD uint32_t kmb_sector_header(uint32_t remaining, uint32_t next_sector) {
+    return remaining > KMB_LINE_SLOTS ? (KMB_HDR_CHAIN | next_sector) : remaining;
+}
+KMB_HD uint32_t kmb_header_count(uint32_t hdr) { return (hdr & KMB_HDR_CHAIN) ? (uint32_t)KMB_LINE_SLOTS : hdr; }
+
+// Hit log: node ids are appended to one of KMB_LOG_BINS logs by node range, so that applying a
+// log touches a window of the count array small enough to stay in L2.
+#define KMB_LOG_BINS 8
+KMB_HD uint32_t kmb_log_bin(uint32_t node, uint32_t bin_shift) {
+    uint32_t b = node >> bin_shift;
+    return b < KMB_LOG_BINS ? b : (uint32_t)(KMB_LOG_BINS - 1);
 }
 
 // Filter (probe level 0): one bit per 2^fs consecutive buckets, 32 of them per word.  Every live

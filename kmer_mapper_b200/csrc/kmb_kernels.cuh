@@ -1,22 +1,22 @@
 // kmb_kernels.cuh -- hand-written sm_100a kernels of the k-mer mapping path.
 //
-//   K5  kmb_v2_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sector lines (once per index)
+//   K5  kmb_v2_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sectors (once per index)
 //   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
-//   K1-4 kmb_map_reads_kernel     fused encode + window + filter + line probe + count  (production path)
-//   K3-4 kmb_map_kmers_kernel     probe + count on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
-//   K4b kmb_flush_kernel          per-slot hit counters -> per-node counts (frequency cut-off applied here)
+//   K1-4 kmb_map_reads_kernel     fused encode + window + filter + sector probe + hit log  (production path)
+//   K3-4 kmb_map_kmers_kernel     probe + hit log on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
+//   K4b kmb_log_apply_kernel      hit log -> per-node counts, one L2-sized window of nodes at a time
 //   K6  kmb_in_graph_kernel       membership mask (mapper.pyx:81)
 //   K2  kmb_hash_count/_scan/_emit  flat hash array (util.py:71-75 drop-in)
 //   E1  kmb_codec_* kernels       legacy 2-bit codec (encodings.py)
-//   B   kmb_gather_bench_kernel   random-line gather micro-roofline
+//   B   kmb_gather_bench_kernel   random-gather micro-roofline
 //
 // Nothing here is a dense contraction, so no tensor-core / TMEM / TMA-tile machinery is used: the
-// path is bound by random line fetches from HBM plus one L2 hit per k-mer (the filter) and a thin
-// coalesced stream of bases.  What matters: as few fetches per k-mer as possible
-// (L2-resident filter), one 32-byte sector answers its query completely and takes the count at
-// once (keys and counters share the sector), warp-compacted second-level work so hits do not
-// serialise the warp, the fetch latency overlapped with the next batch's arithmetic, no-return
-// reductions (RED) while the sector is still in L2, persistent grid sized to the SMs.
+// path is bound by the rate of random DRAM transactions (38.2 G/s measured) plus one L2 hit per
+// k-mer (the filter) and a thin coalesced stream of bases.  What matters: as few
+// transactions per k-mer as possible -- an L2-resident filter in front, one read-only 32-byte sector
+// that answers a query completely, and no read-modify-write of random memory on the hot path: hits
+// are appended to coalesced logs and applied later to node windows that fit in L2 -- the fetch
+// latency overlapped with the next batch's arithmetic, persistent grid sized to the SMs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,20 +33,30 @@
 struct KmbStatus {
     unsigned long long first_bad_offset;   // min flat offset of an invalid byte, ~0 if none
     unsigned long long n_kmers_mapped;     // windows looked up
-    unsigned long long n_entries_counted;  // +1s applied to node counts (mapper.pyx:68), known after a flush
+    unsigned long long n_entries_counted;  // +1s destined for node counts (mapper.pyx:68)
     unsigned long long n_live_entries;     // index build: entries reachable through their own bucket
     unsigned int index_flags;              // bit0 bucket out of range, bit1 negative node
-    unsigned int pool_lines;               // index build: overflow lines needed / handed out
+    unsigned int pool_lines;               // index build: overflow sectors needed / handed out
     int max_node;
 };
 
+struct KmbLog {  // hit logs of one mapper: KMB_LOG_BINS arrays of `cap` node ids
+    uint32_t *entries;
+    unsigned long long *cursor;  // [0, BINS): entries reserved so far; [BINS, 2 BINS): first reservation that did not fit
+    uint64_t cap;
+    uint32_t bin_shift;          // bin = node >> bin_shift
+};
+
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
-    uint32_t *lines;                         // 128-byte lines (keys immutable, counters reduced into)
+    const uint32_t *__restrict__ lines;      // 32-byte sectors, read-only
     const uint32_t *__restrict__ filter;     // blocked Bloom filter over the buckets (kmb_filter_mask), or nullptr
     uint32_t filter_cfg;                     // bits 0-4 buckets-per-bit shift, bit 8 two probes
     KmbMod mod;
-    uint32_t line_shift;                     // g: line = h >> g
-    uint32_t policies;                       // L2 priority of: filter (bits 0-1), line loads (2-3), counter REDs (4-5)
+    uint32_t line_shift;                     // g: sector = h >> g
+    uint32_t policies;                       // L2 priority of: filter (bits 0-1), sector loads (2-3); bits 8+: ablation
+    int32_t max_freq;                        // C int like the reference's cut-off (mapper.pyx:19,64)
+    uint32_t *counts;                        // node counts: target of the log and of the rare direct reductions
+    KmbLog log;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -103,18 +113,13 @@ __device__ __forceinline__ uint4 kmb_ldg_v4_hint(const void *p, uint64_t pol) {
                  : "l"(p), "l"(pol));
     return v;
 }
-// One 32-byte sector of a line.  Plain (coherent) path: counters of the same line are concurrently
-// reduced into.  Normal L2 priority on purpose: the key read and the RED that follow a hit must still
-// find the line in L2 -- marked evict-first it was gone 60 % of the time (profiles/README.md).
+// One 32-byte sector of the index.
 // L2::64B: a miss then fetches 64 bytes from HBM instead of the default 128 (measured: 1.98 vs 3.91
 // DRAM sectors per random load, profiles/README.md).
 __device__ __forceinline__ void kmb_ld_sector(const uint32_t *p, uint32_t (&r)[8], uint64_t pol) {
     asm volatile("ld.global.L1::no_allocate.L2::cache_hint.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void kmb_red_add(uint32_t *p, uint32_t v, uint64_t pol) {
-    asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint2 kmb_ld_u64_volatile(const uint32_t *p) {
     uint2 v;
@@ -178,8 +183,8 @@ __global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *
     }
 }
 
-// pass 2 (ASSIGN = false): total overflow lines needed; (ASSIGN = true): hand them out, write the
-// headers and reset line_fill for the scatter
+// pass 2 (ASSIGN = false): total overflow sectors needed; (ASSIGN = true): hand them out, write the
+// headers of the whole chain and reset line_fill for the scatter
 template <bool ASSIGN>
 __global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, uint32_t *__restrict__ lines,
                             KmbStatus *status) {
@@ -191,7 +196,9 @@ __global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, u
         } else {
             uint32_t base = 0;
             if (extra) base = (uint32_t)n_main + atomicAdd(&status->pool_lines, extra);
-            *reinterpret_cast<uint2 *>(lines + i * KMB_LINE_WORDS) = make_uint2(c, base);
+            lines[i * KMB_LINE_WORDS] = kmb_sector_header(c, base);
+            for (uint32_t t = 0; t < extra; t++)
+                lines[(uint64_t)(base + t) * KMB_LINE_WORDS] = kmb_sector_header(c - KMB_LINE_SLOTS * (t + 1), base + t + 1);
             line_fill[i] = 0;
         }
     }
@@ -201,8 +208,7 @@ __global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, u
 __global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                                const uint16_t *__restrict__ freqs, const int32_t *__restrict__ hashes_to_index,
                                const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, uint32_t line_shift,
-                               uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines,
-                               uint2 *__restrict__ cold) {
+                               uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines) {
     for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_entries; l += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = kmers[l];
         uint64_t q, h;
@@ -210,12 +216,12 @@ __global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t
         if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
         uint64_t main_line = h >> line_shift;
         uint32_t s = atomicAdd(&line_fill[main_line], 1u);
-        uint32_t ovf_base = lines[main_line * KMB_LINE_WORDS + 1];
-        uint64_t line = kmb_chain_line(main_line, ovf_base, s);
+        uint32_t ovf_base = lines[main_line * KMB_LINE_WORDS] & ~KMB_HDR_CHAIN;  // only meaningful (and used) for s >= 2
+        uint32_t *lp = lines + kmb_chain_line(main_line, ovf_base, s) * KMB_LINE_WORDS;
         uint32_t j = kmb_chain_slot(s);
-        *reinterpret_cast<uint2 *>(lines + line * KMB_LINE_WORDS + KMB_LINE_KEY_WORD0 + 2 * j) =
-            make_uint2((uint32_t)key, (uint32_t)(key >> 32));
-        cold[line * KMB_LINE_SLOTS + j] = make_uint2((uint32_t)nodes[l], (uint32_t)freqs[l]);
+        *reinterpret_cast<uint2 *>(lp + KMB_LINE_KEY_WORD0 + 2 * j) = make_uint2((uint32_t)key, (uint32_t)(key >> 32));
+        lp[KMB_LINE_NODE_WORD0 + j] = (uint32_t)nodes[l];
+        reinterpret_cast<uint16_t *>(lp + KMB_LINE_FREQ_WORD)[j] = freqs[l];
     }
 }
 
@@ -251,85 +257,122 @@ __global__ void kmb_mark_read_ends(const int64_t *__restrict__ offsets, uint64_t
 //   -- 57 MB for the reference's default modulo 452 930 477 -- so it stays resident in the L2.  At
 //   the reference's load factor (~0.22 entries per bucket) ~87 % of the absent k-mers end here
 //   without touching HBM.
-// Level 1: survivors are compacted onto a per-warp stack in shared memory and drained 32 at a
-//   time, one per lane (32 independent HBM line fetches in flight per warp): sector 0 of the
-//   candidate's line carries the chain header and eight one-byte tags; a key is read (from L2, the
-//   line has just arrived) only where the tag matches, and every equal key (mapper.pyx:58-62, no
-//   break) gets one no-return reduction on its slot counter -- in that same line.  Chains of
-//   overflow lines are walked the same way.  The frequency cut-off (mapper.pyx:64) and the scatter onto nodes (:68) happen in
-//   the flush pass, once per slot instead of once per hit.
+// Level 1: survivors are compacted onto a per-warp stack in shared memory and drained 32 at a time,
+//   one per lane (32 independent DRAM transactions in flight per warp): the candidate's 32-byte
+//   sector carries keys, nodes and frequencies, so every equal key (mapper.pyx:58-62, no break)
+//   whose frequency passes the cut-off (:64) yields its node id at once.
+// Level 2: the hit.  `node_counts[node] += 1` (:68) on a 320 MB array would be a DRAM read plus a
+//   write-back per hit; instead the node id goes to a per-warp staging area in shared memory, binned
+//   by node range, and leaves in full 128-byte lines to one of KMB_LOG_BINS logs.  kmb_log_apply_kernel
+//   later plays each log into its window of node counts, which is small enough to stay in L2.  uint32
+//   addition wraps, so any order gives the reference's bits.  A full log falls back to the direct
+//   reduction, as do the (rare) hits found in overflow chains.
 // ================================================================================================
 struct KmbPol {
     uint64_t first;   // L2 evict-first: the read stream (use once)
     uint64_t filter;  // the filter words (default evict-last: the structure meant to live in L2)
-    uint64_t line;    // index lines (default normal: the key read and the RED must still find them)
-    uint64_t red;     // counter reductions
+    uint64_t line;    // index sectors (default normal)
 };
 __device__ __forceinline__ KmbPol kmb_make_policies(uint32_t bits) {
     KmbPol p;
     p.first = kmb_policy_evict_first();
     p.filter = kmb_policy_select(bits & 3u);
     p.line = kmb_policy_select((bits >> 2) & 3u);
-    p.red = kmb_policy_select((bits >> 4) & 3u);
     return p;
 }
 
-// Compare the (up to two) keys of a loaded sector with km and count the matches (mapper.pyx:58-68:
-// every equal key counts, no break).  n_here = valid slots of this sector.
+// Compare the (up to two) keys of a loaded sector with km; on_match(node, frequency) for every equal
+// key until it returns true.
 template <class F>
-__device__ __forceinline__ bool kmb_match_sector(const uint32_t (&r)[8], uint32_t n_here, uint64_t km, uint32_t *lp,
-                                                 uint64_t line, F on_match) {
+__device__ __forceinline__ bool kmb_match_sector(const uint32_t (&r)[8], uint64_t km, F on_match) {
     const uint32_t klo = (uint32_t)km, khi = (uint32_t)(km >> 32);
+    const uint32_t n_here = kmb_header_count(r[0]);
     if (n_here >= 1u && r[KMB_LINE_KEY_WORD0] == klo && r[KMB_LINE_KEY_WORD0 + 1] == khi)
-        if (on_match(lp, line, 0u)) return true;
+        if (on_match(r[KMB_LINE_NODE_WORD0], r[KMB_LINE_FREQ_WORD] & 0xFFFFu)) return true;
     if (n_here >= 2u && r[KMB_LINE_KEY_WORD0 + 2] == klo && r[KMB_LINE_KEY_WORD0 + 3] == khi)
-        if (on_match(lp, line, 1u)) return true;
+        if (on_match(r[KMB_LINE_NODE_WORD0 + 1], r[KMB_LINE_FREQ_WORD] >> 16)) return true;
     return false;
 }
 
-// Walk the overflow sectors of a chain (entries 2 .. n_total-1), synchronously.  Rare.
+// Follow the overflow sectors behind a sector whose header has the chain bit, synchronously.  Rare.
 template <class F>
-__device__ __forceinline__ void kmb_walk_overflow(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t n_total,
-                                                  uint32_t ovf_base, F on_match) {
-    for (uint32_t done = KMB_LINE_SLOTS, t = 0; done < n_total; done += KMB_LINE_SLOTS, t++) {
-        const uint64_t line = (uint64_t)ovf_base + t;
-        uint32_t *lp = P.lines + line * KMB_LINE_WORDS;
+__device__ __forceinline__ void kmb_walk_chain(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t hdr, F on_match) {
+    while (hdr & KMB_HDR_CHAIN) {
         uint32_t r[8];
-        kmb_ld_sector(lp, r, pol.line);
-        if (kmb_match_sector(r, min((uint32_t)KMB_LINE_SLOTS, n_total - done), km, lp, line, on_match)) return;
+        kmb_ld_sector(P.lines + (uint64_t)(hdr & ~KMB_HDR_CHAIN) * KMB_LINE_WORDS, r, pol.line);
+        if (kmb_match_sector(r, km, on_match)) return;
+        hdr = r[0];
     }
 }
 
 // Synchronous probe of the whole chain that owns bucket h (cross-check variant, membership, lookup).
 template <class F>
 __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t h, F on_match) {
-    const uint64_t line = (uint64_t)(h >> P.line_shift);
-    uint32_t *lp = P.lines + line * KMB_LINE_WORDS;
     uint32_t r[8];
-    kmb_ld_sector(lp, r, pol.line);
-    const uint32_t n_total = r[0];
-    if (kmb_match_sector(r, min((uint32_t)KMB_LINE_SLOTS, n_total), km, lp, line, on_match)) return;
-    if (n_total > KMB_LINE_SLOTS) kmb_walk_overflow(P, pol, km, n_total, r[1], on_match);
+    kmb_ld_sector(P.lines + (uint64_t)(h >> P.line_shift) * KMB_LINE_WORDS, r, pol.line);
+    if (kmb_match_sector(r, km, on_match)) return;
+    kmb_walk_chain(P, pol, km, r[0], on_match);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split drain.  A warp that has 32 candidates issues their 32 sector loads (one HBM line fetch each)
-// and goes back to work: the Barrett reductions and filter loads of the next batch of windows run
-// while the sectors are on their way, and only then are the keys compared and the counters reduced
-// into -- about a microsecond after the fill, while the sector is still in L2.  (Deferring the
-// second half by a whole drain period, ~10 us per warp, was measured: by then 60 % of the sectors had
-// left the L2 again and the RED had to fetch them a second time.)
+// Hit staging and logs.  Per warp: KMB_LOG_BINS stacks of KMB_STAGE_SLOTS node ids in shared memory
+// (31 left over + at most 2 x 32 new ones per drain).  A stack with >= 32 ids sends its top 32 as one
+// coalesced 128-byte store to the bin's log; the space is reserved with one atomic per 32 hits.
+// ------------------------------------------------------------------------------------------------
+#define KMB_STAGE_SLOTS 96
+struct KmbStage {
+    uint32_t *cnt;  // [KMB_LOG_BINS]
+    uint32_t *buf;  // [KMB_LOG_BINS][KMB_STAGE_SLOTS]
+};
+__device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
+    const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
+    const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
+    st.buf[b * KMB_STAGE_SLOTS + pos] = node;
+}
+// n <= 32 ids from shared memory to the log of bin b (or, if the log is full, straight onto the counts)
+__device__ __forceinline__ void kmb_log_write(const KmbProbe &P, uint32_t b, const uint32_t *src, uint32_t n, int lane) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&P.log.cursor[b], (unsigned long long)n);
+    base = __shfl_sync(KMB_FULL_MASK, base, 0);
+    if (base + n <= P.log.cap) {
+        if ((uint32_t)lane < n) P.log.entries[(uint64_t)b * P.log.cap + base + lane] = src[lane];
+    } else {
+        if (lane == 0) atomicMin(&P.log.cursor[KMB_LOG_BINS + b], base);
+        if ((uint32_t)lane < n) atomicAdd(P.counts + src[lane], 1u);
+    }
+}
+// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything.
+__device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
+    __syncwarp();
+    const uint32_t c = lane < KMB_LOG_BINS ? st.cnt[lane] : 0u;
+    unsigned ready = __ballot_sync(KMB_FULL_MASK, all ? c > 0u : c >= 32u);
+    while (ready) {
+        const int b = __ffs(ready) - 1;
+        ready &= ready - 1u;
+        uint32_t cb = __shfl_sync(KMB_FULL_MASK, c, b);
+        while (cb >= 32u || (all && cb > 0u)) {
+            const uint32_t n = min(cb, 32u);
+            kmb_log_write(P, (uint32_t)b, st.buf + b * KMB_STAGE_SLOTS + (cb - n), n, lane);
+            cb -= n;
+        }
+        if (lane == 0) st.cnt[b] = cb;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split drain.  A warp that has 32 candidates issues their 32 sector loads (one DRAM transaction
+// each) and goes back to work: the Barrett reductions and filter loads of the next batch of windows
+// run while the sectors are on their way, and only then are the keys compared.
 // ------------------------------------------------------------------------------------------------
 struct KmbPipe {
     uint32_t r[8];  // the candidate's main sector, in flight between issue and consume
     uint64_t km;
-    uint32_t line;
     bool valid;
 };
 __device__ __forceinline__ void kmb_pipe_init(KmbPipe &pp) {
     pp.valid = false;
     pp.km = 0;
-    pp.line = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) pp.r[i] = 0;
 }
@@ -337,24 +380,37 @@ __device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &
                                                const uint32_t *q_h, int base, int cnt, int lane) {
     if (lane < cnt && !(P.policies & 0x200u)) {
         pp.km = q_kmer[base + lane];
-        pp.line = q_h[base + lane] >> P.line_shift;
-        kmb_ld_sector(P.lines + (uint64_t)pp.line * KMB_LINE_WORDS, pp.r, pol.line);
+        kmb_ld_sector(P.lines + (uint64_t)(q_h[base + lane] >> P.line_shift) * KMB_LINE_WORDS, pp.r, pol.line);
         pp.valid = true;
     }
 }
-__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp) {
-    if (!pp.valid) return;
-    pp.valid = false;
-    const uint64_t pr = pol.red;
-    const bool no_red = (P.policies & 0x100u) != 0u;
-    auto count = [pr, no_red](uint32_t *lp, uint64_t, uint32_t j) {
-        if (!no_red) kmb_red_add(lp + KMB_LINE_CNT_WORD0 + j, 1u, pr);
-        return false;
-    };
-    const uint32_t n_total = pp.r[0];
-    uint32_t *lp = P.lines + (uint64_t)pp.line * KMB_LINE_WORDS;
-    kmb_match_sector(pp.r, min((uint32_t)KMB_LINE_SLOTS, n_total), pp.km, lp, pp.line, count);
-    if (n_total > KMB_LINE_SLOTS) kmb_walk_overflow(P, pol, pp.km, n_total, pp.r[1], count);
+// Called by all 32 lanes.
+__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
+                                                 unsigned &counted, int lane) {
+    if (!__any_sync(KMB_FULL_MASK, pp.valid)) return;
+    if (pp.valid) {
+        pp.valid = false;
+        const int32_t max_freq = P.max_freq;
+        const bool no_emit = (P.policies & 0x100u) != 0u;
+        kmb_match_sector(pp.r, pp.km, [&](uint32_t node, uint32_t freq) {
+            if ((int32_t)freq <= max_freq) {
+                if (!no_emit) kmb_emit(P, st, node);
+                counted++;
+            }
+            return false;
+        });
+        if (pp.r[0] & KMB_HDR_CHAIN) {
+            uint32_t *counts = P.counts;
+            kmb_walk_chain(P, pol, pp.km, pp.r[0], [&](uint32_t node, uint32_t freq) {
+                if ((int32_t)freq <= max_freq) {
+                    atomicAdd(counts + node, 1u);
+                    counted++;
+                }
+                return false;
+            });
+        }
+    }
+    kmb_stage_flush(P, st, lane, false);
 }
 
 // Push this lane's candidate (if any) on the warp's stack.  Called by all 32 lanes.
@@ -374,8 +430,9 @@ __device__ __forceinline__ void kmb_push_candidate(uint64_t *q_kmer, uint32_t *q
 // query u (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u
 // exists.  The stack holds < 32 entries on entry and on exit, so KMB_QUEUE_SLOTS >= 32 * (U + 1).
 template <int U, bool FILT, class KF>
-__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KF &kf,
-                                                uint32_t vbits, uint64_t *q_kmer, uint32_t *q_h, int &qcount, int lane) {
+__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
+                                                unsigned &counted, const KF &kf, uint32_t vbits, uint64_t *q_kmer,
+                                                uint32_t *q_h, int &qcount, int lane) {
     uint32_t hh[U];
     uint32_t need[U];  // filter bits the query needs; 0 = no query
     uint32_t fw[U];
@@ -393,7 +450,7 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
             fw[u] = 1u;
         }
     }
-    kmb_pipe_consume(P, pol, pp);  // the sectors issued by the previous call have had this long to arrive
+    kmb_pipe_consume(P, pol, pp, st, counted, lane);  // the sectors issued by the previous call have had this long to arrive
 #pragma unroll
     for (int u = 0; u < U; u++) {
         bool cand = need[u] != 0u && (fw[u] & need[u]) == need[u];
@@ -402,20 +459,24 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
     __syncwarp();
 #pragma unroll 1
     while (qcount >= 32) {
-        kmb_pipe_consume(P, pol, pp);
+        kmb_pipe_consume(P, pol, pp, st, counted, lane);
         qcount -= 32;
         kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, 32, lane);
     }
     __syncwarp();
 }
 
-// End of kernel: retire the outstanding batch, then the partial one.
-__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const uint64_t *q_kmer,
-                                                const uint32_t *q_h, int qcount, int lane) {
+// End of kernel: retire the outstanding batch, then the partial one, then the staged hits and the statistics.
+__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
+                                                unsigned &counted, const uint64_t *q_kmer, const uint32_t *q_h, int qcount,
+                                                int lane, KmbStatus *status) {
     __syncwarp();
-    kmb_pipe_consume(P, pol, pp);
+    kmb_pipe_consume(P, pol, pp, st, counted, lane);
     kmb_pipe_issue(P, pol, pp, q_kmer, q_h, 0, qcount, lane);
-    kmb_pipe_consume(P, pol, pp);
+    kmb_pipe_consume(P, pol, pp, st, counted, lane);
+    kmb_stage_flush(P, st, lane, true);
+    for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
+    if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
 }
 
 struct KmbWindowFn {  // forward window b0+u of the 64 bases in hi:lo
@@ -485,12 +546,17 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     __shared__ __align__(16) uint32_t s_pack[KMB_TILE_THREADS / 32][KMB_WTILE_POS / 16 + 4];  // 64 words + halo
     __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
+    __shared__ uint32_t s_stage[KMB_TILE_THREADS / 32][KMB_LOG_BINS * KMB_STAGE_SLOTS];
+    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t *pack = s_pack[warp];
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
+    const KmbStage st = {s_stage_cnt[warp], s_stage[warp]};
+    if (lane < KMB_LOG_BINS) st.cnt[lane] = 0;
+    unsigned counted = 0;
     int qcount = 0;
     KmbPipe pp;
     kmb_pipe_init(pp);
@@ -528,14 +594,14 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             const uint32_t vb = (valid >> b0) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
             if (!__any_sync(KMB_FULL_MASK, vb != 0u)) continue;
             KmbWindowFn fw = {lo, hi, kmask, b0};
-            kmb_probe_batch<U, FILT>(P, pol, pp, fw, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fw, vb, q_kmer, q_h, qcount, lane);
             if (REVCOMP) {
                 KmbRcWindowFn rc = {lo, hi, kmask, b0, k};
-                kmb_probe_batch<U, FILT>(P, pol, pp, rc, vb, q_kmer, q_h, qcount, lane);
+                kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, rc, vb, q_kmer, q_h, qcount, lane);
             }
         }
     }
-    kmb_pipe_finish(P, pol, pp, q_kmer, q_h, qcount, lane);
+    kmb_pipe_finish(P, pol, pp, st, counted, q_kmer, q_h, qcount, lane, status);
     // statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
     if (lane == 0 && mapped) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * mapped : mapped);
@@ -550,11 +616,16 @@ __global__ void __launch_bounds__(KMB_TILE_THREADS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
     __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
+    __shared__ uint32_t s_stage[KMB_TILE_THREADS / 32][KMB_LOG_BINS * KMB_STAGE_SLOTS];
+    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
+    const KmbStage st = {s_stage_cnt[warp], s_stage[warp]};
+    if (lane < KMB_LOG_BINS) st.cnt[lane] = 0;
+    unsigned counted = 0;
     int qcount = 0;
     KmbPipe pp;
     kmb_pipe_init(pp);
@@ -574,14 +645,14 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
             vb |= in ? (1u << u) : 0u;
         }
         KmbArrayFn fa = {km};
-        kmb_probe_batch<U, FILT>(P, pol, pp, fa, vb, q_kmer, q_h, qcount, lane);
+        kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
         if (REVCOMP) {
 #pragma unroll
             for (int u = 0; u < U; u++) km[u] = kmb_revcomp(km[u], k);
-            kmb_probe_batch<U, FILT>(P, pol, pp, fa, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
         }
     }
-    kmb_pipe_finish(P, pol, pp, q_kmer, q_h, qcount, lane);
+    kmb_pipe_finish(P, pol, pp, st, counted, q_kmer, q_h, qcount, lane, status);
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * n : (unsigned long long)n);
 }
 
@@ -605,51 +676,43 @@ template <bool REVCOMP>
 __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P,
                                             KmbStatus *status) {
     const KmbPol pol = kmb_make_policies(P.policies);
+    unsigned long long counted = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t km = kmers[i];
 #pragma unroll
         for (int strand = 0; strand < (REVCOMP ? 2 : 1); strand++) {
             if (strand == 1) km = kmb_revcomp(km, k);
-            kmb_walk_one(P, pol, km, [](uint32_t *lp, uint64_t, uint32_t j) {
-                atomicAdd(lp + KMB_LINE_CNT_WORD0 + j, 1u);
+            kmb_walk_one(P, pol, km, [&](uint32_t node, uint32_t freq) {
+                if ((int32_t)freq <= P.max_freq) {
+                    atomicAdd(P.counts + node, 1u);
+                    counted++;
+                }
                 return false;
             });
         }
     }
+    if (counted) atomicAdd(&status->n_entries_counted, counted);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * n : (unsigned long long)n);
 }
 
 // ================================================================================================
-// K4b flush: slot counters -> node counts.  For every slot with a non-zero counter c whose
-// frequency passes the cut-off (mapper.pyx:64): node_counts[node] += c (mod 2^32, mapper.pyx:68),
-// then the counter is zeroed.  One thread per sector (coalesced 8-byte counter reads at a 32-byte
-// stride); the cold (node, frequency) array is only touched for sectors that were hit.  CLEAR_ONLY zeroes without counting (mapper reset).
+// K4b: play one hit log into the node counts (mapper.pyx:68).  The ids of bin b all fall into one
+// window of 2^bin_shift nodes, launched bin after bin so that the window being reduced into stays in
+// L2; the log itself is a coalesced stream.
 // ================================================================================================
-template <bool CLEAR_ONLY>
-__global__ void kmb_flush_kernel(uint32_t *__restrict__ lines, uint64_t n_lines, const uint2 *__restrict__ cold,
-                                 int32_t max_freq, uint32_t *__restrict__ counts, KmbStatus *status) {
-    unsigned long long counted = 0;
-    for (uint64_t line = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; line < n_lines;
-         line += (uint64_t)gridDim.x * blockDim.x) {
-        uint2 *cp = reinterpret_cast<uint2 *>(lines + line * KMB_LINE_WORDS + KMB_LINE_CNT_WORD0);
-        const uint2 c = *cp;
-        if (!(c.x | c.y)) continue;
-        if (!CLEAR_ONLY) {
-            const uint4 nf = *reinterpret_cast<const uint4 *>(cold + line * KMB_LINE_SLOTS);  // (node0, freq0, node1, freq1)
-            if (c.x && (int32_t)nf.y <= max_freq) {
-                atomicAdd(counts + nf.x, c.x);
-                counted += c.x;
-            }
-            if (c.y && (int32_t)nf.w <= max_freq) {
-                atomicAdd(counts + nf.z, c.y);
-                counted += c.y;
-            }
-        }
-        *cp = make_uint2(0u, 0u);
-    }
-    if (!CLEAR_ONLY) {
-        for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
-        if ((threadIdx.x & 31) == 0 && counted) atomicAdd(&status->n_entries_counted, counted);
+__global__ void kmb_log_apply_kernel(KmbLog log, int bin, uint32_t *__restrict__ counts) {
+    unsigned long long n = log.cursor[bin];
+    const unsigned long long first_overflow = log.cursor[KMB_LOG_BINS + bin];
+    if (first_overflow < n) n = first_overflow;
+    if (n > log.cap) n = log.cap;
+    const uint32_t *__restrict__ e = log.entries + (uint64_t)bin * log.cap;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(counts + e[i], 1u);
+}
+__global__ void kmb_log_reset_kernel(KmbLog log) {
+    if (threadIdx.x < KMB_LOG_BINS) {
+        log.cursor[threadIdx.x] = 0ull;
+        log.cursor[KMB_LOG_BINS + threadIdx.x] = ~0ull;
     }
 }
 
@@ -659,20 +722,19 @@ __global__ void kmb_flush_kernel(uint32_t *__restrict__ lines, uint64_t n_lines,
 // the counter's keys are unique, so "a" matching slot is "the" slot).
 // ================================================================================================
 template <int MODE>
-__global__ void kmb_in_graph_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KmbProbe P,
-                                    const uint2 *__restrict__ cold, const uint32_t *__restrict__ counts,
-                                    uint8_t *out8, uint32_t *out32) {
+__global__ void kmb_in_graph_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KmbProbe P, uint8_t *out8,
+                                    uint32_t *out32) {
     const KmbPol pol = kmb_make_policies(P.policies);
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         bool hit = false;
         uint32_t node = 0;
-        kmb_walk_one(P, pol, kmers[i], [&](uint32_t *, uint64_t line, uint32_t j) {
+        kmb_walk_one(P, pol, kmers[i], [&](uint32_t nd, uint32_t) {
             hit = true;
-            if (MODE == 1) node = cold[line * KMB_LINE_SLOTS + j].x;
+            node = nd;
             return true;
         });
         if (MODE == 0) out8[i] = hit ? 1 : 0;
-        else out32[i] = hit ? counts[node] : 0u;
+        else out32[i] = hit ? P.counts[node] : 0u;
     }
 }
 

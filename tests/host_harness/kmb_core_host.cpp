@@ -21,5 +21,8 @@ uint32_t h_chain_slot(uint32_t s) { return kmb_chain_slot(s); }
 uint32_t h_chain_extra_lines(uint32_t n) { return kmb_chain_extra_lines(n); }
 uint32_t h_filter_mask(uint32_t h, uint64_t q, uint32_t cfg) { return kmb_filter_mask(h, q, cfg); }
 uint32_t h_filter_word(uint32_t h, uint32_t cfg) { return kmb_filter_word(h, cfg); }
+uint32_t h_sector_header(uint32_t remaining, uint32_t next) { return kmb_sector_header(remaining, next); }
+uint32_t h_header_count(uint32_t hdr) { return kmb_header_count(hdr); }
+uint32_t h_log_bin(uint32_t node, uint32_t shift) { return kmb_log_bin(node, shift); }
 
 }

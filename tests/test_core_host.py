@@ -30,6 +30,9 @@ def core():
     lib.h_filter_mask.restype = C.c_uint32
     lib.h_filter_mask.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
     lib.h_filter_word.restype = C.c_uint32
+    lib.h_sector_header.restype = C.c_uint32
+    lib.h_header_count.restype = C.c_uint32
+    lib.h_log_bin.restype = C.c_uint32
     lib.h_filter_word.argtypes = [C.c_uint32, C.c_uint32]
     lib.h_encode16.restype = C.c_uint32
     return lib
@@ -132,6 +135,13 @@ def test_sector_chain_geometry_and_filter_mask(core):
             assert line == 77 if s < 2 else 1000 <= line < 1000 + extra
             seen.add((line, slot))
         assert len(seen) == n_total
+    # sector headers: a count of 0..2, or the chain bit plus the index of the next sector
+    for remaining in range(0, 9):
+        hdr = core.h_sector_header(remaining, 12345)
+        assert core.h_header_count(hdr) == min(remaining, 2)
+        assert (hdr == (0x80000000 | 12345)) == (remaining > 2)
+    # log bins: node ranges of 2^shift, the last bin takes the rest
+    assert [core.h_log_bin(n, 4) for n in (0, 15, 16, 127, 128, 4000)] == [0, 0, 1, 7, 7, 7]
     rng = np.random.default_rng(6)
     for _ in range(2000):
         h = int(rng.integers(0, 2 ** 32))

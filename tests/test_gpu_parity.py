@@ -19,18 +19,18 @@ def kmb():
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_shift", -1),
-                    ("chunk_bytes", 64 << 20)):
+                    ("log_max_entries_per_bin", 256 << 20), ("chunk_bytes", 64 << 20)):
         _lib.set_option(name, v)
 
 
-VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=8),
-            dict(probe_variant=1, use_filter=0, gathers_in_flight=8),
-            dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
-            dict(probe_variant=1, use_filter=0, gathers_in_flight=2),
+VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=4),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=2),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=2),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4, filter_shift=3),
-            dict(probe_variant=0, use_filter=1, gathers_in_flight=8),
-            dict(probe_variant=0, use_filter=0, gathers_in_flight=8)]
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, log_max_entries_per_bin=1024),
+            dict(probe_variant=0, use_filter=1, gathers_in_flight=4),
+            dict(probe_variant=0, use_filter=0, gathers_in_flight=4)]
 
 
 def _fresh(index):
@@ -42,6 +42,7 @@ def _fresh(index):
 
 def _set(kmb, variant):
     kmb.set_option("filter_shift", -1)
+    kmb.set_option("log_max_entries_per_bin", 256 << 20)
     for k, v in variant.items():
         kmb.set_option(k, v)
 

@@ -32,7 +32,7 @@ def main():
     grids = {
         "default": dict(use_filter=[1, 0], gathers_in_flight=[4, 8, 16], map_reads_blocks_per_sm=[0]),
         "occupancy": dict(use_filter=[1], gathers_in_flight=[4, 8, 16], map_reads_blocks_per_sm=[1, 2, 3, 4, 5, 6]),
-        "v21": dict(use_filter=[1], gathers_in_flight=[2, 4, 8], map_reads_blocks_per_sm=[0]),
+        "v21": dict(use_filter=[1], gathers_in_flight=[2, 4], map_reads_blocks_per_sm=[0, 3]),
         "filter": dict(gathers_in_flight=[4], filter_shift=[-1, 0, 1, 2], use_filter=[1]),
         "persist": dict(use_filter=[1], gathers_in_flight=[8], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
     }[a.grid]
