@@ -383,7 +383,7 @@ def main_ours(args):
     def step_resident():
         mapper.reset()
         mapper.map_reads(bases, offsets, k)
-        mapper.flush()                  # slot counters -> node counts (queued on the same stream)
+        mapper.flush()                  # hit logs -> node counts (queued on the same stream)
         if world > 1:
             distributed.all_reduce_counts(counts)
 
@@ -393,6 +393,7 @@ def main_ours(args):
         torch.cuda.synchronize()
         mapper.kernel_time()            # drop warm-up records
         n_kmers_step, n_counted_step = mapper.stats()
+        n_candidates_step = mapper.candidates()   # every step starts with a reset: these are per-step figures
         barrier()
         clocks = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                               os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
@@ -481,7 +482,8 @@ def main_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": known_traffic(args.workload),
                 "kernel": "kmb_map_reads_kernel", "kernel_ms": kernel_avg_ms, "kernel_share_of_step": kernel_ms / ms if ms else None,
-                "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h, "peak_source": peak_src,
+                "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h,
+                "sector_fetches_per_kmer": n_candidates_step / max(n_kmers_step, 1), "peak_source": peak_src,
                 "filter_bytes": di.filter_bytes}
 
     # ---- the random-gather micro-roofline of SURVEY.md 8(d), measured live on this GPU: uniform random 8-byte
@@ -539,8 +541,8 @@ def main_ours(args):
                                l2="inputs larger than L2 (reads %.1f GB, directory %.1f GB per step); no flush"
                                   % (n_bases / 1e9, w["modulo"] * 8 / 1e9),
                                index_device_bytes=di.device_bytes, setup_seconds=round(setup_s, 1),
-                               index_layout=dict(buckets_per_line=di.buckets_per_line, main_lines=di.n_main_lines,
-                                                 overflow_lines=di.n_overflow_lines, filter_bytes=di.filter_bytes),
+                               index_layout=dict(main_sectors=di.n_main_lines, overflow_sectors=di.n_overflow_lines,
+                                                 filter_bytes=di.filter_bytes),
                                options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter",
                                                                         "map_reads_blocks_per_sm")}),
                 "clocks": clock_rec, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -66,11 +66,11 @@ int kmb_index_info(const kmb_index *index, int64_t *max_node_id, uint64_t *n_ent
                    uint64_t *modulo, uint64_t *device_bytes);
 /* Size of the L2-resident bucket filter (probe level 0), 0 when not in use. */
 int kmb_index_filter_bytes(const kmb_index *index, uint64_t *bytes);
-/* Geometry of the sector table: buckets per sector, main sectors, overflow sectors and the number
- * of live entries (entries that lie inside the bucket range of their own key -- the only ones the
- * reference's scan can ever match). */
-int kmb_index_layout(const kmb_index *index, uint32_t *buckets_per_line, uint64_t *n_main_lines,
-                     uint64_t *n_overflow_lines, uint64_t *n_live_entries);
+/* Geometry of the sector table: main sectors, overflow sectors and the number of live entries
+ * (entries that lie inside the bucket range of their own key -- the only ones the reference's scan
+ * can ever match). */
+int kmb_index_layout(const kmb_index *index, uint64_t *n_main_sectors, uint64_t *n_overflow_sectors,
+                     uint64_t *n_live_entries);
 
 /* ---- mapper: replaces map_kmers_to_graph_index (mapper.pyx:19-72), the per-chunk worker map_cpu
  * (command_line_interface.py:32-56) and cucounter's count() as driven by GpuCounter
@@ -169,6 +169,10 @@ int kmb_host_free(void *ptr);
 int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loads, int load_bytes, int unroll,
                      int threads_per_block, int blocks_per_sm, float *ms);
 
+/* Look-ups that passed the filter and fetched an index sector since the last reset (implies kmb_mapper_sync):
+ * the number of random DRAM transactions the probes made. */
+int kmb_mapper_candidates(kmb_mapper *mapper, uint64_t *n_candidates);
+
 /* Sum of the device durations (ms) of the mapping kernels launched on this mapper since the last
  * call -- the fused reads kernel / the k-mer kernel only, not the mask or memset launches -- when
  * option "time_kernels" is 1 (CUDA events on the mapper's stream).  Implies a stream synchronize. */
@@ -176,7 +180,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
 
 /* Tuning knobs (process-wide, read at launch / index-creation time): name in
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
- *  "use_filter", "filter_l2_budget_bytes", "filter_shift", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries_per_bin",
+ *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries_per_bin",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes"}. */
 int kmb_set_option(const char *name, int64_t value);

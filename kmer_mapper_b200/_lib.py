@@ -50,7 +50,7 @@ SIGNATURES = {
     "kmb_index_destroy": (C.c_int, [_vp]),
     "kmb_index_info": (C.c_int, [_vp, C.POINTER(C.c_int64), _u64p, _u64p, _u64p]),
     "kmb_index_filter_bytes": (C.c_int, [_vp, _u64p]),
-    "kmb_index_layout": (C.c_int, [_vp, _u32p, _u64p, _u64p, _u64p]),
+    "kmb_index_layout": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "kmb_mapper_create": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, C.POINTER(_vp)]),
     "kmb_mapper_destroy": (C.c_int, [_vp]),
     "kmb_mapper_set_stream": (C.c_int, [_vp, _vp]),
@@ -78,6 +78,7 @@ SIGNATURES = {
     "kmb_host_free": (C.c_int, [_vp]),
     "kmb_bench_gather": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_float)]),
+    "kmb_mapper_candidates": (C.c_int, [_vp, _u64p]),
     "kmb_mapper_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_double), _u64p]),
     "kmb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "kmb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),

@@ -57,9 +57,9 @@ struct KmbOptions {
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
     int64_t gathers_in_flight = 4;        // U: 2 or 4 independent filter loads per thread
     int64_t log_max_entries_per_bin = 256ll << 20;  // upper bound of one hit log (x 8 bins x 4 bytes)
+    int64_t sectors_per_100_entries = 250; // main sectors per 100 index entries (mean occupancy 0.4 of 2 slots)
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
-    int64_t filter_l2_budget_bytes = 64ll << 20;  // the L2 keeps ~72 MB of randomly accessed data (profiles/README.md)
-    int64_t filter_shift = -1;            // buckets per filter bit = 2^shift; -1 = smallest that fits the budget
+    int64_t filter_l2_budget_bytes = 60ll << 20;  // the L2 keeps ~72 MB of randomly accessed data (profiles/README.md)
     int64_t policy_filter = 2;            // L2 priority hints: 0 normal, 1 evict-first, 2 evict-last
     int64_t policy_line = 0;
     int64_t ablate = 0;                   // measurement only (results become wrong): 1 no RED, 2 no line loads, 4 no filter loads, 8 no key loads
@@ -85,8 +85,8 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(gathers_in_flight)
     OPT(log_max_entries_per_bin)
     OPT(use_filter)
+    OPT(sectors_per_100_entries)
     OPT(filter_l2_budget_bytes)
-    OPT(filter_shift)
     OPT(l2_persist)
     OPT(ablate)
     OPT(policy_filter)
@@ -117,8 +117,8 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(gathers_in_flight)
     OPT(log_max_entries_per_bin)
     OPT(use_filter)
+    OPT(sectors_per_100_entries)
     OPT(filter_l2_budget_bytes)
-    OPT(filter_shift)
     OPT(l2_persist)
     OPT(ablate)
     OPT(policy_filter)
@@ -253,12 +253,11 @@ static int grid_for(size_t work_items, int block, int sms, int per_sm = 8) {
 struct kmb_index {
     int device = 0;
     uint64_t modulo = 0, n_entries = 0, n_live = 0;
-    uint32_t line_shift = 0;            // g: 2^g buckets per 128-byte line
+    KmbAddr addr;                       // key -> sector / filter word / filter bits
     uint64_t n_main = 0, n_lines = 0;   // main lines, main + overflow lines
     uint32_t *lines = nullptr;          // 32-byte sectors (header, frequencies, keys, nodes), read-only after the build
     uint32_t *filter = nullptr;
     size_t filter_bytes = 0;
-    uint32_t filter_cfg = 0;            // kmb_filter_mask configuration
     bool filter_on = false;
     int64_t max_node = -1;
     uint64_t device_bytes = 0;
@@ -274,13 +273,6 @@ extern "C" int kmb_index_destroy(kmb_index *ix) {
     cudaGetLastError();
     delete ix;
     return KMB_OK;
-}
-
-// buckets per line: the largest power of two that keeps the mean sector occupancy <= 0.5 of 2 slots
-static uint32_t choose_line_shift(uint64_t modulo, uint64_t n_entries) {
-    uint32_t g = 0;
-    while (g < 16 && (double)(2ull << g) * (double)n_entries <= 0.5 * (double)modulo && (2ull << g) <= modulo) g++;
-    return g;
 }
 
 extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, const int32_t *n_kmers, uint64_t modulo,
@@ -309,8 +301,10 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     ix->modulo = modulo;
     ix->n_entries = n_entries;
     ix->mod = kmb_mod_make(modulo);
-    ix->line_shift = choose_line_shift(modulo, n_entries);
-    ix->n_main = ((modulo - 1) >> ix->line_shift) + 1;
+    // main sectors: 2.5 per entry (mean occupancy 0.4 of 2 slots: < 1 % of the sectors need an overflow chain)
+    ix->n_main = std::min<uint64_t>(std::max<uint64_t>(n_entries * (uint64_t)std::max<int64_t>(g_opt.sectors_per_100_entries, 50) / 100, 1), 1600000000ull);
+    memset(&ix->addr, 0, sizeof(ix->addr));
+    ix->addr.n_main = (uint32_t)ix->n_main;
     KMB_TRY(dev_info(device, &ix->info));
 
     cudaStream_t s = 0;  // index construction is a one-off: legacy default stream, synchronous
@@ -326,18 +320,17 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     KMB_TRY(to_device(kmers, (size_t)n_entries, device, t_kmers, &d_kmers, s));
     KMB_TRY(to_device(frequencies, (size_t)n_entries, device, t_freq, &d_freq, s));
 
-    // Filter geometry: one bit per 2^fs buckets, fs the smallest shift that fits the L2 budget; a second
-    // probe bit only while the filter has >= 2.5 bits per key; no filter at all below 0.62 bits per key
-    // (more than 80 % of the absent k-mers would pass).
-    uint32_t fs = 0;
-    if (g_opt.filter_shift >= 0) {
-        fs = (uint32_t)std::min<int64_t>(g_opt.filter_shift, 31);
-    } else {
-        while (fs < 31 && (int64_t)((((modulo - 1) >> fs) + 32) / 32 * 4) > g_opt.filter_l2_budget_bytes) fs++;
-    }
-    const double bits_per_key = (double)(((modulo - 1) >> fs) + 1) / (double)std::max<uint64_t>(n_entries, 1);
-    ix->filter_cfg = fs | (bits_per_key >= 2.5 ? KMB_FILTER_TWO : 0u);
-    ix->filter_bytes = (size_t)((((modulo - 1) >> fs) + 32) / 32) * 4;
+    // Filter geometry: as many bits as the L2 budget allows, at most 16 per key; a second probe bit only with
+    // >= 2.5 bits per key; no filter at all below 0.62 bits per key (> 80 % of the absent k-mers would pass).
+    const uint64_t keys_for_filter = std::max<uint64_t>(n_entries, 1);
+    uint64_t filter_words = std::min<uint64_t>((uint64_t)std::max<int64_t>(g_opt.filter_l2_budget_bytes, 4) / 4,
+                                               std::max<uint64_t>(keys_for_filter / 2, 1));
+    const double bits_per_key = 32.0 * (double)filter_words / (double)keys_for_filter;
+    bool want_filter = g_opt.use_filter == 1 || (g_opt.use_filter < 0 && bits_per_key >= 0.62);
+    if (!want_filter) filter_words = 0;
+    ix->addr.n_filter_words = (uint32_t)filter_words;
+    ix->addr.two_probes = bits_per_key >= 2.5 ? 1u : 0u;
+    ix->filter_bytes = (size_t)std::max<uint64_t>(filter_words, 1) * 4;
     KMB_CUDA(cudaMalloc(&ix->filter, ix->filter_bytes));
     KMB_CUDA(cudaMemsetAsync(ix->filter, 0, ix->filter_bytes, s));
     DevBuf<uint32_t> line_fill;
@@ -366,7 +359,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     // 2. per-line counts + filter bits, 3. overflow lines needed
     if (n_entries) {
         kmb_v2_count<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_h2i, d_nk, n_entries, ix->mod,
-                                                                 ix->line_shift, line_fill.p, ix->filter, ix->filter_cfg, d_status.p);
+                                                                 ix->addr, line_fill.p, ix->filter, d_status.p);
         g_launches++;
     }
     kmb_v2_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, d_status.p);
@@ -388,13 +381,12 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     g_launches++;
     if (n_entries) {
         kmb_v2_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
-                                                                   ix->line_shift, line_fill.p, ix->lines);
+                                                                   ix->addr, line_fill.p, ix->lines);
         g_launches++;
     }
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaStreamSynchronize(s));
 
-    bool want_filter = g_opt.use_filter == 1 || (g_opt.use_filter < 0 && bits_per_key >= 0.62);
     ix->filter_on = want_filter;
     if (!want_filter) {
         cudaFree(ix->filter);
@@ -424,10 +416,9 @@ extern "C" int kmb_index_filter_bytes(const kmb_index *ix, uint64_t *bytes) {
 }
 
 // Geometry of the line table: buckets per line, main lines, overflow lines, live entries.
-extern "C" int kmb_index_layout(const kmb_index *ix, uint32_t *buckets_per_line, uint64_t *n_main_lines,
-                                uint64_t *n_overflow_lines, uint64_t *n_live_entries) {
+extern "C" int kmb_index_layout(const kmb_index *ix, uint64_t *n_main_lines, uint64_t *n_overflow_lines,
+                                uint64_t *n_live_entries) {
     if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_index_layout: null index");
-    if (buckets_per_line) *buckets_per_line = 1u << ix->line_shift;
     if (n_main_lines) *n_main_lines = ix->n_main;
     if (n_overflow_lines) *n_overflow_lines = ix->n_lines - ix->n_main;
     if (n_live_entries) *n_live_entries = ix->n_live;
@@ -451,7 +442,7 @@ struct kmb_mapper {
     uint64_t n_counts = 0;
     uint32_t *counts = nullptr;
     bool own_counts = false;
-    KmbLog log = {nullptr, nullptr, 0, 0};  // hit logs (grown on demand) + their cursors
+    KmbLog log = {nullptr, nullptr, 0, 0, 1};  // hit logs (grown on demand) + their cursors
     bool dirty = false;            // the logs may hold hits that are not yet in the node counts
     uint64_t queries_since_flush = 0;
     int32_t max_freq = 1000;
@@ -553,6 +544,9 @@ static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
     } else if (m->dirty && m->queries_since_flush + n_queries > 4 * KMB_LOG_BINS * m->log.cap) {
         KMB_TRY(launch_flush(m));  // make room before the logs overflow into direct reductions
     }
+    // big launches reserve log space eight 128-byte groups at a time (one atomic per 256 hits); small ones group by
+    // group, so that the unused tail of a reservation does not outweigh the hits
+    m->log.chunk_groups = n_queries >= (256ull << 20) ? 8u : 1u;
     m->queries_since_flush += n_queries;
     return KMB_OK;
 }
@@ -649,9 +643,7 @@ static KmbProbe make_probe(const kmb_mapper *m) {
     KmbProbe P;
     P.lines = ix->lines;
     P.filter = ix->filter_on ? ix->filter : nullptr;
-    P.filter_cfg = ix->filter_cfg;
-    P.mod = ix->mod;
-    P.line_shift = ix->line_shift;
+    P.addr = ix->addr;
     P.policies = (uint32_t)((g_opt.policy_filter & 3) | ((g_opt.policy_line & 3) << 2) | ((g_opt.ablate & 15) << 8));
     P.max_freq = m->max_freq;
     P.counts = m->counts;
@@ -968,6 +960,15 @@ extern "C" int kmb_mapper_stats(kmb_mapper *m, uint64_t *n_kmers_mapped, uint64_
 
 // Sum of the device durations of the mapping kernels (the fused reads kernel / the k-mer kernel, not
 // the mask or memset launches) recorded since the last call, with option "time_kernels" = 1.
+// Look-ups that passed the filter and fetched a sector since the last reset (implies a sync).
+extern "C" int kmb_mapper_candidates(kmb_mapper *m, uint64_t *n_candidates) {
+    if (!m || !n_candidates) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_candidates: null argument");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(fetch_status(m));
+    *n_candidates = m->h_status->n_candidates;
+    return KMB_OK;
+}
+
 extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t *n_kernels) {
     if (!m || !ms_total) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_kernel_time: null argument");
     KMB_ON_DEVICE(m->index->device);
@@ -1006,9 +1007,7 @@ static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uin
     memset(&P, 0, sizeof(P));
     P.lines = ix->lines;
     P.filter = ix->filter_on ? ix->filter : nullptr;
-    P.filter_cfg = ix->filter_cfg;
-    P.mod = ix->mod;
-    P.line_shift = ix->line_shift;
+    P.addr = ix->addr;
     P.policies = 2u;
     P.counts = counts;
     kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(

@@ -25,6 +25,10 @@
 
 #define KMB_FULL_MASK 0xFFFFFFFFu
 #define KMB_TILE_THREADS 256
+// Three resident CTAs per SM = up to 85 registers per thread.  At four (64 registers) ptxas spills the sector
+// that is in flight between issue and consume, and the spill store waits for the load: the overlap is gone
+// (30 % of all stall samples sat on three STL instructions, profiles/README.md).
+#define KMB_MAP_MIN_BLOCKS 3
 #define KMB_POS_PER_THREAD 32
 #define KMB_TILE_POS (KMB_TILE_THREADS * KMB_POS_PER_THREAD)  // 8192 window starts per tile
 #define KMB_WTILE_POS (32 * KMB_POS_PER_THREAD)                // 1024 window starts per warp tile
@@ -35,6 +39,7 @@ struct KmbStatus {
     unsigned long long n_kmers_mapped;     // windows looked up
     unsigned long long n_entries_counted;  // +1s destined for node counts (mapper.pyx:68)
     unsigned long long n_live_entries;     // index build: entries reachable through their own bucket
+    unsigned long long n_candidates;       // look-ups that passed the filter and fetched a sector
     unsigned int index_flags;              // bit0 bucket out of range, bit1 negative node
     unsigned int pool_lines;               // index build: overflow sectors needed / handed out
     int max_node;
@@ -45,14 +50,13 @@ struct KmbLog {  // hit logs of one mapper: KMB_LOG_BINS arrays of `cap` node id
     unsigned long long *cursor;  // [0, BINS): entries reserved so far; [BINS, 2 BINS): first reservation that did not fit
     uint64_t cap;
     uint32_t bin_shift;          // bin = node >> bin_shift
+    uint32_t chunk_groups;       // 32-id groups reserved per atomic (unused ones are filled with KMB_LOG_HOLE)
 };
 
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
     const uint32_t *__restrict__ lines;      // 32-byte sectors, read-only
-    const uint32_t *__restrict__ filter;     // blocked Bloom filter over the buckets (kmb_filter_mask), or nullptr
-    uint32_t filter_cfg;                     // bits 0-4 buckets-per-bit shift, bit 8 two probes
-    KmbMod mod;
-    uint32_t line_shift;                     // g: sector = h >> g
+    const uint32_t *__restrict__ filter;     // word-blocked Bloom filter over the keys, or nullptr
+    KmbAddr addr;                            // key -> sector, filter word, filter bits (kmb_locate)
     uint32_t policies;                       // L2 priority of: filter (bits 0-1), sector loads (2-3); bits 8+: ablation
     int32_t max_freq;                        // C int like the reference's cut-off (mapper.pyx:19,64)
     uint32_t *counts;                        // node counts: target of the log and of the rare direct reductions
@@ -155,8 +159,8 @@ __device__ __forceinline__ bool kmb_entry_live(const int32_t *__restrict__ hashe
 // pass 1: per-line entry counts, filter bits, node statistics
 __global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                              const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
-                             uint64_t n_entries, KmbMod mod, uint32_t line_shift, uint32_t *__restrict__ line_fill,
-                             uint32_t *__restrict__ filter, uint32_t filter_cfg, KmbStatus *status) {
+                             uint64_t n_entries, KmbMod mod, KmbAddr addr, uint32_t *__restrict__ line_fill,
+                             uint32_t *__restrict__ filter, KmbStatus *status) {
     int local_max = -1;
     bool neg = false;
     unsigned long long live_n = 0;
@@ -165,11 +169,13 @@ __global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *
         neg |= node < 0;
         local_max = max(local_max, node);
         uint64_t q, h;
-        kmb_divmod(kmers[l], mod, q, h);
+        const uint64_t key = kmers[l];
+        kmb_divmod(key, mod, q, h);  // the reference's bucket (mapper.pyx:54) decides liveness, nothing else
         if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
         live_n++;
-        atomicAdd(&line_fill[h >> line_shift], 1u);
-        atomicOr(&filter[kmb_filter_word((uint32_t)h, filter_cfg)], kmb_filter_mask((uint32_t)h, q, filter_cfg));
+        const KmbLoc loc = kmb_locate(key, addr);
+        atomicAdd(&line_fill[loc.sector], 1u);
+        if (addr.n_filter_words) atomicOr(&filter[loc.fword], loc.fmask);
     }
     for (int o = 16; o > 0; o >>= 1) {
         local_max = max(local_max, __shfl_xor_sync(KMB_FULL_MASK, local_max, o));
@@ -207,14 +213,14 @@ __global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, u
 // pass 3: place every live entry; slot order inside a chain is whatever the atomics give
 __global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                                const uint16_t *__restrict__ freqs, const int32_t *__restrict__ hashes_to_index,
-                               const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, uint32_t line_shift,
+                               const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, KmbAddr addr,
                                uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines) {
     for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_entries; l += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = kmers[l];
         uint64_t q, h;
         kmb_divmod(key, mod, q, h);
         if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
-        uint64_t main_line = h >> line_shift;
+        uint64_t main_line = kmb_locate(key, addr).sector;
         uint32_t s = atomicAdd(&line_fill[main_line], 1u);
         uint32_t ovf_base = lines[main_line * KMB_LINE_WORDS] & ~KMB_HDR_CHAIN;  // only meaningful (and used) for s >= 2
         uint32_t *lp = lines + kmb_chain_line(main_line, ovf_base, s) * KMB_LINE_WORDS;
@@ -305,11 +311,11 @@ __device__ __forceinline__ void kmb_walk_chain(const KmbProbe &P, const KmbPol &
     }
 }
 
-// Synchronous probe of the whole chain that owns bucket h (cross-check variant, membership, lookup).
+// Synchronous probe of the whole chain behind a main sector (cross-check variant, membership, lookup).
 template <class F>
-__device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t h, F on_match) {
+__device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t sector, F on_match) {
     uint32_t r[8];
-    kmb_ld_sector(P.lines + (uint64_t)(h >> P.line_shift) * KMB_LINE_WORDS, r, pol.line);
+    kmb_ld_sector(P.lines + (uint64_t)sector * KMB_LINE_WORDS, r, pol.line);
     if (kmb_match_sector(r, km, on_match)) return;
     kmb_walk_chain(P, pol, km, r[0], on_match);
 }
@@ -320,28 +326,45 @@ __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &
 // coalesced 128-byte store to the bin's log; the space is reserved with one atomic per 32 hits.
 // ------------------------------------------------------------------------------------------------
 #define KMB_STAGE_SLOTS 96
+#define KMB_LOG_HOLE 0xFFFFFFFFu
 struct KmbStage {
-    uint32_t *cnt;  // [KMB_LOG_BINS]
-    uint32_t *buf;  // [KMB_LOG_BINS][KMB_STAGE_SLOTS]
+    uint32_t *cnt;                 // [KMB_LOG_BINS] ids staged per bin
+    uint32_t *buf;                 // [KMB_LOG_BINS][KMB_STAGE_SLOTS]
+    unsigned long long *res_base;  // [KMB_LOG_BINS] next free position of this warp's reservation in the bin's log
+    uint32_t *res_left;            // [KMB_LOG_BINS] groups left in that reservation
 };
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
     const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
     const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
     st.buf[b * KMB_STAGE_SLOTS + pos] = node;
 }
-// n <= 32 ids from shared memory to the log of bin b (or, if the log is full, straight onto the counts)
-__device__ __forceinline__ void kmb_log_write(const KmbProbe &P, uint32_t b, const uint32_t *src, uint32_t n, int lane) {
+// One group of 32 ids (lanes >= n write holes) to the log of bin b -- or, if the log is full, straight onto
+// the counts.  Log space is reserved chunk_groups groups at a time, so the atomic (and the wait for its
+// result) is paid once per chunk.
+__device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage &st, uint32_t b, const uint32_t *src,
+                                              uint32_t n, int lane) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&P.log.cursor[b], (unsigned long long)n);
+    if (lane == 0) {
+        uint32_t left = st.res_left[b];
+        base = st.res_base[b];
+        if (left == 0) {
+            left = P.log.chunk_groups;
+            base = atomicAdd(&P.log.cursor[b], 32ull * left);
+        }
+        st.res_left[b] = left - 1;
+        st.res_base[b] = base + 32;
+    }
     base = __shfl_sync(KMB_FULL_MASK, base, 0);
-    if (base + n <= P.log.cap) {
-        if ((uint32_t)lane < n) P.log.entries[(uint64_t)b * P.log.cap + base + lane] = src[lane];
+    const uint32_t id = (uint32_t)lane < n ? src[lane] : KMB_LOG_HOLE;
+    if (base + 32 <= P.log.cap) {
+        P.log.entries[(uint64_t)b * P.log.cap + base + lane] = id;
     } else {
         if (lane == 0) atomicMin(&P.log.cursor[KMB_LOG_BINS + b], base);
-        if ((uint32_t)lane < n) atomicAdd(P.counts + src[lane], 1u);
+        if (id != KMB_LOG_HOLE) atomicAdd(P.counts + id, 1u);
     }
 }
-// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything.
+// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything, and
+// fill what is left of the reservations with holes.
 __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
     __syncwarp();
     const uint32_t c = lane < KMB_LOG_BINS ? st.cnt[lane] : 0u;
@@ -352,10 +375,26 @@ __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStag
         uint32_t cb = __shfl_sync(KMB_FULL_MASK, c, b);
         while (cb >= 32u || (all && cb > 0u)) {
             const uint32_t n = min(cb, 32u);
-            kmb_log_write(P, (uint32_t)b, st.buf + b * KMB_STAGE_SLOTS + (cb - n), n, lane);
+            kmb_log_write(P, st, (uint32_t)b, st.buf + b * KMB_STAGE_SLOTS + (cb - n), n, lane);
             cb -= n;
         }
         if (lane == 0) st.cnt[b] = cb;
+        __syncwarp();
+    }
+    if (all) {
+        for (uint32_t b = 0; b < KMB_LOG_BINS; b++) {
+            __syncwarp();
+            const uint32_t left = st.res_left[b];
+            for (uint32_t g = 0; g < left; g++) kmb_log_write(P, st, b, st.buf, 0u, lane);
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane) {
+    if (lane < KMB_LOG_BINS) {
+        st.cnt[lane] = 0;
+        st.res_left[lane] = 0;
+        st.res_base[lane] = 0;
     }
     __syncwarp();
 }
@@ -368,19 +407,22 @@ __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStag
 struct KmbPipe {
     uint32_t r[8];  // the candidate's main sector, in flight between issue and consume
     uint64_t km;
+    unsigned issued;  // candidates of this warp so far (warp-uniform)
     bool valid;
 };
 __device__ __forceinline__ void kmb_pipe_init(KmbPipe &pp) {
     pp.valid = false;
+    pp.issued = 0;
     pp.km = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) pp.r[i] = 0;
 }
 __device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const uint64_t *q_kmer,
                                                const uint32_t *q_h, int base, int cnt, int lane) {
+    pp.issued += (unsigned)cnt;
     if (lane < cnt && !(P.policies & 0x200u)) {
         pp.km = q_kmer[base + lane];
-        kmb_ld_sector(P.lines + (uint64_t)(q_h[base + lane] >> P.line_shift) * KMB_LINE_WORDS, pp.r, pol.line);
+        kmb_ld_sector(P.lines + (uint64_t)q_h[base + lane] * KMB_LINE_WORDS, pp.r, pol.line);
         pp.valid = true;
     }
 }
@@ -429,22 +471,23 @@ __device__ __forceinline__ void kmb_push_candidate(uint64_t *q_kmer, uint32_t *q
 // of the previous drain placed between the issue of those loads and their first use.  kf(u) yields
 // query u (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u
 // exists.  The stack holds < 32 entries on entry and on exit, so KMB_QUEUE_SLOTS >= 32 * (U + 1).
+// (Measured alternatives, both slower: consuming a whole drain period later, and keeping two batches of
+// sector loads in flight per warp.)
 template <int U, bool FILT, class KF>
 __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
                                                 unsigned &counted, const KF &kf, uint32_t vbits, uint64_t *q_kmer,
                                                 uint32_t *q_h, int &qcount, int lane) {
-    uint32_t hh[U];
+    uint32_t hh[U];    // main sector of the query
     uint32_t need[U];  // filter bits the query needs; 0 = no query
     uint32_t fw[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        uint64_t q, h;
-        kmb_divmod(kf(u), P.mod, q, h);
-        hh[u] = (uint32_t)h;
+        const KmbLoc loc = kmb_locate(kf(u), P.addr);
+        hh[u] = loc.sector;
         const bool valid = (vbits >> u) & 1u;
         if (FILT) {
-            need[u] = valid ? kmb_filter_mask((uint32_t)h, q, P.filter_cfg) : 0u;
-            fw[u] = (valid && !(P.policies & 0x400u)) ? kmb_ldg_u32_hint(P.filter + kmb_filter_word(hh[u], P.filter_cfg), pol.filter) : 0u;
+            need[u] = valid ? loc.fmask : 0u;
+            fw[u] = (valid && !(P.policies & 0x400u)) ? kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter) : 0u;
         } else {
             need[u] = valid ? 1u : 0u;
             fw[u] = 1u;
@@ -477,6 +520,7 @@ __device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol 
     kmb_stage_flush(P, st, lane, true);
     for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
     if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
+    if (lane == 0 && pp.issued) atomicAdd(&status->n_candidates, (unsigned long long)pp.issued);
 }
 
 struct KmbWindowFn {  // forward window b0+u of the 64 bases in hi:lo
@@ -503,7 +547,7 @@ struct KmbArrayFn {
 //   2. each thread owns 32 consecutive positions: two 64-bit shared loads give it every window
 //      (window i = bits [2i, 2i+2k) -- the reference's first-base-lowest hash, util.py:71-75);
 //      one 32-bit word of the read-boundary mask says which of its 32 starts are real windows;
-//   3. in batches of U positions: exact kmer % modulo (Barrett), then the probe levels above.
+//   3. in batches of U positions: kmb_locate (sector + filter bits of the k-mer), then the probe levels above.
 // base0 = flat offset of bases[0] inside the caller's buffer (chunked host input), only used to
 // report the position of an invalid byte.
 // ================================================================================================
@@ -538,7 +582,7 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
 }
 
 template <int U, bool FILT, bool REVCOMP>
-__global__ void __launch_bounds__(KMB_TILE_THREADS)
+__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
                      const uint32_t *__restrict__ mask, int k, bool n_to_a, KmbProbe P, KmbStatus *status) {
     // Everything is per warp (tile of 1024 window starts, packed stream, candidate stack): no CTA barrier,
@@ -547,15 +591,16 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     __shared__ uint32_t s_stage[KMB_TILE_THREADS / 32][KMB_LOG_BINS * KMB_STAGE_SLOTS];
-    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
+    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][2 * KMB_LOG_BINS];
+    __shared__ unsigned long long s_stage_res[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t *pack = s_pack[warp];
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
-    const KmbStage st = {s_stage_cnt[warp], s_stage[warp]};
-    if (lane < KMB_LOG_BINS) st.cnt[lane] = 0;
+    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS};
+    kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
     KmbPipe pp;
@@ -612,19 +657,20 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 // Coalesced 8-byte loads, U filter loads in flight per thread, same probe.
 // ================================================================================================
 template <int U, bool FILT, bool REVCOMP>
-__global__ void __launch_bounds__(KMB_TILE_THREADS)
+__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
     __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
     __shared__ uint32_t s_stage[KMB_TILE_THREADS / 32][KMB_LOG_BINS * KMB_STAGE_SLOTS];
-    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
+    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][2 * KMB_LOG_BINS];
+    __shared__ unsigned long long s_stage_res[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
-    const KmbStage st = {s_stage_cnt[warp], s_stage[warp]};
-    if (lane < KMB_LOG_BINS) st.cnt[lane] = 0;
+    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS};
+    kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
     KmbPipe pp;
@@ -662,14 +708,12 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
 // ------------------------------------------------------------------------------------------------
 template <class F>
 __device__ __forceinline__ void kmb_walk_one(const KmbProbe &P, const KmbPol &pol, uint64_t km, F on_match) {
-    uint64_t q, h;
-    kmb_divmod(km, P.mod, q, h);
+    const KmbLoc loc = kmb_locate(km, P.addr);
     if (P.filter != nullptr) {
-        uint32_t need = kmb_filter_mask((uint32_t)h, q, P.filter_cfg);
-        uint32_t w = kmb_ldg_u32_hint(P.filter + kmb_filter_word((uint32_t)h, P.filter_cfg), pol.filter);
-        if ((w & need) != need) return;
+        uint32_t w = kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter);
+        if ((w & loc.fmask) != loc.fmask) return;
     }
-    kmb_probe_line(P, pol, km, (uint32_t)h, on_match);
+    kmb_probe_line(P, pol, km, loc.sector, on_match);
 }
 
 template <bool REVCOMP>
@@ -706,8 +750,10 @@ __global__ void kmb_log_apply_kernel(KmbLog log, int bin, uint32_t *__restrict__
     if (first_overflow < n) n = first_overflow;
     if (n > log.cap) n = log.cap;
     const uint32_t *__restrict__ e = log.entries + (uint64_t)bin * log.cap;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(counts + e[i], 1u);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = e[i];
+        if (id != KMB_LOG_HOLE) atomicAdd(counts + id, 1u);
+    }
 }
 __global__ void kmb_log_reset_kernel(KmbLog log) {
     if (threadIdx.x < KMB_LOG_BINS) {

@@ -83,10 +83,9 @@ class DeviceIndex:
         fb = C.c_uint64()
         check(lib().kmb_index_filter_bytes(h, C.byref(fb)))
         self.filter_bytes = fb.value
-        bpl, nm, no, nl = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64()
-        check(lib().kmb_index_layout(h, C.byref(bpl), C.byref(nm), C.byref(no), C.byref(nl)))
-        self.buckets_per_line, self.n_main_lines, self.n_overflow_lines, self.n_live_entries = (
-            bpl.value, nm.value, no.value, nl.value)
+        nm, no, nl = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().kmb_index_layout(h, C.byref(nm), C.byref(no), C.byref(nl)))
+        self.n_main_lines, self.n_overflow_lines, self.n_live_entries = nm.value, no.value, nl.value
 
     @classmethod
     def from_index(cls, index, device=None) -> "DeviceIndex":
@@ -211,6 +210,12 @@ class Mapper:
         a, b = C.c_uint64(), C.c_uint64()
         check(lib().kmb_mapper_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def candidates(self) -> int:
+        """Look-ups that passed the filter and fetched an index sector since the last reset."""
+        v = C.c_uint64()
+        check(lib().kmb_mapper_candidates(self._h, C.byref(v)))
+        return v.value
 
     def kernel_time(self):
         """(total ms, n kernels) of the mapping kernels since the last call (option time_kernels=1)."""

@@ -19,8 +19,16 @@ uint64_t h_revcomp(uint64_t x, int k) { return kmb_revcomp(x, k); }
 uint64_t h_chain_line(uint64_t main_line, uint32_t ovf_base, uint32_t s) { return kmb_chain_line(main_line, ovf_base, s); }
 uint32_t h_chain_slot(uint32_t s) { return kmb_chain_slot(s); }
 uint32_t h_chain_extra_lines(uint32_t n) { return kmb_chain_extra_lines(n); }
-uint32_t h_filter_mask(uint32_t h, uint64_t q, uint32_t cfg) { return kmb_filter_mask(h, q, cfg); }
-uint32_t h_filter_word(uint32_t h, uint32_t cfg) { return kmb_filter_word(h, cfg); }
+void h_locate(uint64_t key, uint32_t n_main, uint32_t n_words, uint32_t two, uint32_t *out) {
+    KmbAddr a;
+    a.n_main = n_main;
+    a.n_filter_words = n_words;
+    a.two_probes = two;
+    KmbLoc l = kmb_locate(key, a);
+    out[0] = l.sector;
+    out[1] = l.fword;
+    out[2] = l.fmask;
+}
 uint32_t h_sector_header(uint32_t remaining, uint32_t next) { return kmb_sector_header(remaining, next); }
 uint32_t h_header_count(uint32_t hdr) { return kmb_header_count(hdr); }
 uint32_t h_log_bin(uint32_t node, uint32_t shift) { return kmb_log_bin(node, shift); }

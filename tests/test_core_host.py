@@ -27,13 +27,10 @@ def core():
     lib.h_chain_line.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
     lib.h_chain_slot.restype = C.c_uint32
     lib.h_chain_extra_lines.restype = C.c_uint32
-    lib.h_filter_mask.restype = C.c_uint32
-    lib.h_filter_mask.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
-    lib.h_filter_word.restype = C.c_uint32
+    lib.h_locate.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.h_sector_header.restype = C.c_uint32
     lib.h_header_count.restype = C.c_uint32
     lib.h_log_bin.restype = C.c_uint32
-    lib.h_filter_word.argtypes = [C.c_uint32, C.c_uint32]
     lib.h_encode16.restype = C.c_uint32
     return lib
 
@@ -121,7 +118,7 @@ def test_revcomp(core):
             assert core.h_revcomp(want, k) == x
 
 
-def test_sector_chain_geometry_and_filter_mask(core):
+def test_sector_chain_geometry_headers_bins_and_addressing(core):
     # two slots per 32-byte sector; entry s of a chain lives in the main sector (s < 2) or in overflow sector
     # ovf_base + (s-2)//2; every (sector, slot) pair is used exactly once
     for n_total in (0, 1, 2, 3, 4, 5, 17, 1234):
@@ -142,15 +139,20 @@ def test_sector_chain_geometry_and_filter_mask(core):
         assert (hdr == (0x80000000 | 12345)) == (remaining > 2)
     # log bins: node ranges of 2^shift, the last bin takes the rest
     assert [core.h_log_bin(n, 4) for n in (0, 15, 16, 127, 128, 4000)] == [0, 0, 1, 7, 7, 7]
+    # addressing: sector / filter word stay in range for any table size, the mask has one or two bits, and
+    # k-mer-like keys spread evenly (multiply-shift hashing)
     rng = np.random.default_rng(6)
-    for _ in range(2000):
-        h = int(rng.integers(0, 2 ** 32))
-        q = int(rng.integers(0, 2 ** 40))
-        m = core.h_filter_mask(h, q, 0x100)
-        assert m & (1 << (h & 31))
-        assert bin(m).count("1") in (1, 2)
-        assert m == core.h_filter_mask((h + 32 * 5) & 0xFFFFFFFF, q, 0x100)        # depends on h only through h & 31
-        fs = int(rng.integers(0, 6))
-        m1 = core.h_filter_mask(h, q, fs)                        # one probe, 2^fs buckets per bit
-        assert m1 == 1 << ((h >> fs) & 31) and core.h_filter_word(h, fs) == (h >> fs) >> 5
-        assert core.h_filter_mask(h, q, fs | 0x100) & m1
+    out = (C.c_uint32 * 3)()
+    for n_main, n_words in ((1, 1), (7, 3), (1000, 77), (250_000_000, 16_000_000), (2 ** 31 - 1, 2 ** 24)):
+        for key in [0, 1, 2 ** 62 - 1, 2 ** 64 - 1] + [int(x) for x in rng.integers(0, 2 ** 62, size=300, dtype=np.uint64)]:
+            core.h_locate(key, n_main, n_words, 1, out)
+            assert out[0] < n_main and out[1] < n_words and bin(out[2]).count("1") in (1, 2)
+            core.h_locate(key, n_main, n_words, 0, out)
+            assert bin(out[2]).count("1") == 1
+    keys = rng.integers(0, 4 ** 31, size=20_000, dtype=np.uint64)
+    sec = np.zeros(20_000, np.int64)
+    for i, k in enumerate(keys):
+        core.h_locate(int(k), 1000, 64, 1, out)
+        sec[i] = out[0]
+    counts = np.bincount(sec, minlength=1000)
+    assert counts.max() < 60 and counts.min() > 2        # mean 20 per sector

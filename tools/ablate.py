@@ -20,7 +20,7 @@ n_counts = tindex.max_node_id() + 1
 _lib.set_option("time_kernels", 1)
 names = {0: "full", 1: "no RED", 8: "no key loads (and no RED)", 2: "no line loads", 4: "no filter loads (no candidates)",
          6: "compute only"}
-for u in (4, 2):
+for u in (2, 4):
     _lib.set_option("gathers_in_flight", u)
     for ab in (0, 1, 2, 4):
         _lib.set_option("ablate", ab)

@@ -32,8 +32,9 @@ def main():
     grids = {
         "default": dict(use_filter=[1, 0], gathers_in_flight=[4, 8, 16], map_reads_blocks_per_sm=[0]),
         "occupancy": dict(use_filter=[1], gathers_in_flight=[4, 8, 16], map_reads_blocks_per_sm=[1, 2, 3, 4, 5, 6]),
-        "v21": dict(use_filter=[1], gathers_in_flight=[2, 4], map_reads_blocks_per_sm=[0, 3]),
-        "filter": dict(gathers_in_flight=[4], filter_shift=[-1, 0, 1, 2], use_filter=[1]),
+        "v21": dict(use_filter=[1], gathers_in_flight=[2, 4], map_reads_blocks_per_sm=[0, 2]),
+        "filter": dict(gathers_in_flight=[2], filter_l2_budget_bytes=[40 << 20, 48 << 20, 52 << 20, 56 << 20, 60 << 20], use_filter=[1]),
+        "size": dict(gathers_in_flight=[2], filter_l2_budget_bytes=[54 << 20, 57 << 20], sectors_per_100_entries=[200, 226, 250, 300], use_filter=[1]),
         "persist": dict(use_filter=[1], gathers_in_flight=[8], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
     }[a.grid]
     names = list(grids)
@@ -43,13 +44,13 @@ def main():
         opts = dict(zip(names, combo))
         for n, v in opts.items():
             _lib.set_option(n, v)
-        if di is None or opts.get("use_filter") != last_filter:
+        if di is None or (opts.get("use_filter"), opts.get("filter_l2_budget_bytes"), opts.get("sectors_per_100_entries")) != last_filter:
             if hasattr(tindex, "_kmb_device_index"):
                 del tindex._kmb_device_index
             di = None
             torch.cuda.empty_cache()
             di = DeviceIndex.from_index(tindex, device=0)
-            last_filter = opts.get("use_filter")
+            last_filter = (opts.get("use_filter"), opts.get("filter_l2_budget_bytes"), opts.get("sectors_per_100_entries"))
         _lib.set_option("time_kernels", 1)
         m = Mapper(di, n_counts)
         for _ in range(2):
@@ -67,12 +68,13 @@ def main():
         step_ms = (time.perf_counter() - t0) * 1e3 / a.steps
         ms, n = m.kernel_time()
         nk, nc = m.stats()
+        ncand = m.candidates()
         c = m.counts()
         if ref_counts is None:
             ref_counts = c
         same = bool((c == ref_counts).all())
         m.close()
-        print(json.dumps(dict(opts=opts, kernel_ms=ms / n, kernel_GKps=nk / (ms / n) / 1e6, step_ms=step_ms, step_GKps=nk / step_ms / 1e6,
+        print(json.dumps(dict(opts=opts, cand_per_kmer=round(ncand / max(nk, 1), 4), hits_per_kmer=round(nc / max(nk, 1), 4), kernel_ms=ms / n, kernel_GKps=nk / (ms / n) / 1e6, step_ms=step_ms, step_GKps=nk / step_ms / 1e6,
                               filter_bytes=di.filter_bytes, overflow_lines=di.n_overflow_lines,
                               counts_equal_first=same)), flush=True)
 
