@@ -100,8 +100,8 @@ int kmb_mapper_map_kmers(kmb_mapper *mapper, const uint64_t *kmers, uint64_t n, 
 int kmb_mapper_map_reads(kmb_mapper *mapper, const uint8_t *bases, uint64_t n_bases,
                          const int64_t *offsets, uint64_t n_reads, int k, uint32_t flags);
 
-/* Hits (node ids that passed the frequency cut-off, mapper.pyx:64) are first appended to device-side
- * logs binned by node range; the flush plays the logs into the node counts (mapper.pyx:68) one
+/* Hits (node ids that passed the frequency cut-off, mapper.pyx:64) are first appended to a device-side
+ * log in groups tagged by node range; the flush plays the log into the node counts (mapper.pyx:68) one
  * L2-sized window at a time.  kmb_mapper_flush queues that pass on the mapper's stream without waiting
  * (use it before handing the count buffer to an all-reduce on the same stream); sync, read_counts,
  * stats and lookup_counts flush implicitly. */
@@ -180,7 +180,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
 
 /* Tuning knobs (process-wide, read at launch / index-creation time): name in
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
- *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries_per_bin",
+ *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes"}. */
 int kmb_set_option(const char *name, int64_t value);

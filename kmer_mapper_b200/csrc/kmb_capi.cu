@@ -56,7 +56,7 @@ struct KmbOptions {
     int64_t probe_variant = 1;            // map_kmers: 0 = one query per thread, 1 = staged probe with warp stack
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
     int64_t gathers_in_flight = 4;        // U: 2 or 4 independent filter loads per thread
-    int64_t log_max_entries_per_bin = 256ll << 20;  // upper bound of one hit log (x 8 bins x 4 bytes)
+    int64_t log_max_entries = 2048ll << 20;  // upper bound of the hit log (x 4 bytes)
     int64_t sectors_per_100_entries = 250; // main sectors per 100 index entries (mean occupancy 0.4 of 2 slots)
     int64_t use_filter = -1;              // -1 auto (filter fits the L2 budget), 0 off, 1 on
     int64_t filter_l2_budget_bytes = 60ll << 20;  // the L2 keeps ~72 MB of randomly accessed data (profiles/README.md)
@@ -83,7 +83,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
     OPT(gathers_in_flight)
-    OPT(log_max_entries_per_bin)
+    OPT(log_max_entries)
     OPT(use_filter)
     OPT(sectors_per_100_entries)
     OPT(filter_l2_budget_bytes)
@@ -115,7 +115,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
     OPT(gathers_in_flight)
-    OPT(log_max_entries_per_bin)
+    OPT(log_max_entries)
     OPT(use_filter)
     OPT(sectors_per_100_entries)
     OPT(filter_l2_budget_bytes)
@@ -442,7 +442,8 @@ struct kmb_mapper {
     uint64_t n_counts = 0;
     uint32_t *counts = nullptr;
     bool own_counts = false;
-    KmbLog log = {nullptr, nullptr, 0, 0, 1};  // hit logs (grown on demand) + their cursors
+    KmbLog log = {nullptr, nullptr, nullptr, 0, 0, 1};  // hit log (grown on demand), its group tags and cursor
+    int log_bins = 1;              // node ranges in use: ((n_counts - 1) >> bin_shift) + 1
     bool dirty = false;            // the logs may hold hits that are not yet in the node counts
     uint64_t queries_since_flush = 0;
     int32_t max_freq = 1000;
@@ -479,6 +480,7 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
     }
     cudaFree(m->dmask);
     cudaFree(m->log.entries);
+    cudaFree(m->log.tags);
     cudaFree(m->log.cursor);
     if (m->own_counts) cudaFree(m->counts);
     cudaFree(m->d_status);
@@ -501,51 +503,65 @@ static int status_reset(kmb_mapper *m) {
     return KMB_OK;
 }
 
-// Play the hit logs into the node counts (asynchronous on the mapper's stream) and empty them.
+static int launch_log_reset(kmb_mapper *m) {
+    if (!m->log.entries) return KMB_OK;
+    kmb_log_reset_kernel<<<m->index->info.sms * 4, 256, 0, m->stream>>>(m->log);
+    kmb_log_rewind_kernel<<<1, 1, 0, m->stream>>>(m->log);
+    g_launches += 2;
+    KMB_CUDA(cudaGetLastError());
+    return KMB_OK;
+}
+
+// Play the hit log into the node counts (asynchronous on the mapper's stream), one node range after the
+// other, and empty it.
 static int launch_flush(kmb_mapper *m) {
     const kmb_index *ix = m->index;
     if (m->log.entries) {
-        for (int b = 0; b < KMB_LOG_BINS; b++) {
-            kmb_log_apply_kernel<<<ix->info.sms * 8, 256, 0, m->stream>>>(m->log, b, m->counts);
+        for (int b = 0; b < m->log_bins; b++) {
+            kmb_log_apply_kernel<<<ix->info.sms * 4, 256, 0, m->stream>>>(m->log, b, m->counts);
             g_launches++;
         }
-        kmb_log_reset_kernel<<<1, 32, 0, m->stream>>>(m->log);
-        g_launches++;
         KMB_CUDA(cudaGetLastError());
+        KMB_TRY(launch_log_reset(m));
     }
     m->dirty = false;
     m->queries_since_flush = 0;
     return KMB_OK;
 }
 
-// Size the logs for a launch of n_queries look-ups: capacity for one hit per four queries in total
-// (twice the hit rate of the benchmark shapes), between 2^20 and log_max_entries_per_bin per bin.  A log
-// that runs full is not an error: the kernels then reduce directly onto the counts.
+// Size the log for a launch of n_queries look-ups: room for one hit per four queries (twice the hit rate of
+// the benchmark shapes), between 2^23 and log_max_entries ids.  A log that runs full is not an error: the
+// kernels then reduce directly onto the counts.
 static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
-    uint64_t want = std::max<uint64_t>(n_queries / 4 / KMB_LOG_BINS, 1ull << 20);
-    want = std::min<uint64_t>(want, (uint64_t)std::max<int64_t>(g_opt.log_max_entries_per_bin, 1 << 10));
+    uint64_t want = std::max<uint64_t>(n_queries / 4, 1ull << 23);
+    want = std::min<uint64_t>(want, (uint64_t)std::max<int64_t>(g_opt.log_max_entries, 1 << 10));
+    want = (want + 31) & ~31ull;
     if (!m->log.cursor) {
-        KMB_CUDA(cudaMalloc(&m->log.cursor, 2 * KMB_LOG_BINS * sizeof(unsigned long long)));
+        KMB_CUDA(cudaMalloc(&m->log.cursor, sizeof(unsigned long long)));
+        KMB_CUDA(cudaMemsetAsync(m->log.cursor, 0, sizeof(unsigned long long), m->stream));
         uint32_t shift = 0;
         while (((m->n_counts ? m->n_counts - 1 : 0) >> shift) >= KMB_LOG_BINS) shift++;
         m->log.bin_shift = shift;
+        m->log_bins = (int)(((m->n_counts ? m->n_counts - 1 : 0) >> shift) + 1);
     }
     if (want > m->log.cap) {
         if (m->dirty) KMB_TRY(launch_flush(m));
         KMB_CUDA(cudaStreamSynchronize(m->stream));
         cudaFree(m->log.entries);
+        cudaFree(m->log.tags);
         m->log.entries = nullptr;
+        m->log.tags = nullptr;
         m->log.cap = 0;
-        KMB_CUDA(cudaMalloc(&m->log.entries, (size_t)want * KMB_LOG_BINS * sizeof(uint32_t)));
+        KMB_CUDA(cudaMalloc(&m->log.entries, (size_t)want * sizeof(uint32_t)));
+        KMB_CUDA(cudaMalloc(&m->log.tags, (size_t)(want / 32)));
+        KMB_CUDA(cudaMemsetAsync(m->log.tags, KMB_LOG_NO_BIN, (size_t)(want / 32), m->stream));
+        KMB_CUDA(cudaMemsetAsync(m->log.cursor, 0, sizeof(unsigned long long), m->stream));
         m->log.cap = want;
-        kmb_log_reset_kernel<<<1, 32, 0, m->stream>>>(m->log);
-        g_launches++;
-        KMB_CUDA(cudaGetLastError());
-    } else if (m->dirty && m->queries_since_flush + n_queries > 4 * KMB_LOG_BINS * m->log.cap) {
-        KMB_TRY(launch_flush(m));  // make room before the logs overflow into direct reductions
+    } else if (m->dirty && m->queries_since_flush + n_queries > 4 * m->log.cap) {
+        KMB_TRY(launch_flush(m));  // make room before the log overflows into direct reductions
     }
     // big launches reserve log space eight 128-byte groups at a time (one atomic per 256 hits); small ones group by
-    // group, so that the unused tail of a reservation does not outweigh the hits
+    // group, so that the unused tail of the reservations stays small next to the hits
     m->log.chunk_groups = n_queries >= (256ull << 20) ? 8u : 1u;
     m->queries_since_flush += n_queries;
     return KMB_OK;
@@ -924,10 +940,7 @@ extern "C" int kmb_mapper_read_counts(kmb_mapper *m, uint32_t *out, uint64_t n_c
 extern "C" int kmb_mapper_reset(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_reset: null mapper");
     KMB_ON_DEVICE(m->index->device);
-    if (m->log.entries) {
-        kmb_log_reset_kernel<<<1, 32, 0, m->stream>>>(m->log);
-        g_launches++;
-    }
+    KMB_TRY(launch_log_reset(m));
     m->dirty = false;
     m->queries_since_flush = 0;
     KMB_CUDA(cudaMemsetAsync(m->counts, 0, m->n_counts * 4, m->stream));

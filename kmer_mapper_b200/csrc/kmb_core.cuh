@@ -97,8 +97,9 @@ KMB_HD uint32_t kmb_sector_header(uint32_t remaining, uint32_t next_sector) {
 }
 KMB_HD uint32_t kmb_header_count(uint32_t hdr) { return (hdr & KMB_HDR_CHAIN) ? (uint32_t)KMB_LINE_SLOTS : hdr; }
 
-// Hit log: node ids are appended to one of KMB_LOG_BINS logs by node range, so that applying a
-// log touches a window of the count array small enough to stay in L2.
+// Hit log: node ids are appended in groups of 32, each group tagged with one of KMB_LOG_BINS node
+// ranges, so that applying the groups of one range touches a window of the count array small
+// enough to stay in L2.
 #define KMB_LOG_BINS 8
 KMB_HD uint32_t kmb_log_bin(uint32_t node, uint32_t bin_shift) {
     uint32_t b = node >> bin_shift;
@@ -132,8 +133,13 @@ KMB_HD KmbLoc kmb_locate(uint64_t key, const KmbAddr a) {
     // word and the false-pass rate of the 57 MB filter was 19.7 % instead of 12.6 %).
     const uint32_t g = lo * 0xC2B2AE35u + hi;
     KmbLoc l;
+#if defined(__CUDA_ARCH__)
+    l.sector = __umulhi(hi, a.n_main);
+    l.fword = __umulhi(f, a.n_filter_words);
+#else
     l.sector = (uint32_t)(((uint64_t)hi * a.n_main) >> 32);
     l.fword = (uint32_t)(((uint64_t)f * a.n_filter_words) >> 32);
+#endif
     l.fmask = (1u << (g >> 27)) | (a.two_probes ? (1u << ((g >> 22) & 31u)) : 0u);
     return l;
 }

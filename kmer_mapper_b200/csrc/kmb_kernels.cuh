@@ -4,7 +4,8 @@
 //   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
 //   K1-4 kmb_map_reads_kernel     fused encode + window + filter + sector probe + hit log  (production path)
 //   K3-4 kmb_map_kmers_kernel     probe + hit log on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
-//   K4b kmb_log_apply_kernel      hit log -> per-node counts, one L2-sized window of nodes at a time
+//   K4b kmb_log_apply_kernel      hit log -> per-node counts, one L2-sized window of nodes at a time, hot nodes
+//                                 aggregated in shared memory first
 //   K6  kmb_in_graph_kernel       membership mask (mapper.pyx:81)
 //   K2  kmb_hash_count/_scan/_emit  flat hash array (util.py:71-75 drop-in)
 //   E1  kmb_codec_* kernels       legacy 2-bit codec (encodings.py)
@@ -45,12 +46,13 @@ struct KmbStatus {
     int max_node;
 };
 
-struct KmbLog {  // hit logs of one mapper: KMB_LOG_BINS arrays of `cap` node ids
+struct KmbLog {  // hit log of one mapper: `cap` node ids in groups of 32, one node-range tag per group
     uint32_t *entries;
-    unsigned long long *cursor;  // [0, BINS): entries reserved so far; [BINS, 2 BINS): first reservation that did not fit
-    uint64_t cap;
+    uint8_t *tags;               // [cap / 32] bin of the group, KMB_LOG_NO_BIN = reserved but never written
+    unsigned long long *cursor;  // [0] ids reserved so far (may run past cap: those went straight onto the counts)
+    uint64_t cap;                // multiple of 32
     uint32_t bin_shift;          // bin = node >> bin_shift
-    uint32_t chunk_groups;       // 32-id groups reserved per atomic (unused ones are filled with KMB_LOG_HOLE)
+    uint32_t chunk_groups;       // groups reserved per atomic
 };
 
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
@@ -269,10 +271,10 @@ __global__ void kmb_mark_read_ends(const int64_t *__restrict__ offsets, uint64_t
 //   whose frequency passes the cut-off (:64) yields its node id at once.
 // Level 2: the hit.  `node_counts[node] += 1` (:68) on a 320 MB array would be a DRAM read plus a
 //   write-back per hit; instead the node id goes to a per-warp staging area in shared memory, binned
-//   by node range, and leaves in full 128-byte lines to one of KMB_LOG_BINS logs.  kmb_log_apply_kernel
-//   later plays each log into its window of node counts, which is small enough to stay in L2.  uint32
-//   addition wraps, so any order gives the reference's bits.  A full log falls back to the direct
-//   reduction, as do the (rare) hits found in overflow chains.
+//   by node range, and leaves in full 128-byte groups, each tagged with its range.  kmb_log_apply_kernel
+//   later plays the groups of one range at a time into their window of node counts, which is small
+//   enough to stay in L2.  uint32 addition wraps, so any order gives the reference's bits.  A full
+//   log falls back to the direct reduction, as do the (rare) hits found in overflow chains.
 // ================================================================================================
 struct KmbPol {
     uint64_t first;   // L2 evict-first: the read stream (use once)
@@ -327,44 +329,54 @@ __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &
 // ------------------------------------------------------------------------------------------------
 #define KMB_STAGE_SLOTS 96
 #define KMB_LOG_HOLE 0xFFFFFFFFu
+#define KMB_LOG_NO_BIN 0xFFu
+#define KMB_RES_FULL 0xFFFFFFFFu
 struct KmbStage {
     uint32_t *cnt;                 // [KMB_LOG_BINS] ids staged per bin
     uint32_t *buf;                 // [KMB_LOG_BINS][KMB_STAGE_SLOTS]
-    unsigned long long *res_base;  // [KMB_LOG_BINS] next free position of this warp's reservation in the bin's log
-    uint32_t *res_left;            // [KMB_LOG_BINS] groups left in that reservation
+    unsigned long long *res_base;  // [KMB_LOG_BINS] next free position of this warp's reservation for the bin
+    uint32_t *res_left;            // [KMB_LOG_BINS] groups left in that reservation, or KMB_RES_FULL
 };
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
     const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
     const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
     st.buf[b * KMB_STAGE_SLOTS + pos] = node;
 }
-// One group of 32 ids (lanes >= n write holes) to the log of bin b -- or, if the log is full, straight onto
-// the counts.  Log space is reserved chunk_groups groups at a time, so the atomic (and the wait for its
-// result) is paid once per chunk.
+// One group of 32 ids of bin b (lanes >= n write holes) to the log -- or, if the log is full, straight onto
+// the counts.  All bins share one pool: space is reserved chunk_groups groups at a time from a single cursor
+// (one atomic, and one wait for its result, per chunk), and a group is tagged with its bin when it is written,
+// so a skewed node distribution cannot overflow "its" log while the others stay empty.
 __device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage &st, uint32_t b, const uint32_t *src,
                                               uint32_t n, int lane) {
-    unsigned long long base = 0;
+    unsigned long long base = ~0ull;
     if (lane == 0) {
         uint32_t left = st.res_left[b];
-        base = st.res_base[b];
-        if (left == 0) {
-            left = P.log.chunk_groups;
-            base = atomicAdd(&P.log.cursor[b], 32ull * left);
+        if (left != KMB_RES_FULL) {
+            base = st.res_base[b];
+            if (left == 0) {
+                left = P.log.chunk_groups;
+                base = atomicAdd(&P.log.cursor[0], 32ull * left);
+            }
+            if (base + 32 <= P.log.cap) {
+                st.res_left[b] = left - 1;
+                st.res_base[b] = base + 32;
+                P.log.tags[base >> 5] = (uint8_t)b;
+            } else {
+                st.res_left[b] = KMB_RES_FULL;  // stop reserving: every further atomic would hit the same address
+                base = ~0ull;
+            }
         }
-        st.res_left[b] = left - 1;
-        st.res_base[b] = base + 32;
     }
     base = __shfl_sync(KMB_FULL_MASK, base, 0);
     const uint32_t id = (uint32_t)lane < n ? src[lane] : KMB_LOG_HOLE;
-    if (base + 32 <= P.log.cap) {
-        P.log.entries[(uint64_t)b * P.log.cap + base + lane] = id;
-    } else {
-        if (lane == 0) atomicMin(&P.log.cursor[KMB_LOG_BINS + b], base);
-        if (id != KMB_LOG_HOLE) atomicAdd(P.counts + id, 1u);
+    if (base != ~0ull) {
+        P.log.entries[base + lane] = id;
+    } else if (id != KMB_LOG_HOLE) {
+        atomicAdd(P.counts + id, 1u);
     }
 }
-// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything, and
-// fill what is left of the reservations with holes.
+// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything.
+// Groups that were reserved but never written keep the tag KMB_LOG_NO_BIN and are skipped by the apply pass.
 __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
     __syncwarp();
     const uint32_t c = lane < KMB_LOG_BINS ? st.cnt[lane] : 0u;
@@ -380,13 +392,6 @@ __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStag
         }
         if (lane == 0) st.cnt[b] = cb;
         __syncwarp();
-    }
-    if (all) {
-        for (uint32_t b = 0; b < KMB_LOG_BINS; b++) {
-            __syncwarp();
-            const uint32_t left = st.res_left[b];
-            for (uint32_t g = 0; g < left; g++) kmb_log_write(P, st, b, st.buf, 0u, lane);
-        }
     }
     __syncwarp();
 }
@@ -740,27 +745,79 @@ __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, 
 }
 
 // ================================================================================================
-// K4b: play one hit log into the node counts (mapper.pyx:68).  The ids of bin b all fall into one
-// window of 2^bin_shift nodes, launched bin after bin so that the window being reduced into stays in
-// L2; the log itself is a coalesced stream.
+// K4b: play the logged hits of one node range into the node counts (mapper.pyx:68).  The groups of
+// range `bin` all fall into one window of 2^bin_shift nodes, and the ranges are launched one after
+// another, so the window being reduced into stays in L2; the log itself is a coalesced stream.
+//
+// Count accumulation with aggregated atomics: when a few nodes are very hot (config 4: Zipf), their
+// reductions serialise on one L2 atomic unit.  Every CTA therefore walks a contiguous slab of the log
+// and first tries to count an id in a small shared-memory table (first id to claim a slot keeps it;
+// later ids that collide go straight to global memory); the table is flushed with ONE reduction per
+// id at the end.  A warp that finds less than 1 in 16 of its first 256 ids already present switches
+// the table off, so uniformly distributed nodes (config 2) pay almost nothing for it.
 // ================================================================================================
-__global__ void kmb_log_apply_kernel(KmbLog log, int bin, uint32_t *__restrict__ counts) {
-    unsigned long long n = log.cursor[bin];
-    const unsigned long long first_overflow = log.cursor[KMB_LOG_BINS + bin];
-    if (first_overflow < n) n = first_overflow;
+#define KMB_APPLY_TABLE 2048
+__global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin, uint32_t *__restrict__ counts) {
+    __shared__ uint32_t s_id[KMB_APPLY_TABLE];
+    __shared__ uint32_t s_cnt[KMB_APPLY_TABLE];
+    for (int i = threadIdx.x; i < KMB_APPLY_TABLE; i += blockDim.x) {
+        s_id[i] = KMB_LOG_HOLE;
+        s_cnt[i] = 0;
+    }
+    __syncthreads();
+    unsigned long long n = log.cursor[0];
     if (n > log.cap) n = log.cap;
-    const uint32_t *__restrict__ e = log.entries + (uint64_t)bin * log.cap;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = e[i];
-        if (id != KMB_LOG_HOLE) atomicAdd(counts + id, 1u);
+    const uint64_t n_groups = n >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    // slab of this CTA: a multiple of 32 groups, so that a warp reads 32 tags with one coalesced load
+    const uint64_t per_cta = (((n_groups + gridDim.x - 1) / gridDim.x) + 31) & ~31ull;
+    const uint64_t g_lo = (uint64_t)blockIdx.x * per_cta;
+    const uint64_t g_hi = min(g_lo + per_cta, n_groups);
+    bool use_table = true, decided = false;
+    uint32_t seen = 0, present = 0;
+    for (uint64_t g0 = g_lo + (uint64_t)warp * 32; g0 < g_hi; g0 += (uint64_t)warps * 32) {
+        const uint64_t g = g0 + lane;
+        unsigned mine = __ballot_sync(KMB_FULL_MASK, g < g_hi && log.tags[g] == (uint8_t)bin);
+        while (mine) {
+            const int j = __ffs(mine) - 1;
+            mine &= mine - 1u;
+            const uint32_t id = log.entries[((g0 + j) << 5) + lane];
+            if (id != KMB_LOG_HOLE) {
+                if (use_table) {
+                    const uint32_t s = (id * 0x9E3779B1u) >> 21;  // 11 bits
+                    const uint32_t old = atomicCAS(&s_id[s], KMB_LOG_HOLE, id);
+                    if (old == KMB_LOG_HOLE || old == id) atomicAdd(&s_cnt[s], 1u);
+                    else atomicAdd(counts + id, 1u);
+                    present += old == id ? 1u : 0u;
+                    seen++;
+                } else {
+                    atomicAdd(counts + id, 1u);
+                }
+            }
+            if (use_table && !decided && __any_sync(KMB_FULL_MASK, seen >= 8u)) {  // ~256 ids per warp looked at: decide once
+                uint32_t p = present, t = seen;
+                for (int o = 16; o > 0; o >>= 1) {
+                    p += __shfl_xor_sync(KMB_FULL_MASK, p, o);
+                    t += __shfl_xor_sync(KMB_FULL_MASK, t, o);
+                }
+                if (p * 16u < t) use_table = false;
+                decided = true;
+            }
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KMB_APPLY_TABLE; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(counts + s_id[i], s_cnt[i]);
 }
+// Empty the log: untag the groups that were used, rewind the cursor.
 __global__ void kmb_log_reset_kernel(KmbLog log) {
-    if (threadIdx.x < KMB_LOG_BINS) {
-        log.cursor[threadIdx.x] = 0ull;
-        log.cursor[KMB_LOG_BINS + threadIdx.x] = ~0ull;
-    }
+    unsigned long long n = log.cursor[0];
+    if (n > log.cap) n = log.cap;
+    const uint64_t n_groups = (n + 31) >> 5;
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_groups; g += (uint64_t)gridDim.x * blockDim.x)
+        log.tags[g] = KMB_LOG_NO_BIN;
 }
+__global__ void kmb_log_rewind_kernel(KmbLog log) { log.cursor[0] = 0ull; }
 
 // ================================================================================================
 // K6 membership (mapper.pyx:81-130): any key match, frequency ignored.

@@ -19,7 +19,7 @@ def kmb():
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_l2_budget_bytes", 60 << 20),
-                    ("log_max_entries_per_bin", 256 << 20), ("chunk_bytes", 64 << 20)):
+                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20)):
         _lib.set_option(name, v)
 
 
@@ -28,7 +28,7 @@ VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=2),
             dict(probe_variant=1, use_filter=0, gathers_in_flight=2),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4, filter_l2_budget_bytes=512),
-            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, log_max_entries_per_bin=1024),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, log_max_entries=4096),
             dict(probe_variant=0, use_filter=1, gathers_in_flight=4),
             dict(probe_variant=0, use_filter=0, gathers_in_flight=4)]
 
@@ -42,7 +42,7 @@ def _fresh(index):
 
 def _set(kmb, variant):
     kmb.set_option("filter_l2_budget_bytes", 60 << 20)
-    kmb.set_option("log_max_entries_per_bin", 256 << 20)
+    kmb.set_option("log_max_entries", 2048 << 20)
     for k, v in variant.items():
         kmb.set_option(k, v)
 
