@@ -346,7 +346,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
 
     const int sms = ix->info.sms;
     // 1. the directory must stay inside the entry arrays (the reference runs with boundscheck off)
-    kmb_v2_check_buckets<<<grid_for(modulo, 256, sms), 256, 0, s>>>(d_h2i, d_nk, modulo, n_entries, d_status.p);
+    kmb_build_check_buckets<<<grid_for(modulo, 256, sms), 256, 0, s>>>(d_h2i, d_nk, modulo, n_entries, d_status.p);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
@@ -358,11 +358,11 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
                         (unsigned long long)n_entries);
     // 2. per-line counts + filter bits, 3. overflow lines needed
     if (n_entries) {
-        kmb_v2_count<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_h2i, d_nk, n_entries, ix->mod,
+        kmb_build_count<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_h2i, d_nk, n_entries, ix->mod,
                                                                  ix->addr, line_fill.p, ix->filter, d_status.p);
         g_launches++;
     }
-    kmb_v2_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, d_status.p);
+    kmb_build_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, d_status.p);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
@@ -373,14 +373,14 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     ix->n_live = hs.n_live_entries;
     ix->n_lines = ix->n_main + hs.pool_lines;
     if (ix->n_lines >= (1ull << 31)) return kmb_fail(KMB_ERR_BAD_INDEX, "index: too many sectors (%llu) for the 31-bit chain links", (unsigned long long)ix->n_lines);
-    // 4. lines + cold arrays, headers, scatter
+    // 4. sectors: headers of every chain, then placement
     KMB_CUDA(cudaMalloc(&ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
     KMB_CUDA(cudaMemsetAsync(ix->lines, 0, (size_t)ix->n_lines * KMB_LINE_BYTES, s));
     KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
-    kmb_v2_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, d_status.p);
+    kmb_build_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, d_status.p);
     g_launches++;
     if (n_entries) {
-        kmb_v2_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
+        kmb_build_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
                                                                    ix->addr, line_fill.p, ix->lines);
         g_launches++;
     }

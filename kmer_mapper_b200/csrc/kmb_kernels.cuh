@@ -1,6 +1,6 @@
 // kmb_kernels.cuh -- hand-written sm_100a kernels of the k-mer mapping path.
 //
-//   K5  kmb_v2_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sectors (once per index)
+//   K5  kmb_build_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sectors (once per index)
 //   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
 //   K1-4 kmb_map_reads_kernel     fused encode + window + filter + sector probe + hit log  (production path)
 //   K3-4 kmb_map_kmers_kernel     probe + hit log on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
@@ -90,11 +90,6 @@ __device__ __forceinline__ uint64_t kmb_policy_evict_normal() {
 __device__ __forceinline__ uint64_t kmb_policy_select(uint32_t which) {
     return which == 1u ? kmb_policy_evict_first() : (which == 2u ? kmb_policy_evict_last() : kmb_policy_evict_normal());
 }
-__device__ __forceinline__ uint64_t kmb_ldg_u64_nc(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ uint4 kmb_ldg_v4_nc(const void *p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -127,11 +122,6 @@ __device__ __forceinline__ void kmb_ld_sector(const uint32_t *p, uint32_t (&r)[8
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p), "l"(pol));
 }
-__device__ __forceinline__ uint2 kmb_ld_u64_volatile(const uint32_t *p) {
-    uint2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
 
 // ================================================================================================
 // K5: index re-layout.  The reference's structure is "scan n_kmers[h] entries from
@@ -141,7 +131,7 @@ __device__ __forceinline__ uint2 kmb_ld_u64_volatile(const uint32_t *p) {
 // not (overlapping ranges, entries filed under a foreign bucket).  Live entries are scattered into
 // the line of their own bucket; order inside a line is irrelevant for counting.
 // ================================================================================================
-__global__ void kmb_v2_check_buckets(const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
+__global__ void kmb_build_check_buckets(const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
                                      uint64_t modulo, uint64_t n_entries, KmbStatus *status) {
     unsigned flags = 0;
     for (uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; h < modulo; h += (uint64_t)gridDim.x * blockDim.x) {
@@ -159,7 +149,7 @@ __device__ __forceinline__ bool kmb_entry_live(const int32_t *__restrict__ hashe
 }
 
 // pass 1: per-line entry counts, filter bits, node statistics
-__global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
+__global__ void kmb_build_count(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                              const int32_t *__restrict__ hashes_to_index, const int32_t *__restrict__ n_kmers,
                              uint64_t n_entries, KmbMod mod, KmbAddr addr, uint32_t *__restrict__ line_fill,
                              uint32_t *__restrict__ filter, KmbStatus *status) {
@@ -194,7 +184,7 @@ __global__ void kmb_v2_count(const uint64_t *__restrict__ kmers, const int32_t *
 // pass 2 (ASSIGN = false): total overflow sectors needed; (ASSIGN = true): hand them out, write the
 // headers of the whole chain and reset line_fill for the scatter
 template <bool ASSIGN>
-__global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, uint32_t *__restrict__ lines,
+__global__ void kmb_build_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, uint32_t *__restrict__ lines,
                             KmbStatus *status) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_main; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t c = line_fill[i];
@@ -213,7 +203,7 @@ __global__ void kmb_v2_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, u
 }
 
 // pass 3: place every live entry; slot order inside a chain is whatever the atomics give
-__global__ void kmb_v2_scatter(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
+__global__ void kmb_build_scatter(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                                const uint16_t *__restrict__ freqs, const int32_t *__restrict__ hashes_to_index,
                                const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, KmbAddr addr,
                                uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines) {

@@ -101,6 +101,31 @@ def test_compute_fails_loudly_without_a_gpu(kmb, golden_lookup):
     assert rc == kmb.KMB_ERR_CUDA and h.value is None
 
 
+def test_parse_reads_c_abi_needs_no_gpu(kmb):
+    """kmb_parse_reads is host code: counts first, exact capacities, carry-over of the incomplete tail."""
+    lib = kmb.lib()
+    text = np.frombuffer(b"@r1\nACGT\n+\nIIII\n@r2\nGG\n+\n@I\n@r3\nTT", dtype=np.uint8)
+    nr, nb, used = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib.kmb_parse_reads(text.ctypes.data, text.shape[0], 1, 0, 4, None, 0, None, 0, C.byref(nr), C.byref(nb), C.byref(used))
+    assert (rc, nr.value, nb.value, used.value) == (0, 2, 6, 28)           # r3 is incomplete: left for the next chunk
+    bases = np.zeros(6, np.uint8)
+    offsets = np.zeros(3, np.int64)
+    rc = lib.kmb_parse_reads(text.ctypes.data, text.shape[0], 1, 0, 4, bases.ctypes.data, 6, offsets.ctypes.data, 3,
+                             C.byref(nr), C.byref(nb), C.byref(used))
+    assert rc == 0 and bytes(bases) == b"ACGTGG" and list(offsets) == [0, 4, 6]
+    rc = lib.kmb_parse_reads(text.ctypes.data, text.shape[0], 1, 0, 4, bases.ctypes.data, 5, offsets.ctypes.data, 3,
+                             C.byref(nr), C.byref(nb), C.byref(used))
+    assert rc == kmb.KMB_ERR_NOMEM
+    bad = np.frombuffer(b"ACGT\nACGT\n+\nIIII\n", dtype=np.uint8)
+    rc = lib.kmb_parse_reads(bad.ctypes.data, bad.shape[0], 1, 1, 1, None, 0, None, 0, C.byref(nr), C.byref(nb), C.byref(used))
+    assert rc == kmb.KMB_ERR_BAD_ARG
+    fa = np.frombuffer(b">a\nAC\nGT\n>b\n\n>c\nTTT", dtype=np.uint8)
+    rc = lib.kmb_parse_reads(fa.ctypes.data, fa.shape[0], 0, 1, 1, None, 0, None, 0, C.byref(nr), C.byref(nb), C.byref(used))
+    assert (rc, nr.value, nb.value, used.value) == (0, 3, 7, fa.shape[0])
+    rc = lib.kmb_parse_reads(fa.ctypes.data, fa.shape[0], 0, 0, 1, None, 0, None, 0, C.byref(nr), C.byref(nb), C.byref(used))
+    assert (rc, nr.value, nb.value, used.value) == (0, 2, 4, 14)           # record c may continue in the next chunk
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "kmer_mapper_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -12,8 +12,8 @@ import bench  # noqa: E402
 from kmer_mapper_b200 import _lib  # noqa: E402
 from kmer_mapper_b200.device import DeviceIndex, Mapper  # noqa: E402
 
-VARIANTS = [  # (policy_filter, policy_line, policy_red, l2_persist)
-    (2, 0, 0, 1), (2, 0, 0, 0), (2, 2, 1, 1), (2, 0, 1, 1)]
+VARIANTS = [  # (policy_filter, policy_line, l2_persist)
+    (2, 0, 1), (2, 0, 0), (2, 1, 1), (0, 0, 0)]
 
 
 def main():
@@ -26,7 +26,7 @@ def main():
     _lib.set_option("time_kernels", 1)
     ref = None
     for v in VARIANTS:
-        for name, val in zip(("policy_filter", "policy_line", "policy_red", "l2_persist"), v):
+        for name, val in zip(("policy_filter", "policy_line", "l2_persist"), v):
             _lib.set_option(name, val)
         m = Mapper(di, n_counts)
         m.map_reads(bases, offsets, w["k"])     # warm-up: brings the filter into L2 under this policy set
