@@ -518,7 +518,7 @@ static int launch_flush(kmb_mapper *m) {
     const kmb_index *ix = m->index;
     if (m->log.entries) {
         for (int b = 0; b < m->log_bins; b++) {
-            kmb_log_apply_kernel<<<ix->info.sms * 4, 256, 0, m->stream>>>(m->log, b, m->counts);
+            kmb_log_apply_kernel<<<ix->info.sms * 8, 256, 0, m->stream>>>(m->log, b, m->counts);
             g_launches++;
         }
         KMB_CUDA(cudaGetLastError());
@@ -535,7 +535,7 @@ static int launch_flush(kmb_mapper *m) {
 static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
     uint64_t want = std::max<uint64_t>(n_queries / 4, 1ull << 23);
     want = std::min<uint64_t>(want, (uint64_t)std::max<int64_t>(g_opt.log_max_entries, 1 << 10));
-    want = (want + 31) & ~31ull;
+    want = (want + 4095) & ~4095ull;  // whole 128-group blocks: the apply pass reads four tags per 4-byte load
     if (!m->log.cursor) {
         KMB_CUDA(cudaMalloc(&m->log.cursor, sizeof(unsigned long long)));
         KMB_CUDA(cudaMemsetAsync(m->log.cursor, 0, sizeof(unsigned long long), m->stream));

@@ -759,39 +759,44 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin,
     if (n > log.cap) n = log.cap;
     const uint64_t n_groups = n >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    // slab of this CTA: a multiple of 32 groups, so that a warp reads 32 tags with one coalesced load
-    const uint64_t per_cta = (((n_groups + gridDim.x - 1) / gridDim.x) + 31) & ~31ull;
+    // slab of this CTA: a multiple of 128 groups, so that a warp reads 128 tags with one coalesced 4-byte load per lane
+    const uint64_t per_cta = (((n_groups + gridDim.x - 1) / gridDim.x) + 127) & ~127ull;
     const uint64_t g_lo = (uint64_t)blockIdx.x * per_cta;
     const uint64_t g_hi = min(g_lo + per_cta, n_groups);
+    const uint32_t *__restrict__ tags4 = reinterpret_cast<const uint32_t *>(log.tags);  // capacity is a multiple of 4096 ids
     bool use_table = true, decided = false;
     uint32_t seen = 0, present = 0;
-    for (uint64_t g0 = g_lo + (uint64_t)warp * 32; g0 < g_hi; g0 += (uint64_t)warps * 32) {
-        const uint64_t g = g0 + lane;
-        unsigned mine = __ballot_sync(KMB_FULL_MASK, g < g_hi && log.tags[g] == (uint8_t)bin);
-        while (mine) {
-            const int j = __ffs(mine) - 1;
-            mine &= mine - 1u;
-            const uint32_t id = log.entries[((g0 + j) << 5) + lane];
-            if (id != KMB_LOG_HOLE) {
-                if (use_table) {
-                    const uint32_t s = (id * 0x9E3779B1u) >> 21;  // 11 bits
-                    const uint32_t old = atomicCAS(&s_id[s], KMB_LOG_HOLE, id);
-                    if (old == KMB_LOG_HOLE || old == id) atomicAdd(&s_cnt[s], 1u);
-                    else atomicAdd(counts + id, 1u);
-                    present += old == id ? 1u : 0u;
-                    seen++;
-                } else {
-                    atomicAdd(counts + id, 1u);
+    for (uint64_t g0 = g_lo + (uint64_t)warp * 128; g0 < g_hi; g0 += (uint64_t)warps * 128) {
+        const uint64_t gl = g0 + 4ull * lane;  // this lane's four groups
+        const uint32_t t4 = gl < g_hi ? tags4[gl >> 2] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned mine = __ballot_sync(KMB_FULL_MASK, gl + k < g_hi && ((t4 >> (8 * k)) & 0xFFu) == (uint32_t)bin);
+            while (mine) {
+                const int j = __ffs(mine) - 1;
+                mine &= mine - 1u;
+                const uint32_t id = log.entries[((g0 + 4ull * j + k) << 5) + lane];
+                if (id != KMB_LOG_HOLE) {
+                    if (use_table) {
+                        const uint32_t s = (id * 0x9E3779B1u) >> 21;  // 11 bits
+                        const uint32_t old = atomicCAS(&s_id[s], KMB_LOG_HOLE, id);
+                        if (old == KMB_LOG_HOLE || old == id) atomicAdd(&s_cnt[s], 1u);
+                        else atomicAdd(counts + id, 1u);
+                        present += old == id ? 1u : 0u;
+                        seen++;
+                    } else {
+                        atomicAdd(counts + id, 1u);
+                    }
                 }
-            }
-            if (use_table && !decided && __any_sync(KMB_FULL_MASK, seen >= 8u)) {  // ~256 ids per warp looked at: decide once
-                uint32_t p = present, t = seen;
-                for (int o = 16; o > 0; o >>= 1) {
-                    p += __shfl_xor_sync(KMB_FULL_MASK, p, o);
-                    t += __shfl_xor_sync(KMB_FULL_MASK, t, o);
+                if (use_table && !decided && __any_sync(KMB_FULL_MASK, seen >= 8u)) {  // ~256 ids per warp looked at: decide once
+                    uint32_t p = present, t = seen;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        p += __shfl_xor_sync(KMB_FULL_MASK, p, o);
+                        t += __shfl_xor_sync(KMB_FULL_MASK, t, o);
+                    }
+                    if (p * 16u < t) use_table = false;
+                    decided = true;
                 }
-                if (p * 16u < t) use_table = false;
-                decided = true;
             }
         }
     }
