@@ -450,18 +450,6 @@ __device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol
     kmb_stage_flush(P, st, lane, false);
 }
 
-// Push this lane's candidate (if any) on the warp's stack.  Called by all 32 lanes.
-__device__ __forceinline__ void kmb_push_candidate(uint64_t *q_kmer, uint32_t *q_h, int &qcount, bool cand, uint64_t km,
-                                                   uint32_t h, int lane) {
-    unsigned bal = __ballot_sync(KMB_FULL_MASK, cand);
-    if (cand) {
-        int slot = qcount + __popc(bal & ((1u << lane) - 1u));
-        q_kmer[slot] = km;
-        q_h[slot] = h;
-    }
-    qcount += __popc(bal);
-}
-
 // Level 0 for U queries of this lane (all filter loads in flight together), with the consume half
 // of the previous drain placed between the issue of those loads and their first use.  kf(u) yields
 // query u (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u
@@ -472,12 +460,14 @@ template <int U, bool FILT, class KF>
 __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
                                                 unsigned &counted, const KF &kf, uint32_t vbits, uint64_t *q_kmer,
                                                 uint32_t *q_h, int &qcount, int lane) {
+    uint64_t km[U];    // the queries (kept: recomputing them for the push cost more than the registers)
     uint32_t hh[U];    // main sector of the query
     uint32_t need[U];  // filter bits the query needs; 0 = no query
     uint32_t fw[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        const KmbLoc loc = kmb_locate(kf(u), P.addr);
+        km[u] = kf(u);
+        const KmbLoc loc = kmb_locate(km[u], P.addr);
         hh[u] = loc.sector;
         const bool valid = (vbits >> u) & 1u;
         if (FILT) {
@@ -489,10 +479,27 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
         }
     }
     kmb_pipe_consume(P, pol, pp, st, counted, lane);  // the sectors issued by the previous call have had this long to arrive
+    // Survivors go onto the warp's stack: one inclusive scan of the per-lane survivor counts gives every lane
+    // its first slot (instead of one ballot + two popcounts per query).
+    uint32_t cmask = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) cmask |= (need[u] != 0u && (fw[u] & need[u]) == need[u]) ? (1u << u) : 0u;
+    const uint32_t mine = __popc(cmask);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(KMB_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    uint32_t slot = (uint32_t)qcount + incl - mine;
+    qcount += (int)__shfl_sync(KMB_FULL_MASK, incl, 31);
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        bool cand = need[u] != 0u && (fw[u] & need[u]) == need[u];
-        kmb_push_candidate(q_kmer, q_h, qcount, cand, kf(u), hh[u], lane);
+        if ((cmask >> u) & 1u) {
+            q_kmer[slot] = km[u];
+            q_h[slot] = hh[u];
+            slot++;
+        }
     }
     __syncwarp();
 #pragma unroll 1
