@@ -17,9 +17,12 @@ from __future__ import annotations
 
 import ctypes as C
 import gzip
+import mmap
 import os
 import queue
 import threading
+import zlib
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -95,6 +98,124 @@ def _format_of(path: str) -> str:
     raise RuntimeError("Unsupported file suffix in %s (expected .fa/.fasta/.fq/.fastq, optionally .gz)" % path)
 
 
+class ParallelGzip:
+    """Multi-member gzip (bgzip/BGZF files, `cat a.gz b.gz`, the synthetic FASTQ.gz of the benchmark configs)
+    inflated member-parallel: zlib releases the GIL, so a thread pool decompresses several members at once.
+
+    Member starts are not recorded anywhere in a .gz, so they are found speculatively: every occurrence of the
+    member magic (1f 8b 08, reserved flag bits clear) is a candidate that a worker tries to inflate to its end;
+    the consumer walks the chain "a member starts where the previous one ended" and ignores candidates inside a
+    member (they fail within a few bytes anyway).  A member that inflates to more than ``max_member_bytes``
+    (a plain single-member .gz) makes the reader fall back to sequential streaming from that point.
+    """
+
+    SCAN_WINDOW = 32 << 20
+
+    def __init__(self, path, n_threads, max_member_bytes=192 << 20):
+        self.path = path
+        self.n_threads = max(1, int(n_threads))
+        self.max_member_bytes = int(max_member_bytes)
+
+    def _candidates(self, mm, start):
+        """Candidate member starts >= start, in order (lazily, window by window)."""
+        n = len(mm)
+        pos = start
+        while pos < n:
+            end = min(pos + self.SCAN_WINDOW + 3, n)
+            a = np.frombuffer(mm, dtype=np.uint8, count=end - pos, offset=pos)
+            if a.shape[0] >= 4:
+                hit = np.flatnonzero((a[:-3] == 0x1F) & (a[1:-2] == 0x8B) & (a[2:-1] == 8) & ((a[3:] & 0xE0) == 0))
+                for h in hit.tolist():
+                    yield pos + h
+            del a
+            if end >= n:
+                return
+            pos = end - 3
+
+    def _inflate_member(self, mm, start):
+        """(text bytes, offset just past the member) or None for a false candidate / an oversized member."""
+        d = zlib.decompressobj(31)
+        pos = start
+        outs, total = [], 0
+        try:
+            while not d.eof:
+                chunk = mm[pos:pos + (1 << 20)]
+                if not chunk:
+                    return None            # truncated
+                outs.append(d.decompress(chunk))
+                pos += len(chunk)
+                total += len(outs[-1])
+                if total > self.max_member_bytes:
+                    return "big"
+        except zlib.error:
+            return None
+        return b"".join(outs), pos - len(d.unused_data)
+
+    def blocks(self, block_bytes):
+        """Yields decompressed text in file order, at least block_bytes at a time (except the last), then b''."""
+        size = os.path.getsize(self.path)
+        if size == 0:
+            yield b""
+            return
+        with open(self.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm, \
+                ThreadPoolExecutor(self.n_threads) as pool:
+            expected = 0
+            cand = self._candidates(mm, 0)
+            pending = {}                    # start -> future
+            ahead = 2 * self.n_threads
+            exhausted = False
+            acc, acc_len = [], 0
+            fallback_from = None
+            while expected < size:
+                while not exhausted and len(pending) < ahead:
+                    try:
+                        c = next(cand)
+                    except StopIteration:
+                        exhausted = True
+                        break
+                    if c >= expected:
+                        pending[c] = pool.submit(self._inflate_member, mm, c)
+                fut = pending.pop(expected, None)
+                if fut is None:
+                    if not pending and exhausted:
+                        raise OSError("%s: not a gzip member at offset %d" % (self.path, expected))
+                    if any(c < expected for c in pending):
+                        for c in [c for c in pending if c < expected]:
+                            pending.pop(c).cancel()
+                        continue
+                    if expected not in pending and (exhausted or min(pending) > expected):
+                        raise OSError("%s: not a gzip member at offset %d" % (self.path, expected))
+                    continue
+                res = fut.result()
+                if res is None:
+                    raise OSError("%s: corrupt gzip member at offset %d" % (self.path, expected))
+                if res == "big":
+                    fallback_from = expected
+                    break
+                text, expected = res
+                acc.append(text)
+                acc_len += len(text)
+                if acc_len >= block_bytes:
+                    yield b"".join(acc)
+                    acc, acc_len = [], 0
+                for c in [c for c in pending if c < expected]:      # candidates inside the member just consumed
+                    pending.pop(c).cancel()
+            for fu in pending.values():
+                fu.cancel()
+            if acc:
+                yield b"".join(acc)
+        if fallback_from is not None:
+            with open(self.path, "rb") as f:
+                f.seek(fallback_from)
+                with gzip.GzipFile(fileobj=f, mode="rb") as g:
+                    while True:
+                        block = g.read(block_bytes)
+                        if not block:
+                            break
+                        yield block
+        yield b""
+
+
 class ReadFile:
     """``bnp.open(path)`` replacement: ``.read_chunks(min_chunk_size)`` yields ReadChunk objects."""
 
@@ -116,6 +237,10 @@ class ReadFile:
 
         def produce():
             try:
+                if self.path.lower().endswith(".gz"):
+                    for block in ParallelGzip(self.path, self.n_threads).blocks(block_bytes):
+                        q.put(block)
+                    return
                 with self._open() as f:
                     while True:
                         block = f.read(block_bytes)

@@ -118,7 +118,7 @@ def test_reader_matches_independent_parser(tmp_path, suffix, writer):
             got += [bytes(s[i]) for i in range(len(s))]
             n_chunks += 1
         assert got == want, (suffix, chunk_size)
-        if chunk_size == 97:
+        if chunk_size == 97 and not suffix.endswith(".gz"):   # a gzip member is never split into smaller blocks
             assert n_chunks > 10
 
 
@@ -153,6 +153,45 @@ def test_reader_parallel_pieces_resynchronise_on_hostile_text(tmp_path, fmt):
                 assert (lens >= 0).all()
                 got += [bytes(s[i]) for i in range(len(s))]
             assert got == want, (chunk_size, n_threads)
+
+
+def test_parallel_gzip_members_fallback_and_hostile_payload(tmp_path):
+    import zlib
+    from kmer_mapper_b200.reader import ParallelGzip
+    rng = np.random.default_rng(3)
+    text = bytes(rng.choice(np.frombuffer(b"ACGT\n@+I", np.uint8), size=3_000_000))
+    # many members (bgzip-like), cut at arbitrary places
+    cuts = [0] + sorted(rng.integers(1, len(text), size=40).tolist()) + [len(text)]
+    multi = str(tmp_path / "multi.gz")
+    with open(multi, "wb") as f:
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            f.write(gzip.compress(text[a:b], compresslevel=1))
+    for threads in (1, 4):
+        for block in (1 << 16, 1 << 22):
+            blocks = list(ParallelGzip(multi, threads).blocks(block))
+            assert blocks[-1] == b"" and b"".join(blocks) == text
+            assert all(len(x) >= block for x in blocks[:-2])
+    # one big member: falls back to sequential streaming
+    single = str(tmp_path / "single.gz")
+    open(single, "wb").write(gzip.compress(text, compresslevel=1))
+    assert b"".join(ParallelGzip(single, 4, max_member_bytes=1 << 20).blocks(1 << 18)) == text
+    # a big member in the middle of small ones
+    mixed = str(tmp_path / "mixed.gz")
+    open(mixed, "wb").write(gzip.compress(text[:1000]) + gzip.compress(text[1000:2_000_000]) + gzip.compress(text[2_000_000:]))
+    assert b"".join(ParallelGzip(mixed, 3, max_member_bytes=1 << 20).blocks(1 << 18)) == text
+    # the member magic inside the compressed stream (stored blocks keep the payload verbatim)
+    payload = b"@r\nACGT\n+\n\x1f\x8b\x08\x00II\n" * 2000
+    co = zlib.compressobj(0, zlib.DEFLATED, 31)
+    hostile = str(tmp_path / "hostile.gz")
+    open(hostile, "wb").write(co.compress(payload) + co.flush() + gzip.compress(b"tail"))
+    assert b"".join(ParallelGzip(hostile, 4).blocks(1 << 20)) == payload + b"tail"
+    empty = str(tmp_path / "empty.gz")
+    open(empty, "wb").write(gzip.compress(b""))
+    assert b"".join(ParallelGzip(empty, 2).blocks(10)) == b""
+    bad = str(tmp_path / "bad.gz")
+    open(bad, "wb").write(gzip.compress(text[:5000])[:-20] + b"garbage-not-gzip")
+    with pytest.raises(OSError):
+        list(ParallelGzip(bad, 2).blocks(1 << 16))
 
 
 def test_reader_edge_cases(tmp_path):

@@ -26,11 +26,12 @@ del tindex, bases, offsets
 torch.cuda.empty_cache()
 t = time.perf_counter()
 synthetic.write_fastq(os.path.join(d, "reads.fq"), hb, ho)
-os.system("gzip -1 -k %s/reads.fq" % d)
+synthetic.write_fastq(os.path.join(d, "reads.fq.gz"), hb, ho, members=64)      # multi-member, like bgzip output
+os.system("gzip -1 -c %s/reads.fq > %s/reads_single.fq.gz" % (d, d))              # one member: sequential inflate
 synthetic.write_fasta(os.path.join(d, "reads.fa"), hb, ho)
 print("wrote files in %.1f s" % (time.perf_counter() - t), file=sys.stderr)
 ref = None
-for name in ("reads.fa", "reads.fq", "reads.fq.gz"):
+for name in ("reads.fa", "reads.fq", "reads.fq.gz", "reads_single.fq.gz"):
     for chunk in (2_500_000, 10_000_000, 64_000_000):
         out = os.path.join(d, "out")
         t0 = time.perf_counter()
