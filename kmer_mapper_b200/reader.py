@@ -111,7 +111,7 @@ class ParallelGzip:
 
     SCAN_WINDOW = 32 << 20
 
-    def __init__(self, path, n_threads, max_member_bytes=192 << 20):
+    def __init__(self, path, n_threads, max_member_bytes=64 << 20):
         self.path = path
         self.n_threads = max(1, int(n_threads))
         self.max_member_bytes = int(max_member_bytes)
