@@ -55,7 +55,8 @@ int kmb_device_count(int *n_devices);
  * kmers uint64[n_entries], frequencies uint16[n_entries], modulo scalar.
  * The arrays are copied to `device`, validated once (the reference runs with boundscheck off,
  * mapper.pyx:15-18: every bucket must lie inside [0, n_entries], nodes must be >= 0) and re-laid
- * out on the device into a one-sector bucket directory plus packed 16-byte entries. */
+ * out on the device into read-only 32-byte sectors (keys, nodes and frequencies) addressed by a hash
+ * of the key, plus an L2-resident filter.  Limits: modulo < 2^32, n_entries < 2^31. */
 int kmb_index_create(int device,
                      const int32_t *hashes_to_index, const int32_t *n_kmers, uint64_t modulo,
                      const int32_t *nodes, const uint64_t *kmers, const uint16_t *frequencies,

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <vector>
@@ -1048,6 +1049,40 @@ extern "C" int kmb_mapper_lookup_counts(kmb_mapper *m, const uint64_t *keys, uin
 // ------------------------------------------------------------------------------------------------
 // hashing (util.py:71-75)
 // ------------------------------------------------------------------------------------------------
+// Scratch of the hashing entry point (read-boundary mask, per-tile counts, status), kept per device and grown
+// on demand: the call is made once per chunk, and a cudaMalloc/cudaFree pair per call cost more than its kernels.
+struct HashScratch {
+    uint32_t *mask = nullptr;
+    size_t mask_cap = 0;
+    unsigned long long *tiles = nullptr;
+    size_t tiles_cap = 0;
+    KmbStatus *status = nullptr;
+};
+static HashScratch g_hash_scratch[64];
+static std::mutex g_hash_mutex;
+
+static int hash_scratch(int device, size_t mask_words, size_t n_tiles, HashScratch **out) {
+    if (device < 0 || device >= 64) return kmb_fail(KMB_ERR_BAD_ARG, "device %d out of range", device);
+    HashScratch &h = g_hash_scratch[device];
+    if (mask_words > h.mask_cap) {
+        cudaFree(h.mask);
+        h.mask = nullptr;
+        h.mask_cap = 0;
+        KMB_CUDA(cudaMalloc(&h.mask, (mask_words + mask_words / 4) * 4));
+        h.mask_cap = mask_words + mask_words / 4;
+    }
+    if (n_tiles + 1 > h.tiles_cap) {
+        cudaFree(h.tiles);
+        h.tiles = nullptr;
+        h.tiles_cap = 0;
+        KMB_CUDA(cudaMalloc(&h.tiles, (n_tiles + 1 + n_tiles / 4) * 8));
+        h.tiles_cap = n_tiles + 1 + n_tiles / 4;
+    }
+    if (!h.status) KMB_CUDA(cudaMalloc(&h.status, sizeof(KmbStatus)));
+    *out = &h;
+    return KMB_OK;
+}
+
 extern "C" int kmb_hash_reads(int device, const uint8_t *bases, uint64_t n_bases, const int64_t *offsets, uint64_t n_reads,
                               int k, uint32_t flags, uint64_t *out, uint64_t out_capacity, uint64_t *n_out,
                               int64_t *bad_offset) {
@@ -1078,12 +1113,18 @@ extern "C" int kmb_hash_reads(int device, const uint8_t *bases, uint64_t n_bases
     KMB_TRY(to_device(offsets, (size_t)n_reads + 1, device, t_off, &d_off, s));
     const size_t mask_words = (size_t)(n_bases / 32 + 1);
     const uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
-    DevBuf<uint32_t> d_mask;
-    DevBuf<unsigned long long> d_tiles;
-    DevBuf<KmbStatus> d_status;
-    KMB_TRY(d_mask.alloc(mask_words));
-    KMB_TRY(d_tiles.alloc((size_t)n_tiles + 1));
-    KMB_TRY(d_status.alloc(1));
+    std::lock_guard<std::mutex> lock(g_hash_mutex);  // one hashing call per process at a time (shared scratch)
+    HashScratch *hsb = nullptr;
+    KMB_TRY(hash_scratch(device, mask_words, (size_t)n_tiles, &hsb));
+    struct {
+        uint32_t *p;
+    } d_mask{hsb->mask};
+    struct {
+        unsigned long long *p;
+    } d_tiles{hsb->tiles};
+    struct {
+        KmbStatus *p;
+    } d_status{hsb->status};
     KmbStatus hs;
     memset(&hs, 0, sizeof(hs));
     hs.first_bad_offset = ~0ull;

@@ -893,14 +893,22 @@ __global__ void __launch_bounds__(1024) kmb_hash_scan_kernel(unsigned long long 
     }
 }
 
+// Emit: thread t first owns the 32 window starts [32t, 32t+32) of the tile (one mask word) to build the
+// per-word output offsets, then the warps walk the tile 32 consecutive positions at a time: the 32 lanes
+// share two 64-bit words of the packed stream (shared-memory broadcast), compact their valid windows with one
+// popcount of the mask word and store them to consecutive addresses -- the output, 8 bytes per k-mer, is the
+// traffic that bounds this kernel, so it leaves as full coalesced lines.
 __global__ void __launch_bounds__(KMB_TILE_THREADS)
 kmb_hash_emit_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ mask, int k,
                      bool n_to_a, const unsigned long long *__restrict__ tile_offsets, uint64_t *__restrict__ out,
                      uint64_t out_capacity, KmbStatus *status) {
     __shared__ __align__(16) uint32_t s_pack[KMB_TILE_POS / 16 + 8];
+    __shared__ uint32_t s_valid[KMB_TILE_THREADS];  // valid-start bits of word t
+    __shared__ uint32_t s_off[KMB_TILE_THREADS];    // windows of the tile before word t
     __shared__ uint32_t s_w[KMB_TILE_THREADS / 32];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const int warp = tid >> 5;
     const uint64_t tile = blockIdx.x;
     const uint64_t t0 = tile * KMB_TILE_POS;
     const uint64_t n_vec_full = n_bases / 16;
@@ -913,30 +921,32 @@ kmb_hash_emit_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const 
         s_pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
         if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(v * 16 + (uint64_t)(__ffs(inv) - 1)));
     }
-    __syncthreads();
-    const uint64_t p0 = t0 + (uint64_t)tid * KMB_POS_PER_THREAD;
-    uint32_t valid = kmb_valid_starts(mask, p0, n_bases, k);
+    const uint32_t valid = kmb_valid_starts(mask, t0 + (uint64_t)tid * KMB_POS_PER_THREAD, n_bases, k);
     // exclusive prefix of popc(valid) over the CTA
-    uint32_t c = __popc(valid);
+    const uint32_t c = __popc(valid);
     uint32_t incl = c;
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t v = __shfl_up_sync(KMB_FULL_MASK, incl, o);
         if (lane >= o) incl += v;
     }
-    if (lane == 31) s_w[tid >> 5] = incl;
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
     uint32_t warp_base = 0;
-    for (int w = 0; w < (tid >> 5); w++) warp_base += s_w[w];
-    uint64_t o = tile_offsets[tile] + warp_base + (incl - c);
-    const uint2 a = *reinterpret_cast<const uint2 *>(&s_pack[2 * tid]);
-    const uint2 b = *reinterpret_cast<const uint2 *>(&s_pack[2 * tid + 2]);
-    const uint64_t lo = (uint64_t)a.x | ((uint64_t)a.y << 32);
-    const uint64_t hi = (uint64_t)b.x | ((uint64_t)b.y << 32);
-#pragma unroll 4
-    for (int i = 0; i < 32; i++) {
-        if ((valid >> i) & 1u) {
-            if (o < out_capacity) out[o] = kmb_window(lo, hi, i, kmask);
-            o++;
+    for (int w = 0; w < warp; w++) warp_base += s_w[w];
+    s_valid[tid] = valid;
+    s_off[tid] = warp_base + (incl - c);
+    __syncthreads();
+    const uint64_t tile_base = tile_offsets[tile];
+    for (int word = warp; word < KMB_TILE_THREADS; word += KMB_TILE_THREADS / 32) {
+        const uint32_t vw = s_valid[word];
+        if (vw == 0u) continue;
+        const uint2 a = *reinterpret_cast<const uint2 *>(&s_pack[2 * word]);
+        const uint2 b = *reinterpret_cast<const uint2 *>(&s_pack[2 * word + 2]);
+        const uint64_t lo = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        const uint64_t hi = (uint64_t)b.x | ((uint64_t)b.y << 32);
+        if ((vw >> lane) & 1u) {
+            const uint64_t o = tile_base + s_off[word] + __popc(vw & ((1u << lane) - 1u));
+            if (o < out_capacity) out[o] = kmb_window(lo, hi, lane, kmask);
         }
     }
 }
