@@ -81,27 +81,28 @@ def map_gpu(index, chunks, k, hash_map_size=0, map_reverse_complements=False, ra
     return counts
 
 
+def _flag(args, name, default=None):
+    return getattr(args, name, default)
+
+
 def map_bnp(args):
-    """command_line_interface.py:82-151."""
-    if getattr(args, "debug", None):
+    """The run itself (command_line_interface.py:82-151): load the index, stream the reads file in chunks
+    through the GPU, write ``<output>.npy`` -- or return the counts when ``args.output_file`` is None, which
+    is how KAGE calls it with a hand-built Namespace."""
+    if _flag(args, "debug"):
         logging.info("Will print debug log")
         logging.getLogger().setLevel(logging.DEBUG)
-
-    k = args.kmer_size
-    start_time = time.perf_counter()
-    kmer_index = _get_kmer_index_from_args(args)
-
-    n_bytes = os.stat(args.reads).st_size
-    if args.reads.endswith(".gz"):
-        n_bytes *= 6.5  # rough estimate for gzipped to give a progress
-    approx_number_of_chunks = int(n_bytes / args.chunk_size)
-    logging.info("N bytes of reads: %d" % n_bytes)
-    logging.info("Approx number of chunks of %d bytes: %d" % (args.chunk_size, approx_number_of_chunks))
-
-    if not getattr(args, "gpu", False):
+    t_start = time.perf_counter()
+    kmer_size = args.kmer_size
+    want_revcomp = bool(_flag(args, "map_reverse_complements", False))
+    if not _flag(args, "gpu", False):
         # the reference's CPU route refuses reverse complements (command_line_interface.py:107)
-        assert not getattr(args, "map_reverse_complements", False), \
-            "Mapping reverse complements only supported with GPU-mode for now"
+        assert not want_revcomp, "Mapping reverse complements only supported with GPU-mode for now"
+    index = _get_kmer_index_from_args(args)
+
+    file_bytes = os.stat(args.reads).st_size * (6.5 if args.reads.endswith(".gz") else 1)  # same rough gz factor
+    logging.info("N bytes of reads: %d" % file_bytes)
+    logging.info("Approx number of chunks of %d bytes: %d" % (args.chunk_size, int(file_bytes / args.chunk_size)))
 
     rank, world_size, local_rank = distributed.init_process_group()
     if world_size > 1:
@@ -109,29 +110,26 @@ def map_bnp(args):
         if torch.cuda.is_available():
             torch.cuda.set_device(local_rank)
 
-    file = open_reads(args.reads)
-    chunks = file.read_chunks(min_chunk_size=args.chunk_size)
-    t_before_map = time.perf_counter()
-    if world_size == 1:
-        node_counts = map_gpu(kmer_index, chunks, k, getattr(args, "gpu_hash_map_size", 0),
-                              getattr(args, "map_reverse_complements", False))
-    else:
-        node_counts = _map_sharded(kmer_index, chunks, k, getattr(args, "map_reverse_complements", False),
-                                   rank, world_size)
-    file.close()
-    logging.info("Time spent only on hashing and counting hashes: %.4f" % (time.perf_counter() - t_before_map))
+    reads = open_reads(args.reads)
+    t_map = time.perf_counter()
+    try:
+        chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size)
+        if world_size == 1:
+            node_counts = map_gpu(index, chunk_iter, kmer_size, _flag(args, "gpu_hash_map_size", 0), want_revcomp)
+        else:
+            node_counts = _map_sharded(index, chunk_iter, kmer_size, want_revcomp, rank, world_size)
+    finally:
+        reads.close()
+    logging.info("Time spent only on hashing and counting hashes: %.4f" % (time.perf_counter() - t_map))
 
-    args_dict = vars(args)
-    args_dict.pop("func", None)
-
+    vars(args).pop("func", None)  # the reference strips it before handing the dict to its workers (cli:121-122)
     if args.output_file is None:
         return node_counts
-
     if rank == 0:
-        np.save(args.output_file, node_counts)
+        np.save(args.output_file, node_counts)  # numpy appends ".npy" (command_line_interface.py:149)
         logging.info("Saved node counts to %s.npy" % args.output_file)
-    logging.info("Spent %.3f sec in total mapping kmers using %d threads" % (time.perf_counter() - start_time,
-                                                                             args.n_threads))
+    logging.info("Spent %.3f sec in total mapping kmers using %d threads" % (time.perf_counter() - t_start,
+                                                                             _flag(args, "n_threads", 1)))
 
 
 def _map_sharded(kmer_index, chunks, k, map_reverse_complements, rank, world_size):
@@ -154,39 +152,37 @@ def _map_sharded(kmer_index, chunks, k, map_reverse_complements, rank, world_siz
     return out
 
 
+# (short flag, long flag, argparse keywords): names, defaults and types exactly as the reference declares them
+# (command_line_interface.py:164-182) -- including type=bool for -g and -r, for which ANY non-empty string,
+# "False" included, is true, and the untyped -d.  -t and -I are accepted and unused here.
+_MAP_FLAGS = (
+    ("-i", "--kmer-index", dict(required=False, help="KmerIndex .npz file")),
+    ("-b", "--index-bundle", dict(required=False, help="index bundle (not supported by this implementation)")),
+    ("-f", "--reads", dict(required=True, help="reads: .fa / .fq, optionally .gz")),
+    ("-k", "--kmer-size", dict(required=False, default=31, type=int)),
+    ("-t", "--n-threads", dict(required=False, default=16, type=int, help="accepted for compatibility; the GPU path has no worker processes")),
+    ("-c", "--chunk-size", dict(required=False, default=2500000, type=int, help="bytes of the reads file per chunk")),
+    ("-o", "--output-file", dict(required=True, help="node counts are written to <output-file>.npy")),
+    ("-d", "--debug", dict(required=False, help="any value switches the DEBUG log on")),
+    ("-I", "--max-hits-per-kmer", dict(required=False, default=1000, type=int,
+                                       help="parsed and ignored, like the reference: the cut-off is always 1000")),
+    ("-g", "--gpu", dict(default=False, type=bool, help="both routes run on the GPU here; -g additionally allows -r")),
+    ("-s", "--gpu-hash-map-size", dict(default=0, type=int, help="accepted for compatibility")),
+    ("-r", "--map-reverse-complements", dict(default=False, type=bool,
+                                             help="also count the reverse complement of every read k-mer")),
+)
+
+
 def run_argument_parser(args):
-    parser = argparse.ArgumentParser(
-        description='Kmer Mapper',
-        prog='kmer_mapper',
-        formatter_class=lambda prog: argparse.HelpFormatter(prog, max_help_position=50, width=100))
-
-    subparsers = parser.add_subparsers()
-    subparser = subparsers.add_parser("map", help="Map reads to a kmer index")
-    subparser.add_argument("-i", "--kmer-index", required=False)
-    subparser.add_argument("-b", "--index-bundle", required=False)
-    subparser.add_argument("-f", "--reads", required=True, help="Reads in .fa, .fq, .fa.gz, or fq.gz format")
-    subparser.add_argument("-k", "--kmer-size", required=False, default=31, type=int)
-    subparser.add_argument("-t", "--n-threads", required=False, default=16, type=int)
-    subparser.add_argument("-c", "--chunk-size", required=False, type=int, default=2500000,
-                           help="N bytes to process in each chunk")
-    subparser.add_argument("-o", "--output-file", required=True)
-    subparser.add_argument("-d", "--debug", required=False, help="Set to True to print debug log")
-    subparser.add_argument("-I", "--max-hits-per-kmer", required=False, default=1000, type=int,
-                           help="Ignore kmers that have more than this amount of hits in index")
-    subparser.add_argument("-g", "--gpu", default=False, type=bool,
-                           help="Set to True to use GPU-counting. Experimental."
-                           " Requires suitable hardware and dependencies.")
-    subparser.add_argument("-s", "--gpu-hash-map-size", default=0, type=int,
-                           help="Can be overriden to set GPU hash map size. "
-                           "Set to a lower number to decrease GPU memory requirements. Higher number makes things faster")
-    subparser.add_argument("-r", "--map-reverse-complements", default=False, type=bool,
-                           help="Also count kmers in reverse complement of reads. "
-                                "Default False. Not necessary if index contains reverse complements.")
-    subparser.set_defaults(func=map_bnp)
-
-    if len(args) == 0:
+    parser = argparse.ArgumentParser(prog="kmer_mapper", description="Kmer Mapper",
+                                     formatter_class=lambda prog: argparse.HelpFormatter(prog, max_help_position=50, width=100))
+    commands = parser.add_subparsers()
+    map_cmd = commands.add_parser("map", help="Map reads to a kmer index")
+    for short, long_name, kwargs in _MAP_FLAGS:
+        map_cmd.add_argument(short, long_name, **kwargs)
+    map_cmd.set_defaults(func=map_bnp)
+    if len(args) == 0:  # command_line_interface.py:185-187
         parser.print_help()
         sys.exit(1)
-
-    args = parser.parse_args(args)
-    return args.func(args)
+    parsed = parser.parse_args(args)
+    return parsed.func(parsed)

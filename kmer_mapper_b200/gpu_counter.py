@@ -1,8 +1,9 @@
-"""Drop-in for the reference's kmer_mapper/gpu_counter.py.
+"""Drop-in for the reference's ``kmer_mapper/gpu_counter.py`` (class ``GpuCounter``, gpu_counter.py:5-37).
 
-The reference's GpuCounter wraps the third-party ``cucounter`` hash table (gpu_counter.py:14-16).
-Here the table is the same device index the mapper uses, built over the unique keys with
-"node" i = key i, so ``count`` is the mapping kernel and ``counter[keys]`` is its lookup kernel.
+The reference wraps the third-party ``cucounter`` hash table: count occurrences of a fixed set of unique keys,
+then scatter the per-key counts onto nodes.  Here the "hash table" is the same device index the mapper uses,
+built over the unique keys with node ``i`` standing for key ``i``; counting is the mapping kernel and the per-key
+read-back is its lookup kernel.  Method names, arguments and results follow the reference; the bodies do not.
 """
 from __future__ import annotations
 
@@ -13,26 +14,29 @@ import numpy as np
 from .device import DeviceIndex, Mapper
 from .kmer_index import KmerIndex
 
-
-def _auto_capacity(n_keys: int) -> int:
-    """Bucket count when the caller passes 0 (``--gpu-hash-map-size`` default, command_line_interface.py:178):
-    about four buckets per key, odd."""
-    return max(4 * int(n_keys), 1021) | 1
+_QUERY_SLICE = 10_000_000  # the reference reads the per-key counts back in slices of this many keys (gpu_counter.py:29)
 
 
-class _DeviceCounter:
-    """The three operations gpu_counter.py uses from cucounter.Counter: construct over unique keys,
-    ``count(kmers, count_revcomps, k)`` (cumulative), ``counter[keys]``."""
+def _table_size(n_keys: int, requested: int) -> int:
+    """Bucket count of the key table.  ``requested`` is the reference's hash-map size hint
+    (``--gpu-hash-map-size``, 0 = choose: command_line_interface.py:178); the default gives ~4 buckets per key."""
+    size = int(requested) if requested and requested > 0 else max(4 * int(n_keys), 1021) | 1
+    return min(size, 2 ** 32 - 1)
 
-    def __init__(self, unique_kmers, capacity=0):
-        keys = np.ascontiguousarray(unique_kmers, dtype=np.uint64)
-        modulo = int(capacity) if capacity and capacity > 0 else _auto_capacity(keys.shape[0])
-        modulo = min(modulo, 2 ** 32 - 1)
-        idx = KmerIndex.from_flat_kmers(hashes=keys, nodes=np.arange(keys.shape[0], dtype=np.int64), modulo=modulo,
-                                        frequencies=np.ones(keys.shape[0], dtype=np.uint16))
-        idx.convert_to_int32()
-        self._index = DeviceIndex.from_index(idx)
-        self._mapper = Mapper(self._index, n_counts=max(keys.shape[0], 1), max_index_lookup_frequency=65535)
+
+class _KeyCounter:
+    """What ``cucounter.counter.Counter`` is to the reference (gpu_counter.py:16,24,33): built over unique keys,
+    ``count(kmers, count_revcomps, k)`` accumulates, ``counter[keys]`` reads the counts of the given keys."""
+
+    def __init__(self, unique_keys, table_size=0):
+        keys = np.ascontiguousarray(unique_keys, dtype=np.uint64)
+        n = keys.shape[0]
+        table = KmerIndex.from_flat_kmers(hashes=keys, nodes=np.arange(n, dtype=np.int64),
+                                          modulo=_table_size(n, table_size), frequencies=np.ones(n, dtype=np.uint16))
+        table.convert_to_int32()
+        self._index = DeviceIndex.from_index(table)
+        # every key has frequency 1, so no cut-off ever applies: the counter counts all occurrences
+        self._mapper = Mapper(self._index, n_counts=max(n, 1), max_index_lookup_frequency=65535)
 
     def count(self, kmers, count_revcomps=False, k=31):
         self._mapper.map_kmers(kmers, revcomp=bool(count_revcomps), k=k)
@@ -42,38 +46,37 @@ class _DeviceCounter:
 
 
 class GpuCounter:
-    def __init__(self, unique_kmers, kmers, nodes, k):
-        self.unique_kmers = unique_kmers
-        self.kmers = kmers
-        self.nodes = nodes
-        self.counter = None
-        self.k = k
+    """Same constructor, attributes and methods as the reference class."""
 
-    def initialize_cuda(self, modulo):
-        """gpu_counter.py:13-16; ``modulo`` is the table capacity hint, 0 = choose."""
-        logging.info("N unique kmers: %d" % len(self.unique_kmers))
-        self.counter = _DeviceCounter(self.unique_kmers, modulo)
+    def __init__(self, unique_kmers, kmers, nodes, k):
+        self.k = k
+        self.nodes = nodes
+        self.kmers = kmers
+        self.unique_kmers = unique_kmers
+        self.counter = None  # created by initialize_cuda
 
     @classmethod
     def from_kmers_and_nodes(cls, kmers, nodes, k) -> "GpuCounter":
-        unique_kmers = np.unique(kmers)
-        return cls(unique_kmers, kmers, nodes, k)
+        return cls(np.unique(kmers), kmers, nodes, k)
+
+    def initialize_cuda(self, modulo):
+        logging.info("Building the device key table over %d unique k-mers" % len(self.unique_kmers))
+        self.counter = _KeyCounter(self.unique_kmers, modulo)
 
     def count(self, kmers, count_revcomps=False):
-        """gpu_counter.py:23-24; cumulative across calls."""
+        """Accumulates over calls, like the reference's counter."""
+        if self.counter is None:
+            raise RuntimeError("GpuCounter.initialize_cuda() has not been called")
         self.counter.count(kmers, count_revcomps, self.k)
 
     def get_node_counts(self, min_nodes=0):
-        """gpu_counter.py:26-37: per-entry counts scattered onto nodes with
-        ``np.bincount(nodes, counts, minlength=min_nodes)`` -- float64, unfiltered, exactly like the
-        reference method (the mapping CLI does not use this route, see command_line_interface.map_gpu)."""
-        counts = np.zeros(len(self.kmers), dtype=np.uint32)
-        chunk_size = 10_000_000
-        start = 0
-        kmers = np.ascontiguousarray(self.kmers, dtype=np.uint64)
-        for chunk in np.array_split(kmers, max(1, len(kmers) // chunk_size)):
-            logging.debug("Querying chunk %d-%d" % (start, start + len(chunk)))
-            counts[start:start + len(chunk)] = self.counter[chunk]
-            start += len(chunk)
-        logging.info("Doing bincount")
-        return np.bincount(self.nodes, counts, minlength=min_nodes)
+        """Per-key counts of every index entry, summed per node: float64 of length
+        ``max(min_nodes, nodes.max() + 1)`` and without a frequency cut-off, exactly what the reference method
+        returns (gpu_counter.py:37).  The mapping CLI does not take this route: ``map_gpu`` returns the CPU
+        route's uint32 counts with the cut-off applied."""
+        entry_keys = np.ascontiguousarray(self.kmers, dtype=np.uint64)
+        per_entry = np.empty(entry_keys.shape[0], dtype=np.uint32)
+        for lo in range(0, entry_keys.shape[0], _QUERY_SLICE):
+            hi = min(lo + _QUERY_SLICE, entry_keys.shape[0])
+            per_entry[lo:hi] = self.counter[entry_keys[lo:hi]]
+        return np.bincount(np.asarray(self.nodes), weights=per_entry, minlength=min_nodes)
