@@ -26,18 +26,38 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(p) <= t for p in SOURCES + HEADERS if os.path.exists(p))
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
-    if not force and up_to_date():
-        return LIB_PATH
+BOUNDS_LIB_PATH = os.path.join(PKG, "libkmer_mapper_b200_bounds.so")  # debug build, see build_bounds_checked()
+
+
+def _nvcc() -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build %s" % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + SOURCES + ["-o", LIB_PATH]
+    return nvcc
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    if not force and up_to_date():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + SOURCES + ["-o", LIB_PATH]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     return LIB_PATH
 
 
+def build_bounds_checked(verbose: bool = True) -> str:
+    """The same sources with -DKMB_BOUNDS_CHECKS: every device-side index is compared with the size of what it
+    indexes (kmb_kernels.cuh, KMB_BOUND).  Not the product: run the GPU tests against it with
+    ``KMB_LIB_PATH=kmer_mapper_b200/libkmer_mapper_b200_bounds.so python -m pytest tests -m gpu``; the session
+    fails if any check fired (tests/conftest.py)."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DKMB_BOUNDS_CHECKS"] + SOURCES + ["-o", BOUNDS_LIB_PATH]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return BOUNDS_LIB_PATH
+
+
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+    print(build_bounds_checked() if "--bounds" in sys.argv[1:] else build(force=True))

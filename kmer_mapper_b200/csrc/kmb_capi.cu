@@ -130,6 +130,26 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(bench_load_mode)
     OPT(chunk_bytes)
 #undef OPT
+    if (!strcmp(name, "bounds_failures")) {  // read-only: -1 unless this is the bounds-checked build
+#ifdef KMB_BOUNDS_CHECKS
+        unsigned long long h[KMB_BOUND_SITES];
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpyFromSymbol(h, g_kmb_bound_failures, sizeof(h));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return kmb_fail(KMB_ERR_CUDA, "bounds_failures: %s", cudaGetErrorString(e));
+        }
+        unsigned long long total = 0;
+        for (int i = 0; i < KMB_BOUND_SITES; i++) {
+            if (h[i]) fprintf(stderr, "kmer_mapper_b200: bounds check site %d failed %llu times\n", i, h[i]);
+            total += h[i];
+        }
+        *value = (int64_t)total;
+#else
+        *value = -1;
+#endif
+        return KMB_OK;
+    }
     return kmb_fail(KMB_ERR_BAD_ARG, "kmb_get_option: unknown option '%s'", name);
 }
 
@@ -363,7 +383,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
                                                                  ix->addr, line_fill.p, ix->filter, d_status.p);
         g_launches++;
     }
-    kmb_build_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, d_status.p);
+    kmb_build_plan<false><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, nullptr, 0, d_status.p);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
@@ -378,11 +398,11 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     KMB_CUDA(cudaMalloc(&ix->lines, (size_t)ix->n_lines * KMB_LINE_BYTES));
     KMB_CUDA(cudaMemsetAsync(ix->lines, 0, (size_t)ix->n_lines * KMB_LINE_BYTES, s));
     KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
-    kmb_build_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, d_status.p);
+    kmb_build_plan<true><<<grid_for(ix->n_main, 256, sms), 256, 0, s>>>(line_fill.p, ix->n_main, ix->lines, ix->n_lines, d_status.p);
     g_launches++;
     if (n_entries) {
         kmb_build_scatter<<<grid_for(n_entries, 256, sms), 256, 0, s>>>(d_kmers, d_nodes, d_freq, d_h2i, d_nk, n_entries, ix->mod,
-                                                                   ix->addr, line_fill.p, ix->lines);
+                                                                   ix->addr, line_fill.p, ix->lines, ix->n_lines);
         g_launches++;
     }
     KMB_CUDA(cudaGetLastError());
@@ -665,6 +685,8 @@ static KmbProbe make_probe(const kmb_mapper *m) {
     P.max_freq = m->max_freq;
     P.counts = m->counts;
     P.log = m->log;
+    P.n_lines = ix->n_lines;
+    P.n_counts = m->n_counts;
     return P;
 }
 
@@ -1003,7 +1025,8 @@ extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t 
 // membership and per-key lookup
 // ------------------------------------------------------------------------------------------------
 template <int MODE, class OutT>
-static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uint64_t *keys, uint64_t n, OutT *out) {
+static int run_lookup(kmb_index *ix, uint32_t *counts, uint64_t n_counts, cudaStream_t s, const uint64_t *keys, uint64_t n,
+                      OutT *out) {
     if (n == 0) return KMB_OK;
     if (!keys || !out) return kmb_fail(KMB_ERR_BAD_ARG, "lookup: null buffer");
     DevBuf<uint64_t> t_keys;
@@ -1024,6 +1047,8 @@ static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uin
     P.addr = ix->addr;
     P.policies = 2u;
     P.counts = counts;
+    P.n_lines = ix->n_lines;
+    P.n_counts = n_counts;
     kmb_in_graph_kernel<MODE><<<grid_for(n, 256, ix->info.sms, 16), 256, 0, s>>>(
         d_keys, n, P, (uint8_t *)(MODE == 0 ? (void *)d_out : nullptr), (uint32_t *)(MODE == 1 ? (void *)d_out : nullptr));
     g_launches++;
@@ -1036,14 +1061,14 @@ static int run_lookup(kmb_index *ix, uint32_t *counts, cudaStream_t s, const uin
 extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t n, uint8_t *out) {
     if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_in_graph_index: null index");
     KMB_ON_DEVICE(ix->device);
-    return run_lookup<0, uint8_t>(ix, nullptr, 0, kmers, n, out);
+    return run_lookup<0, uint8_t>(ix, nullptr, 0, 0, kmers, n, out);
 }
 
 extern "C" int kmb_mapper_lookup_counts(kmb_mapper *m, const uint64_t *keys, uint64_t n, uint32_t *out) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_lookup_counts: null mapper");
     KMB_ON_DEVICE(m->index->device);
     if (m->dirty) KMB_TRY(launch_flush(m));
-    return run_lookup<1, uint32_t>(m->index, m->counts, m->stream, keys, n, out);
+    return run_lookup<1, uint32_t>(m->index, m->counts, m->n_counts, m->stream, keys, n, out);
 }
 
 // ------------------------------------------------------------------------------------------------

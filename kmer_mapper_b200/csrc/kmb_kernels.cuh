@@ -63,7 +63,27 @@ struct KmbProbe {  // everything a probe needs, passed by value to the kernels
     int32_t max_freq;                        // C int like the reference's cut-off (mapper.pyx:19,64)
     uint32_t *counts;                        // node counts: target of the log and of the rare direct reductions
     KmbLog log;
+    uint64_t n_lines;                        // sizes of lines[] (in sectors) and counts[]: only the bounds-checked
+    uint64_t n_counts;                       // build reads them
 };
+
+// Bounds-checked build (-DKMB_BOUNDS_CHECKS: `python -m kmer_mapper_b200._build --bounds`).  Every index the
+// kernels compute is compared with the size of what it indexes; a violation bumps the counter of its site
+// (kmb_get_option("bounds_failures") adds them up) and the access still happens.  Compiled out otherwise.
+#ifdef KMB_BOUNDS_CHECKS
+#define KMB_BOUND_SITES 16
+__device__ unsigned long long g_kmb_bound_failures[KMB_BOUND_SITES];
+#define KMB_BOUND(site, idx, limit)                                                                  \
+    do {                                                                                             \
+        if (!((unsigned long long)(idx) < (unsigned long long)(limit))) atomicAdd(&g_kmb_bound_failures[site], 1ull); \
+    } while (0)
+#else
+#define KMB_BOUND(site, idx, limit) \
+    do {                            \
+    } while (0)
+#endif
+// sites: 0 filter word, 1 main sector, 2 chain sector, 3 staging slot, 4 log entry, 5 log tag, 6 node count,
+//        7 candidate stack, 8 base vector, 9 boundary-mask word, 10 apply: tag word, 11 apply: entry, 12 packed tile word
 
 // ------------------------------------------------------------------------------------------------
 // cache-hinted loads.  Gathers are use-once: keep them out of L1 (L1::no_allocate) and mark their
@@ -166,6 +186,8 @@ __global__ void kmb_build_count(const uint64_t *__restrict__ kmers, const int32_
         if (!kmb_entry_live(hashes_to_index, n_kmers, l, h)) continue;
         live_n++;
         const KmbLoc loc = kmb_locate(key, addr);
+        KMB_BOUND(1, loc.sector, addr.n_main);
+        if (addr.n_filter_words) KMB_BOUND(0, loc.fword, addr.n_filter_words);
         atomicAdd(&line_fill[loc.sector], 1u);
         if (addr.n_filter_words) atomicOr(&filter[loc.fword], loc.fmask);
     }
@@ -185,7 +207,7 @@ __global__ void kmb_build_count(const uint64_t *__restrict__ kmers, const int32_
 // headers of the whole chain and reset line_fill for the scatter
 template <bool ASSIGN>
 __global__ void kmb_build_plan(uint32_t *__restrict__ line_fill, uint64_t n_main, uint32_t *__restrict__ lines,
-                            KmbStatus *status) {
+                            uint64_t n_lines, KmbStatus *status) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_main; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t c = line_fill[i];
         uint32_t extra = kmb_chain_extra_lines(c);
@@ -195,6 +217,7 @@ __global__ void kmb_build_plan(uint32_t *__restrict__ line_fill, uint64_t n_main
             uint32_t base = 0;
             if (extra) base = (uint32_t)n_main + atomicAdd(&status->pool_lines, extra);
             lines[i * KMB_LINE_WORDS] = kmb_sector_header(c, base);
+            for (uint32_t t = 0; t < extra; t++) KMB_BOUND(2, base + t, n_lines);
             for (uint32_t t = 0; t < extra; t++)
                 lines[(uint64_t)(base + t) * KMB_LINE_WORDS] = kmb_sector_header(c - KMB_LINE_SLOTS * (t + 1), base + t + 1);
             line_fill[i] = 0;
@@ -206,7 +229,7 @@ __global__ void kmb_build_plan(uint32_t *__restrict__ line_fill, uint64_t n_main
 __global__ void kmb_build_scatter(const uint64_t *__restrict__ kmers, const int32_t *__restrict__ nodes,
                                const uint16_t *__restrict__ freqs, const int32_t *__restrict__ hashes_to_index,
                                const int32_t *__restrict__ n_kmers, uint64_t n_entries, KmbMod mod, KmbAddr addr,
-                               uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines) {
+                               uint32_t *__restrict__ line_fill, uint32_t *__restrict__ lines, uint64_t n_lines) {
     for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_entries; l += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = kmers[l];
         uint64_t q, h;
@@ -215,6 +238,8 @@ __global__ void kmb_build_scatter(const uint64_t *__restrict__ kmers, const int3
         uint64_t main_line = kmb_locate(key, addr).sector;
         uint32_t s = atomicAdd(&line_fill[main_line], 1u);
         uint32_t ovf_base = lines[main_line * KMB_LINE_WORDS] & ~KMB_HDR_CHAIN;  // only meaningful (and used) for s >= 2
+        KMB_BOUND(1, main_line, addr.n_main);
+        KMB_BOUND(2, kmb_chain_line(main_line, ovf_base, s), n_lines);
         uint32_t *lp = lines + kmb_chain_line(main_line, ovf_base, s) * KMB_LINE_WORDS;
         uint32_t j = kmb_chain_slot(s);
         *reinterpret_cast<uint2 *>(lp + KMB_LINE_KEY_WORD0 + 2 * j) = make_uint2((uint32_t)key, (uint32_t)(key >> 32));
@@ -297,6 +322,7 @@ template <class F>
 __device__ __forceinline__ void kmb_walk_chain(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t hdr, F on_match) {
     while (hdr & KMB_HDR_CHAIN) {
         uint32_t r[8];
+        KMB_BOUND(2, hdr & ~KMB_HDR_CHAIN, P.n_lines);
         kmb_ld_sector(P.lines + (uint64_t)(hdr & ~KMB_HDR_CHAIN) * KMB_LINE_WORDS, r, pol.line);
         if (kmb_match_sector(r, km, on_match)) return;
         hdr = r[0];
@@ -307,6 +333,7 @@ __device__ __forceinline__ void kmb_walk_chain(const KmbProbe &P, const KmbPol &
 template <class F>
 __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &pol, uint64_t km, uint32_t sector, F on_match) {
     uint32_t r[8];
+    KMB_BOUND(1, sector, P.addr.n_main);
     kmb_ld_sector(P.lines + (uint64_t)sector * KMB_LINE_WORDS, r, pol.line);
     if (kmb_match_sector(r, km, on_match)) return;
     kmb_walk_chain(P, pol, km, r[0], on_match);
@@ -329,7 +356,10 @@ struct KmbStage {
 };
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
     const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
+    KMB_BOUND(6, node, P.n_counts);
     const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
+    KMB_BOUND(3, pos, KMB_STAGE_SLOTS);
+    KMB_BOUND(3, b, KMB_LOG_BINS);
     st.buf[b * KMB_STAGE_SLOTS + pos] = node;
 }
 // One group of 32 ids of bin b (lanes >= n write holes) to the log -- or, if the log is full, straight onto
@@ -350,6 +380,7 @@ __device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage 
             if (base + 32 <= P.log.cap) {
                 st.res_left[b] = left - 1;
                 st.res_base[b] = base + 32;
+                KMB_BOUND(5, base >> 5, P.log.cap >> 5);
                 P.log.tags[base >> 5] = (uint8_t)b;
             } else {
                 st.res_left[b] = KMB_RES_FULL;  // stop reserving: every further atomic would hit the same address
@@ -360,8 +391,10 @@ __device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage 
     base = __shfl_sync(KMB_FULL_MASK, base, 0);
     const uint32_t id = (uint32_t)lane < n ? src[lane] : KMB_LOG_HOLE;
     if (base != ~0ull) {
+        KMB_BOUND(4, base + lane, P.log.cap);
         P.log.entries[base + lane] = id;
     } else if (id != KMB_LOG_HOLE) {
+        KMB_BOUND(6, id, P.n_counts);
         atomicAdd(P.counts + id, 1u);
     }
 }
@@ -417,6 +450,7 @@ __device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &
     pp.issued += (unsigned)cnt;
     if (lane < cnt && !(P.policies & 0x200u)) {
         pp.km = q_kmer[base + lane];
+        KMB_BOUND(1, q_h[base + lane], P.addr.n_main);
         kmb_ld_sector(P.lines + (uint64_t)q_h[base + lane] * KMB_LINE_WORDS, pp.r, pol.line);
         pp.valid = true;
     }
@@ -440,6 +474,7 @@ __device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol
             uint32_t *counts = P.counts;
             kmb_walk_chain(P, pol, pp.km, pp.r[0], [&](uint32_t node, uint32_t freq) {
                 if ((int32_t)freq <= max_freq) {
+                    KMB_BOUND(6, node, P.n_counts);
                     atomicAdd(counts + node, 1u);
                     counted++;
                 }
@@ -472,6 +507,7 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
         const bool valid = (vbits >> u) & 1u;
         if (FILT) {
             need[u] = valid ? loc.fmask : 0u;
+            if (valid) KMB_BOUND(0, loc.fword, P.addr.n_filter_words);
             fw[u] = (valid && !(P.policies & 0x400u)) ? kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter) : 0u;
         } else {
             need[u] = valid ? 1u : 0u;
@@ -496,6 +532,7 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
 #pragma unroll
     for (int u = 0; u < U; u++) {
         if ((cmask >> u) & 1u) {
+            KMB_BOUND(7, slot, KMB_QUEUE_SLOTS(U));
             q_kmer[slot] = km[u];
             q_h[slot] = hh[u];
             slot++;
@@ -555,7 +592,10 @@ struct KmbArrayFn {
 // ================================================================================================
 __device__ __forceinline__ uint4 kmb_load_bases16(const uint8_t *__restrict__ bases, uint64_t v, uint64_t n_vec_full,
                                                   uint64_t n_bases, uint64_t pol) {
-    if (v < n_vec_full) return kmb_ldg_v4_hint(bases + v * 16, pol);
+    if (v < n_vec_full) {
+        KMB_BOUND(8, v * 16 + 15, n_bases);
+        return kmb_ldg_v4_hint(bases + v * 16, pol);
+    }
     // tail of the buffer: byte loads, 'A' beyond the end (window starts there are masked out)
     uint32_t t[4];
 #pragma unroll
@@ -575,6 +615,7 @@ __device__ __forceinline__ uint4 kmb_load_bases16(const uint8_t *__restrict__ ba
 __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict__ mask, uint64_t p0, uint64_t n_bases,
                                                      int k) {
     if (p0 >= n_bases) return 0u;
+    KMB_BOUND(9, p0 >> 5, n_bases / 32 + 1);
     uint32_t valid = ~mask[p0 >> 5];
     if (p0 + 32 + (uint64_t)k > n_bases + 1) {  // window must end inside the buffer: p + k <= n_bases
         int64_t last = (int64_t)n_bases - (int64_t)k - (int64_t)p0;  // last valid i
@@ -623,6 +664,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             uint64_t v = t0 / 16 + (uint64_t)i;
             uint4 w = kmb_load_bases16(bases, v, n_vec_full, n_bases, pol.first);
             uint32_t inv;
+            KMB_BOUND(12, i, KMB_WTILE_POS / 16 + 4);
             pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
             if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + v * 16 + (uint64_t)(__ffs(inv) - 1)));
         }
@@ -712,6 +754,7 @@ template <class F>
 __device__ __forceinline__ void kmb_walk_one(const KmbProbe &P, const KmbPol &pol, uint64_t km, F on_match) {
     const KmbLoc loc = kmb_locate(km, P.addr);
     if (P.filter != nullptr) {
+        KMB_BOUND(0, loc.fword, P.addr.n_filter_words);
         uint32_t w = kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter);
         if ((w & loc.fmask) != loc.fmask) return;
     }
@@ -730,6 +773,7 @@ __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, 
             if (strand == 1) km = kmb_revcomp(km, k);
             kmb_walk_one(P, pol, km, [&](uint32_t node, uint32_t freq) {
                 if ((int32_t)freq <= P.max_freq) {
+                    KMB_BOUND(6, node, P.n_counts);
                     atomicAdd(P.counts + node, 1u);
                     counted++;
                 }
@@ -775,6 +819,7 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin,
     uint32_t seen = 0, present = 0;
     for (uint64_t g0 = g_lo + (uint64_t)warp * 128; g0 < g_hi; g0 += (uint64_t)warps * 128) {
         const uint64_t gl = g0 + 4ull * lane;  // this lane's four groups
+        if (gl < g_hi) KMB_BOUND(10, gl >> 2, log.cap >> 7);
         const uint32_t t4 = gl < g_hi ? tags4[gl >> 2] : 0xFFFFFFFFu;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -782,6 +827,7 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin,
             while (mine) {
                 const int j = __ffs(mine) - 1;
                 mine &= mine - 1u;
+                KMB_BOUND(11, ((g0 + 4ull * j + k) << 5) + lane, log.cap);
                 const uint32_t id = log.entries[((g0 + 4ull * j + k) << 5) + lane];
                 if (id != KMB_LOG_HOLE) {
                     if (use_table) {
@@ -839,7 +885,10 @@ __global__ void kmb_in_graph_kernel(const uint64_t *__restrict__ kmers, uint64_t
             return true;
         });
         if (MODE == 0) out8[i] = hit ? 1 : 0;
-        else out32[i] = hit ? P.counts[node] : 0u;
+        else {
+            if (hit) KMB_BOUND(6, node, P.n_counts);
+            out32[i] = hit ? P.counts[node] : 0u;
+        }
     }
 }
 

@@ -15,6 +15,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _bounds_checked_build_is_clean():
+    """With the bounds-checked library (KMB_LIB_PATH=...libkmer_mapper_b200_bounds.so, _build.py) the whole GPU
+    session must end without a single device-side index out of range.  The product build reports -1: no checks."""
+    yield
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return
+        from kmer_mapper_b200 import _lib
+        failures = _lib.get_option("bounds_failures")
+    except Exception:
+        return
+    assert failures in (-1, 0), "%d device-side bounds checks failed (sites on stderr)" % failures
+
+
 class GoldenIndex:
     """Duck-typed index (the six attributes mapper.pyx:22-29 reads) rebuilt from a golden fixture."""
 
