@@ -160,6 +160,19 @@ int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format, int final_
                     uint8_t *bases, uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity,
                     uint64_t *n_reads, uint64_t *n_bases, uint64_t *consumed);
 
+/* ---- packed transport of host-resident reads -----------------------------------------------------
+ * kmb_mapper_map_reads on HOST buffers encodes the bases to 2 bits each on the CPU (all cores, AVX2 when the
+ * CPU has it), straight into pinned staging, and sends a quarter of the bytes over PCIe (option "host_pack": 1 always, 0 never,
+ * default -1 = when the encoder threads outrun the bus: >= 10 threads for a pinned source, >= 2 for a pageable one;
+ * "host_threads", default 0 = every CPU of the affinity mask).  Same table as the kernels apply to
+ * unpacked input (DNAEncoding as used at util.py:71-75; N -> A of command_line_interface.py:41), same invalid-byte
+ * report.  kmb_pack_bases is that encoder on its own: word j of words[] = bases 16j..16j+15, base 16j in the lowest
+ * bits, positions past n_bases read as 'A'; words_capacity >= (n_bases + 15) / 16 + 4 (the last 4 are zero padding).
+ * Returns KMB_ERR_INVALID_BASE and the offset of the first byte outside ACGTacgt (and N unless
+ * KMB_FLAG_NO_N_TO_A) -- the words are still all written.  Host only, no GPU involved. */
+int kmb_pack_bases(const uint8_t *bases, uint64_t n_bases, uint32_t flags, int n_threads, uint32_t *words,
+                   uint64_t words_capacity, int64_t *first_bad_offset);
+
 /* ---- pinned host memory for the chunk reader (command_line_interface.py:102-111 replacement) -- */
 int kmb_host_alloc(void **ptr, size_t bytes);
 int kmb_host_free(void *ptr);
@@ -183,7 +196,9 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
  *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
- *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes"}. */
+ *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads"};
+ * read-only: "h2d_bytes" (bytes the mapping calls have copied host -> device so far), "bounds_failures" (-1 unless
+ * built with -DKMB_BOUNDS_CHECKS). */
 int kmb_set_option(const char *name, int64_t value);
 int kmb_get_option(const char *name, int64_t *value);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/kmer_mapper_b200.h"
+#include "kmb_host.h"
 #include "kmb_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -69,9 +70,17 @@ struct KmbOptions {
     int64_t bench_load_mode = 0;          // kmb_bench_gather, 8-byte loads: 0 .nc, 1-3 L2::64B/128B/256B, 4 plain, 5 .cv
     int64_t bench_grid_blocks = 0;        // kmb_bench_gather: total CTAs (0 = SMs x blocks_per_sm)
     int64_t time_kernels = 0;             // bracket every mapping kernel with CUDA events (kmb_mapper_kernel_time)
+    // Host input of map_reads travels as 2 bits per base, encoded on the CPU (kmb_hostpack.cpp): 1 always, 0 never,
+    // -1 auto = when that beats sending the ASCII bytes.  Measured on the 16-core B200 boxes
+    // (profiles/r01_v7_host_pack.jsonl): a pinned source crosses PCIe at ~48 GB/s as ASCII and the encoder makes
+    // 4.6 GB/s per thread (DRAM-bound at ~78 GB/s), so packing wins from ~10 threads up; a pageable source only
+    // reaches ~10 GB/s through the driver's staging copy, so packing wins from 2 threads up.
+    int64_t host_pack = -1;
+    int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
 };
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_h2d_bytes{0};  // bytes the mapping calls sent host -> device (bench.py's e2e)
 
 extern "C" int kmb_set_option(const char *name, int64_t value) {
     if (!name) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_set_option: null name");
@@ -96,6 +105,8 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(l2_fetch_granularity)
     OPT(bench_grid_blocks)
     OPT(bench_load_mode)
+    OPT(host_pack)
+    OPT(host_threads)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -128,8 +139,14 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(l2_fetch_granularity)
     OPT(bench_grid_blocks)
     OPT(bench_load_mode)
+    OPT(host_pack)
+    OPT(host_threads)
     OPT(chunk_bytes)
 #undef OPT
+    if (!strcmp(name, "h2d_bytes")) {  // read-only
+        *value = (int64_t)g_h2d_bytes.load();
+        return KMB_OK;
+    }
     if (!strcmp(name, "bounds_failures")) {  // read-only: -1 unless this is the bounds-checked build
 #ifdef KMB_BOUNDS_CHECKS
         unsigned long long h[KMB_BOUND_SITES];
@@ -191,9 +208,10 @@ static int dev_info(int device, DevInfo *d) {
 }
 
 // Is p device memory (usable by kernels of `device`)?  Plain malloc / numpy memory is "unregistered".
-static int ptr_on_device(const void *p, int device, bool *on_device) {
+static int ptr_on_device(const void *p, int device, bool *on_device, bool *pinned = nullptr) {
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (pinned) *pinned = e == cudaSuccess && a.type == cudaMemoryTypeHost;
     if (e != cudaSuccess) {
         cudaGetLastError();
         *on_device = false;
@@ -450,13 +468,17 @@ extern "C" int kmb_index_layout(const kmb_index *ix, uint64_t *n_main_lines, uin
 // mapper
 // ------------------------------------------------------------------------------------------------
 struct StageSlot {
-    uint8_t *data = nullptr;  // bases (or k-mers) of one chunk
+    uint8_t *data = nullptr;  // bases (ASCII or packed) or k-mers of one chunk
     int64_t *offsets = nullptr;
     uint32_t *mask = nullptr;
     size_t data_cap = 0, off_cap = 0, mask_cap = 0;
+    uint32_t *h_words = nullptr;  // pinned: the chunk's packed bases, written by the host encoder, read by the DMA engine
+    uint32_t *h_off = nullptr;    // pinned: its chunk-relative read offsets
+    size_t h_words_cap = 0, h_off_cap = 0;
     cudaEvent_t copied = nullptr, consumed = nullptr;
     bool used = false;
 };
+#define KMB_SLOTS 3  // one chunk being encoded, one on the bus, one under the kernel
 
 struct kmb_mapper {
     kmb_index *index = nullptr;
@@ -471,7 +493,8 @@ struct kmb_mapper {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     KmbStatus *d_status = nullptr;
     KmbStatus *h_status = nullptr;  // pinned
-    StageSlot slot[2];
+    StageSlot slot[KMB_SLOTS];
+    uint64_t host_bad = ~0ull;  // first invalid byte met by the host-side encoder since the last reset
     uint32_t *dmask = nullptr;  // read-boundary mask for in-place device input
     size_t dmask_cap = 0;
     int next_slot = 0;
@@ -483,6 +506,8 @@ static void slot_free(StageSlot &s) {
     cudaFree(s.data);
     cudaFree(s.offsets);
     cudaFree(s.mask);
+    if (s.h_words) cudaFreeHost(s.h_words);
+    if (s.h_off) cudaFreeHost(s.h_off);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);
     s = StageSlot();
@@ -493,8 +518,7 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
     DeviceGuard g(m->index->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
-    slot_free(m->slot[0]);
-    slot_free(m->slot[1]);
+    for (int i = 0; i < KMB_SLOTS; i++) slot_free(m->slot[i]);
     for (auto &pr : m->timed) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -518,6 +542,7 @@ static int status_reset(kmb_mapper *m) {
     memset(&hs, 0, sizeof(hs));
     hs.first_bad_offset = ~0ull;
     hs.max_node = -1;
+    m->host_bad = ~0ull;
     *m->h_status = hs;
     KMB_CUDA(cudaMemcpyAsync(m->d_status, m->h_status, sizeof(hs), cudaMemcpyHostToDevice, m->stream));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
@@ -656,7 +681,7 @@ extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *
     KMB_CUDA(cudaMalloc(&m->d_status, sizeof(KmbStatus)));
     KMB_CUDA(cudaMallocHost(&m->h_status, sizeof(KmbStatus)));
     KMB_TRY(status_reset(m));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < KMB_SLOTS; i++) {
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].copied, cudaEventDisableTiming));
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].consumed, cudaEventDisableTiming));
     }
@@ -696,7 +721,7 @@ static int pick_u() {
 }
 
 // ---- kernel dispatch (template instantiation table) ------------------------------------------------
-typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, int, bool, KmbProbe, KmbStatus *);
+typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, int, uint32_t, KmbProbe, KmbStatus *);
 typedef void (*MapKmersFn)(const uint64_t *, uint64_t, int, KmbProbe, KmbStatus *);
 
 template <int U>
@@ -743,16 +768,20 @@ static int timed_end(kmb_mapper *m) {
     return KMB_OK;
 }
 
-// launch the read-boundary mask + the fused kernel over one device-resident batch
-static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_bases, uint64_t base0,
-                            const int64_t *d_offsets, uint64_t n_reads, uint32_t *d_mask, int k, uint32_t flags) {
+// launch the read-boundary mask + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
+// stream of kmb_hostpack.cpp and d_offsets are uint32 offsets relative to the batch (else int64, relative to base0)
+static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_bases, uint64_t base0, const void *d_offsets,
+                            uint64_t n_reads, uint32_t *d_mask, int k, uint32_t flags, bool packed) {
     if (n_bases == 0) return KMB_OK;
     const kmb_index *ix = m->index;
     const size_t mask_words = (size_t)(n_bases / 32 + 1);
     KMB_CUDA(cudaMemsetAsync(d_mask, 0, mask_words * 4, m->stream));
     if (n_reads) {
-        kmb_mark_read_ends<<<grid_for(n_reads, 256, ix->info.sms), 256, 0, m->stream>>>(d_offsets, n_reads, (int64_t)base0,
-                                                                                      k, d_mask);
+        const int grid = grid_for(n_reads, 256, ix->info.sms);
+        if (packed)
+            kmb_mark_read_ends<uint32_t><<<grid, 256, 0, m->stream>>>((const uint32_t *)d_offsets, n_reads, 0, k, d_mask);
+        else
+            kmb_mark_read_ends<int64_t><<<grid, 256, 0, m->stream>>>((const int64_t *)d_offsets, n_reads, (int64_t)base0, k, d_mask);
         g_launches++;
     }
     // every window, both strands when asked: the number of look-ups this launch can make
@@ -763,10 +792,10 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     KMB_TRY(resident_blocks((const void *)fn, g_opt.map_reads_blocks_per_sm, &per_sm));
     uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
+    const uint32_t in_mode = ((flags & KMB_FLAG_NO_N_TO_A) ? 0u : KMB_IN_N_TO_A) | (packed ? KMB_IN_PACKED : 0u);
     m->dirty = true;
     KMB_TRY(timed_begin(m));
-    fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_bases, n_bases, base0, d_mask, k, !(flags & KMB_FLAG_NO_N_TO_A), P,
-                                                m->d_status);
+    fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_bases, n_bases, base0, d_mask, k, in_mode, P, m->d_status);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_TRY(timed_end(m));
@@ -828,6 +857,26 @@ static int slot_reserve(StageSlot &s, size_t data_bytes, size_t n_offsets, size_
     return KMB_OK;
 }
 
+static int slot_reserve_host(StageSlot &s, size_t n_words, size_t n_offsets) {
+    if (n_words > s.h_words_cap) {
+        if (s.h_words) cudaFreeHost(s.h_words);
+        s.h_words = nullptr;
+        s.h_words_cap = 0;
+        size_t cap = n_words + n_words / 8 + 64;
+        KMB_CUDA(cudaMallocHost(&s.h_words, cap * 4));
+        s.h_words_cap = cap;
+    }
+    if (n_offsets > s.h_off_cap) {
+        if (s.h_off) cudaFreeHost(s.h_off);
+        s.h_off = nullptr;
+        s.h_off_cap = 0;
+        size_t cap = n_offsets + n_offsets / 4 + 64;
+        KMB_CUDA(cudaMallocHost(&s.h_off, cap * 4));
+        s.h_off_cap = cap;
+    }
+    return KMB_OK;
+}
+
 static int check_k(int k) {
     if (k <= 0 || k >= 32) return kmb_fail(KMB_ERR_BAD_ARG, "k=%d outside 1..31", k);
     return KMB_OK;
@@ -840,8 +889,8 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
     if (n_bases == 0 || n_reads == 0) return KMB_OK;
     if (!bases || !offsets) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: null buffer");
     KMB_ON_DEVICE(m->index->device);
-    bool dev_b, dev_o;
-    KMB_TRY(ptr_on_device(bases, m->index->device, &dev_b));
+    bool dev_b, dev_o, pinned_b;
+    KMB_TRY(ptr_on_device(bases, m->index->device, &dev_b, &pinned_b));
     KMB_TRY(ptr_on_device(offsets, m->index->device, &dev_o));
     if (dev_b != dev_o)
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: bases and offsets must both be host or both be device buffers");
@@ -857,12 +906,14 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
             KMB_CUDA(cudaMalloc(&m->dmask, (words + words / 8 + 64) * 4));
             m->dmask_cap = words + words / 8 + 64;
         }
-        return launch_map_reads(m, bases, n_bases, 0, offsets, n_reads, m->dmask, k, flags);
+        return launch_map_reads(m, bases, n_bases, 0, offsets, n_reads, m->dmask, k, flags, false);
     }
     // ---- host input: whole reads per chunk, double-buffered H2D on the copy stream
     if (offsets[0] != 0 || (uint64_t)offsets[n_reads] != n_bases)
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: offsets[0] must be 0 and offsets[n_reads] must equal n_bases");
     const uint64_t chunk = (uint64_t)g_opt.chunk_bytes;
+    const int pack_threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
+    const bool want_pack = g_opt.host_pack > 0 || (g_opt.host_pack < 0 && pack_threads >= (pinned_b ? 10 : 2));
     uint64_t r0 = 0;
     while (r0 < n_reads) {
         // largest r1 with offsets[r1] - offsets[r0] <= chunk (at least one read)
@@ -874,14 +925,29 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
         const uint64_t b0 = (uint64_t)offsets[r0], nb = (uint64_t)offsets[r1] - b0, nr = r1 - r0;
         if (nb) {
             StageSlot &s = m->slot[m->next_slot];
-            m->next_slot ^= 1;
+            m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
             if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));  // also makes re-allocation safe
-            KMB_TRY(slot_reserve(s, nb + 16, nr + 1, nb / 32 + 1));
-            KMB_CUDA(cudaMemcpyAsync(s.data, bases + b0, nb, cudaMemcpyHostToDevice, m->copy_stream));
-            KMB_CUDA(cudaMemcpyAsync(s.offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, m->copy_stream));
+            const bool packed = want_pack && nb < (1ull << 32);
+            if (packed) {
+                // encode on the CPU into pinned staging while the previous chunks are on the bus / under the kernel
+                const size_t n_words = (size_t)kmb_packed_words(nb);
+                KMB_TRY(slot_reserve(s, n_words * 4, (nr + 2) / 2, nb / 32 + 1));
+                KMB_TRY(slot_reserve_host(s, n_words, nr + 1));
+                const uint64_t bad = kmb_host_pack(bases + b0, nb, !(flags & KMB_FLAG_NO_N_TO_A), pack_threads, s.h_words);
+                if (bad != ~0ull) m->host_bad = std::min(m->host_bad, b0 + bad);
+                kmb_host_rel_offsets(offsets + r0, nr + 1, (int64_t)b0, pack_threads, s.h_off);
+                KMB_CUDA(cudaMemcpyAsync(s.data, s.h_words, n_words * 4, cudaMemcpyHostToDevice, m->copy_stream));
+                KMB_CUDA(cudaMemcpyAsync(s.offsets, s.h_off, (nr + 1) * 4, cudaMemcpyHostToDevice, m->copy_stream));
+                g_h2d_bytes += n_words * 4 + (nr + 1) * 4;
+            } else {
+                KMB_TRY(slot_reserve(s, nb + 16, nr + 1, nb / 32 + 1));
+                KMB_CUDA(cudaMemcpyAsync(s.data, bases + b0, nb, cudaMemcpyHostToDevice, m->copy_stream));
+                KMB_CUDA(cudaMemcpyAsync(s.offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, m->copy_stream));
+                g_h2d_bytes += nb + (nr + 1) * 8;
+            }
             KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
             KMB_CUDA(cudaStreamWaitEvent(m->stream, s.copied, 0));
-            KMB_TRY(launch_map_reads(m, s.data, nb, b0, s.offsets, nr, s.mask, k, flags));
+            KMB_TRY(launch_map_reads(m, s.data, nb, b0, s.offsets, nr, s.mask, k, flags, packed));
             KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
             s.used = true;
         }
@@ -908,10 +974,11 @@ extern "C" int kmb_mapper_map_kmers(kmb_mapper *m, const uint64_t *kmers, uint64
     for (uint64_t i0 = 0; i0 < n; i0 += per) {
         uint64_t cnt = std::min(per, n - i0);
         StageSlot &s = m->slot[m->next_slot];
-        m->next_slot ^= 1;
+        m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
         if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
         KMB_TRY(slot_reserve(s, cnt * 8, 0, 0));
         KMB_CUDA(cudaMemcpyAsync(s.data, kmers + i0, cnt * 8, cudaMemcpyHostToDevice, m->copy_stream));
+        g_h2d_bytes += cnt * 8;
         KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
         KMB_CUDA(cudaStreamWaitEvent(m->stream, s.copied, 0));
         KMB_TRY(launch_map_kmers(m, reinterpret_cast<const uint64_t *>(s.data), cnt, flags, k));
@@ -926,6 +993,7 @@ static int fetch_status(kmb_mapper *m) {
     if (m->dirty) KMB_TRY(launch_flush(m));
     KMB_CUDA(cudaMemcpyAsync(m->h_status, m->d_status, sizeof(KmbStatus), cudaMemcpyDeviceToHost, m->stream));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->host_bad < m->h_status->first_bad_offset) m->h_status->first_bad_offset = m->host_bad;  // met by the host encoder
     return KMB_OK;
 }
 
@@ -1058,6 +1126,20 @@ static int run_lookup(kmb_index *ix, uint32_t *counts, uint64_t n_counts, cudaSt
     return KMB_OK;
 }
 
+extern "C" int kmb_pack_bases(const uint8_t *bases, uint64_t n_bases, uint32_t flags, int n_threads, uint32_t *words,
+                              uint64_t words_capacity, int64_t *first_bad_offset) {
+    if ((!bases && n_bases) || !words) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_pack_bases: null buffer");
+    if (words_capacity < kmb_packed_words(n_bases))
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_pack_bases: words_capacity %llu < %llu", (unsigned long long)words_capacity,
+                        (unsigned long long)kmb_packed_words(n_bases));
+    const uint64_t bad = kmb_host_pack(bases, n_bases, !(flags & KMB_FLAG_NO_N_TO_A), n_threads, words);
+    if (first_bad_offset) *first_bad_offset = bad == ~0ull ? -1 : (int64_t)bad;
+    if (bad != ~0ull)
+        return kmb_fail(KMB_ERR_INVALID_BASE, "invalid base byte at flat offset %llu (only ACGTacgt%s are accepted)",
+                        (unsigned long long)bad, (flags & KMB_FLAG_NO_N_TO_A) ? "" : " and N");
+    return KMB_OK;
+}
+
 extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t n, uint8_t *out) {
     if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_in_graph_index: null index");
     KMB_ON_DEVICE(ix->device);
@@ -1155,7 +1237,7 @@ extern "C" int kmb_hash_reads(int device, const uint8_t *bases, uint64_t n_bases
     hs.first_bad_offset = ~0ull;
     KMB_CUDA(cudaMemcpyAsync(d_status.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
     KMB_CUDA(cudaMemsetAsync(d_mask.p, 0, mask_words * 4, s));
-    kmb_mark_read_ends<<<grid_for(n_reads, 256, info.sms), 256, 0, s>>>(d_off, n_reads, 0, k, d_mask.p);
+    kmb_mark_read_ends<int64_t><<<grid_for(n_reads, 256, info.sms), 256, 0, s>>>(d_off, n_reads, 0, k, d_mask.p);
     kmb_hash_count_kernel<<<(unsigned)n_tiles, KMB_TILE_THREADS, 0, s>>>(d_mask.p, n_bases, k, d_tiles.p);
     kmb_hash_scan_kernel<<<1, 1024, 0, s>>>(d_tiles.p, n_tiles, d_tiles.p + n_tiles);
     g_launches += 3;

@@ -33,7 +33,9 @@
 #define KMB_POS_PER_THREAD 32
 #define KMB_TILE_POS (KMB_TILE_THREADS * KMB_POS_PER_THREAD)  // 8192 window starts per tile
 #define KMB_WTILE_POS (32 * KMB_POS_PER_THREAD)                // 1024 window starts per warp tile
-#define KMB_QUEUE_SLOTS(U) (32 * ((U) + 1))                   // per-warp candidate stack: < 32 left over + 32 U new
+#define KMB_QUEUE_SLOTS(U) (32 * ((U) + 1))
+#define KMB_IN_N_TO_A 1u  // kmb_map_reads_kernel in_mode: 'N' reads as 'A'
+#define KMB_IN_PACKED 2u  //   the input is the packed 2-bit stream, not ASCII                   // per-warp candidate stack: < 32 left over + 32 U new
 
 struct KmbStatus {
     unsigned long long first_bad_offset;   // min flat offset of an invalid byte, ~0 if none
@@ -253,11 +255,12 @@ __global__ void kmb_build_scatter(const uint64_t *__restrict__ kmers, const int3
 // the last k-1 bases of its read (or the read is shorter than k).  One thread per read; a read
 // touches at most k-1 <= 30 bits = at most two 32-bit words.
 // ================================================================================================
-__global__ void kmb_mark_read_ends(const int64_t *__restrict__ offsets, uint64_t n_reads, int64_t base0, int k,
+template <class OffT>  // int64 offsets of the caller (base0 = the chunk's first base) or uint32 chunk-relative ones
+__global__ void kmb_mark_read_ends(const OffT *__restrict__ offsets, uint64_t n_reads, int64_t base0, int k,
                                    uint32_t *mask) {
     for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
-        int64_t s = offsets[r] - base0;
-        int64_t e = offsets[r + 1] - base0;
+        int64_t s = (int64_t)offsets[r] - base0;
+        int64_t e = (int64_t)offsets[r + 1] - base0;
         int64_t lo = e - (k - 1);
         if (lo < s) lo = s;
         if (lo >= e) continue;
@@ -627,7 +630,12 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
 template <int U, bool FILT, bool REVCOMP>
 __global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
-                     const uint32_t *__restrict__ mask, int k, bool n_to_a, KmbProbe P, KmbStatus *status) {
+                     const uint32_t *__restrict__ mask, int k, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
+    const bool n_to_a = (in_mode & KMB_IN_N_TO_A) != 0u;
+    // packed transport (host input, kmb_hostpack.cpp): `bases` holds the 2-bit stream already, validated on the host
+    const bool packed = (in_mode & KMB_IN_PACKED) != 0u;
+    const uint32_t *__restrict__ words = reinterpret_cast<const uint32_t *>(bases);
+    const uint64_t n_words = (n_bases + 15) / 16 + 4;  // kmb_packed_words
     // Everything is per warp (tile of 1024 window starts, packed stream, candidate stack): no CTA barrier,
     // so a warp that is walking a long chain never holds the other seven back.
     __shared__ __align__(16) uint32_t s_pack[KMB_TILE_THREADS / 32][KMB_WTILE_POS / 16 + 4];  // 64 words + halo
@@ -662,9 +670,13 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 #pragma unroll
         for (int i = lane; i < KMB_WTILE_POS / 16 + 2; i += 32) {
             uint64_t v = t0 / 16 + (uint64_t)i;
+            KMB_BOUND(12, i, KMB_WTILE_POS / 16 + 4);
+            if (packed) {
+                pack[i] = v < n_words ? kmb_ldg_u32_hint(words + v, pol.first) : 0u;
+                continue;
+            }
             uint4 w = kmb_load_bases16(bases, v, n_vec_full, n_bases, pol.first);
             uint32_t inv;
-            KMB_BOUND(12, i, KMB_WTILE_POS / 16 + 4);
             pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
             if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + v * 16 + (uint64_t)(__ffs(inv) - 1)));
         }

@@ -21,12 +21,25 @@ def world():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+def host_threads_per_rank() -> int:
+    """CPU threads each rank of this node may use for host-side work (the 2-bit encoder of host input, the read
+    parser): the CPUs of the affinity mask shared fairly between the ranks torchrun started on this node."""
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    return max(1, len(os.sched_getaffinity(0)) // local_world)
+
+
 def init_process_group(backend=None):
     """Join the job torchrun started (MASTER_ADDR/MASTER_PORT from the environment).  Returns
     (rank, world_size, local_rank); a no-op for a single process."""
     rank, world_size, local_rank = world()
     if world_size == 1:
         return rank, world_size, local_rank
+    if backend != "gloo":
+        try:  # the ranks of a node share its cores: without this every rank would start one encoder thread per core
+            from . import _lib
+            _lib.set_option("host_threads", host_threads_per_rank())
+        except Exception:
+            pass
     import torch
     import torch.distributed as dist
     if not dist.is_initialized():

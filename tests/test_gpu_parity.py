@@ -19,7 +19,7 @@ def kmb():
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_l2_budget_bytes", 60 << 20),
-                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20)):
+                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0)):
         _lib.set_option(name, v)
 
 
@@ -267,27 +267,33 @@ def test_map_reads_vs_oracle(kmb, k, variant):
                                       ragged=ragged)
         want, n_want = c_oracle.map_reads(idx, mx, bases, offsets, k, n_threads=4)
         m = Mapper(di, mx + 1)
-        m.map_reads(bases, offsets, k)                      # host buffers (staged, chunked)
-        got = m.counts()
-        assert np.array_equal(got, want)
-        assert m.stats() == (n_want, int(want.astype(np.uint64).sum()))
-        m.reset()
+        for host_pack in (1, 0):                            # host buffers: 2-bit packed transport, then plain ASCII
+            kmb.set_option("host_pack", host_pack)
+            m.map_reads(bases, offsets, k)
+            got = m.counts()
+            assert np.array_equal(got, want)
+            assert m.stats() == (n_want, int(want.astype(np.uint64).sum()))
+            m.reset()
+        kmb.set_option("host_pack", -1)
         tb, to = torch.from_numpy(bases).cuda(), torch.from_numpy(offsets).cuda()
         m.map_reads(tb, to, k)                              # device buffers (in place)
         assert np.array_equal(m.counts(), want)
         m.close()
 
 
-def test_map_reads_chunked_host_path_and_linearity(kmb):
+@pytest.mark.parametrize("host_pack,host_threads", [(1, 0), (1, 3), (0, 0)])
+def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads):
     from kmer_mapper_b200 import synthetic as S
     from kmer_mapper_b200.device import DeviceIndex, Mapper
+    kmb.set_option("host_pack", host_pack)
+    kmb.set_option("host_threads", host_threads)
     k = 31
     g, idx = _small_world(k, 300)
     di = DeviceIndex.from_index(_fresh(idx))
     mx = idx.max_node_id()
     bases, offsets = S.make_reads(g, 50_000, 150, seed=9, ragged=True, n_rate=0.01)
     want, _ = c_oracle.map_reads(idx, mx, bases, offsets, k, n_threads=4)
-    kmb.set_option("chunk_bytes", 1 << 16)                  # ~60 chunks: exercises the double buffering
+    kmb.set_option("chunk_bytes", 1 << 16)                  # ~120 chunks: exercises the slot ring
     m = Mapper(di, mx + 1)
     m.map_reads(bases, offsets, k)
     assert np.array_equal(m.counts(), want)
@@ -299,6 +305,8 @@ def test_map_reads_chunked_host_path_and_linearity(kmb):
     assert np.array_equal(m.counts(), want)
     m.close()
     kmb.set_option("chunk_bytes", 64 << 20)
+    kmb.set_option("host_pack", -1)
+    kmb.set_option("host_threads", 0)
 
 
 def test_map_reads_reverse_complement_flag(kmb):
@@ -325,10 +333,12 @@ def test_map_reads_reverse_complement_flag(kmb):
     m.close()
 
 
-def test_map_reads_invalid_base_reports_offset(kmb):
+@pytest.mark.parametrize("host_pack", [1, 0])
+def test_map_reads_invalid_base_reports_offset(kmb, host_pack):
     from kmer_mapper_b200 import synthetic as S
     from kmer_mapper_b200._lib import InvalidBaseError
     from kmer_mapper_b200.device import DeviceIndex, Mapper
+    kmb.set_option("host_pack", host_pack)
     g, idx = _small_world(31, 500, n_entries=2000, hot=0)
     bases, offsets = S.make_reads(g, 3000, 100, seed=1)
     bases[123_457] = ord("n")
@@ -351,6 +361,7 @@ def test_map_reads_invalid_base_reports_offset(kmb):
     assert e.value.offset == 77
     m.close()
     kmb.set_option("chunk_bytes", 64 << 20)
+    kmb.set_option("host_pack", -1)
 
 
 def test_map_cpu_chunk_worker_shape(kmb):

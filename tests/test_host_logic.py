@@ -275,3 +275,78 @@ def test_sharding_covers_every_read_once():
             seen += list(range(lo, hi))
         assert seen == list(range(1001))
         assert sum(distributed.chunk_belongs_to_rank(i, r, world) for i in range(50) for r in range(world)) == 50
+
+
+# ---------------------------------------------------------------------------------------------
+# packed transport: the host-side 2-bit encoder (kmb_pack_bases, kmb_hostpack.cpp) against the oracle's
+# N policy + DNAEncoding restatement (oracle.replace_n_with_a / encode_bases)
+# ---------------------------------------------------------------------------------------------
+def _pack(bases, flags=0, threads=0):
+    import ctypes as C
+    from kmer_mapper_b200 import _lib
+    n = len(bases)
+    cap = (n + 15) // 16 + 4
+    words = np.full(cap, 0xDEADBEEF, dtype=np.uint32)
+    bad = C.c_int64(-5)
+    rc = _lib.lib().kmb_pack_bases(bases.ctypes.data, n, flags, threads, words.ctypes.data, cap, C.byref(bad))
+    return rc, words, bad.value
+
+
+def _oracle_words(bases, n_to_a=True):
+    codes = oracle.encode_bases(oracle.replace_n_with_a(bases) if n_to_a else bases).astype(np.uint64)
+    cap = (len(bases) + 15) // 16 + 4
+    padded = np.zeros(cap * 16, dtype=np.uint64)
+    padded[:len(codes)] = codes
+    return (padded.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+
+
+@pytest.mark.parametrize("threads", [1, 0, 3])
+def test_host_pack_matches_oracle_encoding(threads):
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    for n in (0, 1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 1000, 4097, 65_536 * 16 + 7, (1 << 22) + 5):
+        bases = rng.choice(alphabet, size=n)
+        rc, words, bad = _pack(bases, 0, threads)
+        assert (rc, bad) == (0, -1)
+        assert np.array_equal(words, _oracle_words(bases)), n
+        # an unaligned start inside a bigger buffer (chunks begin at arbitrary read offsets)
+        if n > 40:
+            rc, words, bad = _pack(bases[3:], 0, threads)
+            assert rc == 0 and np.array_equal(words, _oracle_words(bases[3:])), n
+
+
+def test_host_pack_reports_first_invalid_byte_like_the_oracle():
+    rng = np.random.default_rng(6)
+    for n in (20, 1000, 300_000, (1 << 21) + 11):
+        bases = rng.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), size=n)
+        for junk in (b"n", b"X", b"@", b"\x00", b"\xff", b"N"):
+            flags = 2 if junk == b"N" else 0           # KMB_FLAG_NO_N_TO_A: 'N' is then invalid as well
+            b = bases.copy()
+            pos = np.sort(rng.integers(0, n, size=3))
+            b[pos] = junk[0]
+            rc, _, bad = _pack(b, flags)
+            with pytest.raises(oracle.InvalidBaseError) as e:
+                oracle.encode_bases(b if flags else oracle.replace_n_with_a(b))
+            assert rc == -2 and bad == e.value.offset == pos[0]
+    import ctypes as C
+    from kmer_mapper_b200 import _lib
+    words = np.zeros(4, np.uint32)
+    assert _lib.lib().kmb_pack_bases(bases.ctypes.data, 100, 0, 1, words.ctypes.data, 4, None) == -1   # capacity
+
+
+def test_host_pack_worker_pool_survives_fork():
+    """bench.py and the reference-style CLI fork workers; a child must not wait for the parent's pool threads."""
+    import multiprocessing as mp
+    bases = np.frombuffer(b"ACGT" * (1 << 20), dtype=np.uint8).copy()
+    want = _oracle_words(bases)
+    assert np.array_equal(_pack(bases, 0, 4)[1], want)          # the pool now exists in this process
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+
+    def child():
+        q.put(bool(np.array_equal(_pack(bases, 0, 4)[1], want)))
+
+    p = ctx.Process(target=child)
+    p.start()
+    p.join(60)
+    assert p.exitcode == 0 and q.get(timeout=5) is True
