@@ -160,6 +160,14 @@ int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format, int final_
                     uint8_t *bases, uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity,
                     uint64_t *n_reads, uint64_t *n_bases, uint64_t *consumed);
 
+/* First record start AFTER the first newline of text[0, n_text) (n_text when there is none): how a rank of a
+ * multi-GPU job finds the beginning of its byte range of a plain FASTA/FASTQ file -- pass the text from one byte
+ * before the nominal cut, so that a cut that falls exactly on a record start is found.  FASTQ: a line starting with
+ * '@' whose next-but-one line starts with '+' (a quality line may start with '@', but is then followed by a header
+ * and a base line); FASTA: a line starting with '>'.  (No counterpart in the reference, whose workers all receive
+ * chunks from one reader process: command_line_interface.py:124-130.) */
+int kmb_find_record_start(const uint8_t *text, uint64_t n_text, int format, uint64_t *offset);
+
 /* ---- packed transport of host-resident reads -----------------------------------------------------
  * kmb_mapper_map_reads on HOST buffers encodes the bases to 2 bits each on the CPU (all cores, AVX2 when the
  * CPU has it), straight into pinned staging, and sends a quarter of the bytes over PCIe (option "host_pack": 1 always, 0 never,

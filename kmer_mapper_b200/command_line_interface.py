@@ -113,7 +113,7 @@ def map_bnp(args):
     reads = open_reads(args.reads)
     t_map = time.perf_counter()
     try:
-        chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size)
+        chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size, rank=rank, world_size=world_size)
         if world_size == 1:
             node_counts = map_gpu(index, chunk_iter, kmer_size, _flag(args, "gpu_hash_map_size", 0), want_revcomp)
         else:
@@ -139,9 +139,7 @@ def _map_sharded(kmer_index, chunks, k, map_reverse_complements, rank, world_siz
     n_counts = di.max_node_id() + 1
     counts = torch.zeros(n_counts, dtype=torch.int32, device="cuda")
     mapper = Mapper(di, n_counts, DEFAULT_MAX_FREQUENCY, counts_tensor=counts)
-    for i, chunk in enumerate(chunks):
-        if not distributed.chunk_belongs_to_rank(i, rank, world_size):
-            continue
+    for chunk in chunks:    # the reader already hands this rank its share only (reader.py: read_chunks)
         seq = chunk.sequence
         mapper.map_reads(seq.bases, seq.offsets, k, revcomp=bool(map_reverse_complements), n_to_a=True)
     mapper.sync()

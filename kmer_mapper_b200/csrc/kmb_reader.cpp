@@ -17,10 +17,11 @@
 #include <string.h>
 
 #include <algorithm>
-#include <thread>
+#include <functional>
 #include <vector>
 
 #include "../../include/kmer_mapper_b200.h"
+#include "kmb_host.h"
 
 namespace {
 
@@ -180,6 +181,18 @@ const uint8_t *fasta_resync(const uint8_t *p, const uint8_t *e) {
 
 }  // namespace
 
+extern "C" int kmb_find_record_start(const uint8_t *text, uint64_t n_text, int format, uint64_t *offset) {
+    if (!offset || (!text && n_text) || (format != 0 && format != 1)) return KMB_ERR_BAD_ARG;
+    const uint8_t *e = text + n_text;
+    const uint8_t *p = format == 1 ? fastq_resync(text, e) : fasta_resync(text, e);
+    *offset = (uint64_t)(p - text);
+    return KMB_OK;
+}
+
+// one piece per worker of the library's thread pool (kmb_hostpack.cpp)
+static void run_piece_trampoline(void *ctx, int part) { (*static_cast<std::function<void(int)> *>(ctx))(part); }
+static void run_pieces(int n, std::function<void(int)> fn) { kmb_host_parallel(n, n, run_piece_trampoline, &fn); }
+
 extern "C" int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format, int final_chunk, int n_threads,
                                uint8_t *bases, uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity,
                                uint64_t *n_reads, uint64_t *n_bases, uint64_t *consumed) {
@@ -209,12 +222,7 @@ extern "C" int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format,
         piece_end[t] = fastq ? fastq_walk<false>(text, cut[t], cut[t + 1], fin, pc[t], nullptr, nullptr)
                              : fasta_walk<false>(cut[t], cut[t + 1], fin, pc[t], nullptr, nullptr);
     };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < T; t++) th.emplace_back(count_piece, t);
-        count_piece(0);
-        for (auto &x : th) x.join();
-    }
+    run_pieces(T, count_piece);
     uint64_t r = 0, b = 0;
     const uint8_t *done = text;
     for (int t = 0; t < T; t++) {
@@ -244,12 +252,8 @@ extern "C" int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format,
         if (fastq) fastq_walk<true>(text, cut[t], piece_end[t], true, tmp, bases, offsets);
         else fasta_walk<true>(cut[t], piece_end[t], true, tmp, bases, offsets);
     };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < T; t++)
-            if (pc[t].n_reads) th.emplace_back(copy_piece, t);
-        if (pc[0].n_reads) copy_piece(0);
-        for (auto &x : th) x.join();
-    }
+    run_pieces(T, [&](int t) {
+        if (pc[t].n_reads) copy_piece(t);
+    });
     return KMB_OK;
 }

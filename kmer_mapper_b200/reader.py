@@ -70,6 +70,10 @@ class _PinnedPool:
             self._bufs[i] = buf
         return buf
 
+    def untake(self):
+        """Give back the buffer of the last take() (nothing was handed to a consumer)."""
+        self._i ^= 1
+
     def _release(self, i):
         self._bufs[i] = None
         if self._ptrs[i] is not None:
@@ -224,7 +228,9 @@ class ReadFile:
         self.format = _format_of(self.path)
         self._bases_pool = _PinnedPool(pinned)
         self._offsets_pool = _PinnedPool(pinned)
-        self.n_threads = int(n_threads or min(os.cpu_count() or 1, 16))
+        self.n_threads = int(n_threads or min(len(os.sched_getaffinity(0)) or 1, 32))
+        self._bases_per_byte = 0.0   # densest window seen so far: sizes the next window's output buffers
+        self._reads_per_byte = 0.0
 
     def _open(self):
         if self.path.lower().endswith(".gz"):
@@ -260,37 +266,111 @@ class ReadFile:
             if not item:
                 return
 
-    def _parse(self, text: np.ndarray, final: bool):
-        """One call of the native parser; returns (RaggedSequence, bytes consumed)."""
+    def _parse(self, text_ptr: int, n_text: int, final: bool, count_only: bool = False):
+        """The native parser on one window of text (address + length: no view of the file mapping is created, so
+        the mapping can be closed even while an exception's traceback is alive); returns (RaggedSequence, bytes
+        consumed).  The output buffers
+        are sized from the previous window (bases and reads per byte of text, plus slack), so the usual window
+        costs one call; a window that needs more answers KMB_ERR_NOMEM with the exact sizes and is parsed again."""
         lib = _lib.lib()
-        n_text = int(text.shape[0])
         fmt = 1 if self.format == "fastq" else 0
         n_reads, n_bases, consumed = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        rc = lib.kmb_parse_reads(text.ctypes.data, n_text, fmt, int(final), self.n_threads, None, 0, None, 0,
-                                 C.byref(n_reads), C.byref(n_bases), C.byref(consumed))
-        if rc != _lib.KMB_OK:
-            raise ValueError("%s: malformed %s record" % (self.path, self.format.upper()))
-        if n_reads.value == 0:
+        if count_only:      # another rank's chunk: only where it ends matters
+            rc = lib.kmb_parse_reads(text_ptr, n_text, fmt, int(final), self.n_threads, None, 0, None, 0,
+                                     C.byref(n_reads), C.byref(n_bases), C.byref(consumed))
+            if rc == _lib.KMB_ERR_BAD_ARG:
+                raise ValueError("%s: malformed %s record" % (self.path, self.format.upper()))
+            _lib.check(rc)
             return RaggedSequence(np.zeros(0, np.uint8), np.zeros(1, np.int64)), int(consumed.value)
-        bases = self._bases_pool.take(n_bases.value + 16)
-        offsets = self._offsets_pool.take(8 * (n_reads.value + 1)).view(np.int64)
-        rc = lib.kmb_parse_reads(text.ctypes.data, n_text, fmt, int(final), self.n_threads, bases.ctypes.data,
-                                 bases.shape[0], offsets.ctypes.data, offsets.shape[0], C.byref(n_reads),
-                                 C.byref(n_bases), C.byref(consumed))
+        want_bases = int(n_text * self._bases_per_byte * 1.05) + 4096
+        want_reads = int(n_text * self._reads_per_byte * 1.05) + 64
+        for attempt in range(2):
+            bases = self._bases_pool.take(want_bases + 16)
+            offsets = self._offsets_pool.take(8 * (want_reads + 1)).view(np.int64)
+            rc = lib.kmb_parse_reads(text_ptr, n_text, fmt, int(final), self.n_threads, bases.ctypes.data,
+                                     bases.shape[0], offsets.ctypes.data, offsets.shape[0], C.byref(n_reads),
+                                     C.byref(n_bases), C.byref(consumed))
+            if rc == _lib.KMB_ERR_NOMEM and attempt == 0:
+                self._bases_pool.untake()
+                self._offsets_pool.untake()
+                want_bases, want_reads = n_bases.value, n_reads.value
+                continue
+            break
+        if rc == _lib.KMB_ERR_BAD_ARG:
+            raise ValueError("%s: malformed %s record" % (self.path, self.format.upper()))
         _lib.check(rc)
+        if consumed.value:
+            self._bases_per_byte = max(self._bases_per_byte, n_bases.value / consumed.value)
+            self._reads_per_byte = max(self._reads_per_byte, n_reads.value / consumed.value)
+        if n_reads.value == 0:
+            self._bases_pool.untake()
+            self._offsets_pool.untake()
+            return RaggedSequence(np.zeros(0, np.uint8), np.zeros(1, np.int64)), int(consumed.value)
         return RaggedSequence(bases[:n_bases.value], offsets[:n_reads.value + 1]), int(consumed.value)
 
-    def read_chunks(self, min_chunk_size=5_000_000):
+    def _shard_start(self, base_ptr, file_size, cut):
+        """First record start at or after byte ``cut`` (the file size when there is none)."""
+        if cut <= 0:
+            return 0
+        if cut >= file_size:
+            return file_size
+        off = C.c_uint64()
+        fmt = 1 if self.format == "fastq" else 0
+        _lib.check(_lib.lib().kmb_find_record_start(base_ptr + cut - 1, file_size - (cut - 1), fmt, C.byref(off)))
+        return cut - 1 + off.value
+
+    def _windows_of_file(self, min_chunk_size, rank=0, world_size=1):
+        """Plain (uncompressed) file: the parser reads the page cache through a read-only mapping -- no copy of the
+        text into Python objects, no carry-over buffer: the next window simply starts where the last complete
+        record ended.  With world_size > 1 this rank takes the records that START inside its 1/world_size of the
+        file's bytes, so the ranks of a multi-GPU job parse disjoint parts.  Yields RaggedSequence objects."""
+        file_size = os.path.getsize(self.path)
+        if file_size == 0:
+            return
+        with open(self.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            if hasattr(mm, "madvise"):
+                mm.madvise(mmap.MADV_SEQUENTIAL)
+            whole = np.frombuffer(mm, dtype=np.uint8)
+            base_ptr = whole.ctypes.data
+            try:
+                pos = self._shard_start(base_ptr, file_size, file_size * rank // world_size)
+                size = self._shard_start(base_ptr, file_size, file_size * (rank + 1) // world_size)
+                while pos < size:
+                    want = int(min_chunk_size)
+                    while True:
+                        end = min(size, pos + want)
+                        final = end == size
+                        if not final and hasattr(mm, "madvise"):   # start reading the next window from disk now
+                            a = end - end % mmap.PAGESIZE
+                            mm.madvise(mmap.MADV_WILLNEED, a, min(want, size - a))
+                        seq, consumed = self._parse(base_ptr + pos, end - pos, final)
+                        if consumed or final:
+                            break
+                        want *= 2                                   # one record longer than the window
+                    if final and consumed < end - pos and len(seq) == 0 and self.format == "fasta":
+                        raise ValueError("%s: FASTA data without a '>' header line" % self.path)
+                    pos += consumed if not final else end - pos
+                    yield seq
+            finally:
+                del whole
+
+    def read_chunks(self, min_chunk_size=5_000_000, rank=0, world_size=1):
+        """Chunks of at least ``min_chunk_size`` bytes of the file, cut at record boundaries.  ``rank`` /
+        ``world_size``: only this rank's share -- a contiguous byte range of a plain file, every world_size-th chunk
+        of a .gz (which has to be inflated from the start by everyone)."""
+        if not self.path.lower().endswith(".gz"):
+            for seq in self._windows_of_file(min_chunk_size, rank, world_size):
+                if len(seq):
+                    yield ReadChunk(seq)
+            return
         carry = b""
-        seen_data = False
-        for block in self._blocks(int(min_chunk_size)):
+        for i, block in enumerate(self._blocks(int(min_chunk_size))):
             final = len(block) == 0
             data = carry + block if carry else block
             if not data:
                 break
-            seen_data = True
             text = np.frombuffer(data, dtype=np.uint8)
-            seq, consumed = self._parse(text, final)
+            seq, consumed = self._parse(text.ctypes.data, int(text.shape[0]), final, count_only=i % world_size != rank)
             if final and consumed < len(data) and len(seq) == 0 and self.format == "fasta":
                 raise ValueError("%s: FASTA data without a '>' header line" % self.path)
             carry = bytes(data[consumed:]) if consumed < len(data) else b""
@@ -298,7 +378,6 @@ class ReadFile:
                 yield ReadChunk(seq)
             if final:
                 break
-        del seen_data
 
     def close(self):
         self._bases_pool.close()

@@ -350,3 +350,47 @@ def test_host_pack_worker_pool_survives_fork():
     p.start()
     p.join(60)
     assert p.exitcode == 0 and q.get(timeout=5) is True
+
+
+@pytest.mark.parametrize("fmt", ["fastq", "fasta", "fastq.gz"])
+def test_reader_rank_shards_cover_every_read_once_in_order(tmp_path, fmt):
+    """Multi-GPU CLI: rank r of world_size parses the records that start in its 1/world_size of a plain file's
+    bytes (found by resynchronisation on hostile text), or every world_size-th chunk of a .gz; concatenated in rank
+    order (plain) / chunk order (.gz) the shards are the file."""
+    rng = np.random.default_rng(11)
+    g = synthetic.make_genome(60_000, 8)
+    n = 6_000
+    bases, offsets = synthetic.make_reads(g, n, 120, seed=12, ragged=True)
+    want = [bytes(bases[offsets[r]:offsets[r + 1]]) for r in range(n)]
+    path = str(tmp_path / ("shards." + {"fastq": "fq", "fasta": "fa", "fastq.gz": "fq.gz"}[fmt]))
+    if fmt == "fastq.gz":
+        synthetic.write_fastq(path, bases, offsets, members=7)
+    else:
+        qual_alphabet = np.frombuffer(b"@+>I#", np.uint8)
+        with open(path, "wb") as f:
+            for r, seq in enumerate(want):
+                if fmt == "fastq":
+                    f.write(b"@read%d\n%s\n+\n%s\n" % (r, seq, bytes(rng.choice(qual_alphabet, size=len(seq)))))
+                else:
+                    w = int(rng.integers(1, 70))
+                    f.write(b">read%d\n" % r)
+                    for i in range(0, len(seq), w):
+                        f.write(seq[i:i + w] + b"\n")
+    for world in (1, 2, 3, 7, 64):
+        per_rank = []
+        for rank in range(world):
+            mine = []
+            for chunk in open_reads(path, pinned=False).read_chunks(min_chunk_size=20_000, rank=rank, world_size=world):
+                s = chunk.sequence
+                mine.append([bytes(s[i]) for i in range(len(s))])
+            per_rank.append(mine)
+        if fmt == "fastq.gz":      # round-robin over chunks: interleave them back
+            n_chunks = sum(len(m) for m in per_rank)
+            got = []
+            for i in range(n_chunks):
+                got += per_rank[i % world][i // world]
+        else:
+            got = [read for mine in per_rank for chunk in mine for read in chunk]
+            if world in (2, 3):    # every rank has a real share
+                assert all(sum(len(c) for c in mine) > n // (2 * world) for mine in per_rank)
+        assert got == want, (fmt, world)
