@@ -75,6 +75,12 @@ struct KmbOptions {
     // (profiles/r01_v7_host_pack.jsonl): a pinned source crosses PCIe at ~48 GB/s as ASCII and the encoder makes
     // 4.6 GB/s per thread (DRAM-bound at ~78 GB/s), so packing wins from ~10 threads up; a pageable source only
     // reaches ~10 GB/s through the driver's staging copy, so packing wins from 2 threads up.
+    // Fused reads kernel over the minimizer-bucketed read-path table (kmb_core.cuh): 1 = whenever k == 31 and no
+    // reverse complements are asked for; 0 (default) = never.  Measured on config 2 (profiles/README.md): the table
+    // halves the DRAM traffic and cuts the fetches per k-mer from 0.19 to 0.12, but computing the minimizers costs
+    // more issue slots than the saved look-ups give back -- 70 ms per 6.0 G k-mers against 48 ms for the
+    // key-addressed kernel -- so it stays opt-in (and parity-tested) until that changes.
+    int64_t read_table = 0;
     int64_t host_pack = -1;
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
 };
@@ -107,6 +113,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(bench_load_mode)
     OPT(host_pack)
     OPT(host_threads)
+    OPT(read_table)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -141,6 +148,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(bench_load_mode)
     OPT(host_pack)
     OPT(host_threads)
+    OPT(read_table)
     OPT(chunk_bytes)
 #undef OPT
     if (!strcmp(name, "h2d_bytes")) {  // read-only
@@ -302,6 +310,15 @@ struct kmb_index {
     uint64_t device_bytes = 0;
     KmbMod mod;
     DevInfo info;
+    // read-path table: the same live entries filed under the minimizer of their key (built on first use)
+    std::mutex mz_mu;
+    int mz_k = 0;                       // 0 = not built
+    KmbAddr mz_addr;                    // n_main = buckets (two sectors each)
+    uint64_t mz_n_lines = 0;
+    uint32_t *mz_lines = nullptr;
+    uint32_t *mz_filter = nullptr;
+    size_t mz_filter_bytes = 0;
+    uint64_t mz_entries = 0;
 };
 
 extern "C" int kmb_index_destroy(kmb_index *ix) {
@@ -309,6 +326,8 @@ extern "C" int kmb_index_destroy(kmb_index *ix) {
     DeviceGuard g(ix->device);
     cudaFree(ix->lines);
     cudaFree(ix->filter);
+    cudaFree(ix->mz_lines);
+    cudaFree(ix->mz_filter);
     cudaGetLastError();
     delete ix;
     return KMB_OK;
@@ -768,6 +787,71 @@ static int timed_end(kmb_mapper *m) {
     return KMB_OK;
 }
 
+// Build the read-path table of an index for window length k (once; mappers on any stream share it).
+static int ensure_read_table(kmb_index *ix, int k) {
+    std::lock_guard<std::mutex> lock(ix->mz_mu);
+    if (ix->mz_k == k || ix->mz_k < 0) return KMB_OK;
+    if (ix->mz_k != 0) return kmb_fail(KMB_ERR_BAD_ARG, "read-path table already built for k=%d", ix->mz_k);
+    cudaStream_t s = 0;  // one-off, synchronous
+    const uint64_t n_buckets = std::min<uint64_t>(std::max<uint64_t>(ix->n_live, 1024), 1ull << 30);
+    KmbAddr addr;
+    memset(&addr, 0, sizeof(addr));
+    addr.n_main = (uint32_t)n_buckets;
+    // filter over the distinct minimizers (at most one per entry): same sizing rule as the key filter
+    const uint64_t keys = std::max<uint64_t>(ix->n_live, 1);
+    uint64_t filter_words = std::min<uint64_t>((uint64_t)std::max<int64_t>(g_opt.filter_l2_budget_bytes, 4) / 4,
+                                               std::max<uint64_t>(keys / 2, 1));
+    const double bits_per_key = 32.0 * (double)filter_words / (double)keys;
+    const bool want_filter = g_opt.use_filter == 1 || (g_opt.use_filter < 0 && bits_per_key >= 0.62);
+    if (!want_filter) filter_words = 0;
+    addr.n_filter_words = (uint32_t)filter_words;
+    addr.two_probes = bits_per_key >= 2.5 ? 1u : 0u;
+    DevBuf<uint32_t> filter, fill, lines;
+    KMB_TRY(filter.alloc((size_t)std::max<uint64_t>(filter_words, 1)));
+    KMB_CUDA(cudaMemsetAsync(filter.p, 0, (size_t)std::max<uint64_t>(filter_words, 1) * 4, s));
+    KMB_TRY(fill.alloc((size_t)n_buckets));
+    KMB_CUDA(cudaMemsetAsync(fill.p, 0, (size_t)n_buckets * 4, s));
+    DevBuf<KmbStatus> d_status;
+    KMB_TRY(d_status.alloc(1));
+    KmbStatus hs;
+    memset(&hs, 0, sizeof(hs));
+    KMB_CUDA(cudaMemcpyAsync(d_status.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+    const int sms = ix->info.sms;
+    kmb_mz_build_count<<<grid_for(ix->n_lines, 256, sms), 256, 0, s>>>(ix->lines, ix->n_lines, k, addr, fill.p, filter.p, d_status.p);
+    kmb_mz_build_plan<false><<<grid_for(n_buckets, 256, sms), 256, 0, s>>>(fill.p, n_buckets, nullptr, 0, d_status.p);
+    g_launches += 2;
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaMemcpyAsync(&hs, d_status.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    KMB_CUDA(cudaStreamSynchronize(s));
+    const uint64_t n_lines = 2 * n_buckets + hs.pool_lines;
+    if (n_lines >= (1ull << 31) || (hs.index_flags & 4u)) {
+        ix->mz_k = -1;  // cannot be built for this index: the key-addressed path serves it
+        return KMB_OK;
+    }
+    KMB_TRY(lines.alloc((size_t)n_lines * KMB_LINE_WORDS));
+    KMB_CUDA(cudaMemsetAsync(lines.p, 0, (size_t)n_lines * KMB_LINE_BYTES, s));
+    KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
+    kmb_mz_build_plan<true><<<grid_for(n_buckets, 256, sms), 256, 0, s>>>(fill.p, n_buckets, lines.p, n_lines, d_status.p);
+    kmb_mz_build_scatter<<<grid_for(ix->n_lines, 256, sms), 256, 0, s>>>(ix->lines, ix->n_lines, k, addr, fill.p, lines.p, n_lines);
+    g_launches += 2;
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaStreamSynchronize(s));
+    ix->mz_addr = addr;
+    ix->mz_n_lines = n_lines;
+    ix->mz_entries = hs.n_live_entries;
+    ix->mz_filter_bytes = want_filter ? (size_t)filter_words * 4 : 0;
+    ix->mz_lines = lines.release();
+    if (want_filter) ix->mz_filter = filter.release();
+    ix->device_bytes += n_lines * KMB_LINE_BYTES + ix->mz_filter_bytes;
+    ix->mz_k = k;
+    return KMB_OK;
+}
+
+static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
+    (void)ix;
+    return k == KMB_MZ_K && !(flags & KMB_FLAG_REVCOMP) && g_opt.read_table > 0;
+}
+
 // launch the read-boundary mask + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
 // stream of kmb_hostpack.cpp and d_offsets are uint32 offsets relative to the batch (else int64, relative to base0)
 static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_bases, uint64_t base0, const void *d_offsets,
@@ -787,12 +871,34 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     // every window, both strands when asked: the number of look-ups this launch can make
     KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases));
     KmbProbe P = make_probe(m);
+    const uint32_t in_mode = ((flags & KMB_FLAG_NO_N_TO_A) ? 0u : KMB_IN_N_TO_A) | (packed ? KMB_IN_PACKED : 0u);
+    uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
+    if (use_read_table(ix, k, flags)) KMB_TRY(ensure_read_table(m->index, k));
+    if (use_read_table(ix, k, flags) && ix->mz_k == k) {
+        P.lines = ix->mz_lines;
+        P.filter = ix->mz_filter;
+        P.addr = ix->mz_addr;
+        P.n_lines = ix->mz_n_lines;
+        typedef void (*MzFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, uint32_t, KmbProbe, KmbStatus *);
+        MzFn fn = P.filter ? kmb_map_reads_mz_kernel<true> : kmb_map_reads_mz_kernel<false>;
+        KMB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KMB_MZ_SMEM_BYTES));
+        int per_sm = 0;
+        KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, KMB_TILE_THREADS, KMB_MZ_SMEM_BYTES));
+        if (per_sm < 1) per_sm = 1;
+        if (g_opt.map_reads_blocks_per_sm > 0) per_sm = (int)std::min<int64_t>(g_opt.map_reads_blocks_per_sm, per_sm);
+        int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
+        m->dirty = true;
+        KMB_TRY(timed_begin(m));
+        fn<<<grid, KMB_TILE_THREADS, KMB_MZ_SMEM_BYTES, m->stream>>>(d_bases, n_bases, base0, d_mask, in_mode, P, m->d_status);
+        g_launches++;
+        KMB_CUDA(cudaGetLastError());
+        KMB_TRY(timed_end(m));
+        return KMB_OK;
+    }
     MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
     int per_sm;
     KMB_TRY(resident_blocks((const void *)fn, g_opt.map_reads_blocks_per_sm, &per_sm));
-    uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
-    const uint32_t in_mode = ((flags & KMB_FLAG_NO_N_TO_A) ? 0u : KMB_IN_N_TO_A) | (packed ? KMB_IN_PACKED : 0u);
     m->dirty = true;
     KMB_TRY(timed_begin(m));
     fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_bases, n_bases, base0, d_mask, k, in_mode, P, m->d_status);

@@ -211,6 +211,63 @@ KMB_HD uint64_t kmb_revcomp(uint64_t x, int k) {
     return x >> (64 - 2 * k);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Read-path table (second device structure over the same live entries, used by the fused reads kernel
+// only): entries are filed under the MINIMIZER of their key instead of the key itself.
+//
+// Consecutive windows of a read overlap in k-1 bases, and the minimizer of a k-mer -- the smallest
+// hash among its k-m+1 m-mers (m = 15) -- is shared by ~(k-m+2)/2 consecutive windows on average (9
+// at k = 31).  Filing the index entries under hash(minimizer) therefore sends a whole RUN of windows
+// to the same bucket: one filter word and one sector fetch per run instead of one per window, after
+// which every window of the run is compared, in registers, with the full keys the bucket holds.
+// Exactness is untouched: equal keys have equal minimizers, so a query meets every live entry with
+// its key, and only those can match.  (The key-addressed sectors remain what map_kmers, membership
+// and per-key look-ups use: a lone key has no neighbours to share a bucket with.)
+//
+// Bucket b = two adjacent 32-byte sectors 2b, 2b+1 -- one 64-byte DRAM fetch (L2::64B) brings both:
+// the primary holds entries 0-1, the secondary entries 2-3 and, beyond that, the link into a pool of
+// ordinary chained sectors.
+// ---------------------------------------------------------------------------------------------
+#define KMB_MZ_M 15
+#define KMB_MZ_MASK ((1u << (2 * KMB_MZ_M)) - 1u)
+// Ordering key of an m-mer: 26 hash bits above 6 bits that the caller fills with the m-mer's position, so that one
+// 32-bit minimum yields the minimizer AND where it sits (leftmost among equal hashes).  The bucket is addressed by
+// the m-mer itself, not by this hash, so the 26 bits only decide which m-mer wins.
+KMB_HD uint32_t kmb_mmer_order(uint32_t mmer) {
+    uint32_t x = (mmer ^ 0x2C1B3C6Du) * 0x9E3779B1u;  // the xor keeps poly-A (0) from always winning
+    x ^= x >> 15;
+    return (x * 0x85EBCA6Bu) & ~63u;
+}
+// minimizer m-mer of a k-mer hash (first base in the lowest bits), k >= KMB_MZ_M, and its base offset inside the k-mer
+KMB_HD uint32_t kmb_minimizer(uint64_t key, int k, uint32_t *offset) {
+    uint32_t best = 0xFFFFFFFFu, best_mmer = 0;
+    for (int j = 0; j + KMB_MZ_M <= k; j++) {
+        const uint32_t x = (uint32_t)(key >> (2 * j)) & KMB_MZ_MASK;
+        const uint32_t v = kmb_mmer_order(x) | (uint32_t)j;
+        if (v < best) {
+            best = v;
+            best_mmer = x;
+        }
+    }
+    *offset = best & 63u;
+    return best_mmer;
+}
+// Bucket header (word 0 of the primary sector 2b): bits 0-2 = entries under this minimizer (5 = more than four),
+// bits 3+5s .. 7+5s = minimizer offset of entry s (s = 0..3).  An entry can only equal the window that puts the
+// run's minimizer at that offset, so a run costs one key comparison per ENTRY, not one per window.
+// Secondary sector 2b+1: word 0 = 0, or KMB_HDR_CHAIN | first pool sector when there are more than four entries.
+// The pool sectors of a bucket are contiguous; word 0 of each = entries left in the chain including its own
+// (bits 0-21) | offset of its entry 0 (bits 22-26) | offset of its entry 1 (bits 27-31).
+#define KMB_MZ_HDR_COUNT(h) ((h) & 7u)
+#define KMB_MZ_HDR_OFFSET(h, s) (((h) >> (3u + 5u * (s))) & 31u)
+#define KMB_MZ_POOL_MAX_ENTRIES ((1u << 22) - 1u)
+#define KMB_MZ_POOL_LEFT(h) ((h) & KMB_MZ_POOL_MAX_ENTRIES)
+#define KMB_MZ_POOL_OFFSET(h, t) (((h) >> (22u + 5u * (t))) & 31u)
+KMB_HD uint64_t kmb_mz_sector(uint64_t bucket, uint32_t pool_base, uint32_t s) {
+    return s < 4u ? 2ull * bucket + (s >> 1) : (uint64_t)pool_base + ((s - 4u) >> 1);
+}
+KMB_HD uint32_t kmb_mz_pool_sectors(uint32_t n_total) { return n_total > 4u ? (n_total - 3u) / 2u : 0u; }
+
 // 64-bit mix (splitmix64 finaliser) for the synthetic-address generator of the gather benchmark.
 KMB_HD uint64_t kmb_mix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;

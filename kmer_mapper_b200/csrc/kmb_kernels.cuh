@@ -405,7 +405,7 @@ __device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage 
 // Groups that were reserved but never written keep the tag KMB_LOG_NO_BIN and are skipped by the apply pass.
 __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
     __syncwarp();
-    const uint32_t c = lane < KMB_LOG_BINS ? st.cnt[lane] : 0u;
+    const uint32_t c = lane < KMB_LOG_BINS ? min(st.cnt[lane], (uint32_t)KMB_STAGE_SLOTS) : 0u;  // clamp: kmb_mz_emit
     unsigned ready = __ballot_sync(KMB_FULL_MASK, all ? c > 0u : c >= 32u);
     while (ready) {
         const int b = __ffs(ready) - 1;
@@ -706,6 +706,477 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     // statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
     if (lane == 0 && mapped) atomicAdd(&status->n_kmers_mapped, REVCOMP ? 2ull * mapped : mapped);
+}
+
+// ================================================================================================
+// K1-4 over the read-path table (kmb_core.cuh, "Read-path table"): the fused kernel for k = 31 reads.
+// Same tiles, same encode, same hit log as kmb_map_reads_kernel; what differs is the unit of a
+// look-up: a RUN of consecutive windows with the same minimizer costs one filter word, one 64-byte
+// bucket fetch, and one key comparison per entry of the bucket (the entry's minimizer offset says
+// which window of the run it could equal).  Tile-synchronous, per warp:
+//   1. load + encode the tile (as in kmb_map_reads_kernel);
+//   2. per lane: 48 m-mer ordering keys (26 hash bits | position) and a log-step sliding minimum
+//      (window 17 = k - 15 + 1) give minimizer and position for its 32 windows; a bit mask marks
+//      where runs start;
+//   3. one filter word per run; the runs that pass get a staging slot;
+//   4. all their primary sectors are fetched with cp.async in one burst (~100 independent 64-byte
+//      DRAM fetches in flight per warp, no registers held), then the secondary sectors of the fuller
+//      buckets (L2 hits: same 64 bytes);
+//   5. per lane, per run, per entry: the one window that could match is extracted and compared.
+// No cross-tile state except the staged hits.
+// ================================================================================================
+#define KMB_MZ_K 31
+#define KMB_MZ_U 2          // runs taken per lane and round (filter loads in flight)
+#define KMB_MZ_SLOTS 128    // primary sectors staged per tile (a tile has ~145 runs, ~105 pass the filter)
+#define KMB_MZ_SLOTS2 64    // secondary sectors staged per tile (buckets with more than two entries)
+#define KMB_MZ_NONE 0xFFu   // run table: nothing to compare (no valid window, or the filter said no)
+#define KMB_MZ_LATE 0xFEu   // run table / secondary table: no staging slot left, load from global memory instead
+#define KMB_MZ_PACK_WORDS (KMB_WTILE_POS / 16 + 4)
+#define KMB_MZ_LATE_CAP 64  // < 32 left over + at most 32 new per round
+struct KmbMzShared {  // per warp
+    unsigned long long stage_res[KMB_LOG_BINS];
+    uint32_t pack[KMB_MZ_PACK_WORDS];
+    union {
+        uint32_t mz[32][32];                             // [window of the lane][lane], until the runs are enumerated
+        uint32_t slots[KMB_MZ_SLOTS][KMB_LINE_WORDS];    // then: the primary sectors of the runs that passed
+    } a;
+    uint32_t slots2[KMB_MZ_SLOTS2][KMB_LINE_WORDS];
+    uint32_t slot_sector[KMB_MZ_SLOTS];
+    uint8_t slot2_of[KMB_MZ_SLOTS];  // secondary slot of a primary slot, KMB_MZ_NONE, or KMB_MZ_LATE
+    uint8_t run_slot[32][32];        // [run of the lane][lane] -> primary slot, KMB_MZ_NONE, or KMB_MZ_LATE
+    uint8_t run_pos[32][32];         // position (base offset from the lane's first base, 0..47) of the run's minimizer
+    // runs whose bucket continues in the pool (more than four entries): retired 32 at a time, one per lane
+    unsigned long long late_lo[KMB_MZ_LATE_CAP], late_hi[KMB_MZ_LATE_CAP];  // the 64 bases of the run's lane
+    uint32_t late_valid[KMB_MZ_LATE_CAP], late_sector[KMB_MZ_LATE_CAP], late_sej[KMB_MZ_LATE_CAP];  // s | e << 8 | jpos << 16
+    uint32_t stage[KMB_LOG_BINS * KMB_STAGE_SLOTS];
+    uint32_t stage_cnt[2 * KMB_LOG_BINS];
+};
+#define KMB_MZ_SMEM_BYTES ((KMB_TILE_THREADS / 32) * sizeof(KmbMzShared))
+
+// ---- index side: file every live entry of the key-addressed sectors under its minimizer -------------
+__global__ void kmb_mz_build_count(const uint32_t *__restrict__ lines, uint64_t n_lines, int k, KmbAddr addr,
+                                   uint32_t *__restrict__ fill, uint32_t *__restrict__ filter, KmbStatus *status) {
+    unsigned long long n_here_total = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t *lp = lines + i * KMB_LINE_WORDS;
+        const uint32_t n = kmb_header_count(lp[0]);
+        for (uint32_t j = 0; j < n; j++) {
+            const uint64_t key = (uint64_t)lp[KMB_LINE_KEY_WORD0 + 2 * j] | ((uint64_t)lp[KMB_LINE_KEY_WORD0 + 2 * j + 1] << 32);
+            if (key >> (2 * k)) continue;  // cannot equal a k-base window
+            uint32_t off;
+            const KmbLoc loc = kmb_locate((uint64_t)kmb_minimizer(key, k, &off), addr);
+            KMB_BOUND(1, loc.sector, addr.n_main);
+            atomicAdd(&fill[loc.sector], 1u);
+            if (addr.n_filter_words) atomicOr(&filter[loc.fword], loc.fmask);
+            n_here_total++;
+        }
+    }
+    if (n_here_total) atomicAdd(&status->n_live_entries, n_here_total);
+}
+
+template <bool ASSIGN>
+__global__ void kmb_mz_build_plan(uint32_t *__restrict__ fill, uint64_t n_buckets, uint32_t *__restrict__ lines,
+                                  uint64_t n_lines, KmbStatus *status) {
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_buckets; b += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = fill[b];
+        const uint32_t extra = kmb_mz_pool_sectors(c);
+        if (!ASSIGN) {
+            if (extra) atomicAdd(&status->pool_lines, extra);
+            if (extra && c - 4u > KMB_MZ_POOL_MAX_ENTRIES) atomicOr(&status->index_flags, 4u);  // does not fit the pool header
+            continue;
+        }
+        uint32_t base = 0;
+        if (extra) base = (uint32_t)(2 * n_buckets) + atomicAdd(&status->pool_lines, extra);
+        lines[(2 * b) * KMB_LINE_WORDS] = c < 5u ? c : 5u;  // the scatter ORs the minimizer offsets in
+        lines[(2 * b + 1) * KMB_LINE_WORDS] = extra ? (KMB_HDR_CHAIN | base) : 0u;
+        for (uint32_t t = 0; t < extra; t++) {
+            KMB_BOUND(2, base + t, n_lines);
+            lines[(uint64_t)(base + t) * KMB_LINE_WORDS] = (c - 4u - 2u * t) & KMB_MZ_POOL_MAX_ENTRIES;  // offsets: scatter
+        }
+        fill[b] = 0;
+    }
+}
+
+__global__ void kmb_mz_build_scatter(const uint32_t *__restrict__ src, uint64_t n_src_lines, int k, KmbAddr addr,
+                                     uint32_t *__restrict__ fill, uint32_t *__restrict__ lines, uint64_t n_lines) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_src_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t *sp = src + i * KMB_LINE_WORDS;
+        const uint32_t n = kmb_header_count(sp[0]);
+        for (uint32_t j = 0; j < n; j++) {
+            const uint32_t klo = sp[KMB_LINE_KEY_WORD0 + 2 * j], khi = sp[KMB_LINE_KEY_WORD0 + 2 * j + 1];
+            const uint64_t key = (uint64_t)klo | ((uint64_t)khi << 32);
+            if (key >> (2 * k)) continue;
+            uint32_t off;
+            const uint64_t b = kmb_locate((uint64_t)kmb_minimizer(key, k, &off), addr).sector;
+            const uint32_t s = atomicAdd(&fill[b], 1u);
+            const uint32_t pool_base = lines[(2 * b + 1) * KMB_LINE_WORDS] & ~KMB_HDR_CHAIN;  // used for s >= 4 only
+            const uint64_t sec = kmb_mz_sector(b, pool_base, s);
+            KMB_BOUND(2, sec, n_lines);
+            uint32_t *lp = lines + sec * KMB_LINE_WORDS;
+            const uint32_t slot = s & 1u;
+            *reinterpret_cast<uint2 *>(lp + KMB_LINE_KEY_WORD0 + 2 * slot) = make_uint2(klo, khi);
+            lp[KMB_LINE_NODE_WORD0 + slot] = sp[KMB_LINE_NODE_WORD0 + j];
+            reinterpret_cast<uint16_t *>(lp + KMB_LINE_FREQ_WORD)[slot] = reinterpret_cast<const uint16_t *>(sp + KMB_LINE_FREQ_WORD)[j];
+            if (s < 4u) atomicOr(&lines[(2 * b) * KMB_LINE_WORDS], off << (3u + 5u * s));
+            else atomicOr(&lp[0], off << (22u + 5u * slot));
+        }
+    }
+}
+
+// ---- query side ---------------------------------------------------------------------------------------
+// Minimizers of windows 16 H .. 16 H + 15 of this lane: w = its 64 bases (4 packed words).  Value stored per
+// window: ordering key of the winning m-mer (26 bits) | its base position relative to the lane's first base.
+template <int H>
+__device__ __forceinline__ void kmb_mz_half(const uint32_t (&w)[4], uint32_t *mz_col, uint32_t &prev, uint32_t &startbits) {
+    uint32_t a[32];
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+        const int j = 16 * H + t;  // m-mer starting at base j: bits [2j, 2j + 30) of the 128-bit stream
+        a[t] = kmb_mmer_order(__funnelshift_r(w[j >> 4], w[(j >> 4) + 1], (2 * j) & 31) & KMB_MZ_MASK) | (uint32_t)j;
+    }
+    // sliding minimum over 17 = 16 + 1 by doubling: after the four rounds a[t] = min of m-mers t .. t+15
+#pragma unroll
+    for (int t = 0; t < 31; t++) a[t] = min(a[t], a[t + 1]);
+#pragma unroll
+    for (int t = 0; t < 29; t++) a[t] = min(a[t], a[t + 2]);
+#pragma unroll
+    for (int t = 0; t < 25; t++) a[t] = min(a[t], a[t + 4]);
+#pragma unroll
+    for (int t = 0; t < 17; t++) a[t] = min(a[t], a[t + 8]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t v = min(a[i], a[i + 1]);
+        mz_col[(16 * H + i) * 32] = v;
+        startbits |= (v != prev ? 1u : 0u) << (16 * H + i);
+        prev = v;
+    }
+}
+
+__device__ __forceinline__ void kmb_cp_async_sector(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 16u), "l"(gmem_src + 4) : "memory");
+}
+__device__ __forceinline__ void kmb_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// staging with a safety valve: a hit that finds its bin full goes straight onto the counts (the flush clamps)
+__device__ __forceinline__ void kmb_mz_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
+    const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
+    KMB_BOUND(6, node, P.n_counts);
+    const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
+    if (pos < KMB_STAGE_SLOTS) st.buf[b * KMB_STAGE_SLOTS + pos] = node;
+    else atomicAdd(P.counts + node, 1u);
+}
+// The two entries of one sector (words r[1..7]: frequencies, keys, nodes) of a bucket against the run [s, e) of a
+// lane whose minimizer sits at base position jpos: entry t of the sector is entry `first + t` of the bucket.
+__device__ __forceinline__ void kmb_mz_match_pair(const KmbProbe &P, const KmbStage &st, const uint32_t (&r)[8], uint32_t hdr,
+                                                  uint32_t first, uint32_t n_entries, int jpos, int s, int e, uint32_t valid,
+                                                  uint64_t lo, uint64_t hi, uint64_t kmask, unsigned &counted) {
+#pragma unroll
+    for (uint32_t t = 0; t < 2u; t++) {
+        if (first + t >= n_entries) break;
+        const int i = jpos - (int)KMB_MZ_HDR_OFFSET(hdr, first + t);  // the only window that has the minimizer at that offset
+        if (i < s || i >= e || !((valid >> i) & 1u)) continue;
+        const uint64_t km = kmb_window(lo, hi, i, kmask);
+        if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
+        const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
+        if ((int32_t)freq > P.max_freq) continue;
+        kmb_mz_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
+        counted++;
+    }
+}
+
+// Retire `n` (<= 32) runs from the top of the late list, one per lane: walk the contiguous pool sectors of the run's
+// bucket; every entry names, through its minimizer offset, the one window it could equal.  Called by all lanes.
+__device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPol &pol, KmbMzShared &S, const KmbStage &st,
+                                                  int top, int n, uint64_t kmask, unsigned &counted, unsigned &fetched, int lane) {
+    __syncwarp();
+    bool more = lane < n;
+    uint64_t lo = 0, hi = 0;
+    uint32_t valid = 0, sector = 0;
+    int s = 0, e = 0, jpos = 0;
+    if (more) {
+        const int idx = top - 1 - lane;
+        lo = S.late_lo[idx];
+        hi = S.late_hi[idx];
+        valid = S.late_valid[idx];
+        sector = S.late_sector[idx];
+        const uint32_t sej = S.late_sej[idx];
+        s = (int)(sej & 255u), e = (int)((sej >> 8) & 255u), jpos = (int)(sej >> 16);
+    }
+    fetched += (unsigned)n;
+    while (__any_sync(KMB_FULL_MASK, more)) {
+        if (more) {
+            uint32_t r[8];
+            KMB_BOUND(2, sector, P.n_lines);
+            kmb_ld_sector(P.lines + (uint64_t)sector * KMB_LINE_WORDS, r, pol.line);
+            const uint32_t left = KMB_MZ_POOL_LEFT(r[0]);
+#pragma unroll
+            for (uint32_t t = 0; t < 2u; t++) {
+                if (t >= left) break;
+                const int i = jpos - (int)KMB_MZ_POOL_OFFSET(r[0], t);
+                if (i < s || i >= e || !((valid >> i) & 1u)) continue;
+                const uint64_t km = kmb_window(lo, hi, i, kmask);
+                if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
+                const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
+                if ((int32_t)freq > P.max_freq) continue;
+                kmb_mz_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
+                counted++;
+            }
+            more = left > 2u;
+            sector++;
+        }
+        kmb_stage_flush(P, st, lane, false);
+    }
+}
+
+template <bool FILT>
+__global__ void __launch_bounds__(KMB_TILE_THREADS, 2)
+kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
+                        const uint32_t *__restrict__ mask, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
+    extern __shared__ __align__(16) unsigned char kmb_mz_smem[];
+    KmbMzShared &S = reinterpret_cast<KmbMzShared *>(kmb_mz_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool n_to_a = (in_mode & KMB_IN_N_TO_A) != 0u;
+    const bool packed = (in_mode & KMB_IN_PACKED) != 0u;
+    const uint32_t *__restrict__ words = reinterpret_cast<const uint32_t *>(bases);
+    const uint64_t n_words = (n_bases + 15) / 16 + 4;
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS};
+    kmb_stage_init(st, lane);
+    unsigned counted = 0, fetched = 0;
+    const KmbPol pol = kmb_make_policies(P.policies);
+    const int k = KMB_MZ_K;
+    const uint64_t kmask = kmb_kmer_mask(k);
+    const uint64_t n_tiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
+    const uint64_t n_vec_full = n_bases / 16;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_TILE_THREADS / 32);
+    unsigned long long mapped = 0;
+    uint32_t *pack = S.pack;
+    int late_n = 0;  // warp-uniform
+
+    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_TILE_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
+        const uint64_t t0 = tile * KMB_WTILE_POS;
+        __syncwarp();
+        // ---- 1. load + encode
+#pragma unroll
+        for (int i = lane; i < KMB_WTILE_POS / 16 + 2; i += 32) {
+            uint64_t v = t0 / 16 + (uint64_t)i;
+            if (packed) {
+                pack[i] = v < n_words ? kmb_ldg_u32_hint(words + v, pol.first) : 0u;
+                continue;
+            }
+            uint4 w = kmb_load_bases16(bases, v, n_vec_full, n_bases, pol.first);
+            uint32_t inv;
+            pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
+            if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + v * 16 + (uint64_t)(__ffs(inv) - 1)));
+        }
+        __syncwarp();
+        // ---- 2. this lane's 32 windows: which exist, their minimizers, where runs start
+        const uint64_t p0 = t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
+        const uint32_t valid = kmb_valid_starts(mask, p0, n_bases, k);
+        mapped += __popc(valid);
+        if (!__any_sync(KMB_FULL_MASK, valid != 0u)) continue;
+        const uint2 qa = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
+        const uint2 qb = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
+        uint32_t startbits = 0;
+        {
+            const uint32_t w[4] = {qa.x, qa.y, qb.x, qb.y};
+            uint32_t prev = 0;
+            kmb_mz_half<0>(w, &S.a.mz[0][lane], prev, startbits);
+            kmb_mz_half<1>(w, &S.a.mz[0][lane], prev, startbits);
+            startbits |= 1u;
+        }
+        // ---- 3. runs -> filter -> staging slots
+        unsigned n_slots = 0;  // warp-uniform; may run past KMB_MZ_SLOTS (those runs load their bucket late)
+        {
+            uint32_t bits = startbits;
+            int run = 0;
+#pragma unroll 1
+            while (__any_sync(KMB_FULL_MASK, bits != 0u)) {
+                uint32_t sec[KMB_MZ_U], need[KMB_MZ_U], fw[KMB_MZ_U];
+                int rid[KMB_MZ_U];
+#pragma unroll
+                for (int u = 0; u < KMB_MZ_U; u++) {
+                    need[u] = 0;
+                    fw[u] = 0;
+                    sec[u] = 0;
+                    rid[u] = -1;
+                    if (bits) {
+                        const int s = __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        const int e = bits ? __ffs(bits) - 1 : 32;
+                        const uint32_t v = (valid >> s) & (e - s == 32 ? 0xFFFFFFFFu : ((1u << (e - s)) - 1u));
+                        rid[u] = run++;
+                        if (v) {
+                            const uint32_t jpos = S.a.mz[s][lane] & 63u;
+                            S.run_pos[rid[u]][lane] = (uint8_t)jpos;
+                            // the minimizer m-mer itself: 15 bases from base jpos of this lane
+                            const uint32_t p = (uint32_t)lane * KMB_POS_PER_THREAD + jpos;
+                            const uint32_t mmer = __funnelshift_r(pack[p >> 4], pack[(p >> 4) + 1], (p & 15u) * 2u) & KMB_MZ_MASK;
+                            const KmbLoc loc = kmb_locate((uint64_t)mmer, P.addr);
+                            sec[u] = 2u * loc.sector;
+                            if (FILT) {
+                                need[u] = loc.fmask;
+                                KMB_BOUND(0, loc.fword, P.addr.n_filter_words);
+                                fw[u] = kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter);
+                            } else {
+                                need[u] = 1u;
+                                fw[u] = 1u;
+                            }
+                        }
+                    }
+                }
+                uint32_t cmask = 0;
+#pragma unroll
+                for (int u = 0; u < KMB_MZ_U; u++) cmask |= (need[u] != 0u && (fw[u] & need[u]) == need[u]) ? (1u << u) : 0u;
+                const uint32_t mine = __popc(cmask);
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(KMB_FULL_MASK, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                unsigned slot = n_slots + incl - mine;
+                n_slots += __shfl_sync(KMB_FULL_MASK, incl, 31);
+#pragma unroll
+                for (int u = 0; u < KMB_MZ_U; u++) {
+                    if (rid[u] < 0) continue;
+                    uint8_t tag = KMB_MZ_NONE;
+                    if ((cmask >> u) & 1u) {
+                        if (slot < KMB_MZ_SLOTS) {
+                            S.slot_sector[slot] = sec[u];
+                            tag = (uint8_t)slot;
+                        } else {
+                            tag = KMB_MZ_LATE;
+                        }
+                        slot++;
+                    }
+                    S.run_slot[rid[u]][lane] = tag;
+                }
+            }
+        }
+        __syncwarp();  // the minimizers are no longer needed: their space becomes the staging slots
+        // ---- 4. fetch: primaries in one burst, then the secondaries of the buckets with more than two entries
+        const unsigned n_staged = min(n_slots, (unsigned)KMB_MZ_SLOTS);
+        fetched += n_slots;
+        for (unsigned sl = (unsigned)lane; sl < n_staged; sl += 32u) {
+            KMB_BOUND(1, S.slot_sector[sl], 2ull * P.addr.n_main);
+            kmb_cp_async_sector(S.a.slots[sl], P.lines + (uint64_t)S.slot_sector[sl] * KMB_LINE_WORDS);
+        }
+        kmb_cp_async_wait_all();
+        __syncwarp();
+        {
+            unsigned n2 = 0;
+#pragma unroll 1
+            for (unsigned base = 0; base < n_staged; base += 32u) {
+                const unsigned sl = base + (unsigned)lane;
+                const bool more = sl < n_staged && KMB_MZ_HDR_COUNT(S.a.slots[sl][0]) > 2u;
+                const unsigned m = __ballot_sync(KMB_FULL_MASK, more);
+                if (sl < n_staged) {
+                    uint8_t tag = KMB_MZ_NONE;
+                    if (more) {
+                        const unsigned j = n2 + __popc(m & ((1u << lane) - 1u));
+                        if (j < KMB_MZ_SLOTS2) {
+                            kmb_cp_async_sector(S.slots2[j], P.lines + (uint64_t)(S.slot_sector[sl] + 1u) * KMB_LINE_WORDS);
+                            tag = (uint8_t)j;
+                        } else {
+                            tag = KMB_MZ_LATE;
+                        }
+                    }
+                    S.slot2_of[sl] = tag;
+                }
+                n2 += __popc(m);
+            }
+            if (n2) kmb_cp_async_wait_all();
+        }
+        __syncwarp();
+        // ---- 5. per run, per entry of its bucket: the one window that could match
+        {
+            const uint64_t lo = (uint64_t)qa.x | ((uint64_t)qa.y << 32);
+            const uint64_t hi = (uint64_t)qb.x | ((uint64_t)qb.y << 32);
+            uint32_t bits = valid ? startbits : 0u;
+            int run = 0;
+#pragma unroll 1
+            while (__any_sync(KMB_FULL_MASK, bits != 0u)) {
+                uint32_t pool_sector = 0, pool_sej = 0;  // set when this lane's run continues in the pool
+                if (bits) {
+                    const int s = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    const int e = bits ? __ffs(bits) - 1 : 32;
+                    const uint32_t tag = S.run_slot[run][lane];
+                    const int jpos = (int)S.run_pos[run][lane];
+                    run++;
+                    if (tag != KMB_MZ_NONE) {
+                        uint32_t r[8];
+                        uint32_t sector1;  // the bucket's secondary sector
+                        uint32_t t2;
+                        if (tag < KMB_MZ_SLOTS) {
+                            const uint4 x = *reinterpret_cast<const uint4 *>(&S.a.slots[tag][0]);
+                            const uint4 y = *reinterpret_cast<const uint4 *>(&S.a.slots[tag][4]);
+                            r[0] = x.x, r[1] = x.y, r[2] = x.z, r[3] = x.w, r[4] = y.x, r[5] = y.y, r[6] = y.z, r[7] = y.w;
+                            sector1 = S.slot_sector[tag] + 1u;
+                            t2 = S.slot2_of[tag];
+                        } else {  // the tile had more runs than staging slots: find and load the bucket again
+                            const uint32_t p = (uint32_t)lane * KMB_POS_PER_THREAD + (uint32_t)jpos;
+                            const uint32_t mmer = __funnelshift_r(pack[p >> 4], pack[(p >> 4) + 1], (p & 15u) * 2u) & KMB_MZ_MASK;
+                            sector1 = 2u * kmb_locate((uint64_t)mmer, P.addr).sector + 1u;
+                            kmb_ld_sector(P.lines + (uint64_t)(sector1 - 1u) * KMB_LINE_WORDS, r, pol.line);
+                            t2 = KMB_MZ_LATE;
+                        }
+                        const uint32_t hdr = r[0];
+                        const uint32_t n_entries = KMB_MZ_HDR_COUNT(hdr);
+                        kmb_mz_match_pair(P, st, r, hdr, 0u, n_entries, jpos, s, e, valid, lo, hi, kmask, counted);
+                        if (n_entries > 2u) {
+                            if (t2 < KMB_MZ_SLOTS2) {
+                                const uint4 x = *reinterpret_cast<const uint4 *>(&S.slots2[t2][0]);
+                                const uint4 y = *reinterpret_cast<const uint4 *>(&S.slots2[t2][4]);
+                                r[0] = x.x, r[1] = x.y, r[2] = x.z, r[3] = x.w, r[4] = y.x, r[5] = y.y, r[6] = y.z, r[7] = y.w;
+                            } else {
+                                kmb_ld_sector(P.lines + (uint64_t)sector1 * KMB_LINE_WORDS, r, pol.line);
+                            }
+                            kmb_mz_match_pair(P, st, r, hdr, 2u, n_entries, jpos, s, e, valid, lo, hi, kmask, counted);
+                            if (n_entries > 4u) {
+                                pool_sector = r[0] & ~KMB_HDR_CHAIN;
+                                pool_sej = (uint32_t)s | ((uint32_t)e << 8) | ((uint32_t)jpos << 16);
+                            }
+                        }
+                    }
+                }
+                kmb_stage_flush(P, st, lane, false);
+                const unsigned pm = __ballot_sync(KMB_FULL_MASK, pool_sector != 0u);
+                if (pm) {
+                    if (pool_sector) {
+                        const int idx = late_n + __popc(pm & ((1u << lane) - 1u));
+                        KMB_BOUND(7, idx, KMB_MZ_LATE_CAP);
+                        S.late_lo[idx] = lo;
+                        S.late_hi[idx] = hi;
+                        S.late_valid[idx] = valid;
+                        S.late_sector[idx] = pool_sector;
+                        S.late_sej[idx] = pool_sej;
+                    }
+                    late_n += __popc(pm);
+                    if (late_n >= 32) {
+                        kmb_mz_late_drain(P, pol, S, st, late_n, 32, kmask, counted, fetched, lane);
+                        late_n -= 32;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    // ---- the rest
+    if (late_n) kmb_mz_late_drain(P, pol, S, st, late_n, late_n, kmask, counted, fetched, lane);
+    kmb_stage_flush(P, st, lane, true);
+    for (int o = 16; o > 0; o >>= 1) {
+        counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
+        mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
+    }
+    if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
+    if (lane == 0 && fetched) atomicAdd(&status->n_candidates, (unsigned long long)fetched);  // warp-uniform: bucket and pool fetches
+    if (lane == 0 && mapped) atomicAdd(&status->n_kmers_mapped, mapped);
 }
 
 // ================================================================================================

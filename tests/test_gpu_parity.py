@@ -19,7 +19,7 @@ def kmb():
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_l2_budget_bytes", 60 << 20),
-                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0)):
+                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0), ("read_table", 0)):
         _lib.set_option(name, v)
 
 
@@ -31,6 +31,10 @@ VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4, log_max_entries=4096),
             dict(probe_variant=0, use_filter=1, gathers_in_flight=4),
             dict(probe_variant=0, use_filter=0, gathers_in_flight=4)]
+# the fused reads kernel over the minimizer-bucketed read-path table (k = 31 only; opt-in)
+READ_TABLE_VARIANTS = [dict(read_table=1, use_filter=1), dict(read_table=1, use_filter=0),
+                       dict(read_table=1, use_filter=1, filter_l2_budget_bytes=512),
+                       dict(read_table=1, use_filter=1, log_max_entries=4096)]
 
 
 def _fresh(index):
@@ -43,6 +47,7 @@ def _fresh(index):
 def _set(kmb, variant):
     kmb.set_option("filter_l2_budget_bytes", 60 << 20)
     kmb.set_option("log_max_entries", 2048 << 20)
+    kmb.set_option("read_table", 0)
     for k, v in variant.items():
         kmb.set_option(k, v)
 
@@ -251,8 +256,9 @@ def _small_world(k, seed, n_entries=60_000, modulo=262_147, zipf=False, hot=1200
     return g, idx
 
 
-@pytest.mark.parametrize("variant", VARIANTS[:6], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
-@pytest.mark.parametrize("k", [31, 21, 15, 5])
+@pytest.mark.parametrize("k,variant", [(k, v) for k in (31, 21, 15, 5) for v in VARIANTS[:6]] +
+                         [(31, v) for v in READ_TABLE_VARIANTS],
+                         ids=lambda x: str(x) if isinstance(x, int) else "-".join("%s%d" % (k[0], v) for k, v in x.items()))
 def test_map_reads_vs_oracle(kmb, k, variant):
     import torch
     from kmer_mapper_b200 import synthetic as S
@@ -262,7 +268,8 @@ def test_map_reads_vs_oracle(kmb, k, variant):
     di = DeviceIndex.from_index(_fresh(idx))
     assert (di.filter_bytes > 0) == bool(variant["use_filter"])
     mx = idx.max_node_id()
-    for ragged, n_reads, L, n_rate in ((False, 20_000, 150, 0.0), (True, 30_000, 120, 0.03), (False, 40, 10_000, 0.05)):
+    for ragged, n_reads, L, n_rate in ((False, 20_000, 150, 0.0), (True, 30_000, 120, 0.03), (False, 40, 10_000, 0.05),
+                                       (True, 3_000, 40, 0.0)):
         bases, offsets = S.make_reads(g, n_reads, L, seed=7 * k + L, n_rate=n_rate, lower_rate=0.5 if n_rate else 0.0,
                                       ragged=ragged)
         want, n_want = c_oracle.map_reads(idx, mx, bases, offsets, k, n_threads=4)
@@ -281,12 +288,13 @@ def test_map_reads_vs_oracle(kmb, k, variant):
         m.close()
 
 
-@pytest.mark.parametrize("host_pack,host_threads", [(1, 0), (1, 3), (0, 0)])
-def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads):
+@pytest.mark.parametrize("host_pack,host_threads,read_table", [(1, 0, 0), (1, 3, 0), (0, 0, 0), (1, 0, 1), (0, 0, 1)])
+def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads, read_table):
     from kmer_mapper_b200 import synthetic as S
     from kmer_mapper_b200.device import DeviceIndex, Mapper
     kmb.set_option("host_pack", host_pack)
     kmb.set_option("host_threads", host_threads)
+    kmb.set_option("read_table", read_table)
     k = 31
     g, idx = _small_world(k, 300)
     di = DeviceIndex.from_index(_fresh(idx))
@@ -307,6 +315,7 @@ def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads)
     kmb.set_option("chunk_bytes", 64 << 20)
     kmb.set_option("host_pack", -1)
     kmb.set_option("host_threads", 0)
+    kmb.set_option("read_table", 0)
 
 
 def test_map_reads_reverse_complement_flag(kmb):
