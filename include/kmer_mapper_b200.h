@@ -171,8 +171,9 @@ int kmb_find_record_start(const uint8_t *text, uint64_t n_text, int format, uint
 /* ---- packed transport of host-resident reads -----------------------------------------------------
  * kmb_mapper_map_reads on HOST buffers encodes the bases to 2 bits each on the CPU (all cores, AVX2 when the
  * CPU has it), straight into pinned staging, and sends a quarter of the bytes over PCIe (option "host_pack": 1 always, 0 never,
- * default -1 = when the encoder threads outrun the bus: >= 10 threads for a pinned source, >= 2 for a pageable one;
- * "host_threads", default 0 = every CPU of the affinity mask).  Same table as the kernels apply to
+ * default -1 = when the encoder threads outrun the bus: a pinned source with >= 10 threads and the host to itself
+ * ("host_ranks" = 1: the encoder is bound by host DRAM bandwidth, which the ranks of a node share), a pageable source
+ * with >= 2 threads; "host_threads", default 0 = every CPU of the affinity mask).  Same table as the kernels apply to
  * unpacked input (DNAEncoding as used at util.py:71-75; N -> A of command_line_interface.py:41), same invalid-byte
  * report.  kmb_pack_bases is that encoder on its own: word j of words[] = bases 16j..16j+15, base 16j in the lowest
  * bits, positions past n_bases read as 'A'; words_capacity >= (n_bases + 15) / 16 + 4 (the last 4 are zero padding).
@@ -204,7 +205,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
  *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
- *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads",
+ *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks",
  *  "read_table" (1 = k = 31 reads go through the minimizer-bucketed second table, see csrc/kmb_core.cuh; default 0)};
  * read-only: "h2d_bytes" (bytes the mapping calls have copied host -> device so far), "bounds_failures" (-1 unless
  * built with -DKMB_BOUNDS_CHECKS). */

@@ -81,8 +81,12 @@ struct KmbOptions {
     // more issue slots than the saved look-ups give back -- 70 ms per 6.0 G k-mers against 48 ms for the
     // key-addressed kernel -- so it stays opt-in (and parity-tested) until that changes.
     int64_t read_table = 0;
+    // The encoder is bound by the host's DRAM bandwidth, which the ranks of a multi-GPU node share, while every GPU
+    // has its own PCIe link: with 2 ranks on one host a pinned source went 46.9 GK/s packed against 74.3 as ASCII
+    // (profiles/README.md), so auto packs a pinned source only when this process has the host to itself.
     int64_t host_pack = -1;
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
+    int64_t host_ranks = 1;               // processes sharing this host's memory system (set by distributed.py)
 };
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
@@ -113,6 +117,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(bench_load_mode)
     OPT(host_pack)
     OPT(host_threads)
+    OPT(host_ranks)
     OPT(read_table)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
@@ -148,6 +153,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(bench_load_mode)
     OPT(host_pack)
     OPT(host_threads)
+    OPT(host_ranks)
     OPT(read_table)
     OPT(chunk_bytes)
 #undef OPT
@@ -1019,7 +1025,8 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: offsets[0] must be 0 and offsets[n_reads] must equal n_bases");
     const uint64_t chunk = (uint64_t)g_opt.chunk_bytes;
     const int pack_threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
-    const bool want_pack = g_opt.host_pack > 0 || (g_opt.host_pack < 0 && pack_threads >= (pinned_b ? 10 : 2));
+    const bool want_pack = g_opt.host_pack > 0 ||
+                           (g_opt.host_pack < 0 && (pinned_b ? (pack_threads >= 10 && g_opt.host_ranks <= 1) : pack_threads >= 2));
     uint64_t r0 = 0;
     while (r0 < n_reads) {
         // largest r1 with offsets[r1] - offsets[r0] <= chunk (at least one read)

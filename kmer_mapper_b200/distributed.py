@@ -38,6 +38,7 @@ def init_process_group(backend=None):
         try:  # the ranks of a node share its cores: without this every rank would start one encoder thread per core
             from . import _lib
             _lib.set_option("host_threads", host_threads_per_rank())
+            _lib.set_option("host_ranks", max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world_size))))
         except Exception:
             pass
     import torch
