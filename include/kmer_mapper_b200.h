@@ -160,6 +160,16 @@ int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format, int final_
                     uint8_t *bases, uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity,
                     uint64_t *n_reads, uint64_t *n_bases, uint64_t *consumed);
 
+/* Member-parallel gzip inflate for the same reader (.fa.gz / .fq.gz: Readme.md:11, command_line_interface.py:166).
+ * gz[0, n_gz) starts at a member boundary of a .gz file.  Whole members are inflated in order, several at a time
+ * (bgzip/BGZF blocks, concatenated .gz files), into out[]; stops before a member that would overflow out_capacity,
+ * or at a member that inflates to more than max_member_bytes (0 = out_capacity): *stopped_at_big_member = 1, the
+ * caller streams that one sequentially (a plain single-member .gz cannot be inflated in parallel), = 2 when the
+ * bytes at *consumed are not a gzip member (corrupt file / trailing garbage).  *consumed / *produced = compressed
+ * bytes used / text bytes written.  KMB_ERR_BAD_ARG when gz[0] itself is not a gzip member. */
+int kmb_gunzip_members(const uint8_t *gz, uint64_t n_gz, int n_threads, uint8_t *out, uint64_t out_capacity,
+                       uint64_t max_member_bytes, uint64_t *consumed, uint64_t *produced, int *stopped_at_big_member);
+
 /* First record start AFTER the first newline of text[0, n_text) (n_text when there is none): how a rank of a
  * multi-GPU job finds the beginning of its byte range of a plain FASTA/FASTQ file -- pass the text from one byte
  * before the nominal cut, so that a cut that falls exactly on a record start is found.  FASTQ: a line starting with

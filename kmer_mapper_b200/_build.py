@@ -12,11 +12,13 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.environ.get("KMB_LIB_PATH") or os.path.join(PKG, "libkmer_mapper_b200.so")  # override: A/B builds only
-SOURCES = [os.path.join(CSRC, "kmb_capi.cu"), os.path.join(CSRC, "kmb_reader.cpp"), os.path.join(CSRC, "kmb_hostpack.cpp")]
+SOURCES = [os.path.join(CSRC, "kmb_capi.cu"), os.path.join(CSRC, "kmb_reader.cpp"), os.path.join(CSRC, "kmb_hostpack.cpp"),
+           os.path.join(CSRC, "kmb_gunzip.cpp")]
 HEADERS = [os.path.join(CSRC, "kmb_kernels.cuh"), os.path.join(CSRC, "kmb_core.cuh"), os.path.join(CSRC, "kmb_host.h"),
            os.path.join(os.path.dirname(PKG), "include", "kmer_mapper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
+LINK_FLAGS = ["-lz"]  # member-parallel gzip inflate of the chunk reader (kmb_gunzip.cpp)
 
 
 def up_to_date() -> bool:
@@ -39,7 +41,7 @@ def _nvcc() -> str:
 def build(force: bool = False, verbose: bool = True) -> str:
     if not force and up_to_date():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + SOURCES + ["-o", LIB_PATH]
+    cmd = [_nvcc()] + NVCC_FLAGS + SOURCES + LINK_FLAGS + ["-o", LIB_PATH]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -51,7 +53,7 @@ def build_bounds_checked(verbose: bool = True) -> str:
     indexes (kmb_kernels.cuh, KMB_BOUND).  Not the product: run the GPU tests against it with
     ``KMB_LIB_PATH=kmer_mapper_b200/libkmer_mapper_b200_bounds.so python -m pytest tests -m gpu``; the session
     fails if any check fired (tests/conftest.py)."""
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-DKMB_BOUNDS_CHECKS"] + SOURCES + ["-o", BOUNDS_LIB_PATH]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DKMB_BOUNDS_CHECKS"] + SOURCES + LINK_FLAGS + ["-o", BOUNDS_LIB_PATH]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

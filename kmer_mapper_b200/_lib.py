@@ -72,6 +72,7 @@ SIGNATURES = {
     "kmb_codec_to_bytes": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
     "kmb_codec_complement": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
     "kmb_codec_twobit_swap": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_int, _vp]),
+    "kmb_gunzip_members": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, C.c_uint64, C.c_uint64, _u64p, _u64p, C.POINTER(C.c_int)]),
     "kmb_find_record_start": (C.c_int, [_vp, C.c_uint64, C.c_int, _u64p]),
     "kmb_pack_bases": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_int64)]),
     "kmb_parse_reads": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp, C.c_uint64,

@@ -110,7 +110,7 @@ def map_bnp(args):
         if torch.cuda.is_available():
             torch.cuda.set_device(local_rank)
 
-    reads = open_reads(args.reads)
+    reads = open_reads(args.reads, n_threads=distributed.host_threads_per_rank() if world_size > 1 else None)
     t_map = time.perf_counter()
     try:
         chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size, rank=rank, world_size=world_size)

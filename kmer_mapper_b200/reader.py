@@ -8,10 +8,11 @@ headers / '+' lines / qualities / newlines, and hand over a ragged byte array.  
 each optionally .gz.  PARITY UNPINNED against bionumpy (absent dependency); tests cross-check
 against an independent pure-Python parser.
 
-Three overlapped stages: a background thread reads (and inflates) the next block of text while the
-native multi-threaded parser (``kmb_parse_reads``, csrc/kmb_reader.cpp) turns the current one into
-bases + offsets written straight into one of two alternating pinned buffers, while the previous
-chunk's asynchronous host-to-device copy and kernels run (copy stream, C ABI).
+Plain files are parsed in place from a read-only mapping of the page cache by the native multi-threaded
+parser (``kmb_parse_reads``, csrc/kmb_reader.cpp), bases + offsets written straight into one of two
+alternating pinned buffers; .gz files are inflated member-parallel by the native library
+(``kmb_gunzip_members``) in a background thread, a few blocks ahead of the parser.  The previous chunk's
+asynchronous host-to-device copy and kernels run meanwhile (copy stream, C ABI).
 """
 from __future__ import annotations
 
@@ -21,8 +22,6 @@ import mmap
 import os
 import queue
 import threading
-import zlib
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -104,119 +103,82 @@ def _format_of(path: str) -> str:
 
 class ParallelGzip:
     """Multi-member gzip (bgzip/BGZF files, `cat a.gz b.gz`, the synthetic FASTQ.gz of the benchmark configs)
-    inflated member-parallel: zlib releases the GIL, so a thread pool decompresses several members at once.
-
-    Member starts are not recorded anywhere in a .gz, so they are found speculatively: every occurrence of the
-    member magic (1f 8b 08, reserved flag bits clear) is a candidate that a worker tries to inflate to its end;
-    the consumer walks the chain "a member starts where the previous one ended" and ignores candidates inside a
-    member (they fail within a few bytes anyway).  A member that inflates to more than ``max_member_bytes``
-    (a plain single-member .gz) makes the reader fall back to sequential streaming from that point.
+    inflated member-parallel by the native library (``kmb_gunzip_members``, csrc/kmb_gunzip.cpp: speculative member
+    starts, worker pool, chain walk).  A member that inflates to more than ``max_member_bytes`` (a plain
+    single-member .gz) makes the reader fall back to sequential streaming from that point.
     """
 
-    SCAN_WINDOW = 32 << 20
+    HEADROOM = 1 << 20   # free bytes in front of every block: the consumer puts its carried-over partial record there
 
     def __init__(self, path, n_threads, max_member_bytes=64 << 20):
         self.path = path
         self.n_threads = max(1, int(n_threads))
         self.max_member_bytes = int(max_member_bytes)
 
-    def _candidates(self, mm, start):
-        """Candidate member starts >= start, in order (lazily, window by window)."""
-        n = len(mm)
-        pos = start
-        while pos < n:
-            end = min(pos + self.SCAN_WINDOW + 3, n)
-            a = np.frombuffer(mm, dtype=np.uint8, count=end - pos, offset=pos)
-            if a.shape[0] >= 4:
-                hit = np.flatnonzero((a[:-3] == 0x1F) & (a[1:-2] == 0x8B) & (a[2:-1] == 8) & ((a[3:] & 0xE0) == 0))
-                for h in hit.tolist():
-                    yield pos + h
-            del a
-            if end >= n:
-                return
-            pos = end - 3
-
-    def _inflate_member(self, mm, start):
-        """(text bytes, offset just past the member) or None for a false candidate / an oversized member."""
-        d = zlib.decompressobj(31)
-        pos = start
-        outs, total = [], 0
-        try:
-            while not d.eof:
-                chunk = mm[pos:pos + (1 << 20)]
-                if not chunk:
-                    return None            # truncated
-                outs.append(d.decompress(chunk))
-                pos += len(chunk)
-                total += len(outs[-1])
-                if total > self.max_member_bytes:
-                    return "big"
-        except zlib.error:
-            return None
-        return b"".join(outs), pos - len(d.unused_data)
-
-    def blocks(self, block_bytes):
-        """Yields decompressed text in file order, at least block_bytes at a time (except the last), then b''."""
+    def arrays(self, block_bytes, n_buffers=4):
+        """Yields (buffer, n): the next n bytes of text are buffer[HEADROOM : HEADROOM + n], at least block_bytes of
+        them except at the end of the file.  Buffers rotate: one stays valid while the next n_buffers - 1 are made."""
         size = os.path.getsize(self.path)
         if size == 0:
-            yield b""
             return
-        with open(self.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm, \
-                ThreadPoolExecutor(self.n_threads) as pool:
-            expected = 0
-            cand = self._candidates(mm, 0)
-            pending = {}                    # start -> future
-            ahead = 2 * self.n_threads
-            exhausted = False
-            acc, acc_len = [], 0
-            fallback_from = None
-            while expected < size:
-                while not exhausted and len(pending) < ahead:
-                    try:
-                        c = next(cand)
-                    except StopIteration:
-                        exhausted = True
+        lib = _lib.lib()
+        # room for one batch of members per worker thread, so that a call keeps all of them busy
+        cap = max(int(block_bytes) + self.max_member_bytes, self.n_threads * (16 << 20))
+        bufs = [None] * n_buffers
+        turn = 0
+
+        def next_buffer():
+            nonlocal turn
+            if bufs[turn] is None:
+                bufs[turn] = np.empty(self.HEADROOM + cap, dtype=np.uint8)
+            buf = bufs[turn]
+            turn = (turn + 1) % n_buffers
+            return buf
+
+        fallback_from = None
+        with open(self.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            whole = np.frombuffer(mm, dtype=np.uint8)
+            base_ptr = whole.ctypes.data
+            try:
+                pos = 0
+                while pos < size:
+                    buf = next_buffer()
+                    consumed, produced, flag = C.c_uint64(), C.c_uint64(), C.c_int()
+                    rc = lib.kmb_gunzip_members(base_ptr + pos, size - pos, self.n_threads, buf.ctypes.data + self.HEADROOM,
+                                                cap, self.max_member_bytes, C.byref(consumed), C.byref(produced), C.byref(flag))
+                    if rc == _lib.KMB_ERR_BAD_ARG:
+                        raise OSError("%s: not a gzip member at offset %d" % (self.path, pos))
+                    _lib.check(rc)
+                    pos += consumed.value
+                    if produced.value:
+                        yield buf, int(produced.value)
+                    if flag.value == 1:
+                        fallback_from = pos
                         break
-                    if c >= expected:
-                        pending[c] = pool.submit(self._inflate_member, mm, c)
-                fut = pending.pop(expected, None)
-                if fut is None:
-                    if not pending and exhausted:
-                        raise OSError("%s: not a gzip member at offset %d" % (self.path, expected))
-                    if any(c < expected for c in pending):
-                        for c in [c for c in pending if c < expected]:
-                            pending.pop(c).cancel()
-                        continue
-                    if expected not in pending and (exhausted or min(pending) > expected):
-                        raise OSError("%s: not a gzip member at offset %d" % (self.path, expected))
-                    continue
-                res = fut.result()
-                if res is None:
-                    raise OSError("%s: corrupt gzip member at offset %d" % (self.path, expected))
-                if res == "big":
-                    fallback_from = expected
-                    break
-                text, expected = res
-                acc.append(text)
-                acc_len += len(text)
-                if acc_len >= block_bytes:
-                    yield b"".join(acc)
-                    acc, acc_len = [], 0
-                for c in [c for c in pending if c < expected]:      # candidates inside the member just consumed
-                    pending.pop(c).cancel()
-            for fu in pending.values():
-                fu.cancel()
-            if acc:
-                yield b"".join(acc)
-        if fallback_from is not None:
+                    if flag.value == 2:
+                        if bytes(mm[pos:pos + 4096]).strip(b"\0") or bytes(mm[pos:]).strip(b"\0"):
+                            raise OSError("%s: corrupt gzip member at offset %d" % (self.path, pos))
+                        break            # zero padding after the last member
+                    if consumed.value == 0 and flag.value == 0:
+                        raise OSError("%s: gzip member at offset %d does not fit the reader's buffer" % (self.path, pos))
+            finally:
+                del whole
+        if fallback_from is not None:     # sequential streaming of the rest
             with open(self.path, "rb") as f:
                 f.seek(fallback_from)
                 with gzip.GzipFile(fileobj=f, mode="rb") as g:
                     while True:
-                        block = g.read(block_bytes)
+                        block = g.read(int(block_bytes))
                         if not block:
                             break
-                        yield block
+                        buf = next_buffer()
+                        buf[self.HEADROOM:self.HEADROOM + len(block)] = np.frombuffer(block, dtype=np.uint8)
+                        yield buf, len(block)
+
+    def blocks(self, block_bytes):
+        """Yields decompressed text in file order as bytes, then b''."""
+        for buf, n in self.arrays(block_bytes):
+            yield buf[self.HEADROOM:self.HEADROOM + n].tobytes()
         yield b""
 
 
@@ -232,27 +194,16 @@ class ReadFile:
         self._bases_per_byte = 0.0   # densest window seen so far: sizes the next window's output buffers
         self._reads_per_byte = 0.0
 
-    def _open(self):
-        if self.path.lower().endswith(".gz"):
-            return gzip.open(self.path, "rb")  # handles multi-member archives
-        return open(self.path, "rb", buffering=0)
-
-    def _blocks(self, block_bytes):
-        """Background thread: read (and inflate) the next block while the current one is parsed and mapped."""
-        q = queue.Queue(maxsize=2)
+    def _gz_arrays(self, block_bytes):
+        """Background thread: inflate the next blocks while the current one is parsed and mapped.  Yields
+        (buffer, n) like ParallelGzip.arrays, then None."""
+        q = queue.Queue(maxsize=1)
 
         def produce():
             try:
-                if self.path.lower().endswith(".gz"):
-                    for block in ParallelGzip(self.path, self.n_threads).blocks(block_bytes):
-                        q.put(block)
-                    return
-                with self._open() as f:
-                    while True:
-                        block = f.read(block_bytes)
-                        q.put(block)
-                        if not block:
-                            return
+                for item in ParallelGzip(self.path, self.n_threads).arrays(block_bytes, n_buffers=4):
+                    q.put(item)          # 1 queued + 1 being parsed + 1 being filled < 4 buffers
+                q.put(None)
             except BaseException as e:  # surfaced in the consumer
                 q.put(e)
 
@@ -263,7 +214,7 @@ class ReadFile:
             if isinstance(item, BaseException):
                 raise item
             yield item
-            if not item:
+            if item is None:
                 return
 
     def _parse(self, text_ptr: int, n_text: int, final: bool, count_only: bool = False):
@@ -363,17 +314,26 @@ class ReadFile:
                 if len(seq):
                     yield ReadChunk(seq)
             return
-        carry = b""
-        for i, block in enumerate(self._blocks(int(min_chunk_size))):
-            final = len(block) == 0
-            data = carry + block if carry else block
-            if not data:
-                break
-            text = np.frombuffer(data, dtype=np.uint8)
+        head = ParallelGzip.HEADROOM
+        carry = np.zeros(0, dtype=np.uint8)
+        for i, item in enumerate(self._gz_arrays(int(min_chunk_size))):
+            final = item is None
+            if final:
+                if not carry.shape[0]:
+                    break
+                text = carry
+            else:
+                buf, n = item
+                if carry.shape[0] <= head:        # the carried-over partial record goes right in front of the new text
+                    start = head - carry.shape[0]
+                    buf[start:head] = carry
+                    text = buf[start:head + n]
+                else:                             # a record longer than the headroom (a chromosome-sized FASTA entry)
+                    text = np.concatenate([carry, buf[head:head + n]])
             seq, consumed = self._parse(text.ctypes.data, int(text.shape[0]), final, count_only=i % world_size != rank)
-            if final and consumed < len(data) and len(seq) == 0 and self.format == "fasta":
+            if final and consumed < text.shape[0] and len(seq) == 0 and self.format == "fasta":
                 raise ValueError("%s: FASTA data without a '>' header line" % self.path)
-            carry = bytes(data[consumed:]) if consumed < len(data) else b""
+            carry = text[consumed:].copy()
             if len(seq):
                 yield ReadChunk(seq)
             if final:
