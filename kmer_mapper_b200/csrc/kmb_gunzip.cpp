@@ -133,9 +133,10 @@ extern "C" int kmb_gunzip_members(const uint8_t *gz, uint64_t n_gz, int n_thread
         }
         scan = std::max(scan, expected + 1);
         const uint64_t span_end = std::min<uint64_t>(n_gz, expected + std::max<uint64_t>((uint64_t)n_threads << 22, 1u << 24));
-        // members that start beyond this are unlikely to fit what is left of the output (text is >= 4x the compressed
-        // bytes for sequence data): inflating them now would be work thrown away
-        const uint64_t fit_end = expected + std::max<uint64_t>((out_capacity - *produced) / 4, 1u << 16);
+        // members that start beyond this are unlikely to fit what is left of the output -- inflating them now would be
+        // work thrown away: expansion as measured in this call so far, 6x (FASTQ at gzip -1 is ~5.5x) before that
+        const double ratio = *consumed ? std::max(1.0, 1.1 * (double)*produced / (double)*consumed) : 6.0;
+        const uint64_t fit_end = expected + std::max<uint64_t>((uint64_t)((double)(out_capacity - *produced) / ratio), 1u << 16);
         uint64_t p = scan;
         while (p + 4 <= n_gz && p < fit_end && (batch.size() < (size_t)(2 * n_threads) || p < span_end) && batch.size() < 65536) {
             const uint8_t *q = (const uint8_t *)memchr(gz + p, 0x1f, (size_t)(n_gz - 3 - p));
