@@ -52,15 +52,27 @@ def map_cpu(args, kmer_index, chunk_sequence):
     return mapped
 
 
+HONOUR_MAX_HITS_ENV = "KMER_MAPPER_B200_HONOUR_MAX_HITS"
+
+
+def _frequency_cutoff(args):
+    """The reference parses ``-I/--max-hits-per-kmer`` and never uses it: every route calls the lookup with its
+    default cut-off of 1000 (command_line_interface.py:51,173; mapper.pyx:19).  Same here -- unless the
+    environment variable KMER_MAPPER_B200_HONOUR_MAX_HITS=1 opts in to what the flag's help text promises."""
+    if os.environ.get(HONOUR_MAX_HITS_ENV, "") == "1" and _flag(args, "max_hits_per_kmer") is not None:
+        return int(args.max_hits_per_kmer)
+    return DEFAULT_MAX_FREQUENCY
+
+
 def map_gpu(index, chunks, k, hash_map_size=0, map_reverse_complements=False, rank=0, world_size=1,
-            return_mapper=False):
+            return_mapper=False, max_index_lookup_frequency=DEFAULT_MAX_FREQUENCY):
     """command_line_interface.py:59-79: map an iterable of chunks (objects with ``.sequence``) against the
     index on the current GPU; returns the node counts.  ``hash_map_size`` is accepted for signature
     compatibility (the device index keeps the reference's own modulo-bucketed layout, so there is no
     separate hash-map capacity to choose)."""
     logging.info("Making counter")
     di = DeviceIndex.from_index(index)
-    mapper = Mapper(di, di.max_node_id() + 1, DEFAULT_MAX_FREQUENCY)
+    mapper = Mapper(di, di.max_node_id() + 1, max_index_lookup_frequency)
     logging.info("CUDA counter initialized")
     t_start = time.perf_counter()
     n_reads = 0
@@ -115,9 +127,11 @@ def map_bnp(args):
     try:
         chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size, rank=rank, world_size=world_size)
         if world_size == 1:
-            node_counts = map_gpu(index, chunk_iter, kmer_size, _flag(args, "gpu_hash_map_size", 0), want_revcomp)
+            node_counts = map_gpu(index, chunk_iter, kmer_size, _flag(args, "gpu_hash_map_size", 0), want_revcomp,
+                                  max_index_lookup_frequency=_frequency_cutoff(args))
         else:
-            node_counts = _map_sharded(index, chunk_iter, kmer_size, want_revcomp, rank, world_size)
+            node_counts = _map_sharded(index, chunk_iter, kmer_size, want_revcomp, rank, world_size,
+                                       _frequency_cutoff(args))
     finally:
         reads.close()
     logging.info("Time spent only on hashing and counting hashes: %.4f" % (time.perf_counter() - t_map))
@@ -132,13 +146,14 @@ def map_bnp(args):
                                                                              _flag(args, "n_threads", 1)))
 
 
-def _map_sharded(kmer_index, chunks, k, map_reverse_complements, rank, world_size):
+def _map_sharded(kmer_index, chunks, k, map_reverse_complements, rank, world_size,
+                 max_index_lookup_frequency=DEFAULT_MAX_FREQUENCY):
     """One rank of a torchrun job: private counts in a torch tensor, one all-reduce at the end."""
     import torch
     di = DeviceIndex.from_index(kmer_index)
     n_counts = di.max_node_id() + 1
     counts = torch.zeros(n_counts, dtype=torch.int32, device="cuda")
-    mapper = Mapper(di, n_counts, DEFAULT_MAX_FREQUENCY, counts_tensor=counts)
+    mapper = Mapper(di, n_counts, max_index_lookup_frequency, counts_tensor=counts)
     for chunk in chunks:    # the reader already hands this rank its share only (reader.py: read_chunks)
         seq = chunk.sequence
         mapper.map_reads(seq.bases, seq.offsets, k, revcomp=bool(map_reverse_complements), n_to_a=True)
@@ -163,7 +178,8 @@ _MAP_FLAGS = (
     ("-o", "--output-file", dict(required=True, help="node counts are written to <output-file>.npy")),
     ("-d", "--debug", dict(required=False, help="any value switches the DEBUG log on")),
     ("-I", "--max-hits-per-kmer", dict(required=False, default=1000, type=int,
-                                       help="parsed and ignored, like the reference: the cut-off is always 1000")),
+                                       help="parsed and ignored, like the reference (the cut-off is always 1000), unless "
+                                            "KMER_MAPPER_B200_HONOUR_MAX_HITS=1 is set in the environment")),
     ("-g", "--gpu", dict(default=False, type=bool, help="both routes run on the GPU here; -g additionally allows -r")),
     ("-s", "--gpu-hash-map-size", dict(default=0, type=int, help="accepted for compatibility")),
     ("-r", "--map-reverse-complements", dict(default=False, type=bool,

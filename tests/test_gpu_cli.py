@@ -57,6 +57,23 @@ def test_map_bnp_programmatic_call_returns_counts(world):
         map_bnp(args)
 
 
+def test_max_hits_flag_is_ignored_like_the_reference_unless_opted_in(world, monkeypatch):
+    """-I is parsed and unused in the reference (cli:51,173): the cut-off stays 1000.  The opt-in environment
+    variable makes it real; the fixture index holds one k-mer on 1100 nodes, so a cut-off of 2000 counts more."""
+    from kmer_mapper_b200.command_line_interface import HONOUR_MAX_HITS_ENV, run_argument_parser
+    d = world["dir"]
+    base = ["map", "-i", str(d / "index.npz"), "-f", str(d / "reads.fa"), "-k", str(world["k"]), "-I", "2000"]
+    monkeypatch.delenv(HONOUR_MAX_HITS_ENV, raising=False)
+    run_argument_parser(base + ["-o", str(d / "maxhits_default")])
+    assert np.array_equal(np.load(str(d / "maxhits_default.npy")), world["want"])
+    monkeypatch.setenv(HONOUR_MAX_HITS_ENV, "1")
+    run_argument_parser(base + ["-o", str(d / "maxhits_opt_in")])
+    got = np.load(str(d / "maxhits_opt_in.npy"))
+    want, _ = c_oracle.map_reads(world["idx"], world["idx"].max_node_id(), world["bases"], world["offsets"], world["k"],
+                                 max_index_lookup_frequency=2000, n_threads=4)
+    assert np.array_equal(got, want)
+
+
 def test_map_gpu_signature_and_invalid_reads(world, tmp_path):
     from kmer_mapper_b200._lib import InvalidBaseError
     from kmer_mapper_b200.command_line_interface import map_gpu
