@@ -881,21 +881,23 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
     if (use_read_table(ix, k, flags)) KMB_TRY(ensure_read_table(m->index, k));
     if (use_read_table(ix, k, flags) && ix->mz_k == k) {
+        const KmbProbe Pkey = P;  // the key-addressed sectors: where the rare tile that overflows the run table goes
         P.lines = ix->mz_lines;
         P.filter = ix->mz_filter;
         P.addr = ix->mz_addr;
         P.n_lines = ix->mz_n_lines;
-        typedef void (*MzFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, uint32_t, KmbProbe, KmbStatus *);
+        typedef void (*MzFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, uint32_t, KmbProbe, KmbProbe, KmbStatus *);
         MzFn fn = P.filter ? kmb_map_reads_mz_kernel<true> : kmb_map_reads_mz_kernel<false>;
         KMB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KMB_MZ_SMEM_BYTES));
         int per_sm = 0;
-        KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, KMB_TILE_THREADS, KMB_MZ_SMEM_BYTES));
+        KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, KMB_MZ_THREADS, KMB_MZ_SMEM_BYTES));
         if (per_sm < 1) per_sm = 1;
         if (g_opt.map_reads_blocks_per_sm > 0) per_sm = (int)std::min<int64_t>(g_opt.map_reads_blocks_per_sm, per_sm);
-        int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
+        const uint64_t n_cta_tiles = (n_bases + (uint64_t)KMB_WTILE_POS * (KMB_MZ_THREADS / 32) - 1) / ((uint64_t)KMB_WTILE_POS * (KMB_MZ_THREADS / 32));
+        int grid = (int)std::min<uint64_t>(n_cta_tiles, (uint64_t)ix->info.sms * per_sm);
         m->dirty = true;
         KMB_TRY(timed_begin(m));
-        fn<<<grid, KMB_TILE_THREADS, KMB_MZ_SMEM_BYTES, m->stream>>>(d_bases, n_bases, base0, d_mask, in_mode, P, m->d_status);
+        fn<<<grid, KMB_MZ_THREADS, KMB_MZ_SMEM_BYTES, m->stream>>>(d_bases, n_bases, base0, d_mask, in_mode, P, Pkey, m->d_status);
         g_launches++;
         KMB_CUDA(cudaGetLastError());
         KMB_TRY(timed_end(m));

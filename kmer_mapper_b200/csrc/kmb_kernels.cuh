@@ -356,14 +356,15 @@ struct KmbStage {
     uint32_t *buf;                 // [KMB_LOG_BINS][KMB_STAGE_SLOTS]
     unsigned long long *res_base;  // [KMB_LOG_BINS] next free position of this warp's reservation for the bin
     uint32_t *res_left;            // [KMB_LOG_BINS] groups left in that reservation, or KMB_RES_FULL
+    uint32_t slots;                // capacity of one bin's stack (KMB_STAGE_SLOTS, or less where shared memory is short)
 };
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
     const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
     KMB_BOUND(6, node, P.n_counts);
     const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
-    KMB_BOUND(3, pos, KMB_STAGE_SLOTS);
+    KMB_BOUND(3, pos, st.slots);
     KMB_BOUND(3, b, KMB_LOG_BINS);
-    st.buf[b * KMB_STAGE_SLOTS + pos] = node;
+    st.buf[b * st.slots + pos] = node;
 }
 // One group of 32 ids of bin b (lanes >= n write holes) to the log -- or, if the log is full, straight onto
 // the counts.  All bins share one pool: space is reserved chunk_groups groups at a time from a single cursor
@@ -405,7 +406,7 @@ __device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage 
 // Groups that were reserved but never written keep the tag KMB_LOG_NO_BIN and are skipped by the apply pass.
 __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
     __syncwarp();
-    const uint32_t c = lane < KMB_LOG_BINS ? min(st.cnt[lane], (uint32_t)KMB_STAGE_SLOTS) : 0u;  // clamp: kmb_mz_emit
+    const uint32_t c = lane < KMB_LOG_BINS ? min(st.cnt[lane], st.slots) : 0u;  // clamp: kmb_mz_emit
     unsigned ready = __ballot_sync(KMB_FULL_MASK, all ? c > 0u : c >= 32u);
     while (ready) {
         const int b = __ffs(ready) - 1;
@@ -413,7 +414,7 @@ __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStag
         uint32_t cb = __shfl_sync(KMB_FULL_MASK, c, b);
         while (cb >= 32u || (all && cb > 0u)) {
             const uint32_t n = min(cb, 32u);
-            kmb_log_write(P, st, (uint32_t)b, st.buf + b * KMB_STAGE_SLOTS + (cb - n), n, lane);
+            kmb_log_write(P, st, (uint32_t)b, st.buf + b * st.slots + (cb - n), n, lane);
             cb -= n;
         }
         if (lane == 0) st.cnt[b] = cb;
@@ -650,7 +651,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     uint32_t *pack = s_pack[warp];
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
-    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS};
+    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS, KMB_STAGE_SLOTS};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
@@ -726,32 +727,48 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 // No cross-tile state except the staged hits.
 // ================================================================================================
 #define KMB_MZ_K 31
-#define KMB_MZ_U 2          // runs taken per lane and round (filter loads in flight)
-#define KMB_MZ_SLOTS 128    // primary sectors staged per tile (a tile has ~145 runs, ~105 pass the filter)
-#define KMB_MZ_SLOTS2 64    // secondary sectors staged per tile (buckets with more than two entries)
-#define KMB_MZ_NONE 0xFFu   // run table: nothing to compare (no valid window, or the filter said no)
-#define KMB_MZ_LATE 0xFEu   // run table / secondary table: no staging slot left, load from global memory instead
+#define KMB_MZ_THREADS 128  // 4 warps per CTA, seven CTAs per SM
+#ifdef KMB_BOUNDS_CHECKS  // the checked build doubles as a stress build: tiny limits, so every overflow path runs in the tests
+#define KMB_MZ_SLOTS 4
+#define KMB_MZ_SLOTS2 2
+#define KMB_MZ_RUNS_KEPT 8
+#else
+// A tile is worked off in two passes of 16 lanes' runs each, so that everything below is sized for half a tile:
+// 7.7 KB of shared memory per warp = 28 warps per SM instead of 20.
+#define KMB_MZ_SLOTS 64     // primary sectors staged per pass (half a tile has ~73 runs, ~52 pass the filter)
+#define KMB_MZ_SLOTS2 24    // secondary sectors staged per pass (buckets with more than two entries)
+#define KMB_MZ_RUNS_KEPT 96  // passing runs remembered per pass; beyond KMB_MZ_SLOTS they load their bucket late
+#endif
+#define KMB_MZ_NONE 0xFFu   // secondary table: the bucket has no secondary sector to look at
+#define KMB_MZ_LATE 0xFEu   // secondary table: no staging slot left, load from global memory instead
 #define KMB_MZ_PACK_WORDS (KMB_WTILE_POS / 16 + 4)
-#define KMB_MZ_LATE_CAP 64  // < 32 left over + at most 32 new per round
-struct KmbMzShared {  // per warp
+#define KMB_MZ_LATE_CAP 40  // <= 8 left over + at most 32 new per round
+#define KMB_MZ_STAGE_SLOTS 48
+// a run of one lane: lane | first window << 5 | last window << 10 | minimizer position (0..47) << 15
+#define KMB_MZ_RUN(lane, s, e, j) ((uint32_t)(lane) | ((uint32_t)(s) << 5) | ((uint32_t)((e) - 1) << 10) | ((uint32_t)(j) << 15))
+struct alignas(16) KmbMzShared {  // per warp
     unsigned long long stage_res[KMB_LOG_BINS];
+    unsigned long long late_lo[KMB_MZ_LATE_CAP], late_hi[KMB_MZ_LATE_CAP];  // the 64 bases of the run's lane
     uint32_t pack[KMB_MZ_PACK_WORDS];
     union {
-        uint32_t mz[32][32];                             // [window of the lane][lane], until the runs are enumerated
+        uint32_t runs[16 * 32];                          // every run of the pass, until the filter has been asked
         uint32_t slots[KMB_MZ_SLOTS][KMB_LINE_WORDS];    // then: the primary sectors of the runs that passed
     } a;
-    uint32_t slots2[KMB_MZ_SLOTS2][KMB_LINE_WORDS];
-    uint32_t slot_sector[KMB_MZ_SLOTS];
-    uint8_t slot2_of[KMB_MZ_SLOTS];  // secondary slot of a primary slot, KMB_MZ_NONE, or KMB_MZ_LATE
-    uint8_t run_slot[32][32];        // [run of the lane][lane] -> primary slot, KMB_MZ_NONE, or KMB_MZ_LATE
-    uint8_t run_pos[32][32];         // position (base offset from the lane's first base, 0..47) of the run's minimizer
-    // runs whose bucket continues in the pool (more than four entries): retired 32 at a time, one per lane
-    unsigned long long late_lo[KMB_MZ_LATE_CAP], late_hi[KMB_MZ_LATE_CAP];  // the 64 bases of the run's lane
+    uint8_t mzpos[32][32];                               // [window of the lane][lane]: where its minimizer sits
+    uint32_t slots2[KMB_MZ_SLOTS2][KMB_LINE_WORDS];      // secondary sectors
+    uint32_t kept_run[KMB_MZ_RUNS_KEPT];     // the runs that passed the filter, in slot order
+    uint32_t kept_sector[KMB_MZ_RUNS_KEPT];  // and the primary sector of their bucket
+    uint32_t valid[32];                      // per lane: which of its 32 windows exist
+    uint8_t slot2_of[KMB_MZ_SLOTS];          // secondary slot of a primary slot, KMB_MZ_NONE, or KMB_MZ_LATE
     uint32_t late_valid[KMB_MZ_LATE_CAP], late_sector[KMB_MZ_LATE_CAP], late_sej[KMB_MZ_LATE_CAP];  // s | e << 8 | jpos << 16
-    uint32_t stage[KMB_LOG_BINS * KMB_STAGE_SLOTS];
+    uint32_t stage[KMB_LOG_BINS * KMB_MZ_STAGE_SLOTS];
     uint32_t stage_cnt[2 * KMB_LOG_BINS];
 };
-#define KMB_MZ_SMEM_BYTES ((KMB_TILE_THREADS / 32) * sizeof(KmbMzShared))
+#define KMB_MZ_SMEM_BYTES ((KMB_MZ_THREADS / 32) * sizeof(KmbMzShared))
+static_assert(sizeof(KmbMzShared) % 16 == 0, "per-warp shared block must keep the 16-byte alignment of the staged sectors");
+#ifndef KMB_BOUNDS_CHECKS
+static_assert(7 * (KMB_MZ_SMEM_BYTES + 1024) <= 233472, "seven CTAs of the read-path kernel must fit one SM");
+#endif
 
 // ---- index side: file every live entry of the key-addressed sectors under its minimizer -------------
 __global__ void kmb_mz_build_count(const uint32_t *__restrict__ lines, uint64_t n_lines, int k, KmbAddr addr,
@@ -824,15 +841,19 @@ __global__ void kmb_mz_build_scatter(const uint32_t *__restrict__ src, uint64_t 
 }
 
 // ---- query side ---------------------------------------------------------------------------------------
-// Minimizers of windows 16 H .. 16 H + 15 of this lane: w = its 64 bases (4 packed words).  Value stored per
-// window: ordering key of the winning m-mer (26 bits) | its base position relative to the lane's first base.
-template <int H>
-__device__ __forceinline__ void kmb_mz_half(const uint32_t (&w)[4], uint32_t *mz_col, uint32_t &prev, uint32_t &startbits) {
+// Minimizers of windows 16 H .. 16 H + 15 of this lane: w = its 64 bases (4 packed words).  Per window the base
+// position (relative to the lane's first base) of the winning m-mer is stored; a bit mask marks where the
+// (ordering key, position) pair changes = where a new run starts.
+// (h is a run-time value and the two halves share one copy of the code: the kernel is long and straight-line, and
+// instruction fetch is what its warps wait for most after memory.)
+__device__ __forceinline__ void kmb_mz_half(const uint32_t (&w4)[4], int h, uint8_t *pos_col, uint32_t &prev, uint32_t &startbits) {
     uint32_t a[32];
+    const uint32_t w[3] = {h ? w4[1] : w4[0], h ? w4[2] : w4[1], h ? w4[3] : w4[2]};  // bases 16 h .. 16 h + 47
+    const uint32_t jbase = 16u * (uint32_t)h;
 #pragma unroll
     for (int t = 0; t < 32; t++) {
-        const int j = 16 * H + t;  // m-mer starting at base j: bits [2j, 2j + 30) of the 128-bit stream
-        a[t] = kmb_mmer_order(__funnelshift_r(w[j >> 4], w[(j >> 4) + 1], (2 * j) & 31) & KMB_MZ_MASK) | (uint32_t)j;
+        // m-mer starting at base 16 h + t: bits [2t, 2t + 30) of the 96-bit stream w
+        a[t] = kmb_mmer_order(__funnelshift_r(w[t >> 4], w[(t >> 4) + 1], (2 * t) & 31) & KMB_MZ_MASK) | (jbase + (uint32_t)t);
     }
     // sliding minimum over 17 = 16 + 1 by doubling: after the four rounds a[t] = min of m-mers t .. t+15
 #pragma unroll
@@ -843,13 +864,15 @@ __device__ __forceinline__ void kmb_mz_half(const uint32_t (&w)[4], uint32_t *mz
     for (int t = 0; t < 25; t++) a[t] = min(a[t], a[t + 4]);
 #pragma unroll
     for (int t = 0; t < 17; t++) a[t] = min(a[t], a[t + 8]);
+    uint32_t sb = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const uint32_t v = min(a[i], a[i + 1]);
-        mz_col[(16 * H + i) * 32] = v;
-        startbits |= (v != prev ? 1u : 0u) << (16 * H + i);
+        pos_col[(jbase + i) * 32] = (uint8_t)(v & 63u);
+        sb |= (v != prev ? 1u : 0u) << i;
         prev = v;
     }
+    startbits |= sb << jbase;
 }
 
 __device__ __forceinline__ void kmb_cp_async_sector(uint32_t *smem_dst, const uint32_t *gmem_src) {
@@ -866,20 +889,28 @@ __device__ __forceinline__ void kmb_mz_emit(const KmbProbe &P, const KmbStage &s
     const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
     KMB_BOUND(6, node, P.n_counts);
     const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
-    if (pos < KMB_STAGE_SLOTS) st.buf[b * KMB_STAGE_SLOTS + pos] = node;
+    if (pos < st.slots) st.buf[b * st.slots + pos] = node;
     else atomicAdd(P.counts + node, 1u);
 }
-// The two entries of one sector (words r[1..7]: frequencies, keys, nodes) of a bucket against the run [s, e) of a
-// lane whose minimizer sits at base position jpos: entry t of the sector is entry `first + t` of the bucket.
-__device__ __forceinline__ void kmb_mz_match_pair(const KmbProbe &P, const KmbStage &st, const uint32_t (&r)[8], uint32_t hdr,
-                                                  uint32_t first, uint32_t n_entries, int jpos, int s, int e, uint32_t valid,
-                                                  uint64_t lo, uint64_t hi, uint64_t kmask, unsigned &counted) {
+// the k-mer that starts at base p of the packed tile
+__device__ __forceinline__ uint64_t kmb_mz_window_at(const uint32_t *pack, uint32_t p, uint64_t kmask) {
+    const uint32_t wi = p >> 4, sh = (p & 15u) * 2u;
+    KMB_BOUND(12, wi + 2, KMB_MZ_PACK_WORDS);
+    const uint32_t w0 = pack[wi], w1 = pack[wi + 1], w2 = pack[wi + 2];
+    return ((uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32)) & kmask;
+}
+// The two entries of one sector (words r[1..7]: frequencies, keys, nodes) against one run.  off0/off1 = minimizer
+// offsets of the two entries, n = how many of them exist; jp = tile position of the run's minimizer; [ps, pe) =
+// tile positions of the run's windows; vrow = valid bits of the run's lane (bit = position - lane_base).
+__device__ __forceinline__ void kmb_mz_match_pair(const KmbProbe &P, const KmbStage &st, const uint32_t (&r)[8], uint32_t off0,
+                                                  uint32_t off1, uint32_t n, int jp, int ps, int pe, int lane_base, uint32_t vrow,
+                                                  const uint32_t *pack, uint64_t kmask, unsigned &counted) {
 #pragma unroll
     for (uint32_t t = 0; t < 2u; t++) {
-        if (first + t >= n_entries) break;
-        const int i = jpos - (int)KMB_MZ_HDR_OFFSET(hdr, first + t);  // the only window that has the minimizer at that offset
-        if (i < s || i >= e || !((valid >> i) & 1u)) continue;
-        const uint64_t km = kmb_window(lo, hi, i, kmask);
+        if (t >= n) break;
+        const int p = jp - (int)(t ? off1 : off0);  // the only window that has the minimizer at that offset
+        if (p < ps || p >= pe || !((vrow >> (p - lane_base)) & 1u)) continue;
+        const uint64_t km = kmb_mz_window_at(pack, (uint32_t)p, kmask);
         if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
         const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
         if ((int32_t)freq > P.max_freq) continue;
@@ -933,9 +964,9 @@ __device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPo
 }
 
 template <bool FILT>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, 2)
+__global__ void __launch_bounds__(KMB_MZ_THREADS, 7)
 kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
-                        const uint32_t *__restrict__ mask, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
+                        const uint32_t *__restrict__ mask, uint32_t in_mode, KmbProbe P, KmbProbe Pkey, KmbStatus *status) {
     extern __shared__ __align__(16) unsigned char kmb_mz_smem[];
     KmbMzShared &S = reinterpret_cast<KmbMzShared *>(kmb_mz_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -944,7 +975,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
     const bool packed = (in_mode & KMB_IN_PACKED) != 0u;
     const uint32_t *__restrict__ words = reinterpret_cast<const uint32_t *>(bases);
     const uint64_t n_words = (n_bases + 15) / 16 + 4;
-    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS};
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, KMB_MZ_STAGE_SLOTS};
     kmb_stage_init(st, lane);
     unsigned counted = 0, fetched = 0;
     const KmbPol pol = kmb_make_policies(P.policies);
@@ -952,16 +983,17 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
     const uint64_t kmask = kmb_kmer_mask(k);
     const uint64_t n_tiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
     const uint64_t n_vec_full = n_bases / 16;
-    const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_TILE_THREADS / 32);
+    const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_MZ_THREADS / 32);
     unsigned long long mapped = 0;
     uint32_t *pack = S.pack;
     int late_n = 0;  // warp-uniform
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
 
-    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_TILE_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
+    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_MZ_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
         const uint64_t t0 = tile * KMB_WTILE_POS;
         __syncwarp();
         // ---- 1. load + encode
-#pragma unroll
+#pragma unroll 1
         for (int i = lane; i < KMB_WTILE_POS / 16 + 2; i += 32) {
             uint64_t v = t0 / 16 + (uint64_t)i;
             if (packed) {
@@ -973,175 +1005,184 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
             if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + v * 16 + (uint64_t)(__ffs(inv) - 1)));
         }
+        if (lane < 2) pack[KMB_WTILE_POS / 16 + 2 + lane] = 0u;  // read (not used) by the window extraction of the last positions
         __syncwarp();
-        // ---- 2. this lane's 32 windows: which exist, their minimizers, where runs start
+        // ---- 2. this lane's 32 windows: which exist, where their minimizers sit, where runs start
         const uint64_t p0 = t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
         const uint32_t valid = kmb_valid_starts(mask, p0, n_bases, k);
         mapped += __popc(valid);
         if (!__any_sync(KMB_FULL_MASK, valid != 0u)) continue;
-        const uint2 qa = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
-        const uint2 qb = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
+        S.valid[lane] = valid;
         uint32_t startbits = 0;
         {
+            const uint2 qa = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
+            const uint2 qb = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
             const uint32_t w[4] = {qa.x, qa.y, qb.x, qb.y};
             uint32_t prev = 0;
-            kmb_mz_half<0>(w, &S.a.mz[0][lane], prev, startbits);
-            kmb_mz_half<1>(w, &S.a.mz[0][lane], prev, startbits);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) kmb_mz_half(w, h, &S.mzpos[0][lane], prev, startbits);
             startbits |= 1u;
         }
-        // ---- 3. runs -> filter -> staging slots
-        unsigned n_slots = 0;  // warp-uniform; may run past KMB_MZ_SLOTS (those runs load their bucket late)
-        {
-            uint32_t bits = startbits;
-            int run = 0;
 #pragma unroll 1
-            while (__any_sync(KMB_FULL_MASK, bits != 0u)) {
-                uint32_t sec[KMB_MZ_U], need[KMB_MZ_U], fw[KMB_MZ_U];
-                int rid[KMB_MZ_U];
-#pragma unroll
-                for (int u = 0; u < KMB_MZ_U; u++) {
-                    need[u] = 0;
-                    fw[u] = 0;
-                    sec[u] = 0;
-                    rid[u] = -1;
-                    if (bits) {
-                        const int s = __ffs(bits) - 1;
-                        bits &= bits - 1u;
-                        const int e = bits ? __ffs(bits) - 1 : 32;
-                        const uint32_t v = (valid >> s) & (e - s == 32 ? 0xFFFFFFFFu : ((1u << (e - s)) - 1u));
-                        rid[u] = run++;
-                        if (v) {
-                            const uint32_t jpos = S.a.mz[s][lane] & 63u;
-                            S.run_pos[rid[u]][lane] = (uint8_t)jpos;
-                            // the minimizer m-mer itself: 15 bases from base jpos of this lane
-                            const uint32_t p = (uint32_t)lane * KMB_POS_PER_THREAD + jpos;
-                            const uint32_t mmer = __funnelshift_r(pack[p >> 4], pack[(p >> 4) + 1], (p & 15u) * 2u) & KMB_MZ_MASK;
-                            const KmbLoc loc = kmb_locate((uint64_t)mmer, P.addr);
-                            sec[u] = 2u * loc.sector;
-                            if (FILT) {
-                                need[u] = loc.fmask;
-                                KMB_BOUND(0, loc.fword, P.addr.n_filter_words);
-                                fw[u] = kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter);
-                            } else {
-                                need[u] = 1u;
-                                fw[u] = 1u;
-                            }
-                        }
-                    }
+        for (int pass_no = 0; pass_no < 2; pass_no++) {
+            __syncwarp();
+            // ---- 2b. the tile's run list: lanes append their runs (those with at least one existing window)
+            unsigned n_runs;
+            {
+                // runs of this lane that contain an existing window: walk the start bits once to count, once to write
+                uint32_t keep = 0;  // bit s set <=> the run starting at s has an existing window
+                for (uint32_t bits = (valid && (lane >> 4) == pass_no) ? startbits : 0u; bits;) {
+                    const int s = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    const int e = bits ? __ffs(bits) - 1 : 32;
+                    const uint32_t v = (valid >> s) & (e - s == 32 ? 0xFFFFFFFFu : ((1u << (e - s)) - 1u));
+                    keep |= (v ? 1u : 0u) << s;
                 }
-                uint32_t cmask = 0;
-#pragma unroll
-                for (int u = 0; u < KMB_MZ_U; u++) cmask |= (need[u] != 0u && (fw[u] & need[u]) == need[u]) ? (1u << u) : 0u;
-                const uint32_t mine = __popc(cmask);
+                const uint32_t mine = __popc(keep);
                 uint32_t incl = mine;
-#pragma unroll
+    #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t v = __shfl_up_sync(KMB_FULL_MASK, incl, o);
                     if (lane >= o) incl += v;
                 }
-                unsigned slot = n_slots + incl - mine;
-                n_slots += __shfl_sync(KMB_FULL_MASK, incl, 31);
-#pragma unroll
-                for (int u = 0; u < KMB_MZ_U; u++) {
-                    if (rid[u] < 0) continue;
-                    uint8_t tag = KMB_MZ_NONE;
-                    if ((cmask >> u) & 1u) {
-                        if (slot < KMB_MZ_SLOTS) {
-                            S.slot_sector[slot] = sec[u];
-                            tag = (uint8_t)slot;
-                        } else {
-                            tag = KMB_MZ_LATE;
-                        }
-                        slot++;
-                    }
-                    S.run_slot[rid[u]][lane] = tag;
+                n_runs = __shfl_sync(KMB_FULL_MASK, incl, 31);
+                unsigned at = incl - mine;
+                for (uint32_t bits = startbits, kb = keep; kb;) {
+                    const int s = __ffs(kb) - 1;
+                    kb &= kb - 1u;
+                    const uint32_t after = bits & ~((2u << s) - 1u);  // start bits above s
+                    const int e = after ? __ffs(after) - 1 : 32;
+                    S.a.runs[at++] = KMB_MZ_RUN(lane, s, e, S.mzpos[s][lane]);
                 }
             }
-        }
-        __syncwarp();  // the minimizers are no longer needed: their space becomes the staging slots
-        // ---- 4. fetch: primaries in one burst, then the secondaries of the buckets with more than two entries
-        const unsigned n_staged = min(n_slots, (unsigned)KMB_MZ_SLOTS);
-        fetched += n_slots;
-        for (unsigned sl = (unsigned)lane; sl < n_staged; sl += 32u) {
-            KMB_BOUND(1, S.slot_sector[sl], 2ull * P.addr.n_main);
-            kmb_cp_async_sector(S.a.slots[sl], P.lines + (uint64_t)S.slot_sector[sl] * KMB_LINE_WORDS);
-        }
-        kmb_cp_async_wait_all();
-        __syncwarp();
-        {
-            unsigned n2 = 0;
-#pragma unroll 1
-            for (unsigned base = 0; base < n_staged; base += 32u) {
-                const unsigned sl = base + (unsigned)lane;
-                const bool more = sl < n_staged && KMB_MZ_HDR_COUNT(S.a.slots[sl][0]) > 2u;
-                const unsigned m = __ballot_sync(KMB_FULL_MASK, more);
-                if (sl < n_staged) {
-                    uint8_t tag = KMB_MZ_NONE;
-                    if (more) {
-                        const unsigned j = n2 + __popc(m & ((1u << lane) - 1u));
-                        if (j < KMB_MZ_SLOTS2) {
-                            kmb_cp_async_sector(S.slots2[j], P.lines + (uint64_t)(S.slot_sector[sl] + 1u) * KMB_LINE_WORDS);
-                            tag = (uint8_t)j;
-                        } else {
-                            tag = KMB_MZ_LATE;
-                        }
+            __syncwarp();
+            // ---- 3. one filter word per run, 32 runs per round; the runs that pass are kept in slot order
+            unsigned n_kept = 0;  // warp-uniform; a tile that exceeds KMB_MZ_RUNS_KEPT takes the slow exit below
+    #pragma unroll 1
+            for (unsigned r0 = 0; r0 < n_runs; r0 += 32u) {
+                const unsigned ri = r0 + (unsigned)lane;
+                uint32_t run = 0, sector = 0;
+                bool pass = false;
+                if (ri < n_runs) {
+                    run = S.a.runs[ri];
+                    const uint32_t p = (run & 31u) * KMB_POS_PER_THREAD + (run >> 15);  // tile position of the minimizer m-mer
+                    const uint32_t mmer = __funnelshift_r(pack[p >> 4], pack[(p >> 4) + 1], (p & 15u) * 2u) & KMB_MZ_MASK;
+                    const KmbLoc loc = kmb_locate((uint64_t)mmer, P.addr);
+                    sector = 2u * loc.sector;
+                    if (FILT) {
+                        KMB_BOUND(0, loc.fword, P.addr.n_filter_words);
+                        const uint32_t fw = kmb_ldg_u32_hint(P.filter + loc.fword, pol.filter);
+                        pass = (fw & loc.fmask) == loc.fmask;
+                    } else {
+                        pass = true;
                     }
-                    S.slot2_of[sl] = tag;
                 }
-                n2 += __popc(m);
+                const unsigned m = __ballot_sync(KMB_FULL_MASK, pass);
+                if (pass) {
+                    const unsigned slot = n_kept + __popc(m & lanemask_lt);
+                    if (slot < KMB_MZ_RUNS_KEPT) {
+                        S.kept_run[slot] = run;
+                        S.kept_sector[slot] = sector;
+                    }
+                }
+                n_kept += __popc(m);
             }
-            if (n2) kmb_cp_async_wait_all();
-        }
-        __syncwarp();
-        // ---- 5. per run, per entry of its bucket: the one window that could match
-        {
-            const uint64_t lo = (uint64_t)qa.x | ((uint64_t)qa.y << 32);
-            const uint64_t hi = (uint64_t)qb.x | ((uint64_t)qb.y << 32);
-            uint32_t bits = valid ? startbits : 0u;
-            int run = 0;
-#pragma unroll 1
-            while (__any_sync(KMB_FULL_MASK, bits != 0u)) {
-                uint32_t pool_sector = 0, pool_sej = 0;  // set when this lane's run continues in the pool
-                if (bits) {
-                    const int s = __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    const int e = bits ? __ffs(bits) - 1 : 32;
-                    const uint32_t tag = S.run_slot[run][lane];
-                    const int jpos = (int)S.run_pos[run][lane];
-                    run++;
-                    if (tag != KMB_MZ_NONE) {
-                        uint32_t r[8];
-                        uint32_t sector1;  // the bucket's secondary sector
-                        uint32_t t2;
-                        if (tag < KMB_MZ_SLOTS) {
-                            const uint4 x = *reinterpret_cast<const uint4 *>(&S.a.slots[tag][0]);
-                            const uint4 y = *reinterpret_cast<const uint4 *>(&S.a.slots[tag][4]);
-                            r[0] = x.x, r[1] = x.y, r[2] = x.z, r[3] = x.w, r[4] = y.x, r[5] = y.y, r[6] = y.z, r[7] = y.w;
-                            sector1 = S.slot_sector[tag] + 1u;
-                            t2 = S.slot2_of[tag];
-                        } else {  // the tile had more runs than staging slots: find and load the bucket again
-                            const uint32_t p = (uint32_t)lane * KMB_POS_PER_THREAD + (uint32_t)jpos;
-                            const uint32_t mmer = __funnelshift_r(pack[p >> 4], pack[(p >> 4) + 1], (p & 15u) * 2u) & KMB_MZ_MASK;
-                            sector1 = 2u * kmb_locate((uint64_t)mmer, P.addr).sector + 1u;
-                            kmb_ld_sector(P.lines + (uint64_t)(sector1 - 1u) * KMB_LINE_WORDS, r, pol.line);
-                            t2 = KMB_MZ_LATE;
+            if (n_kept > KMB_MZ_RUNS_KEPT) {
+                // A pass with more passing runs than can be remembered (a minimizer change at almost every window: never
+                // seen on real or synthetic reads; the checked build forces it).  Forget the runs: every existing window
+                // of the pass's 16 lanes goes through the key-addressed sectors, one at a time.
+                const uint2 qa = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
+                const uint2 qb = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
+                const uint64_t lo = (uint64_t)qa.x | ((uint64_t)qa.y << 32), hi = (uint64_t)qb.x | ((uint64_t)qb.y << 32);
+    #pragma unroll 1
+                for (uint32_t vb = (lane >> 4) == pass_no ? valid : 0u; vb; vb &= vb - 1u) {
+                    kmb_walk_one(Pkey, pol, kmb_window(lo, hi, __ffs(vb) - 1, kmask), [&](uint32_t node, uint32_t freq) {
+                        if ((int32_t)freq <= Pkey.max_freq) {
+                            KMB_BOUND(6, node, Pkey.n_counts);
+                            atomicAdd(Pkey.counts + node, 1u);
+                            counted++;
                         }
-                        const uint32_t hdr = r[0];
-                        const uint32_t n_entries = KMB_MZ_HDR_COUNT(hdr);
-                        kmb_mz_match_pair(P, st, r, hdr, 0u, n_entries, jpos, s, e, valid, lo, hi, kmask, counted);
-                        if (n_entries > 2u) {
-                            if (t2 < KMB_MZ_SLOTS2) {
-                                const uint4 x = *reinterpret_cast<const uint4 *>(&S.slots2[t2][0]);
-                                const uint4 y = *reinterpret_cast<const uint4 *>(&S.slots2[t2][4]);
-                                r[0] = x.x, r[1] = x.y, r[2] = x.z, r[3] = x.w, r[4] = y.x, r[5] = y.y, r[6] = y.z, r[7] = y.w;
+                        return false;
+                    });
+                    fetched++;
+                }
+                continue;
+            }
+            __syncwarp();  // the run list is no longer needed: its space becomes the staging slots
+            // ---- 4. fetch: primaries in one burst, then the secondaries of the buckets with more than two entries
+            const unsigned n_have = n_kept;
+            const unsigned n_staged = min(n_have, (unsigned)KMB_MZ_SLOTS);
+            fetched += n_have;
+            for (unsigned sl = (unsigned)lane; sl < n_staged; sl += 32u) {
+                KMB_BOUND(1, S.kept_sector[sl], 2ull * P.addr.n_main);
+                kmb_cp_async_sector(S.a.slots[sl], P.lines + (uint64_t)S.kept_sector[sl] * KMB_LINE_WORDS);
+            }
+            kmb_cp_async_wait_all();
+            __syncwarp();
+            {
+                unsigned n2 = 0;
+    #pragma unroll 1
+                for (unsigned base = 0; base < n_staged; base += 32u) {
+                    const unsigned sl = base + (unsigned)lane;
+                    const bool more = sl < n_staged && KMB_MZ_HDR_COUNT(S.a.slots[sl][0]) > 2u;
+                    const unsigned m = __ballot_sync(KMB_FULL_MASK, more);
+                    if (sl < n_staged) {
+                        uint8_t tag = KMB_MZ_NONE;
+                        if (more) {
+                            const unsigned j = n2 + __popc(m & lanemask_lt);
+                            if (j < KMB_MZ_SLOTS2) {
+                                kmb_cp_async_sector(S.slots2[j], P.lines + (uint64_t)(S.kept_sector[sl] + 1u) * KMB_LINE_WORDS);
+                                tag = (uint8_t)j;
                             } else {
-                                kmb_ld_sector(P.lines + (uint64_t)sector1 * KMB_LINE_WORDS, r, pol.line);
+                                tag = KMB_MZ_LATE;
                             }
-                            kmb_mz_match_pair(P, st, r, hdr, 2u, n_entries, jpos, s, e, valid, lo, hi, kmask, counted);
-                            if (n_entries > 4u) {
-                                pool_sector = r[0] & ~KMB_HDR_CHAIN;
-                                pool_sej = (uint32_t)s | ((uint32_t)e << 8) | ((uint32_t)jpos << 16);
-                            }
+                        }
+                        S.slot2_of[sl] = tag;
+                    }
+                    n2 += __popc(m);
+                }
+                if (n2) kmb_cp_async_wait_all();
+            }
+            __syncwarp();
+            // ---- 5. 32 kept runs per round, one per lane; per entry of the run's bucket the one window that could match
+    #pragma unroll 1
+            for (unsigned s0 = 0; s0 < n_have; s0 += 32u) {
+                const unsigned sl = s0 + (unsigned)lane;
+                uint32_t pool_sector = 0, pool_run = 0;
+                if (sl < n_have) {
+                    const uint32_t run = S.kept_run[sl];
+                    const int lane_base = (int)(run & 31u) * KMB_POS_PER_THREAD;
+                    const int ps = lane_base + (int)((run >> 5) & 31u), pe = lane_base + (int)((run >> 10) & 31u) + 1;
+                    const int jp = lane_base + (int)(run >> 15);
+                    const uint32_t vrow = S.valid[run & 31u];
+                    uint32_t r[8];
+                    uint32_t t2;
+                    if (sl < n_staged) {
+                        const uint4 x = *reinterpret_cast<const uint4 *>(&S.a.slots[sl][0]);
+                        const uint4 y = *reinterpret_cast<const uint4 *>(&S.a.slots[sl][4]);
+                        r[0] = x.x, r[1] = x.y, r[2] = x.z, r[3] = x.w, r[4] = y.x, r[5] = y.y, r[6] = y.z, r[7] = y.w;
+                        t2 = S.slot2_of[sl];
+                    } else {  // more runs passed than there are staging slots: load the bucket now
+                        kmb_ld_sector(P.lines + (uint64_t)S.kept_sector[sl] * KMB_LINE_WORDS, r, pol.line);
+                        t2 = KMB_MZ_LATE;
+                    }
+                    const uint32_t hdr = r[0];
+                    const uint32_t n_entries = KMB_MZ_HDR_COUNT(hdr);
+                    kmb_mz_match_pair(P, st, r, KMB_MZ_HDR_OFFSET(hdr, 0), KMB_MZ_HDR_OFFSET(hdr, 1), n_entries, jp, ps, pe, lane_base,
+                                      vrow, pack, kmask, counted);
+                    if (n_entries > 2u) {
+                        if (t2 < KMB_MZ_SLOTS2) {
+                            const uint4 x = *reinterpret_cast<const uint4 *>(&S.slots2[t2][0]);
+                            const uint4 y = *reinterpret_cast<const uint4 *>(&S.slots2[t2][4]);
+                            r[0] = x.x, r[1] = x.y, r[2] = x.z, r[3] = x.w, r[4] = y.x, r[5] = y.y, r[6] = y.z, r[7] = y.w;
+                        } else {
+                            kmb_ld_sector(P.lines + (uint64_t)(S.kept_sector[sl] + 1u) * KMB_LINE_WORDS, r, pol.line);
+                        }
+                        kmb_mz_match_pair(P, st, r, KMB_MZ_HDR_OFFSET(hdr, 2), KMB_MZ_HDR_OFFSET(hdr, 3), n_entries - 2u, jp, ps, pe,
+                                          lane_base, vrow, pack, kmask, counted);
+                        if (n_entries > 4u) {
+                            pool_sector = r[0] & ~KMB_HDR_CHAIN;
+                            pool_run = run;
                         }
                     }
                 }
@@ -1149,22 +1190,27 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                 const unsigned pm = __ballot_sync(KMB_FULL_MASK, pool_sector != 0u);
                 if (pm) {
                     if (pool_sector) {
-                        const int idx = late_n + __popc(pm & ((1u << lane) - 1u));
+                        const int idx = late_n + __popc(pm & lanemask_lt);
                         KMB_BOUND(7, idx, KMB_MZ_LATE_CAP);
-                        S.late_lo[idx] = lo;
-                        S.late_hi[idx] = hi;
-                        S.late_valid[idx] = valid;
+                        const uint32_t L = pool_run & 31u;
+                        const uint2 qa = *reinterpret_cast<const uint2 *>(&pack[2 * L]);
+                        const uint2 qb = *reinterpret_cast<const uint2 *>(&pack[2 * L + 2]);
+                        S.late_lo[idx] = (unsigned long long)qa.x | ((unsigned long long)qa.y << 32);
+                        S.late_hi[idx] = (unsigned long long)qb.x | ((unsigned long long)qb.y << 32);
+                        S.late_valid[idx] = S.valid[L];
                         S.late_sector[idx] = pool_sector;
-                        S.late_sej[idx] = pool_sej;
+                        S.late_sej[idx] = ((pool_run >> 5) & 31u) | ((((pool_run >> 10) & 31u) + 1u) << 8) | ((pool_run >> 15) << 16);
                     }
                     late_n += __popc(pm);
-                    if (late_n >= 32) {
-                        kmb_mz_late_drain(P, pol, S, st, late_n, 32, kmask, counted, fetched, lane);
-                        late_n -= 32;
+                    if (late_n > 8) {
+                        const int n = min(late_n, 32);
+                        kmb_mz_late_drain(P, pol, S, st, late_n, n, kmask, counted, fetched, lane);
+                        late_n -= n;
                     }
                     __syncwarp();
                 }
             }
+    
         }
     }
     // ---- the rest
@@ -1175,7 +1221,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
         mapped += __shfl_xor_sync(KMB_FULL_MASK, mapped, o);
     }
     if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
-    if (lane == 0 && fetched) atomicAdd(&status->n_candidates, (unsigned long long)fetched);  // warp-uniform: bucket and pool fetches
+    if (lane == 0 && fetched) atomicAdd(&status->n_candidates, (unsigned long long)fetched);  // approximate: bucket and pool fetches
     if (lane == 0 && mapped) atomicAdd(&status->n_kmers_mapped, mapped);
 }
 
@@ -1196,7 +1242,7 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
     const int warp = tid >> 5;
     uint64_t *q_kmer = s_qk[warp];
     uint32_t *q_h = s_qh[warp];
-    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS};
+    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS, KMB_STAGE_SLOTS};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
