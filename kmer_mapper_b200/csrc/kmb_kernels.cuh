@@ -566,15 +566,32 @@ __device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol 
     if (lane == 0 && pp.issued) atomicAdd(&status->n_candidates, (unsigned long long)pp.issued);
 }
 
-struct KmbWindowFn {  // forward window b0+u of the 64 bases in hi:lo
-    uint64_t lo, hi, kmask;
-    int b0;
-    __device__ __forceinline__ uint64_t operator()(int u) const { return kmb_window(lo, hi, b0 + u, kmask); }
+// Forward windows b0 .. b0+U-1 of a lane's 64 bases (four packed words w0..w3), b0 a multiple of U <= 4.  All
+// windows of a batch start inside the same word, so the three words they can touch are picked once per batch and
+// each window is two 32-bit funnel shifts -- not two 64-bit variable shifts (which were 14 % of the kernel's
+// instructions).  Same value as kmb_window(lo, hi, b0 + u, kmask).
+struct KmbWindowFn {
+    uint32_t a, b, c;    // the words holding bases 16 i .. 16 i + 47, i = b0 / 16
+    uint32_t sh;         // bit offset of window b0 inside a: (2 b0) mod 32 <= 28 and 2 u <= 6 with b0 a multiple of U, so sh + 2 u < 32
+    uint32_t mlo, mhi;   // the k-mer mask
+    __device__ __forceinline__ KmbWindowFn(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int b0, uint64_t kmask) {
+        const bool up = b0 >= 16;
+        a = up ? w1 : w0;
+        b = up ? w2 : w1;
+        c = up ? w3 : w2;
+        sh = (2u * (uint32_t)b0) & 31u;
+        mlo = (uint32_t)kmask;
+        mhi = (uint32_t)(kmask >> 32);
+    }
+    __device__ __forceinline__ uint64_t operator()(int u) const {
+        const uint32_t s = sh + 2u * (uint32_t)u;
+        return (uint64_t)(__funnelshift_r(a, b, s) & mlo) | ((uint64_t)(__funnelshift_r(b, c, s) & mhi) << 32);
+    }
 };
-struct KmbRcWindowFn {  // its reverse complement
-    uint64_t lo, hi, kmask;
-    int b0, k;
-    __device__ __forceinline__ uint64_t operator()(int u) const { return kmb_revcomp(kmb_window(lo, hi, b0 + u, kmask), k); }
+struct KmbRcWindowFn {  // their reverse complements
+    KmbWindowFn fwd;
+    int k;
+    __device__ __forceinline__ uint64_t operator()(int u) const { return kmb_revcomp(fwd(u), k); }
 };
 struct KmbArrayFn {
     const uint64_t *km;
@@ -688,17 +705,15 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
         mapped += __popc(valid);
         const uint2 a = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
         const uint2 b = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
-        const uint64_t lo = (uint64_t)a.x | ((uint64_t)a.y << 32);
-        const uint64_t hi = (uint64_t)b.x | ((uint64_t)b.y << 32);
         // ---- 3. probe in batches of U
 #pragma unroll 1
         for (int b0 = 0; b0 < KMB_POS_PER_THREAD; b0 += U) {
             const uint32_t vb = (valid >> b0) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
             if (!__any_sync(KMB_FULL_MASK, vb != 0u)) continue;
-            KmbWindowFn fw = {lo, hi, kmask, b0};
+            const KmbWindowFn fw(a.x, a.y, b.x, b.y, b0, kmask);
             kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fw, vb, q_kmer, q_h, qcount, lane);
             if (REVCOMP) {
-                KmbRcWindowFn rc = {lo, hi, kmask, b0, k};
+                const KmbRcWindowFn rc = {fw, k};
                 kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, rc, vb, q_kmer, q_h, qcount, lane);
             }
         }
