@@ -215,7 +215,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
  *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
- *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks",
+ *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
  *  "read_table" (1 = k = 31 reads go through the minimizer-bucketed second table, see csrc/kmb_core.cuh; default 0)};
  * read-only: "h2d_bytes" (bytes the mapping calls have copied host -> device so far), "bounds_failures" (-1 unless
  * built with -DKMB_BOUNDS_CHECKS). */

@@ -81,6 +81,7 @@ struct KmbOptions {
     // more issue slots than the saved look-ups give back -- 70 ms per 6.0 G k-mers against 48 ms for the
     // key-addressed kernel -- so it stays opt-in (and parity-tested) until that changes.
     int64_t read_table = 0;
+    int64_t filter_probes = 0;            // filter bits per key: 0 = by filter density (filter_probes()), else 1..3
     // The encoder is bound by the host's DRAM bandwidth, which the ranks of a multi-GPU node share, while every GPU
     // has its own PCIe link: with 2 ranks on one host a pinned source went 46.9 GK/s packed against 74.3 as ASCII
     // (profiles/README.md), so auto packs a pinned source only when this process has the host to itself.
@@ -119,6 +120,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(host_threads)
     OPT(host_ranks)
     OPT(read_table)
+    OPT(filter_probes)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -155,6 +157,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(host_threads)
     OPT(host_ranks)
     OPT(read_table)
+    OPT(filter_probes)
     OPT(chunk_bytes)
 #undef OPT
     if (!strcmp(name, "h2d_bytes")) {  // read-only
@@ -294,6 +297,13 @@ static int to_device(const T *src, size_t n, int device, DevBuf<T> &tmp, const T
     return KMB_OK;
 }
 
+// Bits set per key in the word-blocked filter: the classic optimum is ln 2 x bits per key; inside one 32-bit word
+// more than three bits collide too often to pay, and below 2.5 bits per key a second bit only fills the filter up.
+static uint32_t filter_probes(double bits_per_key) {
+    if (g_opt.filter_probes >= 1 && g_opt.filter_probes <= 3) return (uint32_t)g_opt.filter_probes;
+    return bits_per_key >= 4.0 ? 3u : (bits_per_key >= 2.5 ? 2u : 1u);
+}
+
 static int grid_for(size_t work_items, int block, int sms, int per_sm = 8) {
     size_t need = (work_items + block - 1) / block;
     size_t cap = (size_t)sms * per_sm;
@@ -393,7 +403,7 @@ extern "C" int kmb_index_create(int device, const int32_t *hashes_to_index, cons
     bool want_filter = g_opt.use_filter == 1 || (g_opt.use_filter < 0 && bits_per_key >= 0.62);
     if (!want_filter) filter_words = 0;
     ix->addr.n_filter_words = (uint32_t)filter_words;
-    ix->addr.two_probes = bits_per_key >= 2.5 ? 1u : 0u;
+    ix->addr.n_probes = filter_probes(bits_per_key);
     ix->filter_bytes = (size_t)std::max<uint64_t>(filter_words, 1) * 4;
     KMB_CUDA(cudaMalloc(&ix->filter, ix->filter_bytes));
     KMB_CUDA(cudaMemsetAsync(ix->filter, 0, ix->filter_bytes, s));
@@ -811,7 +821,7 @@ static int ensure_read_table(kmb_index *ix, int k) {
     const bool want_filter = g_opt.use_filter == 1 || (g_opt.use_filter < 0 && bits_per_key >= 0.62);
     if (!want_filter) filter_words = 0;
     addr.n_filter_words = (uint32_t)filter_words;
-    addr.two_probes = bits_per_key >= 2.5 ? 1u : 0u;
+    addr.n_probes = filter_probes(bits_per_key);
     DevBuf<uint32_t> filter, fill, lines;
     KMB_TRY(filter.alloc((size_t)std::max<uint64_t>(filter_words, 1)));
     KMB_CUDA(cudaMemsetAsync(filter.p, 0, (size_t)std::max<uint64_t>(filter_words, 1) * 4, s));

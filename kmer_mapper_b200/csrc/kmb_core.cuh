@@ -114,12 +114,13 @@ KMB_HD uint32_t kmb_log_bin(uint32_t node, uint32_t bin_shift) {
 // filter word by multiply-shift range reduction, so neither count has to be a power of two.
 //
 // Filter (probe level 0): a Bloom filter blocked into single 32-bit words, sized to stay in L2.
-// Every live entry sets one bit of its word or -- when there are >= 2.5 filter bits per key -- two;
-// a query passes iff all of its bits are set.  57-64 MB for 100 M keys: ~10-13 % of absent k-mers pass.
+// Every live entry sets one, two or three bits of its word (the more filter bits per key there are, the more:
+// kmb_filter_probes); a query passes iff all of its bits are set.  57-64 MB for 100 M keys: ~10 % of absent
+// k-mers pass.
 struct KmbAddr {
     uint32_t n_main;          // main sectors
     uint32_t n_filter_words;  // 0 = no filter
-    uint32_t two_probes;
+    uint32_t n_probes;        // filter bits per key: 1, 2 or 3
 };
 struct KmbLoc {
     uint32_t sector, fword, fmask;
@@ -140,7 +141,8 @@ KMB_HD KmbLoc kmb_locate(uint64_t key, const KmbAddr a) {
     l.sector = (uint32_t)(((uint64_t)hi * a.n_main) >> 32);
     l.fword = (uint32_t)(((uint64_t)f * a.n_filter_words) >> 32);
 #endif
-    l.fmask = (1u << (g >> 27)) | (a.two_probes ? (1u << ((g >> 22) & 31u)) : 0u);
+    l.fmask = (1u << (g >> 27)) | (a.n_probes >= 2u ? (1u << ((g >> 22) & 31u)) : 0u) |
+              (a.n_probes >= 3u ? (1u << ((g >> 17) & 31u)) : 0u);
     return l;
 }
 

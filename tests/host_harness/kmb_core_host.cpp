@@ -23,7 +23,7 @@ void h_locate(uint64_t key, uint32_t n_main, uint32_t n_words, uint32_t two, uin
     KmbAddr a;
     a.n_main = n_main;
     a.n_filter_words = n_words;
-    a.two_probes = two;
+    a.n_probes = two ? 2u : 1u;
     KmbLoc l = kmb_locate(key, a);
     out[0] = l.sector;
     out[1] = l.fword;
