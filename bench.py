@@ -488,7 +488,8 @@ def main_ours(args):
     achieved = bytes_per_kmer * n_kmers_step / max(kernels_per_step, 1) / (kernel_avg_ms / 1e3) / 1e9 if kernel_n else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": known_traffic(args.workload),
-                "kernel": "kmb_map_reads_kernel", "kernel_ms": kernel_avg_ms, "kernel_share_of_step": kernel_ms / ms if ms else None,
+                "kernel": "kmb_map_reads_mz_kernel (read-path table)" if _lib.get_option("last_reads_kernel") else "kmb_map_reads_kernel",
+                "kernel_ms": kernel_avg_ms, "kernel_share_of_step": kernel_ms / ms if ms else None,
                 "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h,
                 "sector_fetches_per_kmer": n_candidates_step / max(n_kmers_step, 1), "peak_source": peak_src,
                 "filter_bytes": di.filter_bytes}

@@ -75,12 +75,14 @@ struct KmbOptions {
     // (profiles/r01_v7_host_pack.jsonl): a pinned source crosses PCIe at ~48 GB/s as ASCII and the encoder makes
     // 4.6 GB/s per thread (DRAM-bound at ~78 GB/s), so packing wins from ~10 threads up; a pageable source only
     // reaches ~10 GB/s through the driver's staging copy, so packing wins from 2 threads up.
-    // Fused reads kernel over the minimizer-bucketed read-path table (kmb_core.cuh): 1 = whenever k == 31 and no
-    // reverse complements are asked for; 0 (default) = never.  Measured on config 2 (profiles/README.md): the table
-    // halves the DRAM traffic and cuts the fetches per k-mer from 0.19 to 0.12, but computing the minimizers costs
-    // more issue slots than the saved look-ups give back -- 70 ms per 6.0 G k-mers against 48 ms for the
-    // key-addressed kernel -- so it stays opt-in (and parity-tested) until that changes.
-    int64_t read_table = 0;
+    // Fused reads kernel over the minimizer-bucketed read-path table (kmb_core.cuh), k = 31 without reverse
+    // complements only: 1 = always, 0 = never, -1 (default) = when the key filter is too thin to help.  Measured
+    // (profiles/README.md): with 5 filter bits per key (config 2) the key-addressed kernel needs 0.185 fetches per
+    // k-mer and wins, 46 ms against 54 ms per 6.0 G k-mers -- the minimizer arithmetic costs more issue slots than
+    // the saved look-ups give back; with 1 bit per key (config 3: 500 M entries) it needs 0.68 fetches per k-mer
+    // and loses, 65.9 ms against 50.7 ms per 3.0 G k-mers.  Auto takes the table when the filter has less than 2.5
+    // bits per key (one probe bit, or no filter at all) and the index is too big for the L2 anyway.
+    int64_t read_table = -1;
     int64_t filter_probes = 0;            // filter bits per key: 0 = by filter density (filter_probes()), else 1..3
     // The encoder is bound by the host's DRAM bandwidth, which the ranks of a multi-GPU node share, while every GPU
     // has its own PCIe link: with 2 ranks on one host a pinned source went 46.9 GK/s packed against 74.3 as ASCII
@@ -92,6 +94,7 @@ struct KmbOptions {
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<unsigned long long> g_h2d_bytes{0};  // bytes the mapping calls sent host -> device (bench.py's e2e)
+static std::atomic<int> g_last_reads_kernel{0};  // 0 = key-addressed fused kernel, 1 = read-path table kernel
 
 extern "C" int kmb_set_option(const char *name, int64_t value) {
     if (!name) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_set_option: null name");
@@ -160,6 +163,10 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(filter_probes)
     OPT(chunk_bytes)
 #undef OPT
+    if (!strcmp(name, "last_reads_kernel")) {  // read-only: which fused kernel the last map_reads launch used
+        *value = g_last_reads_kernel.load();
+        return KMB_OK;
+    }
     if (!strcmp(name, "h2d_bytes")) {  // read-only
         *value = (int64_t)g_h2d_bytes.load();
         return KMB_OK;
@@ -823,9 +830,13 @@ static int ensure_read_table(kmb_index *ix, int k) {
     addr.n_filter_words = (uint32_t)filter_words;
     addr.n_probes = filter_probes(bits_per_key);
     DevBuf<uint32_t> filter, fill, lines;
-    KMB_TRY(filter.alloc((size_t)std::max<uint64_t>(filter_words, 1)));
+    // the table is an accelerator, not a requirement: if the device has no room for it the key-addressed path serves
+    if (filter.alloc((size_t)std::max<uint64_t>(filter_words, 1)) != KMB_OK || fill.alloc((size_t)n_buckets) != KMB_OK) {
+        cudaGetLastError();
+        ix->mz_k = -1;
+        return KMB_OK;
+    }
     KMB_CUDA(cudaMemsetAsync(filter.p, 0, (size_t)std::max<uint64_t>(filter_words, 1) * 4, s));
-    KMB_TRY(fill.alloc((size_t)n_buckets));
     KMB_CUDA(cudaMemsetAsync(fill.p, 0, (size_t)n_buckets * 4, s));
     DevBuf<KmbStatus> d_status;
     KMB_TRY(d_status.alloc(1));
@@ -844,7 +855,11 @@ static int ensure_read_table(kmb_index *ix, int k) {
         ix->mz_k = -1;  // cannot be built for this index: the key-addressed path serves it
         return KMB_OK;
     }
-    KMB_TRY(lines.alloc((size_t)n_lines * KMB_LINE_WORDS));
+    if (lines.alloc((size_t)n_lines * KMB_LINE_WORDS) != KMB_OK) {
+        cudaGetLastError();
+        ix->mz_k = -1;
+        return KMB_OK;
+    }
     KMB_CUDA(cudaMemsetAsync(lines.p, 0, (size_t)n_lines * KMB_LINE_BYTES, s));
     KMB_CUDA(cudaMemsetAsync(&d_status.p->pool_lines, 0, sizeof(unsigned int), s));
     kmb_mz_build_plan<true><<<grid_for(n_buckets, 256, sms), 256, 0, s>>>(fill.p, n_buckets, lines.p, n_lines, d_status.p);
@@ -864,8 +879,10 @@ static int ensure_read_table(kmb_index *ix, int k) {
 }
 
 static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
-    (void)ix;
-    return k == KMB_MZ_K && !(flags & KMB_FLAG_REVCOMP) && g_opt.read_table > 0;
+    if (k != KMB_MZ_K || (flags & KMB_FLAG_REVCOMP) || g_opt.read_table == 0 || ix->mz_k < 0) return false;
+    if (g_opt.read_table > 0) return true;
+    const bool thin_filter = !ix->filter_on || ix->addr.n_probes <= 1u;
+    return thin_filter && ix->n_live >= (8u << 20);
 }
 
 // launch the read-boundary mask + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
@@ -891,6 +908,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
     if (use_read_table(ix, k, flags)) KMB_TRY(ensure_read_table(m->index, k));
     if (use_read_table(ix, k, flags) && ix->mz_k == k) {
+        g_last_reads_kernel = 1;
         const KmbProbe Pkey = P;  // the key-addressed sectors: where the rare tile that overflows the run table goes
         P.lines = ix->mz_lines;
         P.filter = ix->mz_filter;
@@ -913,6 +931,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
         KMB_TRY(timed_end(m));
         return KMB_OK;
     }
+    g_last_reads_kernel = 0;
     MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
     int per_sm;
     KMB_TRY(resident_blocks((const void *)fn, g_opt.map_reads_blocks_per_sm, &per_sm));

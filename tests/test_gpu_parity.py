@@ -19,7 +19,7 @@ def kmb():
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_l2_budget_bytes", 60 << 20),
-                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0), ("read_table", 0)):
+                    ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0), ("read_table", -1)):
         _lib.set_option(name, v)
 
 
@@ -315,7 +315,7 @@ def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads,
     kmb.set_option("chunk_bytes", 64 << 20)
     kmb.set_option("host_pack", -1)
     kmb.set_option("host_threads", 0)
-    kmb.set_option("read_table", 0)
+    kmb.set_option("read_table", -1)
 
 
 def test_map_reads_reverse_complement_flag(kmb):
