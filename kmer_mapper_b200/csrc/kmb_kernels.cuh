@@ -1044,14 +1044,21 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             // ---- 2b. the tile's run list: lanes append their runs (those with at least one existing window)
             unsigned n_runs;
             {
-                // runs of this lane that contain an existing window: walk the start bits once to count, once to write
+                // Runs of this lane that contain an existing window, without a loop: smear the valid bits down to the
+                // start of their run (a bit moves d places down unless a run starts in between), then keep the start bits.
                 uint32_t keep = 0;  // bit s set <=> the run starting at s has an existing window
-                for (uint32_t bits = (valid && (lane >> 4) == pass_no) ? startbits : 0u; bits;) {
-                    const int s = __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    const int e = bits ? __ffs(bits) - 1 : 32;
-                    const uint32_t v = (valid >> s) & (e - s == 32 ? 0xFFFFFFFFu : ((1u << (e - s)) - 1u));
-                    keep |= (v ? 1u : 0u) << s;
+                if ((lane >> 4) == pass_no) {
+                    uint32_t d = valid, m = ~(startbits >> 1);  // m: bit i may receive from bit i+1 (no run starts at i+1)
+                    d |= (d >> 1) & m;
+                    m &= m >> 1;
+                    d |= (d >> 2) & m;
+                    m &= m >> 2;
+                    d |= (d >> 4) & m;
+                    m &= m >> 4;
+                    d |= (d >> 8) & m;
+                    m &= m >> 8;
+                    d |= (d >> 16) & m;
+                    keep = d & startbits;
                 }
                 const uint32_t mine = __popc(keep);
                 uint32_t incl = mine;
