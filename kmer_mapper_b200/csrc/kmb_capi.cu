@@ -83,6 +83,9 @@ struct KmbOptions {
     // and loses, 65.9 ms against 50.7 ms per 3.0 G k-mers.  Auto takes the table when the filter has less than 2.5
     // bits per key (one probe bit, or no filter at all) and the index is too big for the L2 anyway.
     int64_t read_table = -1;
+    // buckets (two sectors = 64 bytes each) of the read-path table per 100 live entries: sparser = fewer buckets
+    // that spill into secondary and pool sectors (config 2 kernel: 51.8 / 50.0 / 48.6 ms at 100 / 150 / 200)
+    int64_t read_table_buckets_per_100_entries = 150;
     int64_t filter_probes = 0;            // filter bits per key: 0 = by filter density (filter_probes()), else 1..3
     // The encoder is bound by the host's DRAM bandwidth, which the ranks of a multi-GPU node share, while every GPU
     // has its own PCIe link: with 2 ranks on one host a pinned source went 46.9 GK/s packed against 74.3 as ASCII
@@ -123,6 +126,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(host_threads)
     OPT(host_ranks)
     OPT(read_table)
+    OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
@@ -160,6 +164,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(host_threads)
     OPT(host_ranks)
     OPT(read_table)
+    OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(chunk_bytes)
 #undef OPT
@@ -816,7 +821,8 @@ static int ensure_read_table(kmb_index *ix, int k) {
     if (ix->mz_k == k || ix->mz_k < 0) return KMB_OK;
     if (ix->mz_k != 0) return kmb_fail(KMB_ERR_BAD_ARG, "read-path table already built for k=%d", ix->mz_k);
     cudaStream_t s = 0;  // one-off, synchronous
-    const uint64_t n_buckets = std::min<uint64_t>(std::max<uint64_t>(ix->n_live, 1024), 1ull << 30);
+    const uint64_t per100 = (uint64_t)std::min<int64_t>(std::max<int64_t>(g_opt.read_table_buckets_per_100_entries, 25), 800);
+    const uint64_t n_buckets = std::min<uint64_t>(std::max<uint64_t>(ix->n_live * per100 / 100, 1024), (1ull << 30) - 1);
     KmbAddr addr;
     memset(&addr, 0, sizeof(addr));
     addr.n_main = (uint32_t)n_buckets;
