@@ -3,6 +3,8 @@
 //   K5  kmb_build_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sectors (once per index)
 //   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
 //   K1-4 kmb_map_reads_kernel     fused encode + window + filter + sector probe + hit log  (production path)
+//   K1-4 kmb_map_reads_mz_kernel  the same over the minimizer-bucketed read-path table (k = 31; indexes whose key
+//                                 filter is too thin to screen), kmb_mz_build_* build that table
 //   K3-4 kmb_map_kmers_kernel     probe + hit log on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
 //   K4b kmb_log_apply_kernel      hit log -> per-node counts, one L2-sized window of nodes at a time, hot nodes
 //                                 aggregated in shared memory first
@@ -734,12 +736,16 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 //   2. per lane: 48 m-mer ordering keys (26 hash bits | position) and a log-step sliding minimum
 //      (window 17 = k - 15 + 1) give minimizer and position for its 32 windows; a bit mask marks
 //      where runs start;
-//   3. one filter word per run; the runs that pass get a staging slot;
-//   4. all their primary sectors are fetched with cp.async in one burst (~100 independent 64-byte
+//   then, in two passes of 16 lanes' runs each (so that everything below is sized for half a tile):
+//   2b. the pass's run list (lanes append the runs that hold an existing window);
+//   3. one filter word per run, 32 runs per round; the runs that pass get a staging slot;
+//   4. all their primary sectors are fetched with cp.async in one burst (~50 independent 64-byte
 //      DRAM fetches in flight per warp, no registers held), then the secondary sectors of the fuller
 //      buckets (L2 hits: same 64 bytes);
-//   5. per lane, per run, per entry: the one window that could match is extracted and compared.
-// No cross-tile state except the staged hits.
+//   5. 32 runs per round, one per lane; per entry of the run's bucket the one window that could match
+//      is extracted and compared; buckets that continue in the pool go onto a per-warp list that is
+//      retired 32 runs at a time.
+// No cross-tile state except the staged hits and that list.
 // ================================================================================================
 #define KMB_MZ_K 31
 #define KMB_MZ_THREADS 128  // 4 warps per CTA, seven CTAs per SM
@@ -1062,7 +1068,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                 }
                 const uint32_t mine = __popc(keep);
                 uint32_t incl = mine;
-    #pragma unroll
+#pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t v = __shfl_up_sync(KMB_FULL_MASK, incl, o);
                     if (lane >= o) incl += v;
@@ -1080,7 +1086,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             __syncwarp();
             // ---- 3. one filter word per run, 32 runs per round; the runs that pass are kept in slot order
             unsigned n_kept = 0;  // warp-uniform; a tile that exceeds KMB_MZ_RUNS_KEPT takes the slow exit below
-    #pragma unroll 1
+#pragma unroll 1
             for (unsigned r0 = 0; r0 < n_runs; r0 += 32u) {
                 const unsigned ri = r0 + (unsigned)lane;
                 uint32_t run = 0, sector = 0;
@@ -1116,7 +1122,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                 const uint2 qa = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
                 const uint2 qb = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
                 const uint64_t lo = (uint64_t)qa.x | ((uint64_t)qa.y << 32), hi = (uint64_t)qb.x | ((uint64_t)qb.y << 32);
-    #pragma unroll 1
+#pragma unroll 1
                 for (uint32_t vb = (lane >> 4) == pass_no ? valid : 0u; vb; vb &= vb - 1u) {
                     kmb_walk_one(Pkey, pol, kmb_window(lo, hi, __ffs(vb) - 1, kmask), [&](uint32_t node, uint32_t freq) {
                         if ((int32_t)freq <= Pkey.max_freq) {
@@ -1143,7 +1149,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             __syncwarp();
             {
                 unsigned n2 = 0;
-    #pragma unroll 1
+#pragma unroll 1
                 for (unsigned base = 0; base < n_staged; base += 32u) {
                     const unsigned sl = base + (unsigned)lane;
                     const bool more = sl < n_staged && KMB_MZ_HDR_COUNT(S.a.slots[sl][0]) > 2u;
@@ -1167,7 +1173,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             }
             __syncwarp();
             // ---- 5. 32 kept runs per round, one per lane; per entry of the run's bucket the one window that could match
-    #pragma unroll 1
+#pragma unroll 1
             for (unsigned s0 = 0; s0 < n_have; s0 += 32u) {
                 const unsigned sl = s0 + (unsigned)lane;
                 uint32_t pool_sector = 0, pool_run = 0;
