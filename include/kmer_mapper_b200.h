@@ -170,6 +170,20 @@ int kmb_parse_reads(const uint8_t *text, uint64_t n_text, int format, int final_
 int kmb_gunzip_members(const uint8_t *gz, uint64_t n_gz, int n_threads, uint8_t *out, uint64_t out_capacity,
                        uint64_t max_member_bytes, uint64_t *consumed, uint64_t *produced, int *stopped_at_big_member);
 
+/* Streaming decoder for what kmb_gunzip_members cannot split: a .gz file that is one long deflate stream (plain
+ * `gzip reads.fq`).  A from-scratch DEFLATE decoder tuned for one core (csrc/kmb_inflate.cpp), every member checked
+ * against the CRC-32 and length in its trailer.  gz[0, n_gz) must stay mapped while the stream is open and start at
+ * a member boundary.  kmb_gzstream_read continues the stream into out[0, out_capacity) (>= 64 KB); the last
+ * min(32768, bytes produced so far) bytes of the previous call's output must sit directly in front of `out`
+ * (history_bytes says how many the caller put there).  *finished = 1 after the last member.  Returns
+ * KMB_ERR_BAD_ARG on corrupt or truncated input; kmb_gzstream_error says why. */
+typedef struct kmb_gzstream kmb_gzstream;
+int kmb_gzstream_open(const uint8_t *gz, uint64_t n_gz, int n_threads, kmb_gzstream **out);
+int kmb_gzstream_read(kmb_gzstream *stream, uint8_t *out, uint64_t out_capacity, uint64_t history_bytes,
+                      uint64_t *produced, int *finished);
+const char *kmb_gzstream_error(const kmb_gzstream *stream);
+int kmb_gzstream_close(kmb_gzstream *stream);
+
 /* First record start AFTER the first newline of text[0, n_text) (n_text when there is none): how a rank of a
  * multi-GPU job finds the beginning of its byte range of a plain FASTA/FASTQ file -- pass the text from one byte
  * before the nominal cut, so that a cut that falls exactly on a record start is found.  FASTQ: a line starting with

@@ -73,6 +73,10 @@ SIGNATURES = {
     "kmb_codec_complement": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
     "kmb_codec_twobit_swap": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_int, _vp]),
     "kmb_gunzip_members": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, C.c_uint64, C.c_uint64, _u64p, _u64p, C.POINTER(C.c_int)]),
+    "kmb_gzstream_open": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(_vp)]),
+    "kmb_gzstream_read": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, _u64p, C.POINTER(C.c_int)]),
+    "kmb_gzstream_error": (C.c_char_p, [_vp]),
+    "kmb_gzstream_close": (C.c_int, [_vp]),
     "kmb_find_record_start": (C.c_int, [_vp, C.c_uint64, C.c_int, _u64p]),
     "kmb_pack_bases": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_int64)]),
     "kmb_parse_reads": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp, C.c_uint64,

@@ -17,7 +17,6 @@ asynchronous host-to-device copy and kernels run meanwhile (copy stream, C ABI).
 from __future__ import annotations
 
 import ctypes as C
-import gzip
 import mmap
 import os
 import queue
@@ -105,7 +104,8 @@ class ParallelGzip:
     """Multi-member gzip (bgzip/BGZF files, `cat a.gz b.gz`, the synthetic FASTQ.gz of the benchmark configs)
     inflated member-parallel by the native library (``kmb_gunzip_members``, csrc/kmb_gunzip.cpp: speculative member
     starts, worker pool, chain walk).  A member that inflates to more than ``max_member_bytes`` (a plain
-    single-member .gz) makes the reader fall back to sequential streaming from that point.
+    single-member .gz) makes the reader fall back to sequential streaming from that point, through the native
+    single-core decoder (``kmb_gzstream_*``, csrc/kmb_inflate.cpp: ~2x zlib, CRC-32 checked).
     """
 
     HEADROOM = 1 << 20   # free bytes in front of every block: the consumer puts its carried-over partial record there
@@ -161,19 +161,33 @@ class ParallelGzip:
                         break            # zero padding after the last member
                     if consumed.value == 0 and flag.value == 0:
                         raise OSError("%s: gzip member at offset %d does not fit the reader's buffer" % (self.path, pos))
+                if fallback_from is not None:
+                    # One long deflate stream (plain `gzip file`): the native single-core decoder (kmb_inflate.cpp),
+                    # block after block; the format may refer back 32 KB, so the tail of each block is copied in
+                    # front of the next one (into the headroom; the parser's carry-over lands there later).
+                    stream = C.c_void_p()
+                    _lib.check(lib.kmb_gzstream_open(base_ptr + fallback_from, size - fallback_from, self.n_threads,
+                                                     C.byref(stream)))
+                    try:
+                        window = np.zeros(0, dtype=np.uint8)
+                        finished = C.c_int(0)
+                        while not finished.value:
+                            buf = next_buffer()
+                            buf[self.HEADROOM - window.shape[0]:self.HEADROOM] = window
+                            produced = C.c_uint64()
+                            rc = lib.kmb_gzstream_read(stream, buf.ctypes.data + self.HEADROOM, cap, window.shape[0],
+                                                       C.byref(produced), C.byref(finished))
+                            if rc != _lib.KMB_OK:
+                                raise OSError("%s: %s" % (self.path, lib.kmb_gzstream_error(stream).decode()))
+                            n = int(produced.value)
+                            if n:
+                                have = self.HEADROOM + n
+                                window = buf[max(self.HEADROOM - window.shape[0], have - 32768):have].copy()
+                                yield buf, n
+                    finally:
+                        lib.kmb_gzstream_close(stream)
             finally:
                 del whole
-        if fallback_from is not None:     # sequential streaming of the rest
-            with open(self.path, "rb") as f:
-                f.seek(fallback_from)
-                with gzip.GzipFile(fileobj=f, mode="rb") as g:
-                    while True:
-                        block = g.read(int(block_bytes))
-                        if not block:
-                            break
-                        buf = next_buffer()
-                        buf[self.HEADROOM:self.HEADROOM + len(block)] = np.frombuffer(block, dtype=np.uint8)
-                        yield buf, len(block)
 
     def blocks(self, block_bytes):
         """Yields decompressed text in file order as bytes, then b''."""

@@ -394,3 +394,77 @@ def test_reader_rank_shards_cover_every_read_once_in_order(tmp_path, fmt):
             if world in (2, 3):    # every rank has a real share
                 assert all(sum(len(c) for c in mine) > n // (2 * world) for mine in per_rank)
         assert got == want, (fmt, world)
+
+
+# ---------------------------------------------------------------------------------------------
+# the native single-stream gzip decoder (kmb_gzstream_*, csrc/kmb_inflate.cpp) against zlib
+# ---------------------------------------------------------------------------------------------
+def _gzstream(blob, cap=65536, threads=2):
+    import ctypes as C
+    from kmer_mapper_b200 import _lib
+    lib = _lib.lib()
+    head = 1 << 16
+    gz = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(0, np.uint8)
+    h = C.c_void_p()
+    assert lib.kmb_gzstream_open(gz.ctypes.data if blob else None, len(blob), threads, C.byref(h)) == 0
+    out, tail = [], b""
+    try:
+        while True:
+            buf = np.empty(head + cap, dtype=np.uint8)
+            if tail:
+                buf[head - len(tail):head] = np.frombuffer(tail, dtype=np.uint8)
+            produced, finished = C.c_uint64(), C.c_int()
+            rc = lib.kmb_gzstream_read(h, buf.ctypes.data + head, cap, len(tail), C.byref(produced), C.byref(finished))
+            if rc != 0:
+                raise OSError(lib.kmb_gzstream_error(h).decode())
+            piece = buf[head:head + produced.value].tobytes()
+            out.append(piece)
+            tail = (tail + piece)[-32768:]
+            if finished.value:
+                return b"".join(out)
+    finally:
+        lib.kmb_gzstream_close(h)
+
+
+def test_gzstream_decoder_matches_zlib_on_every_block_type():
+    import io
+    import zlib
+    rng = np.random.default_rng(21)
+    g = synthetic.make_genome(30_000, 2)
+    bases, offsets = synthetic.make_reads(g, 4_000, 150, seed=3, ragged=True)
+    fastq = b"".join(b"@r%d\n%s\n+\n%s\n" % (r, bytes(bases[offsets[r]:offsets[r + 1]]),
+                                                bytes(rng.choice(np.frombuffer(b"FFFF:,#", np.uint8), size=offsets[r + 1] - offsets[r])))
+                     for r in range(4_000))
+    payloads = [b"", b"A", b"hello hello hello world\n" * 3, b"\0" * 300_000, rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes(),
+                fastq, (b"ACGT" * 64 + b"N") * 3000, fastq[:50_000] + rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes() + b"x" * 90_000]
+    for data in payloads:
+        for level in (0, 1, 6, 9):                       # stored, fast and best dynamic blocks
+            assert _gzstream(gzip.compress(data, compresslevel=level)) == data
+        co = zlib.compressobj(6, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)    # fixed Huffman blocks
+        assert _gzstream(co.compress(data) + co.flush(), cap=1 << 20) == data
+    # header with a file name, several members (one empty), zero padding after the last
+    b = io.BytesIO()
+    with gzip.GzipFile(filename="reads.fq", mode="wb", fileobj=b, mtime=0) as f:
+        f.write(b"first member\n" * 1000)
+    blob = b.getvalue() + gzip.compress(b"second\n" * 5000, 1) + gzip.compress(b"") + gzip.compress(fastq, 9) + b"\0" * 37
+    assert _gzstream(blob) == b"first member\n" * 1000 + b"second\n" * 5000 + fastq
+
+
+def test_gzstream_decoder_rejects_corrupt_and_truncated_streams():
+    rng = np.random.default_rng(22)
+    data = bytes(rng.choice(np.frombuffer(b"ACGT\n@+F", np.uint8), size=400_000))
+    base = gzip.compress(data, 6)
+    for t in range(120):
+        b2 = bytearray(base)
+        if t % 3 == 0:
+            b2 = b2[:int(rng.integers(1, len(b2) - 1))]
+        elif t % 3 == 1:
+            for _ in range(3):
+                b2[int(rng.integers(10, len(b2)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            p = int(rng.integers(10, len(b2) - 100))
+            b2[p:p + 50] = rng.integers(0, 256, 50, dtype=np.uint8).tobytes()
+        with pytest.raises(OSError):       # a wrong bit either breaks the code stream or fails the CRC-32 of the trailer
+            _gzstream(bytes(b2))
+    with pytest.raises(OSError):
+        _gzstream(b"this is not gzip at all, not even close....")
