@@ -5,8 +5,8 @@
 // magnitude below what the mapping kernel eats (the reference reads such files through Python's gzip inside
 // bionumpy, command_line_interface.py:102-103).  This is a from-scratch DEFLATE (RFC 1951) decoder built for
 // throughput on one core: 64-bit bit buffer refilled with one unaligned load, 11-bit primary decode tables whose
-// entries carry base value, extra-bit count and code length, literals emitted two at a time, matches copied in
-// 8-byte words.  Every member is verified against the CRC-32 and length of its gzip trailer (RFC 1952), the CRC
+// entries carry base value, extra-bit count and code length, up to three literals per refill, matches copied in
+// 16-byte words, and an inner loop without exhaustion checks while 16 input and 274 output bytes remain.  Every member is verified against the CRC-32 and length of its gzip trailer (RFC 1952), the CRC
 // computed by zlib's crc32 on the worker pool, so a decoder fault cannot go unnoticed.
 //
 // Streaming: the caller owns the output buffers; each call continues the stream into `out`, and the 32 KB of
@@ -306,11 +306,125 @@ bool read_block_header(Stream &s) {
 }
 
 // Decode symbols of the current coded block into [out, out_end); `hist` = first byte the stream may refer back to.
-// Stops at the end of the block, or when fewer than 258 + 8 bytes of output are left.  Returns the new out.
+// Stops at the end of the block, or when fewer than 258 + 16 bytes of output are left.  Returns the new out.
+//
+// Fast loop: while at least 16 input bytes and 274 output bytes remain, one refill guarantees 56 bits -- enough for
+// a literal/length symbol with its extra bits and a distance symbol with its extra bits (15 + 5 + 15 + 13 = 48), or
+// for three literals -- so nothing inside checks for exhaustion.
+inline void copy_match(uint8_t *dst, const uint8_t *src, uint8_t *end, uint32_t dist) {
+    if (dist >= 16) {  // whole 16-byte words; writes up to 15 bytes past `end` (slack guaranteed by the caller)
+        do {
+            memcpy(dst, src, 16);
+            dst += 16;
+            src += 16;
+        } while (dst < end);
+    } else if (dist >= 8) {
+        do {
+            memcpy(dst, src, 8);
+            dst += 8;
+            src += 8;
+        } while (dst < end);
+    } else if (dist == 1) {
+        memset(dst, *src, (size_t)(end - dst));
+    } else {
+        do *dst++ = *src++;
+        while (dst < end);
+    }
+}
+
+uint8_t *decode_block_careful(Stream &s, uint8_t *out, uint8_t *out_end, const uint8_t *hist, bool *block_done);
+
 uint8_t *decode_block(Stream &s, uint8_t *out, uint8_t *out_end, const uint8_t *hist, bool *block_done) {
     *block_done = false;
     const uint32_t lit_mask = (1u << LIT_BITS) - 1, dist_mask = (1u << DIST_BITS) - 1;
-    while (out_end - out >= 258 + 8) {
+    const uint32_t *lit_table = s.lit_table, *dist_table = s.dist_table;
+    const uint8_t *in = s.in, *in_end = s.in_end;
+    uint64_t bitbuf = s.bitbuf;
+    int bitcnt = s.bitcnt;
+#define KMB_REFILL()                               \
+    do {                                           \
+        bitbuf |= load64(in) << bitcnt;            \
+        in += (63 - bitcnt) >> 3;                  \
+        bitcnt |= 56;                              \
+    } while (0)
+#define KMB_LIT_LOOKUP(e)                                                                                           \
+    do {                                                                                                            \
+        e = lit_table[bitbuf & lit_mask];                                                                           \
+        if (e_kind(e) == K_SUBTABLE)                                                                                \
+            e = lit_table[e_value(e) + ((bitbuf >> LIT_BITS) & ((1u << e_extra(e)) - 1))] + (uint32_t)LIT_BITS;     \
+    } while (0)
+    while (in_end - in >= 16 && out_end - out >= 258 + 16) {
+        KMB_REFILL();
+        uint32_t e;
+        KMB_LIT_LOOKUP(e);
+        if (e_kind(e) == K_LITERAL) {
+            bitbuf >>= e_len(e);
+            bitcnt -= (int)e_len(e);
+            *out++ = (uint8_t)e_value(e);
+            KMB_LIT_LOOKUP(e);
+            if (e_kind(e) == K_LITERAL) {
+                bitbuf >>= e_len(e);
+                bitcnt -= (int)e_len(e);
+                *out++ = (uint8_t)e_value(e);
+                KMB_LIT_LOOKUP(e);
+                if (e_kind(e) == K_LITERAL) {
+                    bitbuf >>= e_len(e);
+                    bitcnt -= (int)e_len(e);
+                    *out++ = (uint8_t)e_value(e);
+                    continue;
+                }
+            }
+            KMB_REFILL();  // up to 30 bits went into literals: top up before a length/distance pair (e stays valid)
+        }
+        bitbuf >>= e_len(e);
+        bitcnt -= (int)e_len(e);
+        const uint32_t kind = e_kind(e);
+        if (kind == K_END) {
+            *block_done = true;
+            break;
+        }
+        if (kind != K_BASE) {
+            s.in = in, s.bitbuf = bitbuf, s.bitcnt = bitcnt;
+            fail(s, "invalid literal/length code");
+            return out;
+        }
+        const uint32_t lx = e_extra(e);
+        const uint32_t len = e_value(e) + (uint32_t)(bitbuf & ((1ull << lx) - 1));
+        bitbuf >>= lx;
+        bitcnt -= (int)lx;
+        uint32_t d = dist_table[bitbuf & dist_mask];
+        if (e_kind(d) == K_SUBTABLE) d = dist_table[e_value(d) + ((bitbuf >> DIST_BITS) & ((1u << e_extra(d)) - 1))] + (uint32_t)DIST_BITS;
+        if (e_kind(d) != K_BASE) {
+            s.in = in, s.bitbuf = bitbuf, s.bitcnt = bitcnt;
+            fail(s, "invalid distance code");
+            return out;
+        }
+        bitbuf >>= e_len(d);
+        bitcnt -= (int)e_len(d);
+        const uint32_t dx = e_extra(d);
+        const uint32_t dist = e_value(d) + (uint32_t)(bitbuf & ((1ull << dx) - 1));
+        bitbuf >>= dx;
+        bitcnt -= (int)dx;
+        if ((size_t)(out - hist) < dist) {
+            s.in = in, s.bitbuf = bitbuf, s.bitcnt = bitcnt;
+            fail(s, "distance reaches before the start of the stream");
+            return out;
+        }
+        copy_match(out, out - dist, out + len, dist);
+        out += len;
+    }
+#undef KMB_REFILL
+#undef KMB_LIT_LOOKUP
+    s.in = in, s.bitbuf = bitbuf, s.bitcnt = bitcnt;
+    if (*block_done) return out;
+    return decode_block_careful(s, out, out_end, hist, block_done);
+}
+
+// The same loop with every bit-availability check: used near the end of the input (and of the output buffer).
+uint8_t *decode_block_careful(Stream &s, uint8_t *out, uint8_t *out_end, const uint8_t *hist, bool *block_done) {
+    *block_done = false;
+    const uint32_t lit_mask = (1u << LIT_BITS) - 1, dist_mask = (1u << DIST_BITS) - 1;
+    while (out_end - out >= 258 + 16) {
         if (!refill(s, 48)) {
             // fewer than 48 bits left in the whole input: still decodable if the remaining symbols are short
             if (s.bitcnt == 0) {
@@ -367,19 +481,8 @@ uint8_t *decode_block(Stream &s, uint8_t *out, uint8_t *out_end, const uint8_t *
             fail(s, "distance reaches before the start of the stream");
             return out;
         }
-        const uint8_t *src = out - dist;
-        uint8_t *dst = out;
+        copy_match(out, out - dist, out + len, dist);
         out += len;
-        if (dist >= 8) {  // whole words; may write up to 7 bytes past `out` (the caller leaves the slack)
-            do {
-                memcpy(dst, src, 8);
-                dst += 8;
-                src += 8;
-            } while (dst < out);
-        } else {
-            do *dst++ = *src++;
-            while (dst < out);
-        }
     }
     return out;
 }
