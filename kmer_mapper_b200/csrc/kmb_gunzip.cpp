@@ -3,14 +3,14 @@
 // A .gz file is a sequence of independent members (bgzip/BGZF output, `cat a.gz b.gz`, many sequencer pipelines);
 // the reference reads them through Python's single-threaded gzip inside bionumpy (command_line_interface.py:102-103).
 // Where a member starts is not recorded anywhere, so starts are found speculatively: every occurrence of the member
-// magic (1f 8b 08, reserved flag bits clear) is a candidate that a worker inflates into a private buffer; the chain
+// magic (1f 8b 08, reserved flag bits clear) is a candidate that a worker inflates into a private buffer (with the
+// library's own DEFLATE decoder, kmb_inflate.cpp: ~2x zlib, CRC-32 checked); the chain
 // "a member starts where the previous one ended" then picks the real ones in order, and a second parallel pass
 // copies them to the caller's buffer.  False candidates (magic bytes inside compressed data) fail within a few
 // bytes.  A member whose output does not fit the caller's limit ends the call: the caller streams it sequentially.
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#include <zlib.h>
 
 #include <algorithm>
 #include <functional>
@@ -55,52 +55,15 @@ struct Member {
 
 // inflate one gzip member starting at gz[start]; at most `limit` bytes of output
 void inflate_member(const uint8_t *gz, uint64_t n_gz, uint64_t limit, Member &m) {
-    z_stream z;
-    memset(&z, 0, sizeof(z));
-    if (inflateInit2(&z, 15 + 16) != Z_OK) {
-        m.state = 2;
-        return;
+    uint8_t *buf = nullptr;
+    size_t n = 0;
+    uint64_t used = 0;
+    m.state = kmb_inflate_member(gz + m.start, n_gz - m.start, limit, &buf, &n, &used);
+    if (m.state == 1) {
+        m.out.p = buf;
+        m.out.n = m.out.cap = n;
+        m.end = m.start + used;
     }
-    const uint8_t *in = gz + m.start;
-    uint64_t in_left = n_gz - m.start;
-    uint64_t produced = 0;
-    m.state = 2;
-    if (!m.out.reserve((size_t)std::min<uint64_t>(limit, std::max<uint64_t>(1u << 16, std::min<uint64_t>(in_left * 5, 8u << 20))))) {
-        inflateEnd(&z);
-        return;
-    }
-    for (;;) {
-        if (z.avail_in == 0 && in_left) {
-            const uInt take = (uInt)std::min<uint64_t>(in_left, 1u << 30);
-            z.next_in = const_cast<Bytef *>(in);
-            z.avail_in = take;
-            in += take;
-            in_left -= take;
-        }
-        if (produced == m.out.cap) {
-            if (m.out.cap >= limit) {
-                m.state = 3;
-                break;
-            }
-            if (!m.out.reserve((size_t)std::min<uint64_t>(limit, (uint64_t)m.out.cap * 2))) break;
-        }
-        const uint64_t room = m.out.cap - produced;
-        z.next_out = m.out.p + produced;
-        z.avail_out = (uInt)std::min<uint64_t>(room, 1u << 30);
-        const uInt before = z.avail_out;
-        const int rc = inflate(&z, Z_NO_FLUSH);
-        produced += before - z.avail_out;
-        if (rc == Z_STREAM_END) {
-            m.end = (uint64_t)(in - gz) - z.avail_in;
-            m.out.n = (size_t)produced;
-            m.state = 1;
-            break;
-        }
-        if (rc != Z_OK && rc != Z_BUF_ERROR) break;                      // not deflate data
-        if (rc == Z_BUF_ERROR && z.avail_in == 0 && in_left == 0) break;  // truncated
-    }
-    inflateEnd(&z);
-    if (m.state != 1) m.out.clear();
 }
 
 void run_parallel(int n_threads, int n, std::function<void(int)> fn) {

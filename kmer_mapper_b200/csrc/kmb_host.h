@@ -20,3 +20,7 @@ uint64_t kmb_host_pack(const uint8_t *bases, uint64_t n_bases, bool n_to_a, int 
 
 // out[i] = offsets[i] - base for i in [0, n): the chunk-relative 32-bit read offsets that travel with a packed chunk.
 void kmb_host_rel_offsets(const int64_t *offsets, uint64_t n, int64_t base, int n_threads, uint32_t *out);
+
+// One gzip member from gz[0, n_gz) into a malloc'd buffer (kmb_inflate.cpp's DEFLATE decoder, CRC-32 checked):
+// 1 = ok, 2 = not a member / corrupt / truncated, 3 = inflates to more than `limit` bytes.  The caller frees *buf.
+int kmb_inflate_member(const uint8_t *gz, uint64_t n_gz, uint64_t limit, uint8_t **buf, size_t *n_out, uint64_t *consumed);

@@ -151,6 +151,7 @@ struct Stream {
     uint64_t member_out = 0;
     uint64_t total_out = 0;  // text bytes produced so far over all members (history available = min(total_out, 32768))
     int n_threads = 1;
+    bool stop_after_member = false;  // kmb_inflate_member: one member only
     const char *error = nullptr;
 };
 
@@ -624,6 +625,10 @@ extern "C" int kmb_gzstream_read(kmb_gzstream *g, uint8_t *out, uint64_t out_cap
                 fail(s, "gzip member fails its CRC-32 / length check");
                 break;
             }
+            if (s.stop_after_member) {
+                s.phase = Stream::DONE;
+                continue;
+            }
             // more members?  (zero padding after the last one is tolerated, like gzip does)
             const uint8_t *p = s.in;
             while (p < s.in_end && *p == 0) p++;
@@ -640,4 +645,57 @@ extern "C" int kmb_gzstream_read(kmb_gzstream *g, uint8_t *out, uint64_t out_cap
     *produced = (uint64_t)(o - out);
     s.total_out += *produced;
     return s.phase == Stream::FAILED ? KMB_ERR_BAD_ARG : KMB_OK;
+}
+
+// One gzip member from gz[0, n_gz) into a malloc'd buffer (*buf, caller frees), for the member-parallel reader
+// (kmb_gunzip.cpp).  Returns 1 = ok (*consumed compressed bytes used, *n_out text bytes), 2 = not a member /
+// corrupt / truncated, 3 = the member inflates to more than `limit` bytes.
+int kmb_inflate_member(const uint8_t *gz, uint64_t n_gz, uint64_t limit, uint8_t **buf, size_t *n_out, uint64_t *consumed) {
+    *buf = nullptr;
+    *n_out = 0;
+    *consumed = 0;
+    kmb_gzstream g;
+    Stream &s = g.s;
+    s.in_begin = s.in = gz;
+    s.in_end = gz + n_gz;
+    s.n_threads = 1;  // members are inflated in parallel with each other: the CRC stays on this thread
+    s.stop_after_member = true;
+    const size_t slack = 65536 + 512;  // kmb_gzstream_read wants 64 KB of room to make progress
+    size_t cap = (size_t)std::min<uint64_t>(limit, std::max<uint64_t>(1u << 17, std::min<uint64_t>(n_gz * 5, 8u << 20))) + slack;
+    uint8_t *p = (uint8_t *)malloc(cap);
+    if (!p) return 2;
+    size_t produced = 0;
+    for (;;) {
+        uint64_t got = 0;
+        int finished = 0;
+        const int rc = kmb_gzstream_read(&g, p + produced, cap - produced, produced, &got, &finished);
+        produced += (size_t)got;
+        if (rc != KMB_OK) {
+            free(p);
+            return 2;
+        }
+        if (produced > limit) {
+            free(p);
+            return 3;
+        }
+        if (finished) break;
+        if (cap - produced < slack) {
+            const size_t want = std::min<size_t>((size_t)limit + slack + 1, cap * 2);
+            if (want <= cap) {  // already at the limit and still not finished
+                free(p);
+                return 3;
+            }
+            uint8_t *q = (uint8_t *)realloc(p, want);
+            if (!q) {
+                free(p);
+                return 2;
+            }
+            p = q;
+            cap = want;
+        }
+    }
+    *buf = p;
+    *n_out = produced;
+    *consumed = (uint64_t)(s.in - s.in_begin);
+    return 1;
 }
