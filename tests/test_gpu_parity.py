@@ -280,6 +280,8 @@ def test_map_reads_vs_oracle(kmb, k, variant):
             got = m.counts()
             assert np.array_equal(got, want)
             assert m.stats() == (n_want, int(want.astype(np.uint64).sum()))
+            # the variant really ran the kernel it is named after
+            assert kmb.get_option("last_reads_kernel") == (1 if variant.get("read_table") == 1 and k == 31 else 0)
             m.reset()
         kmb.set_option("host_pack", -1)
         tb, to = torch.from_numpy(bases).cuda(), torch.from_numpy(offsets).cuda()
