@@ -232,6 +232,7 @@ int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_ker
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
  *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
+ *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),
  *  "read_table_buckets_per_100_entries" (150)};
  * read-only: "h2d_bytes" (bytes the mapping calls have copied host -> device so far), "last_reads_kernel" (0 = the
  * key-addressed fused kernel, 1 = the read-path table kernel served the last kmb_mapper_map_reads launch), "bounds_failures" (-1 unless

@@ -83,6 +83,7 @@ struct KmbOptions {
     // and loses, 65.9 ms against 50.7 ms per 3.0 G k-mers.  Auto takes the table when the filter has less than 2.5
     // bits per key (one probe bit, or no filter at all) and the index is too big for the L2 anyway.
     int64_t read_table = -1;
+    int64_t read_table_min_entries = 8ll << 20;  // auto: smaller indexes sit in the L2 anyway
     // buckets (two sectors = 64 bytes each) of the read-path table per 100 live entries: sparser = fewer buckets
     // that spill into secondary and pool sectors (config 2 kernel: 51.8 / 50.0 / 48.6 ms at 100 / 150 / 200)
     int64_t read_table_buckets_per_100_entries = 150;
@@ -126,6 +127,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(host_threads)
     OPT(host_ranks)
     OPT(read_table)
+    OPT(read_table_min_entries)
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
 #undef OPT
@@ -164,6 +166,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(host_threads)
     OPT(host_ranks)
     OPT(read_table)
+    OPT(read_table_min_entries)
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(chunk_bytes)
@@ -888,7 +891,7 @@ static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
     if (k != KMB_MZ_K || (flags & KMB_FLAG_REVCOMP) || g_opt.read_table == 0 || ix->mz_k < 0) return false;
     if (g_opt.read_table > 0) return true;
     const bool thin_filter = !ix->filter_on || ix->addr.n_probes <= 1u;
-    return thin_filter && ix->n_live >= (8u << 20);
+    return thin_filter && ix->n_live >= (uint64_t)std::max<int64_t>(g_opt.read_table_min_entries, 0);
 }
 
 // launch the read-boundary mask + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
