@@ -959,29 +959,47 @@ __device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPo
         s = (int)(sej & 255u), e = (int)((sej >> 8) & 255u), jpos = (int)(sej >> 16);
     }
     fetched += (unsigned)n;
-    while (__any_sync(KMB_FULL_MASK, more)) {
-        if (more) {
-            uint32_t r[8];
-            KMB_BOUND(2, sector, P.n_lines);
-            kmb_ld_sector(P.lines + (uint64_t)sector * KMB_LINE_WORDS, r, pol.line);
-            const uint32_t left = KMB_MZ_POOL_LEFT(r[0]);
+    // the two entries of one pool sector against the run
+    auto match2 = [&](const uint32_t (&r)[8], uint32_t left) {
 #pragma unroll
-            for (uint32_t t = 0; t < 2u; t++) {
-                if (t >= left) break;
-                const int i = jpos - (int)KMB_MZ_POOL_OFFSET(r[0], t);
-                if (i < s || i >= e || !((valid >> i) & 1u)) continue;
-                const uint64_t km = kmb_window(lo, hi, i, kmask);
-                if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
-                const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
-                if ((int32_t)freq > P.max_freq) continue;
-                kmb_mz_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
-                counted++;
-            }
-            more = left > 2u;
-            sector++;
+        for (uint32_t t = 0; t < 2u; t++) {
+            if (t >= left) break;
+            const int i = jpos - (int)KMB_MZ_POOL_OFFSET(r[0], t);
+            if (i < s || i >= e || !((valid >> i) & 1u)) continue;
+            const uint64_t km = kmb_window(lo, hi, i, kmask);
+            if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
+            const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
+            if ((int32_t)freq > P.max_freq) continue;
+            kmb_mz_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
+            counted++;
         }
-        kmb_stage_flush(P, st, lane, false);
+    };
+    // The first sector says how many entries the chain holds; the sectors are contiguous, so from then on two are
+    // fetched per round, independently of each other.  Hits are staged as usual; a bin that fills up before the
+    // flush at the end sends its hits straight to the counts (kmb_mz_emit).
+    uint32_t left = 0;
+    if (more) {
+        uint32_t r[8];
+        KMB_BOUND(2, sector, P.n_lines);
+        kmb_ld_sector(P.lines + (uint64_t)sector * KMB_LINE_WORDS, r, pol.line);
+        left = KMB_MZ_POOL_LEFT(r[0]);
+        match2(r, left);
+        left = left > 2u ? left - 2u : 0u;
+        sector++;
     }
+    while (__any_sync(KMB_FULL_MASK, left != 0u)) {
+        if (left) {
+            uint32_t r[8], q[8];
+            KMB_BOUND(2, sector + (left > 2u ? 1u : 0u), P.n_lines);
+            kmb_ld_sector(P.lines + (uint64_t)sector * KMB_LINE_WORDS, r, pol.line);
+            if (left > 2u) kmb_ld_sector(P.lines + (uint64_t)(sector + 1u) * KMB_LINE_WORDS, q, pol.line);
+            match2(r, left);
+            if (left > 2u) match2(q, left - 2u);
+            left = left > 4u ? left - 4u : 0u;
+            sector += 2u;
+        }
+    }
+    kmb_stage_flush(P, st, lane, false);
 }
 
 template <bool FILT>
