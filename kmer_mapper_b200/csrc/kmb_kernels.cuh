@@ -920,6 +920,13 @@ __device__ __forceinline__ uint64_t kmb_mz_window_at(const uint32_t *pack, uint3
     const uint32_t w0 = pack[wi], w1 = pack[wi + 1], w2 = pack[wi + 2];
     return ((uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32)) & kmask;
 }
+// the k-mer that starts at base i (0..31) of a lane's 64 bases, given as its four packed words
+__device__ __forceinline__ uint64_t kmb_mz_window_of(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int i, uint64_t kmask) {
+    const bool up = i >= 16;
+    const uint32_t a = up ? w1 : w0, b = up ? w2 : w1, c = up ? w3 : w2;
+    const uint32_t sh = (2u * (uint32_t)i) & 31u;
+    return ((uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32)) & kmask;
+}
 // The two entries of one sector (words r[1..7]: frequencies, keys, nodes) against one run.  off0/off1 = minimizer
 // offsets of the two entries, n = how many of them exist; jp = tile position of the run's minimizer; [ps, pe) =
 // tile positions of the run's windows; vrow = valid bits of the run's lane (bit = position - lane_base).
@@ -946,13 +953,13 @@ __device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPo
                                                   int top, int n, uint64_t kmask, unsigned &counted, unsigned &fetched, int lane) {
     __syncwarp();
     bool more = lane < n;
-    uint64_t lo = 0, hi = 0;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;  // the 64 bases of the run's lane
     uint32_t valid = 0, sector = 0;
     int s = 0, e = 0, jpos = 0;
     if (more) {
         const int idx = top - 1 - lane;
-        lo = S.late_lo[idx];
-        hi = S.late_hi[idx];
+        w0 = (uint32_t)S.late_lo[idx], w1 = (uint32_t)(S.late_lo[idx] >> 32);
+        w2 = (uint32_t)S.late_hi[idx], w3 = (uint32_t)(S.late_hi[idx] >> 32);
         valid = S.late_valid[idx];
         sector = S.late_sector[idx];
         const uint32_t sej = S.late_sej[idx];
@@ -966,7 +973,7 @@ __device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPo
             if (t >= left) break;
             const int i = jpos - (int)KMB_MZ_POOL_OFFSET(r[0], t);
             if (i < s || i >= e || !((valid >> i) & 1u)) continue;
-            const uint64_t km = kmb_window(lo, hi, i, kmask);
+            const uint64_t km = kmb_mz_window_of(w0, w1, w2, w3, i, kmask);
             if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
             const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
             if ((int32_t)freq > P.max_freq) continue;
