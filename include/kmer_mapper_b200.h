@@ -225,11 +225,17 @@ int kmb_mapper_candidates(kmb_mapper *mapper, uint64_t *n_candidates);
  * option "time_kernels" is 1 (CUDA events on the mapper's stream).  Implies a stream synchronize. */
 int kmb_mapper_kernel_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kernels);
 
+/* The same for the apply passes (hit log -> node counts, the `node_counts[...] += 1` of mapper.pyx:68 played one
+ * L2-sized window of nodes at a time). */
+int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kernels);
+
 /* Tuning knobs (process-wide, read at launch / index-creation time): name in
  * {"map_reads_blocks_per_sm", "map_kmers_blocks_per_sm", "probe_variant", "gathers_in_flight",
  *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
+ *  "async_sectors" (1 = sector fetches by cp.async into shared memory, 0 = in registers), "apply_window_log2" (nodes per
+ *  apply window, default 24 = 64 MB of counters),
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
  *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
  *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),

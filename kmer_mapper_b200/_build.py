@@ -60,6 +60,23 @@ def build_bounds_checked(verbose: bool = True) -> str:
     return BOUNDS_LIB_PATH
 
 
+def build_variant(name: str, defines, verbose: bool = True) -> str:
+    """An A/B build of the same sources with extra -D flags (tuning experiments: run with KMB_LIB_PATH=<result>)."""
+    out = os.path.join(PKG, "libkmer_mapper_b200_%s.so" % name)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + SOURCES + LINK_FLAGS + ["-o", out]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     import sys
-    print(build_bounds_checked() if "--bounds" in sys.argv[1:] else build(force=True))
+    argv = sys.argv[1:]
+    if "--bounds" in argv:
+        print(build_bounds_checked())
+    elif "--variant" in argv:
+        i = argv.index("--variant")
+        print(build_variant(argv[i + 1], argv[i + 2:]))
+    else:
+        print(build(force=True))

@@ -87,6 +87,7 @@ SIGNATURES = {
                                    C.POINTER(C.c_float)]),
     "kmb_mapper_candidates": (C.c_int, [_vp, _u64p]),
     "kmb_mapper_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_double), _u64p]),
+    "kmb_mapper_apply_time": (C.c_int, [_vp, C.POINTER(C.c_double), _u64p]),
     "kmb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "kmb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
     "kmb_launch_count": (C.c_int, [_u64p]),

@@ -94,6 +94,12 @@ struct KmbOptions {
     int64_t host_pack = -1;
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
     int64_t host_ranks = 1;               // processes sharing this host's memory system (set by distributed.py)
+    // Sector fetches of the key-addressed kernels: 1 = cp.async into shared memory, compared one batch later (four
+    // CTAs per SM); 0 = in registers, requested and compared inside one batch iteration (three CTAs per SM).
+    int64_t async_sectors = 1;
+    // The apply pass reduces into one window of 2^apply_window_log2 nodes at a time (x 4 bytes: 24 = 64 MB); the
+    // window has to stay in the L2 next to the persisting filter lines.
+    int64_t apply_window_log2 = 24;
 };
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
@@ -130,6 +136,8 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(read_table_min_entries)
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
+    OPT(async_sectors)
+    OPT(apply_window_log2)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -169,6 +177,8 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(read_table_min_entries)
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
+    OPT(async_sectors)
+    OPT(apply_window_log2)
     OPT(chunk_bytes)
 #undef OPT
     if (!strcmp(name, "last_reads_kernel")) {  // read-only: which fused kernel the last map_reads launch used
@@ -535,8 +545,8 @@ struct kmb_mapper {
     uint64_t n_counts = 0;
     uint32_t *counts = nullptr;
     bool own_counts = false;
-    KmbLog log = {nullptr, nullptr, nullptr, 0, 0, 1};  // hit log (grown on demand), its group tags and cursor
-    int log_bins = 1;              // node ranges in use: ((n_counts - 1) >> bin_shift) + 1
+    KmbLog log = {nullptr, nullptr, nullptr, 0, 0, 1, 0};  // hit log (grown on demand), its group tags and cursor
+    int log_windows = 1;           // apply windows: ((n_counts - 1) >> win_shift) + 1
     bool dirty = false;            // the logs may hold hits that are not yet in the node counts
     uint64_t queries_since_flush = 0;
     int32_t max_freq = 1000;
@@ -548,9 +558,12 @@ struct kmb_mapper {
     uint32_t *dmask = nullptr;  // read-boundary mask for in-place device input
     size_t dmask_cap = 0;
     int next_slot = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // event pairs around mapping kernels
-    size_t timed_used = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];  // event pairs around [0] mapping kernels, [1] apply passes
+    size_t timed_used[2] = {0, 0};
 };
+
+static int timed_begin(kmb_mapper *m, int klass = 0);
+static int timed_end(kmb_mapper *m, int klass = 0);
 
 static void slot_free(StageSlot &s) {
     cudaFree(s.data);
@@ -569,10 +582,11 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
     for (int i = 0; i < KMB_SLOTS; i++) slot_free(m->slot[i]);
-    for (auto &pr : m->timed) {
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
-    }
+    for (auto &v : m->timed)
+        for (auto &pr : v) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
     cudaFree(m->dmask);
     cudaFree(m->log.entries);
     cudaFree(m->log.tags);
@@ -613,11 +627,16 @@ static int launch_log_reset(kmb_mapper *m) {
 static int launch_flush(kmb_mapper *m) {
     const kmb_index *ix = m->index;
     if (m->log.entries) {
-        for (int b = 0; b < m->log_bins; b++) {
-            kmb_log_apply_kernel<<<ix->info.sms * 8, 256, 0, m->stream>>>(m->log, b, m->counts);
-            g_launches++;
-        }
+        // one launch, blockIdx.y = node window: the windows are worked off in dispatch order
+        const uint64_t last = m->n_counts ? m->n_counts - 1 : 0;
+        const uint32_t want = (uint32_t)std::min<int64_t>(std::max<int64_t>(g_opt.apply_window_log2, 10), 31);
+        m->log.win_shift = std::min(m->log.bin_shift, want);
+        m->log_windows = (int)((last >> m->log.win_shift) + 1);
+        KMB_TRY(timed_begin(m, 1));
+        kmb_log_apply_kernel<<<dim3((unsigned)ix->info.sms * 8u, (unsigned)m->log_windows), 256, 0, m->stream>>>(m->log, m->counts);
+        g_launches++;
         KMB_CUDA(cudaGetLastError());
+        KMB_TRY(timed_end(m, 1));
         KMB_TRY(launch_log_reset(m));
     }
     m->dirty = false;
@@ -638,7 +657,7 @@ static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
         uint32_t shift = 0;
         while (((m->n_counts ? m->n_counts - 1 : 0) >> shift) >= KMB_LOG_BINS) shift++;
         m->log.bin_shift = shift;
-        m->log_bins = (int)(((m->n_counts ? m->n_counts - 1 : 0) >> shift) + 1);
+        m->log.win_shift = shift;
     }
     if (want > m->log.cap) {
         if (m->dirty) KMB_TRY(launch_flush(m));
@@ -774,47 +793,66 @@ static int pick_u() {
 typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, int, uint32_t, KmbProbe, KmbStatus *);
 typedef void (*MapKmersFn)(const uint64_t *, uint64_t, int, KmbProbe, KmbStatus *);
 
-template <int U>
+template <int U, bool ASYNC>
 static MapReadsFn map_reads_fn_u(bool filt, bool rc) {
-    if (filt) return rc ? kmb_map_reads_kernel<U, true, true> : kmb_map_reads_kernel<U, true, false>;
-    return rc ? kmb_map_reads_kernel<U, false, true> : kmb_map_reads_kernel<U, false, false>;
+    if (filt) return rc ? kmb_map_reads_kernel<U, true, true, ASYNC> : kmb_map_reads_kernel<U, true, false, ASYNC>;
+    return rc ? kmb_map_reads_kernel<U, false, true, ASYNC> : kmb_map_reads_kernel<U, false, false, ASYNC>;
 }
-static MapReadsFn map_reads_fn(int u, bool filt, bool rc) {
-    return u == 2 ? map_reads_fn_u<2>(filt, rc) : map_reads_fn_u<4>(filt, rc);
-}
-template <int U>
+template <int U, bool ASYNC>
 static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
-    if (filt) return rc ? kmb_map_kmers_kernel<U, true, true> : kmb_map_kmers_kernel<U, true, false>;
-    return rc ? kmb_map_kmers_kernel<U, false, true> : kmb_map_kmers_kernel<U, false, false>;
+    if (filt) return rc ? kmb_map_kmers_kernel<U, true, true, ASYNC> : kmb_map_kmers_kernel<U, true, false, ASYNC>;
+    return rc ? kmb_map_kmers_kernel<U, false, true, ASYNC> : kmb_map_kmers_kernel<U, false, false, ASYNC>;
 }
-static MapKmersFn map_kmers_fn(int u, bool filt, bool rc) {
-    return u == 2 ? map_kmers_fn_u<2>(filt, rc) : map_kmers_fn_u<4>(filt, rc);
+// The key-addressed kernels exist as: sectors by cp.async (U = 4), sectors in registers (U = 2 or 4).
+struct MapKernel {
+    const void *fn;
+    int u;
+    size_t smem;
+    bool async;
+};
+static MapKernel pick_map_kernel(bool reads, bool filt, bool rc) {
+    MapKernel mk;
+    mk.async = g_opt.async_sectors != 0;
+    mk.u = mk.async ? 4 : pick_u();
+    if (mk.async) {
+        mk.fn = reads ? (const void *)map_reads_fn_u<4, true>(filt, rc) : (const void *)map_kmers_fn_u<4, true>(filt, rc);
+        mk.smem = KMB_MAP_SMEM_BYTES(4, true);
+    } else if (mk.u == 2) {
+        mk.fn = reads ? (const void *)map_reads_fn_u<2, false>(filt, rc) : (const void *)map_kmers_fn_u<2, false>(filt, rc);
+        mk.smem = KMB_MAP_SMEM_BYTES(2, false);
+    } else {
+        mk.fn = reads ? (const void *)map_reads_fn_u<4, false>(filt, rc) : (const void *)map_kmers_fn_u<4, false>(filt, rc);
+        mk.smem = KMB_MAP_SMEM_BYTES(4, false);
+    }
+    return mk;
 }
 
-static int resident_blocks(const void *fn, int64_t opt, int *out) {
+static int resident_blocks(const MapKernel &mk, int64_t opt, int *out) {
     int b = 0;
-    KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, KMB_TILE_THREADS, 0));
+    KMB_CUDA(cudaFuncSetAttribute(mk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk.smem));
+    KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mk.fn, KMB_TILE_THREADS, mk.smem));
     if (b < 1) b = 1;
     if (opt > 0) b = (int)std::min<int64_t>(opt, 32);
     *out = b;
     return KMB_OK;
 }
 
-static int timed_begin(kmb_mapper *m) {
+static int timed_begin(kmb_mapper *m, int klass) {
     if (!g_opt.time_kernels) return KMB_OK;
-    if (m->timed_used == m->timed.size()) {
+    auto &v = m->timed[klass];
+    if (m->timed_used[klass] == v.size()) {
         cudaEvent_t a, b;
         KMB_CUDA(cudaEventCreate(&a));
         KMB_CUDA(cudaEventCreate(&b));
-        m->timed.emplace_back(a, b);
+        v.emplace_back(a, b);
     }
-    KMB_CUDA(cudaEventRecord(m->timed[m->timed_used].first, m->stream));
+    KMB_CUDA(cudaEventRecord(v[m->timed_used[klass]].first, m->stream));
     return KMB_OK;
 }
-static int timed_end(kmb_mapper *m) {
+static int timed_end(kmb_mapper *m, int klass) {
     if (!g_opt.time_kernels) return KMB_OK;
-    KMB_CUDA(cudaEventRecord(m->timed[m->timed_used].second, m->stream));
-    m->timed_used++;
+    KMB_CUDA(cudaEventRecord(m->timed[klass][m->timed_used[klass]].second, m->stream));
+    m->timed_used[klass]++;
     return KMB_OK;
 }
 
@@ -941,13 +979,13 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
         return KMB_OK;
     }
     g_last_reads_kernel = 0;
-    MapReadsFn fn = map_reads_fn(pick_u(), P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
+    const MapKernel mk = pick_map_kernel(true, P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
     int per_sm;
-    KMB_TRY(resident_blocks((const void *)fn, g_opt.map_reads_blocks_per_sm, &per_sm));
+    KMB_TRY(resident_blocks(mk, g_opt.map_reads_blocks_per_sm, &per_sm));
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
     m->dirty = true;
     KMB_TRY(timed_begin(m));
-    fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_bases, n_bases, base0, d_mask, k, in_mode, P, m->d_status);
+    ((MapReadsFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_bases, n_bases, base0, d_mask, k, in_mode, P, m->d_status);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_TRY(timed_end(m));
@@ -967,13 +1005,12 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
         if (rc) kmb_map_kmers_simple_kernel<true><<<grid, 256, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
         else kmb_map_kmers_simple_kernel<false><<<grid, 256, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
     } else {
-        int u = pick_u();
-        MapKmersFn fn = map_kmers_fn(u, P.filter != nullptr, rc);
+        const MapKernel mk = pick_map_kernel(false, P.filter != nullptr, rc);
         int per_sm;
-        KMB_TRY(resident_blocks((const void *)fn, g_opt.map_kmers_blocks_per_sm, &per_sm));
-        uint64_t n_blocks = (n + (uint64_t)KMB_TILE_THREADS * u - 1) / ((uint64_t)KMB_TILE_THREADS * u);
+        KMB_TRY(resident_blocks(mk, g_opt.map_kmers_blocks_per_sm, &per_sm));
+        uint64_t n_blocks = (n + (uint64_t)KMB_TILE_THREADS * mk.u - 1) / ((uint64_t)KMB_TILE_THREADS * mk.u);
         int grid = (int)std::min<uint64_t>(n_blocks, (uint64_t)ix->info.sms * per_sm);
-        fn<<<grid, KMB_TILE_THREADS, 0, m->stream>>>(d_kmers, n, k, P, m->d_status);
+        ((MapKmersFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_kmers, n, k, P, m->d_status);
     }
     g_launches++;
     KMB_CUDA(cudaGetLastError());
@@ -1226,20 +1263,27 @@ extern "C" int kmb_mapper_candidates(kmb_mapper *m, uint64_t *n_candidates) {
     return KMB_OK;
 }
 
-extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t *n_kernels) {
-    if (!m || !ms_total) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_kernel_time: null argument");
+static int timed_total(kmb_mapper *m, int klass, double *ms_total, uint64_t *n_kernels) {
+    if (!m || !ms_total) return kmb_fail(KMB_ERR_BAD_ARG, "kernel time: null argument");
     KMB_ON_DEVICE(m->index->device);
     KMB_CUDA(cudaStreamSynchronize(m->stream));
     double total = 0;
-    for (size_t i = 0; i < m->timed_used; i++) {
+    for (size_t i = 0; i < m->timed_used[klass]; i++) {
         float ms = 0;
-        KMB_CUDA(cudaEventElapsedTime(&ms, m->timed[i].first, m->timed[i].second));
+        KMB_CUDA(cudaEventElapsedTime(&ms, m->timed[klass][i].first, m->timed[klass][i].second));
         total += ms;
     }
     *ms_total = total;
-    if (n_kernels) *n_kernels = m->timed_used;
-    m->timed_used = 0;
+    if (n_kernels) *n_kernels = m->timed_used[klass];
+    m->timed_used[klass] = 0;
     return KMB_OK;
+}
+extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t *n_kernels) {
+    return timed_total(m, 0, ms_total, n_kernels);
+}
+// The same for the apply passes (hit log -> node counts).
+extern "C" int kmb_mapper_apply_time(kmb_mapper *m, double *ms_total, uint64_t *n_kernels) {
+    return timed_total(m, 1, ms_total, n_kernels);
 }
 
 // ------------------------------------------------------------------------------------------------

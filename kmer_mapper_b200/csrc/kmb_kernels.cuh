@@ -35,9 +35,9 @@
 #define KMB_POS_PER_THREAD 32
 #define KMB_TILE_POS (KMB_TILE_THREADS * KMB_POS_PER_THREAD)  // 8192 window starts per tile
 #define KMB_WTILE_POS (32 * KMB_POS_PER_THREAD)                // 1024 window starts per warp tile
-#define KMB_QUEUE_SLOTS(U) (32 * ((U) + 1))
+#define KMB_QUEUE_SLOTS(U) (32 * ((U) + 2))  // per-warp candidate stack: < 64 waiting + 32 U new
 #define KMB_IN_N_TO_A 1u  // kmb_map_reads_kernel in_mode: 'N' reads as 'A'
-#define KMB_IN_PACKED 2u  //   the input is the packed 2-bit stream, not ASCII                   // per-warp candidate stack: < 32 left over + 32 U new
+#define KMB_IN_PACKED 2u  //   the input is the packed 2-bit stream, not ASCII
 
 struct KmbStatus {
     unsigned long long first_bad_offset;   // min flat offset of an invalid byte, ~0 if none
@@ -57,6 +57,7 @@ struct KmbLog {  // hit log of one mapper: `cap` node ids in groups of 32, one n
     uint64_t cap;                // multiple of 32
     uint32_t bin_shift;          // bin = node >> bin_shift
     uint32_t chunk_groups;       // groups reserved per atomic
+    uint32_t win_shift;          // apply pass: one window of 2^win_shift nodes at a time (<= bin_shift)
 };
 
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
@@ -345,49 +346,64 @@ __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &
 }
 
 // ------------------------------------------------------------------------------------------------
-// Hit staging and logs.  Per warp: KMB_LOG_BINS stacks of KMB_STAGE_SLOTS node ids in shared memory
-// (31 left over + at most 2 x 32 new ones per drain).  A stack with >= 32 ids sends its top 32 as one
-// coalesced 128-byte store to the bin's log; the space is reserved with one atomic per 32 hits.
+// Hit staging and logs.  Per warp: KMB_LOG_BINS stacks of node ids in shared memory (31 left over + at
+// most 2 x 32 new ones per drain = KMB_STAGE_SLOTS; kernels that are short of shared memory use fewer
+// and let the overflow valve of kmb_emit work).  A stack with >= 32 ids sends its top 32 as one
+// coalesced 128-byte store to the log; the space is reserved with one atomic per 32 hits or more.
 // ------------------------------------------------------------------------------------------------
 #define KMB_STAGE_SLOTS 96
+#define KMB_STAGE_SLOTS_SMALL 64
 #define KMB_LOG_HOLE 0xFFFFFFFFu
 #define KMB_LOG_NO_BIN 0xFFu
 #define KMB_RES_FULL 0xFFFFFFFFu
 struct KmbStage {
     uint32_t *cnt;                 // [KMB_LOG_BINS] ids staged per bin
-    uint32_t *buf;                 // [KMB_LOG_BINS][KMB_STAGE_SLOTS]
+    uint32_t *buf;                 // [KMB_LOG_BINS][slots]
     unsigned long long *res_base;  // [KMB_LOG_BINS] next free position of this warp's reservation for the bin
     uint32_t *res_left;            // [KMB_LOG_BINS] groups left in that reservation, or KMB_RES_FULL
-    uint32_t slots;                // capacity of one bin's stack (KMB_STAGE_SLOTS, or less where shared memory is short)
+    uint32_t slots;                // capacity of one bin's stack
 };
+// `node_counts[node] += 1` (mapper.pyx:68) straight onto the count array: the fallback of every path that cannot
+// use the log (log full, hit found in an overflow chain, staging stack full, apply-table collision).  Warp-
+// aggregated: the lanes that arrive here together group equal node ids (match.any) and the lowest lane of
+// each group adds the group's size, so a hot node costs one atomic per warp instead of one per hit.
+__device__ __forceinline__ void kmb_count_direct(uint32_t *counts, uint32_t node, uint32_t weight = 1u) {
+    const unsigned here = __activemask();
+    const unsigned same = __match_any_sync(here, node);
+    if (weight == 1u) {
+        if ((int)(threadIdx.x & 31u) == __ffs(same) - 1) atomicAdd(counts + node, (uint32_t)__popc(same));
+    } else {
+        atomicAdd(counts + node, weight);
+    }
+}
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
     const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
     KMB_BOUND(6, node, P.n_counts);
-    const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
-    KMB_BOUND(3, pos, st.slots);
     KMB_BOUND(3, b, KMB_LOG_BINS);
-    st.buf[b * st.slots + pos] = node;
+    const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
+    if (pos < st.slots) st.buf[b * st.slots + pos] = node;
+    else kmb_count_direct(P.counts, node);  // valve: the stack is full (the flush clamps the count)
 }
 // One group of 32 ids of bin b (lanes >= n write holes) to the log -- or, if the log is full, straight onto
 // the counts.  All bins share one pool: space is reserved chunk_groups groups at a time from a single cursor
 // (one atomic, and one wait for its result, per chunk), and a group is tagged with its bin when it is written,
 // so a skewed node distribution cannot overflow "its" log while the others stay empty.
-__device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage &st, uint32_t b, const uint32_t *src,
-                                              uint32_t n, int lane) {
+__device__ __forceinline__ void kmb_log_write(const KmbLog &log, uint32_t *counts, const KmbStage &st, uint32_t b,
+                                              const uint32_t *src, uint32_t n, int lane) {
     unsigned long long base = ~0ull;
     if (lane == 0) {
         uint32_t left = st.res_left[b];
         if (left != KMB_RES_FULL) {
             base = st.res_base[b];
             if (left == 0) {
-                left = P.log.chunk_groups;
-                base = atomicAdd(&P.log.cursor[0], 32ull * left);
+                left = log.chunk_groups;
+                base = atomicAdd(&log.cursor[0], 32ull * left);
             }
-            if (base + 32 <= P.log.cap) {
+            if (base + 32 <= log.cap) {
                 st.res_left[b] = left - 1;
                 st.res_base[b] = base + 32;
-                KMB_BOUND(5, base >> 5, P.log.cap >> 5);
-                P.log.tags[base >> 5] = (uint8_t)b;
+                KMB_BOUND(5, base >> 5, log.cap >> 5);
+                log.tags[base >> 5] = (uint8_t)b;
             } else {
                 st.res_left[b] = KMB_RES_FULL;  // stop reserving: every further atomic would hit the same address
                 base = ~0ull;
@@ -397,31 +413,35 @@ __device__ __forceinline__ void kmb_log_write(const KmbProbe &P, const KmbStage 
     base = __shfl_sync(KMB_FULL_MASK, base, 0);
     const uint32_t id = (uint32_t)lane < n ? src[lane] : KMB_LOG_HOLE;
     if (base != ~0ull) {
-        KMB_BOUND(4, base + lane, P.log.cap);
-        P.log.entries[base + lane] = id;
+        KMB_BOUND(4, base + lane, log.cap);
+        log.entries[base + lane] = id;
     } else if (id != KMB_LOG_HOLE) {
-        KMB_BOUND(6, id, P.n_counts);
-        atomicAdd(P.counts + id, 1u);
+        kmb_count_direct(counts, id);
     }
 }
-// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything.
-// Groups that were reserved but never written keep the tag KMB_LOG_NO_BIN and are skipped by the apply pass.
-__device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
-    __syncwarp();
-    const uint32_t c = lane < KMB_LOG_BINS ? min(st.cnt[lane], st.slots) : 0u;  // clamp: kmb_mz_emit
-    unsigned ready = __ballot_sync(KMB_FULL_MASK, all ? c > 0u : c >= 32u);
+// The bins named in `ready` have something to send: full groups of 32, or (all = true, end of kernel) everything.
+// Out of line: the mapping kernels reach this from several places, and it runs once per 32 hits of a bin.
+__device__ __noinline__ void kmb_stage_send(KmbLog log, uint32_t *counts, KmbStage st, unsigned ready, uint32_t c, int lane, bool all) {
     while (ready) {
         const int b = __ffs(ready) - 1;
         ready &= ready - 1u;
         uint32_t cb = __shfl_sync(KMB_FULL_MASK, c, b);
         while (cb >= 32u || (all && cb > 0u)) {
             const uint32_t n = min(cb, 32u);
-            kmb_log_write(P, st, (uint32_t)b, st.buf + b * st.slots + (cb - n), n, lane);
+            kmb_log_write(log, counts, st, (uint32_t)b, st.buf + b * st.slots + (cb - n), n, lane);
             cb -= n;
         }
         if (lane == 0) st.cnt[b] = cb;
         __syncwarp();
     }
+}
+// Called by all 32 lanes.  all = false: send full groups of 32; all = true (end of kernel): everything.
+// Groups that were reserved but never written keep the tag KMB_LOG_NO_BIN and are skipped by the apply pass.
+__device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
+    __syncwarp();
+    const uint32_t c = lane < KMB_LOG_BINS ? min(st.cnt[lane], st.slots) : 0u;  // clamp: the valve of kmb_emit
+    const unsigned ready = __ballot_sync(KMB_FULL_MASK, all ? c > 0u : c >= 32u);
+    if (ready) kmb_stage_send(P.log, P.counts, st, ready, c, lane, all);
     __syncwarp();
 }
 __device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane) {
@@ -434,24 +454,68 @@ __device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split drain.  A warp that has 32 candidates issues their 32 sector loads (one DRAM transaction
-// each) and goes back to work: the Barrett reductions and filter loads of the next batch of windows
-// run while the sectors are on their way, and only then are the keys compared.
+// The sector fetch pipeline.  A warp that has 32 candidates requests their 32 sectors (one DRAM
+// transaction each) and goes on with the next batch of windows; the keys are compared when the
+// sectors have had that long to arrive.
+//
+// ASYNC = true (default): the sectors are copied into the warp's shared memory with cp.async (two slots of
+//   32 x 32 bytes); a batch requested in iteration i is compared in iteration i + 1.  Nothing is held in
+//   registers and, above all, nothing is tracked by the register scoreboard: with the sector in registers
+//   (the first version of this kernel) ptxas made every iteration of the batch loop begin with a wait for
+//   ALL outstanding loads (the loop header carried `wait=01245` in its control code; 19 % of the stall
+//   samples sat on that one instruction), so the fetch never overlapped the next batch's arithmetic.
+// ASYNC = false: the sector travels in registers, requested at the top of a batch iteration and compared
+//   at its bottom, so that no load is in flight across the loop's back edge.
 // ------------------------------------------------------------------------------------------------
-struct KmbPipe {
+__device__ __forceinline__ void kmb_cp_async_sector(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 16u), "l"(gmem_src + 4) : "memory");
+}
+__device__ __forceinline__ void kmb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void kmb_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void kmb_cp_async_wait_all() {
+    kmb_cp_async_commit();
+    kmb_cp_async_wait<0>();
+}
+
+#define KMB_SECT_SLOT_WORDS (2 * 32 * KMB_LINE_WORDS)  // per warp: two batches of 32 sectors
+template <bool ASYNC>
+struct KmbPipe;
+template <>
+struct KmbPipe<false> {
     uint32_t r[8];  // the candidate's main sector, in flight between issue and consume
     uint64_t km;
     unsigned issued;  // candidates of this warp so far (warp-uniform)
     bool valid;
 };
-__device__ __forceinline__ void kmb_pipe_init(KmbPipe &pp) {
+template <>
+struct KmbPipe<true> {
+    uint32_t *slots;          // [2][32][8] words of this warp's shared memory
+    uint64_t km_new, km_old;  // the candidate whose sector this lane requested in this / the previous round
+    unsigned issued;
+    int buf;                  // slot the next request goes to (warp-uniform)
+    bool valid_new, valid_old;
+};
+__device__ __forceinline__ void kmb_pipe_init(KmbPipe<false> &pp, uint32_t *) {
     pp.valid = false;
     pp.issued = 0;
     pp.km = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) pp.r[i] = 0;
 }
-__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const uint64_t *q_kmer,
+__device__ __forceinline__ void kmb_pipe_init(KmbPipe<true> &pp, uint32_t *slots) {
+    pp.slots = slots;
+    pp.km_new = pp.km_old = 0;
+    pp.issued = 0;
+    pp.buf = 0;
+    pp.valid_new = pp.valid_old = false;
+}
+// Request the sectors of candidates [base, base + cnt) of the warp's stack, one per lane.  Called by all lanes.
+__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &pol, KmbPipe<false> &pp, const uint64_t *q_kmer,
                                                const uint32_t *q_h, int base, int cnt, int lane) {
     pp.issued += (unsigned)cnt;
     if (lane < cnt && !(P.policies & 0x200u)) {
@@ -461,46 +525,103 @@ __device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &
         pp.valid = true;
     }
 }
-// Called by all 32 lanes.
-__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
-                                                 unsigned &counted, int lane) {
-    if (!__any_sync(KMB_FULL_MASK, pp.valid)) return;
-    if (pp.valid) {
-        pp.valid = false;
-        const int32_t max_freq = P.max_freq;
-        const bool no_emit = (P.policies & 0x100u) != 0u;
-        kmb_match_sector(pp.r, pp.km, [&](uint32_t node, uint32_t freq) {
+__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &, KmbPipe<true> &pp, const uint64_t *q_kmer,
+                                               const uint32_t *q_h, int base, int cnt, int lane) {
+    pp.issued += (unsigned)cnt;
+    if (lane < cnt && !(P.policies & 0x200u)) {
+        pp.km_new = q_kmer[base + lane];
+        KMB_BOUND(1, q_h[base + lane], P.addr.n_main);
+        kmb_cp_async_sector(pp.slots + (pp.buf * 32 + lane) * KMB_LINE_WORDS, P.lines + (uint64_t)q_h[base + lane] * KMB_LINE_WORDS);
+        pp.valid_new = true;
+    }
+    kmb_cp_async_commit();
+}
+// The overflow sectors behind a full main sector (0.8 % of them): walked synchronously, hits straight onto the
+// counts.  Out of line, to keep the rare path out of the hot loop's instruction stream.
+__device__ __forceinline__ unsigned kmb_chain_count(const uint32_t *__restrict__ lines, uint64_t pol_line, uint64_t km, uint32_t hdr,
+                                                 int32_t max_freq, uint32_t *counts) {
+    unsigned counted = 0;
+    while (hdr & KMB_HDR_CHAIN) {
+        uint32_t r[8];
+        kmb_ld_sector(lines + (uint64_t)(hdr & ~KMB_HDR_CHAIN) * KMB_LINE_WORDS, r, pol_line);
+        kmb_match_sector(r, km, [&](uint32_t node, uint32_t freq) {
             if ((int32_t)freq <= max_freq) {
-                if (!no_emit) kmb_emit(P, st, node);
+                kmb_count_direct(counts, node);
                 counted++;
             }
             return false;
         });
-        if (pp.r[0] & KMB_HDR_CHAIN) {
-            uint32_t *counts = P.counts;
-            kmb_walk_chain(P, pol, pp.km, pp.r[0], [&](uint32_t node, uint32_t freq) {
-                if ((int32_t)freq <= max_freq) {
-                    KMB_BOUND(6, node, P.n_counts);
-                    atomicAdd(counts + node, 1u);
-                    counted++;
-                }
-                return false;
-            });
+        hdr = r[0];
+    }
+    return counted;
+}
+// Compare a sector that has arrived with its candidate, stage the hits.  The rare chain behind a full sector is
+// walked synchronously and its hits go straight onto the counts.
+__device__ __forceinline__ void kmb_pipe_match(const KmbProbe &P, const KmbPol &pol, const KmbStage &st, const uint32_t (&r)[8],
+                                               uint64_t km, unsigned &counted) {
+    const int32_t max_freq = P.max_freq;
+    const bool no_emit = (P.policies & 0x100u) != 0u;
+    kmb_match_sector(r, km, [&](uint32_t node, uint32_t freq) {
+        if ((int32_t)freq <= max_freq) {
+            if (!no_emit) kmb_emit(P, st, node);
+            counted++;
         }
+        return false;
+    });
+    if (r[0] & KMB_HDR_CHAIN) counted += kmb_chain_count(P.lines, pol.line, km, r[0], max_freq, P.counts);
+}
+// Called by all 32 lanes.  Register version: the batch requested by the last kmb_pipe_issue.
+__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe<false> &pp, const KmbStage &st,
+                                                 unsigned &counted, int lane) {
+    if (!__any_sync(KMB_FULL_MASK, pp.valid)) return;
+    if (pp.valid) {
+        pp.valid = false;
+        kmb_pipe_match(P, pol, st, pp.r, pp.km, counted);
     }
     kmb_stage_flush(P, st, lane, false);
 }
+// Asynchronous version: wait until at most the newest request group is still on its way, compare the batch
+// before it, and make the newest the next one to be compared.
+__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe<true> &pp, const KmbStage &st,
+                                                 unsigned &counted, int lane) {
+    kmb_cp_async_wait<1>();
+    if (__any_sync(KMB_FULL_MASK, pp.valid_old)) {
+        if (pp.valid_old) {
+            const uint32_t *sp = pp.slots + ((pp.buf ^ 1) * 32 + lane) * KMB_LINE_WORDS;
+            const uint4 x = *reinterpret_cast<const uint4 *>(sp);
+            const uint4 y = *reinterpret_cast<const uint4 *>(sp + 4);
+            const uint32_t r[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            kmb_pipe_match(P, pol, st, r, pp.km_old, counted);
+        }
+        kmb_stage_flush(P, st, lane, false);
+    }
+    pp.km_old = pp.km_new;
+    pp.valid_old = pp.valid_new;
+    pp.valid_new = false;
+    pp.buf ^= 1;
+}
 
-// Level 0 for U queries of this lane (all filter loads in flight together), with the consume half
-// of the previous drain placed between the issue of those loads and their first use.  kf(u) yields
-// query u (cheap to recompute, so it is not kept in registers); bit u of vbits says whether query u
-// exists.  The stack holds < 32 entries on entry and on exit, so KMB_QUEUE_SLOTS >= 32 * (U + 1).
-// (Measured alternatives, both slower: consuming a whole drain period later, and keeping two batches of
-// sector loads in flight per warp.)
-template <int U, bool FILT, class KF>
-__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
+// Level 0 for U queries of this lane (all filter loads in flight together).  kf(u) yields query u; bit u of
+// vbits says whether query u exists.  Order of one batch:
+//   0. request the sectors of 32 candidates that earlier batches left on the stack;
+//   1. kmb_locate + the U filter loads of this batch;
+//   2. (ASYNC) compare the sectors requested one batch ago -- between the issue of the filter loads and
+//      their first use;
+//   3. test the filter words; survivors go onto the warp's stack (one inclusive scan of the per-lane
+//      survivor counts gives every lane its first slot);
+//   4. (registers) compare the sectors requested in step 0;
+//   5. if two or more batches of candidates are still waiting (thin or no filter), fetch them now.
+// The stack holds < 64 entries on entry and on exit, so KMB_QUEUE_SLOTS >= 32 * (U + 2).
+template <int U, bool FILT, bool ASYNC, class KF>
+__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe<ASYNC> &pp, const KmbStage &st,
                                                 unsigned &counted, const KF &kf, uint32_t vbits, uint64_t *q_kmer,
                                                 uint32_t *q_h, int &qcount, int lane) {
+    if (qcount >= 32) {
+        qcount -= 32;
+        kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, 32, lane);
+    } else if (ASYNC) {
+        kmb_cp_async_commit();  // one request group per batch, empty or not: the consume step counts groups
+    }
     uint64_t km[U];    // the queries (kept: recomputing them for the push cost more than the registers)
     uint32_t hh[U];    // main sector of the query
     uint32_t need[U];  // filter bits the query needs; 0 = no query
@@ -520,9 +641,7 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
             fw[u] = 1u;
         }
     }
-    kmb_pipe_consume(P, pol, pp, st, counted, lane);  // the sectors issued by the previous call have had this long to arrive
-    // Survivors go onto the warp's stack: one inclusive scan of the per-lane survivor counts gives every lane
-    // its first slot (instead of one ballot + two popcounts per query).
+    if (ASYNC) kmb_pipe_consume(P, pol, pp, st, counted, lane);
     uint32_t cmask = 0;
 #pragma unroll
     for (int u = 0; u < U; u++) cmask |= (need[u] != 0u && (fw[u] & need[u]) == need[u]) ? (1u << u) : 0u;
@@ -545,23 +664,35 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
         }
     }
     __syncwarp();
+    if (!ASYNC) kmb_pipe_consume(P, pol, pp, st, counted, lane);
 #pragma unroll 1
-    while (qcount >= 32) {
-        kmb_pipe_consume(P, pol, pp, st, counted, lane);
+    while (qcount >= 64) {
         qcount -= 32;
         kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, 32, lane);
+        kmb_pipe_consume(P, pol, pp, st, counted, lane);  // ASYNC: the batch before the one just requested
     }
     __syncwarp();
 }
 
-// End of kernel: retire the outstanding batch, then the partial one, then the staged hits and the statistics.
-__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
+// End of kernel: retire the outstanding batches, then what is left on the stack, then the staged hits and the statistics.
+template <bool ASYNC>
+__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe<ASYNC> &pp, const KmbStage &st,
                                                 unsigned &counted, const uint64_t *q_kmer, const uint32_t *q_h, int qcount,
                                                 int lane, KmbStatus *status) {
     __syncwarp();
-    kmb_pipe_consume(P, pol, pp, st, counted, lane);
-    kmb_pipe_issue(P, pol, pp, q_kmer, q_h, 0, qcount, lane);
-    kmb_pipe_consume(P, pol, pp, st, counted, lane);
+#pragma unroll 1
+    while (qcount > 0) {
+        const int n = min(qcount, 32);
+        qcount -= n;
+        kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, n, lane);
+        kmb_pipe_consume(P, pol, pp, st, counted, lane);
+    }
+    if (ASYNC) {  // the newest request, if any, is still on its way
+        kmb_cp_async_commit();
+        kmb_pipe_consume(P, pol, pp, st, counted, lane);
+        kmb_cp_async_commit();
+        kmb_pipe_consume(P, pol, pp, st, counted, lane);
+    }
     kmb_stage_flush(P, st, lane, true);
     for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
     if (lane == 0 && counted) atomicAdd(&status->n_entries_counted, (unsigned long long)counted);
@@ -647,8 +778,28 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
     return valid;
 }
 
-template <int U, bool FILT, bool REVCOMP>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
+// Per-warp shared memory of the key-addressed mapping kernels (dynamic: with ASYNC the CTA needs more than the
+// 48 KB a static allocation may have).  ASYNC: 6.8 KB per warp = 54.4 KB per CTA, four CTAs per SM.
+template <int U, bool ASYNC>
+struct alignas(16) KmbWarpShared {
+    static constexpr int kStageSlots = ASYNC ? KMB_STAGE_SLOTS_SMALL : KMB_STAGE_SLOTS;
+    uint32_t sect[ASYNC ? KMB_SECT_SLOT_WORDS : 4];       // sectors on their way (cp.async), 32-byte slots
+    uint64_t qk[KMB_QUEUE_SLOTS(U)];                      // candidate stack: k-mer
+    unsigned long long stage_res[KMB_LOG_BINS];
+    uint32_t qh[KMB_QUEUE_SLOTS(U)];                      //                  its sector
+    uint32_t pack[KMB_WTILE_POS / 16 + 4];                // the tile's packed 2-bit stream: 64 words + halo
+    uint32_t stage[KMB_LOG_BINS * kStageSlots];           // staged hits per node range
+    uint32_t stage_cnt[2 * KMB_LOG_BINS];
+};
+#define KMB_MAP_SMEM_BYTES(U, ASYNC) ((KMB_TILE_THREADS / 32) * sizeof(KmbWarpShared<U, ASYNC>))
+// Resident CTAs per SM.  Registers in flight were what held the first version at three (85 registers: at 64 the
+// sector between issue and consume was spilled); with the sectors in shared memory four CTAs = 32 warps fit.
+#ifndef KMB_MAP_MIN_BLOCKS_ASYNC
+#define KMB_MAP_MIN_BLOCKS_ASYNC 4
+#endif
+
+template <int U, bool FILT, bool REVCOMP, bool ASYNC>
+__global__ void __launch_bounds__(KMB_TILE_THREADS, ASYNC ? KMB_MAP_MIN_BLOCKS_ASYNC : KMB_MAP_MIN_BLOCKS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
                      const uint32_t *__restrict__ mask, int k, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
     const bool n_to_a = (in_mode & KMB_IN_N_TO_A) != 0u;
@@ -658,24 +809,19 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     const uint64_t n_words = (n_bases + 15) / 16 + 4;  // kmb_packed_words
     // Everything is per warp (tile of 1024 window starts, packed stream, candidate stack): no CTA barrier,
     // so a warp that is walking a long chain never holds the other seven back.
-    __shared__ __align__(16) uint32_t s_pack[KMB_TILE_THREADS / 32][KMB_WTILE_POS / 16 + 4];  // 64 words + halo
-    __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
-    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
-    __shared__ uint32_t s_stage[KMB_TILE_THREADS / 32][KMB_LOG_BINS * KMB_STAGE_SLOTS];
-    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][2 * KMB_LOG_BINS];
-    __shared__ unsigned long long s_stage_res[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
-
+    extern __shared__ __align__(16) unsigned char kmb_map_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint32_t *pack = s_pack[warp];
-    uint64_t *q_kmer = s_qk[warp];
-    uint32_t *q_h = s_qh[warp];
-    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS, KMB_STAGE_SLOTS};
+    KmbWarpShared<U, ASYNC> &S = reinterpret_cast<KmbWarpShared<U, ASYNC> *>(kmb_map_smem)[warp];
+    uint32_t *pack = S.pack;
+    uint64_t *q_kmer = S.qk;
+    uint32_t *q_h = S.qh;
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U, ASYNC>::kStageSlots};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
-    KmbPipe pp;
-    kmb_pipe_init(pp);
+    KmbPipe<ASYNC> pp;
+    kmb_pipe_init(pp, S.sect);
     const KmbPol pol = kmb_make_policies(P.policies);
     const uint64_t kmask = kmb_kmer_mask(k);
     const uint64_t n_tiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
@@ -713,10 +859,10 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             const uint32_t vb = (valid >> b0) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
             if (!__any_sync(KMB_FULL_MASK, vb != 0u)) continue;
             const KmbWindowFn fw(a.x, a.y, b.x, b.y, b0, kmask);
-            kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fw, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, fw, vb, q_kmer, q_h, qcount, lane);
             if (REVCOMP) {
                 const KmbRcWindowFn rc = {fw, k};
-                kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, rc, vb, q_kmer, q_h, qcount, lane);
+                kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, rc, vb, q_kmer, q_h, qcount, lane);
             }
         }
     }
@@ -896,23 +1042,6 @@ __device__ __forceinline__ void kmb_mz_half(const uint32_t (&w4)[4], int h, uint
     startbits |= sb << jbase;
 }
 
-__device__ __forceinline__ void kmb_cp_async_sector(uint32_t *smem_dst, const uint32_t *gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 16u), "l"(gmem_src + 4) : "memory");
-}
-__device__ __forceinline__ void kmb_cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-// staging with a safety valve: a hit that finds its bin full goes straight onto the counts (the flush clamps)
-__device__ __forceinline__ void kmb_mz_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
-    const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
-    KMB_BOUND(6, node, P.n_counts);
-    const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
-    if (pos < st.slots) st.buf[b * st.slots + pos] = node;
-    else atomicAdd(P.counts + node, 1u);
-}
 // the k-mer that starts at base p of the packed tile
 __device__ __forceinline__ uint64_t kmb_mz_window_at(const uint32_t *pack, uint32_t p, uint64_t kmask) {
     const uint32_t wi = p >> 4, sh = (p & 15u) * 2u;
@@ -942,7 +1071,7 @@ __device__ __forceinline__ void kmb_mz_match_pair(const KmbProbe &P, const KmbSt
         if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
         const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
         if ((int32_t)freq > P.max_freq) continue;
-        kmb_mz_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
+        kmb_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
         counted++;
     }
 }
@@ -977,13 +1106,13 @@ __device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPo
             if (r[KMB_LINE_KEY_WORD0 + 2 * t] != (uint32_t)km || r[KMB_LINE_KEY_WORD0 + 2 * t + 1] != (uint32_t)(km >> 32)) continue;
             const uint32_t freq = t ? (r[KMB_LINE_FREQ_WORD] >> 16) : (r[KMB_LINE_FREQ_WORD] & 0xFFFFu);
             if ((int32_t)freq > P.max_freq) continue;
-            kmb_mz_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
+            kmb_emit(P, st, r[KMB_LINE_NODE_WORD0 + t]);
             counted++;
         }
     };
     // The first sector says how many entries the chain holds; the sectors are contiguous, so from then on two are
     // fetched per round, independently of each other.  Hits are staged as usual; a bin that fills up before the
-    // flush at the end sends its hits straight to the counts (kmb_mz_emit).
+    // flush at the end sends its hits straight to the counts (kmb_emit).
     uint32_t left = 0;
     if (more) {
         uint32_t r[8];
@@ -1152,7 +1281,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                     kmb_walk_one(Pkey, pol, kmb_window(lo, hi, __ffs(vb) - 1, kmask), [&](uint32_t node, uint32_t freq) {
                         if ((int32_t)freq <= Pkey.max_freq) {
                             KMB_BOUND(6, node, Pkey.n_counts);
-                            atomicAdd(Pkey.counts + node, 1u);
+                            kmb_count_direct(Pkey.counts, node);
                             counted++;
                         }
                         return false;
@@ -1282,25 +1411,22 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
 // K3-4 on ready-made k-mers (drop-in for map_kmers_to_graph_index, mapper.pyx:19-72).
 // Coalesced 8-byte loads, U filter loads in flight per thread, same probe.
 // ================================================================================================
-template <int U, bool FILT, bool REVCOMP>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
+template <int U, bool FILT, bool REVCOMP, bool ASYNC>
+__global__ void __launch_bounds__(KMB_TILE_THREADS, ASYNC ? KMB_MAP_MIN_BLOCKS_ASYNC : KMB_MAP_MIN_BLOCKS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
-    __shared__ uint64_t s_qk[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
-    __shared__ uint32_t s_qh[KMB_TILE_THREADS / 32][KMB_QUEUE_SLOTS(U)];
-    __shared__ uint32_t s_stage[KMB_TILE_THREADS / 32][KMB_LOG_BINS * KMB_STAGE_SLOTS];
-    __shared__ uint32_t s_stage_cnt[KMB_TILE_THREADS / 32][2 * KMB_LOG_BINS];
-    __shared__ unsigned long long s_stage_res[KMB_TILE_THREADS / 32][KMB_LOG_BINS];
+    extern __shared__ __align__(16) unsigned char kmb_map_smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    uint64_t *q_kmer = s_qk[warp];
-    uint32_t *q_h = s_qh[warp];
-    const KmbStage st = {s_stage_cnt[warp], s_stage[warp], s_stage_res[warp], s_stage_cnt[warp] + KMB_LOG_BINS, KMB_STAGE_SLOTS};
+    KmbWarpShared<U, ASYNC> &S = reinterpret_cast<KmbWarpShared<U, ASYNC> *>(kmb_map_smem)[warp];
+    uint64_t *q_kmer = S.qk;
+    uint32_t *q_h = S.qh;
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U, ASYNC>::kStageSlots};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
-    KmbPipe pp;
-    kmb_pipe_init(pp);
+    KmbPipe<ASYNC> pp;
+    kmb_pipe_init(pp, S.sect);
     const KmbPol pol = kmb_make_policies(P.policies);
     const uint64_t per_block = (uint64_t)KMB_TILE_THREADS * U;
     const uint64_t n_blocks = (n + per_block - 1) / per_block;
@@ -1317,11 +1443,11 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
             vb |= in ? (1u << u) : 0u;
         }
         KmbArrayFn fa = {km};
-        kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
+        kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
         if (REVCOMP) {
 #pragma unroll
             for (int u = 0; u < U; u++) km[u] = kmb_revcomp(km[u], k);
-            kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
         }
     }
     kmb_pipe_finish(P, pol, pp, st, counted, q_kmer, q_h, qcount, lane, status);
@@ -1356,7 +1482,7 @@ __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, 
             kmb_walk_one(P, pol, km, [&](uint32_t node, uint32_t freq) {
                 if ((int32_t)freq <= P.max_freq) {
                     KMB_BOUND(6, node, P.n_counts);
-                    atomicAdd(P.counts + node, 1u);
+                    kmb_count_direct(P.counts, node);
                     counted++;
                 }
                 return false;
@@ -1368,19 +1494,24 @@ __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, 
 }
 
 // ================================================================================================
-// K4b: play the logged hits of one node range into the node counts (mapper.pyx:68).  The groups of
-// range `bin` all fall into one window of 2^bin_shift nodes, and the ranges are launched one after
-// another, so the window being reduced into stays in L2; the log itself is a coalesced stream.
+// K4b: play the logged hits into the node counts (mapper.pyx:68), one WINDOW of 2^win_shift nodes at a
+// time, so that the window being reduced into stays in L2; the log itself is a coalesced stream.
+// One launch: blockIdx.y = window.  CTAs are dispatched x-fastest, so the windows are worked off in
+// order (the last CTAs of one overlap the first of the next, which fills the tails).  A group is
+// tagged with its node range (bin = node >> bin_shift, one of KMB_LOG_BINS); a range wider than a
+// window (large count arrays: 400 M nodes = 6 ranges of 268 MB) is played in 2^(bin_shift - win_shift)
+// windows, each re-reading the range's groups and keeping the ids that fall inside it -- a few extra
+// coalesced passes over the log instead of reductions that miss the L2.
 //
 // Count accumulation with aggregated atomics: when a few nodes are very hot (config 4: Zipf), their
 // reductions serialise on one L2 atomic unit.  Every CTA therefore walks a contiguous slab of the log
 // and first tries to count an id in a small shared-memory table (first id to claim a slot keeps it;
-// later ids that collide go straight to global memory); the table is flushed with ONE reduction per
-// id at the end.  A warp that finds less than 1 in 16 of its first 256 ids already present switches
-// the table off, so uniformly distributed nodes (config 2) pay almost nothing for it.
+// later ids that collide go straight to global memory, grouped by match.any); the table is flushed
+// with ONE reduction per id at the end.  A warp that finds less than 1 in 16 of its first 256 ids
+// already present switches the table off, so uniformly distributed nodes (config 2) pay almost nothing.
 // ================================================================================================
 #define KMB_APPLY_TABLE 2048
-__global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin, uint32_t *__restrict__ counts) {
+__global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, uint32_t *__restrict__ counts) {
     __shared__ uint32_t s_id[KMB_APPLY_TABLE];
     __shared__ uint32_t s_cnt[KMB_APPLY_TABLE];
     for (int i = threadIdx.x; i < KMB_APPLY_TABLE; i += blockDim.x) {
@@ -1388,6 +1519,13 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin,
         s_cnt[i] = 0;
     }
     __syncthreads();
+    const uint32_t window = blockIdx.y;
+    const uint32_t sub_shift = log.bin_shift - log.win_shift;
+    const uint32_t bin = min(window >> sub_shift, (uint32_t)(KMB_LOG_BINS - 1));
+    // the last range takes every node beyond it (kmb_log_bin clamps), so only a window that is not the last one of
+    // its range has to look at the ids; with one window per range nothing does
+    const bool filter_ids = sub_shift != 0u;
+    const bool last_window = window + 1u == gridDim.y;
     unsigned long long n = log.cursor[0];
     if (n > log.cap) n = log.cap;
     const uint64_t n_groups = n >> 5;
@@ -1405,18 +1543,22 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, int bin,
         const uint32_t t4 = gl < g_hi ? tags4[gl >> 2] : 0xFFFFFFFFu;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            unsigned mine = __ballot_sync(KMB_FULL_MASK, gl + k < g_hi && ((t4 >> (8 * k)) & 0xFFu) == (uint32_t)bin);
+            unsigned mine = __ballot_sync(KMB_FULL_MASK, gl + k < g_hi && ((t4 >> (8 * k)) & 0xFFu) == bin);
             while (mine) {
                 const int j = __ffs(mine) - 1;
                 mine &= mine - 1u;
                 KMB_BOUND(11, ((g0 + 4ull * j + k) << 5) + lane, log.cap);
-                const uint32_t id = log.entries[((g0 + 4ull * j + k) << 5) + lane];
+                uint32_t id = log.entries[((g0 + 4ull * j + k) << 5) + lane];
+                if (filter_ids && id != KMB_LOG_HOLE) {
+                    const uint32_t w = id >> log.win_shift;
+                    if (!(w == window || (last_window && w > window))) id = KMB_LOG_HOLE;
+                }
                 if (id != KMB_LOG_HOLE) {
                     if (use_table) {
                         const uint32_t s = (id * 0x9E3779B1u) >> 21;  // 11 bits
                         const uint32_t old = atomicCAS(&s_id[s], KMB_LOG_HOLE, id);
                         if (old == KMB_LOG_HOLE || old == id) atomicAdd(&s_cnt[s], 1u);
-                        else atomicAdd(counts + id, 1u);
+                        else kmb_count_direct(counts, id);
                         present += old == id ? 1u : 0u;
                         seen++;
                     } else {

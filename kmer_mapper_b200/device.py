@@ -223,6 +223,12 @@ class Mapper:
         check(lib().kmb_mapper_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def apply_time(self):
+        """(total ms, n launches) of the apply passes (hit log -> node counts) since the last call."""
+        ms, n = C.c_double(), C.c_uint64()
+        check(lib().kmb_mapper_apply_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def close(self):
         self._finalizer()
 

@@ -36,6 +36,9 @@ def main():
         "filter": dict(gathers_in_flight=[2], filter_l2_budget_bytes=[40 << 20, 48 << 20, 52 << 20, 56 << 20, 60 << 20], use_filter=[1]),
         "size": dict(gathers_in_flight=[2], filter_l2_budget_bytes=[54 << 20, 57 << 20], sectors_per_100_entries=[200, 226, 250, 300], use_filter=[1]),
         "persist": dict(use_filter=[1], gathers_in_flight=[8], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
+        "r2": dict(async_sectors=[1, 0], apply_window_log2=[24, 23, 22]),
+        "r2occ": dict(async_sectors=[1], map_reads_blocks_per_sm=[0, 3, 2]),
+        "window": dict(apply_window_log2=[26, 25, 24, 23, 22, 21]),
     }[a.grid]
     names = list(grids)
     last_filter = None
@@ -57,6 +60,7 @@ def main():
             m.reset()
             m.map_reads(bases, offsets, w["k"])
         m.kernel_time()
+        m.apply_time()
         torch.cuda.synchronize()
         import time
         t0 = time.perf_counter()
@@ -67,6 +71,7 @@ def main():
         m.sync()
         step_ms = (time.perf_counter() - t0) * 1e3 / a.steps
         ms, n = m.kernel_time()
+        ams, an = m.apply_time()
         nk, nc = m.stats()
         ncand = m.candidates()
         c = m.counts()
@@ -74,7 +79,7 @@ def main():
             ref_counts = c
         same = bool((c == ref_counts).all())
         m.close()
-        print(json.dumps(dict(opts=opts, cand_per_kmer=round(ncand / max(nk, 1), 4), hits_per_kmer=round(nc / max(nk, 1), 4), kernel_ms=ms / n, kernel_GKps=nk / (ms / n) / 1e6, step_ms=step_ms, step_GKps=nk / step_ms / 1e6,
+        print(json.dumps(dict(opts=opts, cand_per_kmer=round(ncand / max(nk, 1), 4), hits_per_kmer=round(nc / max(nk, 1), 4), apply_ms=ams / max(an, 1), kernel_ms=ms / n, kernel_GKps=nk / (ms / n) / 1e6, step_ms=step_ms, step_GKps=nk / step_ms / 1e6,
                               filter_bytes=di.filter_bytes, overflow_lines=di.n_overflow_lines,
                               counts_equal_first=same)), flush=True)
 
