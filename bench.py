@@ -50,8 +50,9 @@ WORKLOADS = {
     "config2": dict(k=31, genome=1_000_000_000, entries=100_000_000, nodes=80_000_000, modulo=452_930_477,
                     reads=50_000_000, read_len=150, seed=201),
     # configs[2]: multi-GB table; 200 M reads sharded over the GPUs of the job (25 M per GPU at 8)
-    "config3": dict(k=31, genome=2_000_000_000, entries=500_000_000, nodes=400_000_000, modulo=1_000_000_007,
-                    reads=25_000_000, read_len=150, seed=301),
+    # (5 Gbp genome, 200 M reads in total; strong scaling)
+    "config3": dict(k=31, genome=5_000_000_000, entries=500_000_000, nodes=400_000_000, modulo=1_000_000_007,
+                    reads=200_000_000, reads_total=200_000_000, read_len=150, seed=301),
     # configs[3]: small k, higher hit rate, Zipf nodes (atomic contention)
     "config4_k21": dict(k=21, genome=1_000_000_000, entries=100_000_000, nodes=80_000_000, modulo=452_930_477,
                         reads=50_000_000, read_len=150, seed=401, zipf=True),
@@ -73,6 +74,8 @@ def parse_args(argv=None):
     p.add_argument("--scale", type=float, default=1.0, help="shrink genome/index/reads (smoke runs only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-oracle", action="store_true", help="skip the oracle parity checks (tuning runs only)")
+    p.add_argument("--full-oracle", action="store_true", help="N=1: also run EVERY read of the step through the oracle")
     p.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     p.add_argument("--opt", action="append", default=[], help="library option name=value (tuning)")
     # internal: the CPU baseline runs in a CUDA-free child process
@@ -84,8 +87,9 @@ def parse_args(argv=None):
 def workload(name, scale):
     w = dict(WORKLOADS[name])
     if scale != 1.0:
-        for key in ("genome", "entries", "nodes", "reads"):
-            w[key] = max(int(w[key] * scale), 1000)
+        for key in ("genome", "entries", "nodes", "reads", "reads_total"):
+            if key in w:
+                w[key] = max(int(w[key] * scale), 1000)
         w["modulo"] = max(int(w["modulo"] * scale) | 1, 1009)
     return w
 
@@ -101,12 +105,16 @@ def measured_peak():
 
 
 def known_traffic(name):
-    """DRAM bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    """DRAM bytes per launch of the fused kernel from the committed ncu --set full capture, if any, and where
+    the figure comes from (it is evidence of that capture, not of this run: ncu cannot run inside a timed bench)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(name)
+        rec = json.load(open(path)).get(name)
     except Exception:
-        return None
+        return None, None
+    if isinstance(rec, dict):
+        return rec.get("bytes"), "static ncu capture: " + str(rec.get("source"))
+    return rec, ("static ncu capture (profiles/traffic.json)" if rec is not None else None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -298,11 +306,12 @@ def main_reference(args):
     import torch
     w = workload(args.workload, args.scale)
     device = "cuda" if torch.cuda.is_available() else "cpu"
+    cores = os.cpu_count() or 1
+    sample_reads = args.cpu_sample_reads or min(w["reads"], max(cores * 100_000 * 150 // w["read_len"], 1000))
+    w = dict(w, reads=min(w["reads"], max(sample_reads, 2_000_000)))   # only the sample is needed here
     tindex, bases, offsets = generate(w, 0, device)
     host_index = tindex.to_host()
     max_node = host_index.max_node_id()
-    cores = os.cpu_count() or 1
-    sample_reads = args.cpu_sample_reads or min(w["reads"], max(cores * 100_000 * 150 // w["read_len"], 1000))
     hb = bases[:int(offsets[sample_reads].item())].cpu().numpy()
     ho = offsets[:sample_reads + 1].cpu().numpy()
     del tindex, bases, offsets
@@ -330,6 +339,15 @@ def main_reference(args):
     print(json.dumps(line))
 
 
+def _oracle_index(host_index):
+    """The host arrays as the object the oracle reads (mapper.pyx:22-29 attribute names)."""
+    from oracle.oracle import OracleIndex
+    oi = OracleIndex.__new__(OracleIndex)
+    oi._hashes_to_index, oi._n_kmers, oi._nodes = host_index._hashes_to_index, host_index._n_kmers, host_index._nodes
+    oi._kmers, oi._frequencies, oi._modulo = host_index._kmers, host_index._frequencies, int(host_index._modulo)
+    return oi
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -346,6 +364,10 @@ def main_ours(args):
     _lib.set_option("time_kernels", 1)
     w = workload(args.workload, args.scale)
     k, L = w["k"], w["read_len"]
+    strong = "reads_total" in w            # the job's reads are fixed and sharded over the GPUs (BASELINE configs[2])
+    if strong:
+        lo, hi = distributed.shard_range(w["reads_total"], rank, world)
+        w["reads"] = hi - lo
     t_setup = time.perf_counter()
     tindex, bases, offsets = generate(w, rank, device)
     n_reads = w["reads"]
@@ -353,18 +375,21 @@ def main_ours(args):
     max_node = tindex.max_node_id()
     n_counts = max_node + 1
 
-    # ---- CPU baseline sample (rank 0, N == 1 only), written before the raw index tensors are dropped
+    # ---- host copy of the index for the oracle checks (rank 0) and the CPU baseline sample (N == 1 only),
+    # taken before the raw index tensors are dropped
     cpu_dir = None
     do_cpu = (not args.no_cpu_baseline) and world == 1 and rank == 0
-    sample_reads = 0
-    if do_cpu:
-        cores = os.cpu_count() or 1
-        sample_reads = args.cpu_sample_reads or min(n_reads, max(cores * 100_000 * 150 // L, 1000))
-        cpu_dir = tempfile.mkdtemp(prefix="kmb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    do_oracle = rank == 0 and not args.no_oracle
+    cores = os.cpu_count() or 1
+    # reads per rank in the parity sample: 1.6 M in total (192 M k-mers at k = 31), at least 100 k per rank
+    sample_reads = min(n_reads, args.cpu_sample_reads or max(cores * 100_000 * 150 // L // world, 100_000 * 150 // L, 1000))
+    host_index = None
+    if do_cpu or do_oracle:
         host_index = tindex.to_host()
+    if do_cpu:
+        cpu_dir = tempfile.mkdtemp(prefix="kmb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         write_cpu_sample(cpu_dir, host_index, max_node, bases[:int(offsets[sample_reads].item())].cpu().numpy(),
                          offsets[:sample_reads + 1].cpu().numpy(), sample_reads, w)
-        del host_index
 
     di = DeviceIndex.from_index(tindex, device=local_rank)
     del tindex
@@ -374,24 +399,31 @@ def main_ours(args):
     counts = torch.zeros(n_counts, dtype=torch.int32, device=device)
     mapper = Mapper(di, n_counts, counts_tensor=counts)
     mapper.set_stream(stream)
+    comm = distributed.Comm(device=local_rank) if world > 1 else None   # NCCL behind the C ABI (kmb_comm_*)
     setup_s = time.perf_counter() - t_setup
 
     def barrier():
         if world > 1:
             dist.barrier()
 
+    def reduce_counts():
+        """hit log -> node counts [-> sum over the GPUs], queued on the mapper's stream"""
+        if comm is not None:
+            comm.all_reduce(mapper)
+        else:
+            mapper.flush()
+
     def step_resident():
         mapper.reset()
         mapper.map_reads(bases, offsets, k)
-        mapper.flush()                  # hit logs -> node counts (queued on the same stream)
-        if world > 1:
-            distributed.all_reduce_counts(counts)
+        reduce_counts()
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step_resident()
         torch.cuda.synchronize()
         mapper.kernel_time()            # drop warm-up records
+        mapper.apply_time()
         n_kmers_step, n_counted_step = mapper.stats()
         n_candidates_step = mapper.candidates()   # every step starts with a reset: these are per-step figures
         barrier()
@@ -412,25 +444,84 @@ def main_ours(args):
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - launches0
         kernel_ms, kernel_n = mapper.kernel_time()
+        apply_ms, apply_n = mapper.apply_time()
     clock_rec = clocks.stop() if rank == 0 else None
     mapper.sync()                        # raises on an invalid base
 
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    total_kmers = n_kmers_step * world   # weak scaling: every rank maps the same number of windows
+    def over_ranks(value, op):
+        t = torch.tensor([value], dtype=torch.float64 if isinstance(value, float) else torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.item()
+
+    ms_max = float(over_ranks(float(ms), dist.ReduceOp.MAX))
+    total_kmers = int(over_ranks(int(n_kmers_step), dist.ReduceOp.SUM))
+    total_counted = int(over_ranks(int(n_counted_step), dist.ReduceOp.SUM))
     value = total_kmers * args.steps / (ms_max / 1e3) / 1e9
 
-    # ---- checks at full size (size-independent properties)
+    # ---- checks at full size (size-independent properties); every False fails the run (exit code 3)
     checks = {}
-    full_counts = counts.clone()
-    if world == 1:
-        s = int(full_counts.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
-        checks["sum_counts_equals_entries_counted"] = (s == n_counted_step)
-    checks["kmers_per_step"] = n_kmers_step
-    checks["expected_kmers_per_step"] = n_reads * max(L - k + 1, 0)
-    assert n_kmers_step == n_reads * max(L - k + 1, 0), (n_kmers_step, n_reads, L, k)
+    full_counts = counts.clone()         # after the last timed step: the job's total on every rank
+    s = int(full_counts.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+    checks["sum_reduced_counts_equals_entries_counted_by_all_ranks"] = (s == total_counted)
+    checks["kmers_per_step"] = total_kmers
+    checks["expected_kmers_per_step"] = int(over_ranks(int(n_reads * max(L - k + 1, 0)), dist.ReduceOp.SUM))
+    checks["kmers_per_step_as_expected"] = checks["kmers_per_step"] == checks["expected_kmers_per_step"]
+
+    # ---- parity of the multi-GPU path against the oracle: every rank maps the first `sample_reads` of its own
+    # reads through the same device-resident path, the count arrays are summed by the same all-reduce, and rank
+    # 0 compares with the oracle run over the concatenated samples (N == 1: the plain sample check)
+    if not args.no_oracle:
+        with torch.cuda.stream(stream):
+            nb_s = int(offsets[sample_reads].item())
+            mapper.reset()
+            mapper.map_reads(bases[:nb_s], offsets[:sample_reads + 1], k)
+            reduce_counts()
+            torch.cuda.synchronize()
+        got = counts.cpu().numpy().view(np.uint32)
+        if world > 1:
+            sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([nb_s, sample_reads], dtype=torch.int64, device=device))
+            sizes = [tuple(int(x) for x in t.tolist()) for t in sizes]
+            cap_b, cap_r = max(b for b, _ in sizes), max(r for _, r in sizes)
+            sb = torch.zeros(cap_b, dtype=torch.uint8, device=device)
+            sb[:nb_s] = bases[:nb_s]
+            so = torch.zeros(cap_r + 1, dtype=torch.int64, device=device)
+            so[:sample_reads + 1] = offsets[:sample_reads + 1]
+            gb = [torch.empty_like(sb) for _ in range(world)] if rank == 0 else None
+            go = [torch.empty_like(so) for _ in range(world)] if rank == 0 else None
+            dist.gather(sb, gb, dst=0)
+            dist.gather(so, go, dst=0)
+            if rank == 0:
+                parts_b = [gb[r][:sizes[r][0]].cpu().numpy() for r in range(world)]
+                parts_o, base = [np.zeros(1, np.int64)], 0
+                for r in range(world):
+                    o = go[r][:sizes[r][1] + 1].cpu().numpy()
+                    parts_o.append(o[1:] + base)
+                    base += sizes[r][0]
+                samp_b, samp_o = np.concatenate(parts_b), np.concatenate(parts_o)
+                del gb, go
+        else:
+            samp_b, samp_o = bases[:nb_s].cpu().numpy(), offsets[:sample_reads + 1].cpu().numpy()
+        if rank == 0:
+            from oracle import c_oracle
+            want, n_want = c_oracle.map_reads(_oracle_index(host_index), max_node, samp_b, samp_o, k, n_threads=cores)
+            checks["sample_counts_bit_exact_vs_oracle"] = bool(np.array_equal(got, want))
+            checks["sample_kmers"] = int(n_want)
+            checks["sample"] = "first %d reads of each of %d rank(s), mapped device-resident, %s" % (
+                sample_reads, world, "summed by kmb_mapper_allreduce (NCCL)" if world > 1 else "one GPU")
+            del samp_b, samp_o, want
+
+    # ---- the whole step against the oracle (N == 1, --full-oracle): every read of the timed batch
+    if args.full_oracle and world == 1 and not args.no_oracle:
+        from oracle import c_oracle
+        t0 = time.perf_counter()
+        hb_all, ho_all = bases.cpu().numpy(), offsets.cpu().numpy()
+        want, n_want = c_oracle.map_reads(_oracle_index(host_index), max_node, hb_all, ho_all, k, n_threads=cores)
+        checks["full_step_counts_bit_exact_vs_oracle"] = bool(np.array_equal(full_counts.cpu().numpy().view(np.uint32), want))
+        checks["full_step_kmers"] = int(n_want)
+        checks["full_step_oracle_seconds"] = round(time.perf_counter() - t0, 1)
+        del hb_all, ho_all, want
 
     # ---- e2e: host buffers through the public API, H2D and D2H inside the timed region
     e2e = None
@@ -446,10 +537,7 @@ def main_ours(args):
         def step_e2e():
             mapper.reset()
             mapper.map_reads(hb_np, ho_np, k)            # pinned host -> staged H2D (copy stream) -> kernels
-            mapper.flush()
-            if world > 1:
-                with torch.cuda.stream(stream):
-                    distributed.all_reduce_counts(counts)
+            reduce_counts()
             mapper.counts(out=hc_np)                       # result D2H, synchronises
 
         for _ in range(max(1, min(args.warmup, 2))):
@@ -462,35 +550,46 @@ def main_ours(args):
             step_e2e()
         torch.cuda.synchronize()
         barrier()
-        dt = time.perf_counter() - t0
+        dt = float(over_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX))
         h2d_per_step = (_lib.get_option("h2d_bytes") - h2d_before) // args.steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_kmers * args.steps / float(tt.item()) / 1e9, "unit": UNIT,
+        e2e = {"value": total_kmers * args.steps / dt / 1e9, "unit": UNIT,
                # bytes the library actually put on the bus (counted where it issues the copies): with the packed
                # transport the bases cross as 2 bits each, encoded on the host inside the timed region
                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(4 * n_counts),
                "host_input_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
                "host_transport": "2-bit packed on %d CPU threads" % (_lib.get_option("host_threads") or len(os.sched_getaffinity(0)))
                if h2d_per_step < n_bases else "ascii",
-               "ms_per_step": float(tt.item()) * 1e3 / args.steps, "timing": "host wall clock between device synchronisations"}
-        if world == 1:
-            checks["e2e_counts_equal_resident_counts"] = bool(np.array_equal(hc_np, full_counts.cpu().numpy().view(np.uint32)))
+               "ms_per_step": dt * 1e3 / args.steps, "timing": "host wall clock between device synchronisations",
+               "bytes_are": "per rank"}
+        checks["e2e_counts_equal_resident_counts"] = bool(np.array_equal(hc_np, full_counts.cpu().numpy().view(np.uint32)))
         del hb, ho, hc
 
-    # ---- roofline of the fused kernel
+    # ---- roofline.  SURVEY.md 8(d): A = L/(L-k+1) + 32 + 8h bytes per k-mer.  The fused kernel streams the bases
+    # and gathers the sectors (L/(L-k+1) + 32); the 8h counter bytes belong to the apply pass, which is what
+    # touches the counters.  `frac` = the dominant (fused) kernel, `frac_step` = all of A over the whole step.
     h = n_counted_step / max(n_kmers_step, 1)
-    bytes_per_kmer = L / max(L - k + 1, 1) + 32.0 + 8.0 * h
+    kernel_bytes_per_kmer = L / max(L - k + 1, 1) + 32.0
+    bytes_per_kmer = kernel_bytes_per_kmer + 8.0 * h
     peak, peak_src = measured_peak()
     kernel_avg_ms = kernel_ms / max(kernel_n, 1)
     kernels_per_step = kernel_n / max(args.steps, 1)
-    achieved = bytes_per_kmer * n_kmers_step / max(kernels_per_step, 1) / (kernel_avg_ms / 1e3) / 1e9 if kernel_n else None
+    achieved = kernel_bytes_per_kmer * n_kmers_step / max(kernels_per_step, 1) / (kernel_avg_ms / 1e3) / 1e9 if kernel_n else None
+    step_ms_rank = ms / args.steps
+    achieved_step = bytes_per_kmer * n_kmers_step / (step_ms_rank / 1e3) / 1e9
+    apply_avg_ms = apply_ms / max(apply_n, 1)
+    traffic, traffic_src = known_traffic(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": known_traffic(args.workload),
+                "frac": (achieved / peak) if achieved else None,
+                "achieved_step": achieved_step, "frac_step": achieved_step / peak,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "kmb_map_reads_mz_kernel (read-path table)" if _lib.get_option("last_reads_kernel") else "kmb_map_reads_kernel",
                 "kernel_ms": kernel_avg_ms, "kernel_share_of_step": kernel_ms / ms if ms else None,
-                "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h,
+                "kernel_bytes_per_kmer": kernel_bytes_per_kmer, "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h,
+                "apply": {"kernel": "kmb_log_apply_kernel", "ms": apply_avg_ms, "share_of_step": apply_ms / ms if ms else None,
+                          "bytes_per_kmer": 8.0 * h,
+                          "achieved": (8.0 * h * n_kmers_step / (apply_avg_ms / 1e3) / 1e9) if apply_n else None,
+                          "reductions_per_s": (n_counted_step / (apply_avg_ms / 1e3)) if apply_n else None},
+                "non_kernel_share_of_step": 1.0 - (kernel_ms + apply_ms) / ms if ms else None,
                 "sector_fetches_per_kmer": n_candidates_step / max(n_kmers_step, 1), "peak_source": peak_src,
                 "filter_bytes": di.filter_bytes}
 
@@ -514,54 +613,47 @@ def main_ours(args):
         except Exception as e:  # measurement helper only
             roofline["gather_roofline"] = {"error": str(e)}
 
-    # ---- CPU baseline + parity on the sample
+    # ---- CPU baseline (the reference's path on the host cores, bounded sample)
     cpu_rec = None
     if do_cpu:
         try:
+            del host_index
             res = run_cpu_child(cpu_dir, steps=2, warmup=1)
             desc = "first %d reads of %s (%d k-mers per pass)" % (sample_reads, args.workload, res["n_kmers"])
             cpu_rec = cpu_baseline_record(res, desc)
-            # parity: the GPU counts of the same sample == the oracle's (C port, pinned against the compiled reference)
-            from oracle import c_oracle
-            from oracle.oracle import OracleIndex
-            ld = lambda n: np.load(os.path.join(cpu_dir, n + ".npy"), mmap_mode="r")  # noqa: E731
-            oi = OracleIndex.__new__(OracleIndex)
-            oi._hashes_to_index, oi._n_kmers, oi._nodes, oi._kmers, oi._frequencies = (
-                ld("hashes_to_index"), ld("n_kmers"), ld("nodes"), ld("kmers"), ld("frequencies"))
-            oi._modulo = w["modulo"]
-            sb, so = np.load(os.path.join(cpu_dir, "bases.npy")), np.load(os.path.join(cpu_dir, "offsets.npy"))
-            want, n_want = c_oracle.map_reads(oi, max_node, sb, so, k, n_threads=os.cpu_count() or 1)
-            mapper.reset()
-            mapper.map_reads(sb, so, k)
-            got = mapper.counts()
-            checks["sample_counts_bit_exact_vs_oracle"] = bool(np.array_equal(got, want))
-            checks["sample_kmers"] = int(n_want)
         finally:
             shutil.rmtree(cpu_dir, ignore_errors=True)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u64", "data": "synthetic",
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": dict(workload=args.workload, k=k, index_entries=w["entries"], modulo=w["modulo"], nodes=w["nodes"],
-                               reads_per_gpu_per_step=n_reads, read_len=L, kmers_per_step=total_kmers, scale=args.scale,
-                               parallelism="reads sharded over %d GPU(s), index replicated, one uint32 all-reduce per step" % world,
-                               l2="inputs larger than L2 (reads %.1f GB, directory %.1f GB per step); no flush"
-                                  % (n_bases / 1e9, w["modulo"] * 8 / 1e9),
+                               genome_bases=w["genome"], reads_per_gpu_per_step=n_reads,
+                               reads_per_step=int(w.get("reads_total", n_reads * world)), read_len=L,
+                               kmers_per_step=total_kmers, scale=args.scale,
+                               parallelism="reads sharded over %d GPU(s), index replicated, one uint32 all-reduce per step "
+                                           "(kmb_mapper_allreduce: NCCL through the C ABI)" % world,
+                               l2="inputs larger than L2 (reads %.1f GB, index %.1f GB per step); no flush"
+                                  % (n_bases / 1e9, di.device_bytes / 1e9),
                                index_device_bytes=di.device_bytes, setup_seconds=round(setup_s, 1),
                                index_layout=dict(main_sectors=di.n_main_lines, overflow_sectors=di.n_overflow_lines,
                                                  filter_bytes=di.filter_bytes),
-                               options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter",
+                               options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter", "apply_window_log2",
                                                                         "map_reads_blocks_per_sm")}),
                 "clocks": clock_rec, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_rec, "checks": checks}
         print(json.dumps(line))
+    bad = [k_ for k_, v in checks.items() if v is False]
+    bad_any = int(over_ranks(len(bad), dist.ReduceOp.SUM))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    bad = [k_ for k_, v in checks.items() if v is False]
     if bad:
         print("PARITY CHECK FAILED: %s" % bad, file=sys.stderr)
+    if bad_any:
         sys.exit(3)
 
 

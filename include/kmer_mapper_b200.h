@@ -114,12 +114,39 @@ int kmb_mapper_sync(kmb_mapper *mapper);
 int kmb_mapper_bad_offset(kmb_mapper *mapper, int64_t *offset);
 /* Copy the n_counts node counts to a host (or device) buffer; implies kmb_mapper_sync. */
 int kmb_mapper_read_counts(kmb_mapper *mapper, uint32_t *out, uint64_t n_counts);
+/* Replace the counts by n_counts (= the mapper's) values from a host or device buffer; hits mapped before the
+ * call are dropped.  This is `counter._values = node_counts` of the CounterKmerIndex route
+ * (command_line_interface.py:136) and the `initial_data` of the additive map-reduce (:116-119). */
+int kmb_mapper_write_counts(kmb_mapper *mapper, const uint32_t *values, uint64_t n_counts);
 /* Zero the counts, the statistics and the error state. */
 int kmb_mapper_reset(kmb_mapper *mapper);
 /* Device pointer of the count buffer (for an in-place NCCL all-reduce by the host framework). */
 int kmb_mapper_counts_device(kmb_mapper *mapper, uint32_t **counts_device, uint64_t *n_counts);
 /* Windows looked up and index entries counted since the last reset (implies kmb_mapper_sync). */
 int kmb_mapper_stats(kmb_mapper *mapper, uint64_t *n_kmers_mapped, uint64_t *n_entries_counted);
+
+/* ---- multi-GPU reduction: replaces the additive map-reduce of command_line_interface.py:124-130 ----
+ * The reference's only parallelism is data parallelism over read chunks: every worker process returns a
+ * uint32[max_node_id+1] array and shared_memory_wrapper's additative_shared_array_map_reduce sums them
+ * element-wise.  Here every GPU (one process per GPU) maps its share of the reads into the private count
+ * buffer of its mapper and the buffers are summed in place by ONE ncclAllReduce(ncclUint32, ncclSum) over
+ * NVLink; uint32 addition wraps, so the result has the reference's bits whatever the reduction order.
+ * NCCL is loaded at run time (dlopen of libnccl.so.2 -- the copy a host framework such as PyTorch already
+ * loaded, else $KMB_NCCL_LIB, else the loader path); without it these calls return KMB_ERR_NCCL.
+ *   rank 0:     kmb_comm_unique_id(id)  and sends the 128 bytes to the other ranks by any means
+ *   every rank: kmb_comm_init_rank(device, n_ranks, rank, id, &comm)      (collective, blocking)
+ *               ... kmb_mapper_map_reads(...) on its own reads ...
+ *               kmb_mapper_allreduce(mapper, comm)   queues flush + all-reduce on the mapper's stream
+ *               kmb_mapper_read_counts(mapper, ...)  now yields the job's total on every rank
+ * The count buffer is registered with the communicator (ncclCommRegister) on first use, so NCCL can use it
+ * in place.  n_counts must be equal on all ranks. */
+#define KMB_ERR_NCCL (-6)
+#define KMB_COMM_ID_BYTES 128
+typedef struct kmb_comm kmb_comm;
+int kmb_comm_unique_id(uint8_t id[KMB_COMM_ID_BYTES]);
+int kmb_comm_init_rank(int device, int n_ranks, int rank, const uint8_t id[KMB_COMM_ID_BYTES], kmb_comm **comm);
+int kmb_comm_destroy(kmb_comm *comm);
+int kmb_mapper_allreduce(kmb_mapper *mapper, kmb_comm *comm);
 
 /* ---- membership: replaces in_graph_index / in_graph_index_no_memory_maps (mapper.pyx:81,137) --
  * out[i] = 1 iff some entry of bucket kmers[i] % modulo has key kmers[i]; frequency ignored. */
@@ -234,8 +261,7 @@ int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kern
  *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
- *  "async_sectors" (1 = sector fetches by cp.async into shared memory, 0 = in registers), "apply_window_log2" (nodes per
- *  apply window, default 24 = 64 MB of counters),
+ *  "apply_window_log2" (nodes per apply window, default 23 = 32 MB of counters),
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
  *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
  *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),

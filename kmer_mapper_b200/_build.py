@@ -18,7 +18,7 @@ HEADERS = [os.path.join(CSRC, "kmb_kernels.cuh"), os.path.join(CSRC, "kmb_core.c
            os.path.join(os.path.dirname(PKG), "include", "kmer_mapper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
-LINK_FLAGS = ["-lz"]  # member-parallel gzip inflate of the chunk reader (kmb_gunzip.cpp)
+LINK_FLAGS = ["-lz", "-ldl"]  # member-parallel gzip inflate of the chunk reader (kmb_gunzip.cpp)
 
 
 def up_to_date() -> bool:

@@ -18,6 +18,8 @@ KMB_ERR_INVALID_BASE = -2
 KMB_ERR_CUDA = -3
 KMB_ERR_BAD_INDEX = -4
 KMB_ERR_NOMEM = -5
+KMB_ERR_NCCL = -6
+COMM_ID_BYTES = 128
 
 FLAG_REVCOMP = 1
 FLAG_NO_N_TO_A = 2
@@ -60,9 +62,14 @@ SIGNATURES = {
     "kmb_mapper_sync": (C.c_int, [_vp]),
     "kmb_mapper_bad_offset": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "kmb_mapper_read_counts": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "kmb_mapper_write_counts": (C.c_int, [_vp, _vp, C.c_uint64]),
     "kmb_mapper_reset": (C.c_int, [_vp]),
     "kmb_mapper_counts_device": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "kmb_mapper_stats": (C.c_int, [_vp, _u64p, _u64p]),
+    "kmb_comm_unique_id": (C.c_int, [_vp]),
+    "kmb_comm_init_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "kmb_comm_destroy": (C.c_int, [_vp]),
+    "kmb_mapper_allreduce": (C.c_int, [_vp, _vp]),
     "kmb_in_graph_index": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "kmb_hash_reads": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int, C.c_uint32, _vp, C.c_uint64,
                                  _u64p, C.POINTER(C.c_int64)]),

@@ -23,6 +23,7 @@ import numpy as np
 logging.basicConfig(stream=sys.stdout, level=logging.INFO, format='%(asctime)s %(levelname)s: %(message)s')
 
 from . import distributed  # noqa: E402
+from .counter_index import CounterKmerIndex  # noqa: E402
 from .device import DEFAULT_MAX_FREQUENCY, DeviceIndex, Mapper  # noqa: E402
 from .reader import open_reads  # noqa: E402
 from .sequences import as_ragged  # noqa: E402
@@ -41,6 +42,16 @@ def map_cpu(args, kmer_index, chunk_sequence):
     t = time.perf_counter()
     seq = as_ragged(chunk_sequence)
     logging.debug("N sequences in chunk: %d" % len(seq))
+    if isinstance(kmer_index, CounterKmerIndex):
+        # command_line_interface.py:46-49: count per unique k-mer; the chunk's result is the counter's value array.
+        # The counter is zeroed first, so that the result is THIS chunk's counts and the caller's additive reduce
+        # (:124-130) gives the totals.
+        counter = kmer_index.counter
+        counter._values = np.zeros(counter.n_keys, dtype=np.uint32)
+        counter.count_reads(seq.bases, seq.offsets, kmer_size)
+        mapped = counter._values
+        logging.debug("Mapped with counter. Got values of length %d" % len(mapped))
+        return mapped
     di = DeviceIndex.from_index(kmer_index)
     m = Mapper(di, kmer_index.max_node_id() + 1, DEFAULT_MAX_FREQUENCY)
     try:
@@ -126,7 +137,9 @@ def map_bnp(args):
     t_map = time.perf_counter()
     try:
         chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size, rank=rank, world_size=world_size)
-        if world_size == 1:
+        if isinstance(index, CounterKmerIndex):
+            node_counts = _map_counter_index(index, chunk_iter, kmer_size, want_revcomp, rank, world_size)
+        elif world_size == 1:
             node_counts = map_gpu(index, chunk_iter, kmer_size, _flag(args, "gpu_hash_map_size", 0), want_revcomp,
                                   max_index_lookup_frequency=_frequency_cutoff(args))
         else:
@@ -146,22 +159,42 @@ def map_bnp(args):
                                                                              _flag(args, "n_threads", 1)))
 
 
+def _map_counter_index(kmer_index, chunks, k, map_reverse_complements, rank, world_size):
+    """The CounterKmerIndex route (command_line_interface.py:118-119, 133-138): k-mer counts per unique key summed over
+    the chunks (and, under torchrun, over the GPUs), then ``counter._values = totals`` and ``get_node_counts()`` once."""
+    counter = kmer_index.counter
+    counter._values = np.zeros(counter.n_keys, dtype=np.uint32)      # initial_data = zeros_like(counter._values)
+    for chunk in chunks:
+        seq = as_ragged(chunk.sequence if hasattr(chunk, "sequence") else chunk)
+        counter.count_reads(seq.bases, seq.offsets, k, count_revcomps=bool(map_reverse_complements))
+    counter._mapper.sync()
+    if world_size > 1:
+        comm = distributed.Comm(device=counter._index.device)
+        comm.all_reduce(counter._mapper)
+        counter._mapper.sync()
+        comm.close()
+    t = time.perf_counter()
+    node_counts = kmer_index.get_node_counts()
+    logging.info("Time spent getting node counts in the end: %.3f" % (time.perf_counter() - t))
+    return node_counts
+
+
 def _map_sharded(kmer_index, chunks, k, map_reverse_complements, rank, world_size,
                  max_index_lookup_frequency=DEFAULT_MAX_FREQUENCY):
-    """One rank of a torchrun job: private counts in a torch tensor, one all-reduce at the end."""
-    import torch
+    """One rank of a torchrun job: a private count array per GPU, summed once at the end by one all-reduce
+    (``kmb_mapper_allreduce``: NCCL through the C ABI) -- the additive reduce of command_line_interface.py:124-130."""
     di = DeviceIndex.from_index(kmer_index)
     n_counts = di.max_node_id() + 1
-    counts = torch.zeros(n_counts, dtype=torch.int32, device="cuda")
-    mapper = Mapper(di, n_counts, max_index_lookup_frequency, counts_tensor=counts)
+    mapper = Mapper(di, n_counts, max_index_lookup_frequency)
+    comm = distributed.Comm(device=di.device)
     for chunk in chunks:    # the reader already hands this rank its share only (reader.py: read_chunks)
         seq = chunk.sequence
         mapper.map_reads(seq.bases, seq.offsets, k, revcomp=bool(map_reverse_complements), n_to_a=True)
-    mapper.sync()
-    distributed.all_reduce_counts(counts)
-    torch.cuda.synchronize()
-    out = counts.cpu().numpy().view(np.uint32)
+    mapper.sync()           # an invalid base on any rank raises here, before the collective
+    comm.all_reduce(mapper)
+    out = mapper.counts()
     mapper.close()
+    comm.close()
     return out
 
 

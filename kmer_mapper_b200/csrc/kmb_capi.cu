@@ -5,8 +5,10 @@
 // compute stream) and launches the kernels of kmb_kernels.cuh.  Without a CUDA device every compute
 // entry point returns KMB_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -94,12 +96,10 @@ struct KmbOptions {
     int64_t host_pack = -1;
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
     int64_t host_ranks = 1;               // processes sharing this host's memory system (set by distributed.py)
-    // Sector fetches of the key-addressed kernels: 1 = cp.async into shared memory, compared one batch later (four
-    // CTAs per SM); 0 = in registers, requested and compared inside one batch iteration (three CTAs per SM).
-    int64_t async_sectors = 1;
-    // The apply pass reduces into one window of 2^apply_window_log2 nodes at a time (x 4 bytes: 24 = 64 MB); the
-    // window has to stay in the L2 next to the persisting filter lines.
-    int64_t apply_window_log2 = 24;
+    // The apply pass reduces into one window of 2^apply_window_log2 nodes at a time (x 4 bytes: 23 = 32 MB).  The
+    // windows of one launch overlap where one ends and the next begins, so two must fit the L2 together: measured on
+    // config 2 (516 M reductions): 9.4 ms at 2^24, 5.3 ms at 2^23, 6.2 ms at 2^22 (more passes over the log).
+    int64_t apply_window_log2 = 23;
 };
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
@@ -136,7 +136,6 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(read_table_min_entries)
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
-    OPT(async_sectors)
     OPT(apply_window_log2)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
@@ -177,7 +176,6 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(read_table_min_entries)
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
-    OPT(async_sectors)
     OPT(apply_window_log2)
     OPT(chunk_bytes)
 #undef OPT
@@ -530,8 +528,8 @@ extern "C" int kmb_index_layout(const kmb_index *ix, uint64_t *n_main_lines, uin
 struct StageSlot {
     uint8_t *data = nullptr;  // bases (ASCII or packed) or k-mers of one chunk
     int64_t *offsets = nullptr;
-    uint32_t *mask = nullptr;
-    size_t data_cap = 0, off_cap = 0, mask_cap = 0;
+    uint32_t *tiles = nullptr;  // per 1024-position tile: the read it begins in (kmb_tile_reads_kernel)
+    size_t data_cap = 0, off_cap = 0, tiles_cap = 0;
     uint32_t *h_words = nullptr;  // pinned: the chunk's packed bases, written by the host encoder, read by the DMA engine
     uint32_t *h_off = nullptr;    // pinned: its chunk-relative read offsets
     size_t h_words_cap = 0, h_off_cap = 0;
@@ -555,8 +553,8 @@ struct kmb_mapper {
     KmbStatus *h_status = nullptr;  // pinned
     StageSlot slot[KMB_SLOTS];
     uint64_t host_bad = ~0ull;  // first invalid byte met by the host-side encoder since the last reset
-    uint32_t *dmask = nullptr;  // read-boundary mask for in-place device input
-    size_t dmask_cap = 0;
+    uint32_t *dtiles = nullptr;  // tile -> read table for in-place device input
+    size_t dtiles_cap = 0;
     int next_slot = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];  // event pairs around [0] mapping kernels, [1] apply passes
     size_t timed_used[2] = {0, 0};
@@ -568,7 +566,7 @@ static int timed_end(kmb_mapper *m, int klass = 0);
 static void slot_free(StageSlot &s) {
     cudaFree(s.data);
     cudaFree(s.offsets);
-    cudaFree(s.mask);
+    cudaFree(s.tiles);
     if (s.h_words) cudaFreeHost(s.h_words);
     if (s.h_off) cudaFreeHost(s.h_off);
     if (s.copied) cudaEventDestroy(s.copied);
@@ -587,7 +585,7 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
         }
-    cudaFree(m->dmask);
+    cudaFree(m->dtiles);
     cudaFree(m->log.entries);
     cudaFree(m->log.tags);
     cudaFree(m->log.cursor);
@@ -790,39 +788,33 @@ static int pick_u() {
 }
 
 // ---- kernel dispatch (template instantiation table) ------------------------------------------------
-typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, int, uint32_t, KmbProbe, KmbStatus *);
+typedef void (*MapReadsFn)(const uint8_t *, uint64_t, uint64_t, KmbReads, int, uint32_t, KmbProbe, KmbStatus *);
 typedef void (*MapKmersFn)(const uint64_t *, uint64_t, int, KmbProbe, KmbStatus *);
 
-template <int U, bool ASYNC>
+template <int U>
 static MapReadsFn map_reads_fn_u(bool filt, bool rc) {
-    if (filt) return rc ? kmb_map_reads_kernel<U, true, true, ASYNC> : kmb_map_reads_kernel<U, true, false, ASYNC>;
-    return rc ? kmb_map_reads_kernel<U, false, true, ASYNC> : kmb_map_reads_kernel<U, false, false, ASYNC>;
+    if (filt) return rc ? kmb_map_reads_kernel<U, true, true> : kmb_map_reads_kernel<U, true, false>;
+    return rc ? kmb_map_reads_kernel<U, false, true> : kmb_map_reads_kernel<U, false, false>;
 }
-template <int U, bool ASYNC>
+template <int U>
 static MapKmersFn map_kmers_fn_u(bool filt, bool rc) {
-    if (filt) return rc ? kmb_map_kmers_kernel<U, true, true, ASYNC> : kmb_map_kmers_kernel<U, true, false, ASYNC>;
-    return rc ? kmb_map_kmers_kernel<U, false, true, ASYNC> : kmb_map_kmers_kernel<U, false, false, ASYNC>;
+    if (filt) return rc ? kmb_map_kmers_kernel<U, true, true> : kmb_map_kmers_kernel<U, true, false>;
+    return rc ? kmb_map_kmers_kernel<U, false, true> : kmb_map_kmers_kernel<U, false, false>;
 }
-// The key-addressed kernels exist as: sectors by cp.async (U = 4), sectors in registers (U = 2 or 4).
 struct MapKernel {
     const void *fn;
     int u;
     size_t smem;
-    bool async;
 };
 static MapKernel pick_map_kernel(bool reads, bool filt, bool rc) {
     MapKernel mk;
-    mk.async = g_opt.async_sectors != 0;
-    mk.u = mk.async ? 4 : pick_u();
-    if (mk.async) {
-        mk.fn = reads ? (const void *)map_reads_fn_u<4, true>(filt, rc) : (const void *)map_kmers_fn_u<4, true>(filt, rc);
-        mk.smem = KMB_MAP_SMEM_BYTES(4, true);
-    } else if (mk.u == 2) {
-        mk.fn = reads ? (const void *)map_reads_fn_u<2, false>(filt, rc) : (const void *)map_kmers_fn_u<2, false>(filt, rc);
-        mk.smem = KMB_MAP_SMEM_BYTES(2, false);
+    mk.u = pick_u();
+    if (mk.u == 2) {
+        mk.fn = reads ? (const void *)map_reads_fn_u<2>(filt, rc) : (const void *)map_kmers_fn_u<2>(filt, rc);
+        mk.smem = KMB_MAP_SMEM_BYTES(2);
     } else {
-        mk.fn = reads ? (const void *)map_reads_fn_u<4, false>(filt, rc) : (const void *)map_kmers_fn_u<4, false>(filt, rc);
-        mk.smem = KMB_MAP_SMEM_BYTES(4, false);
+        mk.fn = reads ? (const void *)map_reads_fn_u<4>(filt, rc) : (const void *)map_kmers_fn_u<4>(filt, rc);
+        mk.smem = KMB_MAP_SMEM_BYTES(4);
     }
     return mk;
 }
@@ -932,22 +924,21 @@ static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
     return thin_filter && ix->n_live >= (uint64_t)std::max<int64_t>(g_opt.read_table_min_entries, 0);
 }
 
-// launch the read-boundary mask + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
+// launch the tile -> read table + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
 // stream of kmb_hostpack.cpp and d_offsets are uint32 offsets relative to the batch (else int64, relative to base0)
 static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_bases, uint64_t base0, const void *d_offsets,
-                            uint64_t n_reads, uint32_t *d_mask, int k, uint32_t flags, bool packed) {
+                            uint64_t n_reads, uint32_t *d_tiles, int k, uint32_t flags, bool packed) {
     if (n_bases == 0) return KMB_OK;
     const kmb_index *ix = m->index;
-    const size_t mask_words = (size_t)(n_bases / 32 + 1);
-    KMB_CUDA(cudaMemsetAsync(d_mask, 0, mask_words * 4, m->stream));
-    if (n_reads) {
-        const int grid = grid_for(n_reads, 256, ix->info.sms);
-        if (packed)
-            kmb_mark_read_ends<uint32_t><<<grid, 256, 0, m->stream>>>((const uint32_t *)d_offsets, n_reads, 0, k, d_mask);
-        else
-            kmb_mark_read_ends<int64_t><<<grid, 256, 0, m->stream>>>((const int64_t *)d_offsets, n_reads, (int64_t)base0, k, d_mask);
-        g_launches++;
-    }
+    const uint64_t n_wtiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
+    KmbReads R;
+    R.offsets = d_offsets;
+    R.tile_read = d_tiles;
+    R.n_reads = n_reads;
+    R.base0 = packed ? 0 : (int64_t)base0;
+    R.off32 = packed ? 1u : 0u;
+    kmb_tile_reads_kernel<<<grid_for(n_wtiles, 256, ix->info.sms), 256, 0, m->stream>>>(R, n_bases, n_wtiles, d_tiles, m->d_status);
+    g_launches++;
     // every window, both strands when asked: the number of look-ups this launch can make
     KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases));
     KmbProbe P = make_probe(m);
@@ -961,7 +952,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
         P.filter = ix->mz_filter;
         P.addr = ix->mz_addr;
         P.n_lines = ix->mz_n_lines;
-        typedef void (*MzFn)(const uint8_t *, uint64_t, uint64_t, const uint32_t *, uint32_t, KmbProbe, KmbProbe, KmbStatus *);
+        typedef void (*MzFn)(const uint8_t *, uint64_t, uint64_t, KmbReads, uint32_t, KmbProbe, KmbProbe, KmbStatus *);
         MzFn fn = P.filter ? kmb_map_reads_mz_kernel<true> : kmb_map_reads_mz_kernel<false>;
         KMB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KMB_MZ_SMEM_BYTES));
         int per_sm = 0;
@@ -972,7 +963,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
         int grid = (int)std::min<uint64_t>(n_cta_tiles, (uint64_t)ix->info.sms * per_sm);
         m->dirty = true;
         KMB_TRY(timed_begin(m));
-        fn<<<grid, KMB_MZ_THREADS, KMB_MZ_SMEM_BYTES, m->stream>>>(d_bases, n_bases, base0, d_mask, in_mode, P, Pkey, m->d_status);
+        fn<<<grid, KMB_MZ_THREADS, KMB_MZ_SMEM_BYTES, m->stream>>>(d_bases, n_bases, base0, R, in_mode, P, Pkey, m->d_status);
         g_launches++;
         KMB_CUDA(cudaGetLastError());
         KMB_TRY(timed_end(m));
@@ -985,7 +976,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
     m->dirty = true;
     KMB_TRY(timed_begin(m));
-    ((MapReadsFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_bases, n_bases, base0, d_mask, k, in_mode, P, m->d_status);
+    ((MapReadsFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_bases, n_bases, base0, R, k, in_mode, P, m->d_status);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_TRY(timed_end(m));
@@ -1018,7 +1009,7 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
     return KMB_OK;
 }
 
-static int slot_reserve(StageSlot &s, size_t data_bytes, size_t n_offsets, size_t mask_words) {
+static int slot_reserve(StageSlot &s, size_t data_bytes, size_t n_offsets, size_t n_tiles) {
     if (data_bytes > s.data_cap) {
         cudaFree(s.data);
         s.data = nullptr;
@@ -1035,13 +1026,13 @@ static int slot_reserve(StageSlot &s, size_t data_bytes, size_t n_offsets, size_
         KMB_CUDA(cudaMalloc(&s.offsets, cap * 8));
         s.off_cap = cap;
     }
-    if (mask_words > s.mask_cap) {
-        cudaFree(s.mask);
-        s.mask = nullptr;
-        s.mask_cap = 0;
-        size_t cap = mask_words + mask_words / 4 + 64;
-        KMB_CUDA(cudaMalloc(&s.mask, cap * 4));
-        s.mask_cap = cap;
+    if (n_tiles > s.tiles_cap) {
+        cudaFree(s.tiles);
+        s.tiles = nullptr;
+        s.tiles_cap = 0;
+        size_t cap = n_tiles + n_tiles / 4 + 64;
+        KMB_CUDA(cudaMalloc(&s.tiles, cap * 4));
+        s.tiles_cap = cap;
     }
     return KMB_OK;
 }
@@ -1086,16 +1077,16 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
     if (dev_b) {
         if (((uintptr_t)bases & 15u) != 0)
             return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: device bases buffer must be 16-byte aligned");
-        size_t words = (size_t)(n_bases / 32 + 1);
-        if (words > m->dmask_cap) {
+        size_t words = (size_t)(n_bases / KMB_WTILE_POS + 1);
+        if (words > m->dtiles_cap) {
             KMB_CUDA(cudaStreamSynchronize(m->stream));
-            cudaFree(m->dmask);
-            m->dmask = nullptr;
-            m->dmask_cap = 0;
-            KMB_CUDA(cudaMalloc(&m->dmask, (words + words / 8 + 64) * 4));
-            m->dmask_cap = words + words / 8 + 64;
+            cudaFree(m->dtiles);
+            m->dtiles = nullptr;
+            m->dtiles_cap = 0;
+            KMB_CUDA(cudaMalloc(&m->dtiles, (words + words / 8 + 64) * 4));
+            m->dtiles_cap = words + words / 8 + 64;
         }
-        return launch_map_reads(m, bases, n_bases, 0, offsets, n_reads, m->dmask, k, flags, false);
+        return launch_map_reads(m, bases, n_bases, 0, offsets, n_reads, m->dtiles, k, flags, false);
     }
     // ---- host input: whole reads per chunk, double-buffered H2D on the copy stream
     if (offsets[0] != 0 || (uint64_t)offsets[n_reads] != n_bases)
@@ -1121,7 +1112,7 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
             if (packed) {
                 // encode on the CPU into pinned staging while the previous chunks are on the bus / under the kernel
                 const size_t n_words = (size_t)kmb_packed_words(nb);
-                KMB_TRY(slot_reserve(s, n_words * 4, (nr + 2) / 2, nb / 32 + 1));
+                KMB_TRY(slot_reserve(s, n_words * 4, (nr + 2) / 2, nb / KMB_WTILE_POS + 1));
                 KMB_TRY(slot_reserve_host(s, n_words, nr + 1));
                 const uint64_t bad = kmb_host_pack(bases + b0, nb, !(flags & KMB_FLAG_NO_N_TO_A), pack_threads, s.h_words);
                 if (bad != ~0ull) m->host_bad = std::min(m->host_bad, b0 + bad);
@@ -1130,14 +1121,14 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
                 KMB_CUDA(cudaMemcpyAsync(s.offsets, s.h_off, (nr + 1) * 4, cudaMemcpyHostToDevice, m->copy_stream));
                 g_h2d_bytes += n_words * 4 + (nr + 1) * 4;
             } else {
-                KMB_TRY(slot_reserve(s, nb + 16, nr + 1, nb / 32 + 1));
+                KMB_TRY(slot_reserve(s, nb + 16, nr + 1, nb / KMB_WTILE_POS + 1));
                 KMB_CUDA(cudaMemcpyAsync(s.data, bases + b0, nb, cudaMemcpyHostToDevice, m->copy_stream));
                 KMB_CUDA(cudaMemcpyAsync(s.offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, m->copy_stream));
                 g_h2d_bytes += nb + (nr + 1) * 8;
             }
             KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
             KMB_CUDA(cudaStreamWaitEvent(m->stream, s.copied, 0));
-            KMB_TRY(launch_map_reads(m, s.data, nb, b0, s.offsets, nr, s.mask, k, flags, packed));
+            KMB_TRY(launch_map_reads(m, s.data, nb, b0, s.offsets, nr, s.tiles, k, flags, packed));
             KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
             s.used = true;
         }
@@ -1191,6 +1182,8 @@ extern "C" int kmb_mapper_sync(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_sync: null mapper");
     KMB_ON_DEVICE(m->index->device);
     KMB_TRY(fetch_status(m));
+    if (m->h_status->index_flags & KMB_FLAG_BAD_OFFSETS)
+        return kmb_fail(KMB_ERR_BAD_ARG, "read offsets are not non-decreasing from 0 to n_bases (a map_reads call since the last reset)");
     if (m->h_status->first_bad_offset != ~0ull)
         return kmb_fail(KMB_ERR_INVALID_BASE, "invalid base byte at flat offset %llu (only ACGTacgt and N are accepted)",
                         m->h_status->first_bad_offset);
@@ -1214,6 +1207,20 @@ extern "C" int kmb_mapper_read_counts(kmb_mapper *m, uint32_t *out, uint64_t n_c
     if (n_counts) {
         KMB_CUDA(cudaMemcpyAsync(out, m->counts, n_counts * 4, cudaMemcpyDefault, m->stream));
         KMB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_write_counts(kmb_mapper *m, const uint32_t *values, uint64_t n_counts) {
+    if (!m || (!values && n_counts)) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_write_counts: null argument");
+    if (n_counts != m->n_counts) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_write_counts: n_counts must equal the mapper's (%llu)", (unsigned long long)m->n_counts);
+    KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(launch_log_reset(m));   // hits that were logged but not applied belong to the counts being replaced
+    m->dirty = false;
+    m->queries_since_flush = 0;
+    if (n_counts) {
+        KMB_CUDA(cudaMemcpyAsync(m->counts, values, n_counts * 4, cudaMemcpyDefault, m->stream));
+        KMB_CUDA(cudaStreamSynchronize(m->stream));  // the caller may reuse `values` at once
     }
     return KMB_OK;
 }
@@ -1284,6 +1291,135 @@ extern "C" int kmb_mapper_kernel_time(kmb_mapper *m, double *ms_total, uint64_t 
 // The same for the apply passes (hit log -> node counts).
 extern "C" int kmb_mapper_apply_time(kmb_mapper *m, double *ms_total, uint64_t *n_kernels) {
     return timed_total(m, 1, ms_total, n_kernels);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU reduction of the node counts over NCCL (command_line_interface.py:124-130)
+// ------------------------------------------------------------------------------------------------
+// NCCL is bound at run time, by name, so that the library loads (and the single-GPU path works) where NCCL is
+// not installed.  The five prototypes below restate nccl.h (NCCL 2.x ABI): ncclUniqueId is a 128-byte struct
+// passed by value, ncclComm_t an opaque pointer, ncclUint32 = 3, ncclSum = 0.
+struct KmbNcclId {
+    char internal[KMB_COMM_ID_BYTES];
+};
+struct KmbNccl {
+    void *lib = nullptr;
+    int (*GetUniqueId)(KmbNcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, KmbNcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*CommRegister)(void *, void *, size_t, void **) = nullptr;  // optional (NCCL >= 2.19)
+    int (*CommDeregister)(void *, void *) = nullptr;
+};
+static KmbNccl g_nccl;
+static std::mutex g_nccl_mu;
+
+static int nccl_load() {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.lib) return KMB_OK;
+    const char *env = getenv("KMB_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return kmb_fail(KMB_ERR_NCCL, "NCCL not found: dlopen(libnccl.so.2) failed (%s); set KMB_NCCL_LIB to its path", dlerror());
+#define NCCL_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name)
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    NCCL_SYM(AllReduce, "ncclAllReduce");
+    NCCL_SYM(GetErrorString, "ncclGetErrorString");
+    NCCL_SYM(CommRegister, "ncclCommRegister");
+    NCCL_SYM(CommDeregister, "ncclCommDeregister");
+#undef NCCL_SYM
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString) {
+        dlclose(h);
+        return kmb_fail(KMB_ERR_NCCL, "the NCCL library found lacks a required symbol");
+    }
+    g_nccl.lib = h;
+    return KMB_OK;
+}
+#define KMB_NCCL(call)                                                                                    \
+    do {                                                                                                  \
+        int r__ = (call);                                                                                 \
+        if (r__ != 0) return kmb_fail(KMB_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+    } while (0)
+
+struct kmb_comm {
+    void *comm = nullptr;
+    int device = 0, n_ranks = 1, rank = 0;
+    std::vector<std::pair<void *, void *>> registered;  // (buffer, NCCL registration handle)
+};
+
+extern "C" int kmb_comm_unique_id(uint8_t id[KMB_COMM_ID_BYTES]) {
+    if (!id) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_comm_unique_id: null id");
+    KMB_TRY(nccl_load());
+    KmbNcclId nid;
+    KMB_NCCL(g_nccl.GetUniqueId(&nid));
+    memcpy(id, nid.internal, KMB_COMM_ID_BYTES);
+    return KMB_OK;
+}
+
+extern "C" int kmb_comm_init_rank(int device, int n_ranks, int rank, const uint8_t id[KMB_COMM_ID_BYTES], kmb_comm **out) {
+    if (!out) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_comm_init_rank: out is null");
+    *out = nullptr;
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_comm_init_rank: bad rank %d of %d", rank, n_ranks);
+    KMB_TRY(nccl_load());
+    KMB_ON_DEVICE(device);
+    kmb_comm *c = new (std::nothrow) kmb_comm;
+    if (!c) return kmb_fail(KMB_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->n_ranks = n_ranks;
+    c->rank = rank;
+    KmbNcclId nid;
+    memcpy(nid.internal, id, KMB_COMM_ID_BYTES);
+    int r = g_nccl.CommInitRank(&c->comm, n_ranks, nid, rank);
+    if (r != 0) {
+        delete c;
+        return kmb_fail(KMB_ERR_NCCL, "ncclCommInitRank(rank %d of %d): %s", rank, n_ranks, g_nccl.GetErrorString(r));
+    }
+    *out = c;
+    return KMB_OK;
+}
+
+extern "C" int kmb_comm_destroy(kmb_comm *c) {
+    if (!c) return KMB_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    if (g_nccl.CommDeregister)
+        for (auto &pr : c->registered)
+            if (pr.second) g_nccl.CommDeregister(c->comm, pr.second);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    cudaGetLastError();
+    delete c;
+    return KMB_OK;
+}
+
+// Hit log -> counts, then the in-place sum over the ranks, both queued on the mapper's stream.
+extern "C" int kmb_mapper_allreduce(kmb_mapper *m, kmb_comm *c) {
+    if (!m || !c) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_allreduce: null argument");
+    if (c->device != m->index->device)
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_allreduce: communicator is on GPU %d, mapper on GPU %d", c->device, m->index->device);
+    KMB_ON_DEVICE(m->index->device);
+    if (m->dirty) KMB_TRY(launch_flush(m));
+    if (c->n_ranks == 1 || m->n_counts == 0) return KMB_OK;
+    if (g_nccl.CommRegister) {
+        bool have = false;
+        for (auto &pr : c->registered) have |= pr.first == (void *)m->counts;
+        if (!have) {
+            void *handle = nullptr;
+            if (g_nccl.CommRegister(c->comm, m->counts, (size_t)m->n_counts * 4, &handle) == 0 && handle)
+                c->registered.emplace_back((void *)m->counts, handle);
+            else
+                c->registered.emplace_back((void *)m->counts, nullptr);  // registration is an optimisation: do not retry
+        }
+    }
+    KMB_NCCL(g_nccl.AllReduce(m->counts, m->counts, (size_t)m->n_counts, /*ncclUint32*/ 3, /*ncclSum*/ 0, c->comm, m->stream));
+    return KMB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1587,9 +1723,21 @@ extern "C" int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loa
     KMB_CUDA(cudaEventCreate(&e0));
     KMB_CUDA(cudaEventCreate(&e1));
     int grid = g_opt.bench_grid_blocks > 0 ? (int)g_opt.bench_grid_blocks : info.sms * blocks_per_sm;
-    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads / 8 + 1, 1, sink.p, (int)g_opt.bench_load_mode);  // warm-up
+    size_t smem = 0;
+    if (g_opt.bench_load_mode >= 6) {  // the cp.async variant: 32-byte sectors into per-thread shared-memory slots
+        if (load_bytes != 32) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_bench_gather: the cp.async modes copy 32-byte sectors");
+        switch (unroll) {
+            case 1: fn = kmb_gather_async_bench_kernel<1>; break;
+            case 2: fn = kmb_gather_async_bench_kernel<2>; break;
+            case 4: fn = kmb_gather_async_bench_kernel<4>; break;
+            default: return kmb_fail(KMB_ERR_BAD_ARG, "kmb_bench_gather: cp.async modes take unroll 1, 2 or 4");
+        }
+        smem = (size_t)threads_per_block * unroll * 32;
+        KMB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    fn<<<grid, threads_per_block, smem>>>(table.p, table_bytes / 32, n_loads / 8 + 1, 1, sink.p, (int)g_opt.bench_load_mode);  // warm-up
     KMB_CUDA(cudaEventRecord(e0));
-    fn<<<grid, threads_per_block>>>(table.p, table_bytes / 32, n_loads, 2, sink.p, (int)g_opt.bench_load_mode);
+    fn<<<grid, threads_per_block, smem>>>(table.p, table_bytes / 32, n_loads, 2, sink.p, (int)g_opt.bench_load_mode);
     KMB_CUDA(cudaEventRecord(e1));
     g_launches += 2;
     KMB_CUDA(cudaEventSynchronize(e1));

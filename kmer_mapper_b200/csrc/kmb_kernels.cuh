@@ -280,6 +280,92 @@ __global__ void kmb_mark_read_ends(const OffT *__restrict__ offsets, uint64_t n_
 }
 
 // ================================================================================================
+// K0 for the fused kernels: where reads begin and end, without a pass over the bases.
+//
+// The fused kernels work on tiles of 1024 window starts per warp.  A small table -- for every tile the last read
+// that starts at or before the tile's first position (one binary search per tile, kmb_tile_reads_kernel: 4 bytes
+// per 1024 bases) -- lets a warp load just the offsets of the handful of reads that touch its tile and mark the
+// last k-1 positions of each in a 1024-bit mask in shared memory.  This replaces the global read-boundary bitmask
+// of the first version (one bit per base: a 0.94 GB memset + an atomicOr kernel + a mask load per tile, for the
+// 7.5 G bases of the benchmark batch), and no malformed offset can make anyone write outside the tile's 32 words.
+// ================================================================================================
+struct KmbReads {
+    const void *offsets;        // n_reads + 1 values: int64 of the caller (base0 is subtracted) or uint32 chunk-relative
+    const uint32_t *tile_read;  // [n_tiles] see above
+    uint64_t n_reads;
+    int64_t base0;
+    uint32_t off32;             // offsets are uint32
+};
+__device__ __forceinline__ int64_t kmb_read_offset(const KmbReads &R, uint64_t r) {
+    return R.off32 ? (int64_t)reinterpret_cast<const uint32_t *>(R.offsets)[r]
+                   : reinterpret_cast<const int64_t *>(R.offsets)[r] - R.base0;
+}
+#define KMB_FLAG_BAD_OFFSETS 8u  // KmbStatus::index_flags: offsets not monotonic, or not covering [0, n_bases]
+__global__ void kmb_tile_reads_kernel(KmbReads R, uint64_t n_bases, uint64_t n_tiles, uint32_t *__restrict__ tile_read,
+                                      KmbStatus *status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && R.n_reads &&
+        (kmb_read_offset(R, 0) != 0 || kmb_read_offset(R, R.n_reads) != (int64_t)n_bases))
+        atomicOr(&status->index_flags, KMB_FLAG_BAD_OFFSETS);
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t t0 = (int64_t)(t * KMB_WTILE_POS);
+        uint64_t lo = 0, hi = R.n_reads;  // first read in [lo, hi) that starts after t0
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (kmb_read_offset(R, mid) <= t0) lo = mid + 1;
+            else hi = mid;
+        }
+        tile_read[t] = (uint32_t)(lo ? lo - 1 : 0);
+    }
+}
+// Valid window starts among this lane's 32 positions [t0 + 32 lane, +32) of tile `tile`.  Called by all 32 lanes;
+// tmask = 32 words of the warp's shared memory.
+__device__ __forceinline__ uint32_t kmb_tile_valid_starts(const KmbReads &R, uint64_t tile, uint64_t n_bases, int k,
+                                                          uint32_t *tmask, int lane, KmbStatus *status) {
+    const int64_t t0 = (int64_t)(tile * KMB_WTILE_POS), t1 = t0 + KMB_WTILE_POS;
+    tmask[lane] = 0u;
+    __syncwarp();
+    uint64_t r = R.tile_read[tile];
+#pragma unroll 1
+    for (;;) {
+        const uint64_t mine = r + (uint64_t)lane;
+        int64_t s = INT64_MAX, e = INT64_MAX;
+        if (mine < R.n_reads) {
+            s = kmb_read_offset(R, mine);
+            e = kmb_read_offset(R, mine + 1);
+            if (e < s) atomicOr(&status->index_flags, KMB_FLAG_BAD_OFFSETS);
+            // the last k-1 bases of the read (all of it if shorter) cannot start a window: [lo, hi) within the tile
+            int64_t lo = e - (int64_t)(k - 1);
+            if (lo < s) lo = s;
+            if (lo < t0) lo = t0;
+            const int64_t hi = e < t1 ? e : t1;
+            if (lo < hi) {
+                const uint32_t a = (uint32_t)(lo - t0), b = (uint32_t)(hi - 1 - t0);  // first and last bit, < 1024
+                const uint32_t wa = a >> 5, wb = b >> 5;
+                const uint32_t from_a = ~0u << (a & 31u), upto_b = ~0u >> (31u - (b & 31u));
+                if (wa == wb) {
+                    atomicOr(&tmask[wa], from_a & upto_b);
+                } else {  // k - 1 <= 30 bits, but a read shorter than k... no: at most k-1 bits, so at most two words
+                    atomicOr(&tmask[wa], from_a);
+                    for (uint32_t w = wa + 1; w < wb; w++) atomicOr(&tmask[w], ~0u);
+                    atomicOr(&tmask[wb], upto_b);
+                }
+            }
+        }
+        if (__shfl_sync(KMB_FULL_MASK, s, 31) >= t1) break;  // the next read starts beyond the tile (or there is none)
+        r += 32;
+    }
+    __syncwarp();
+    const uint64_t p0 = (uint64_t)t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
+    if (p0 >= n_bases) return 0u;
+    uint32_t valid = ~tmask[lane];
+    if (p0 + 32 + (uint64_t)k > n_bases + 1) {  // window must end inside the buffer: p + k <= n_bases
+        const int64_t last = (int64_t)n_bases - (int64_t)k - (int64_t)p0;  // last valid i
+        valid &= last < 0 ? 0u : (last >= 31 ? 0xFFFFFFFFu : ((1u << (last + 1)) - 1u));
+    }
+    return valid;
+}
+
+// ================================================================================================
 // The probe, shared by every mapping kernel.
 //
 // Level 0 (FILT): one or two bits of one filter word per query (kmb_filter_mask).  modulo/8 bytes
@@ -352,7 +438,6 @@ __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &
 // coalesced 128-byte store to the log; the space is reserved with one atomic per 32 hits or more.
 // ------------------------------------------------------------------------------------------------
 #define KMB_STAGE_SLOTS 96
-#define KMB_STAGE_SLOTS_SMALL 64
 #define KMB_LOG_HOLE 0xFFFFFFFFu
 #define KMB_LOG_NO_BIN 0xFFu
 #define KMB_RES_FULL 0xFFFFFFFFu
@@ -420,8 +505,7 @@ __device__ __forceinline__ void kmb_log_write(const KmbLog &log, uint32_t *count
     }
 }
 // The bins named in `ready` have something to send: full groups of 32, or (all = true, end of kernel) everything.
-// Out of line: the mapping kernels reach this from several places, and it runs once per 32 hits of a bin.
-__device__ __noinline__ void kmb_stage_send(KmbLog log, uint32_t *counts, KmbStage st, unsigned ready, uint32_t c, int lane, bool all) {
+__device__ __forceinline__ void kmb_stage_send(const KmbLog &log, uint32_t *counts, const KmbStage &st, unsigned ready, uint32_t c, int lane, bool all) {
     while (ready) {
         const int b = __ffs(ready) - 1;
         ready &= ready - 1u;
@@ -454,111 +538,60 @@ __device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The sector fetch pipeline.  A warp that has 32 candidates requests their 32 sectors (one DRAM
-// transaction each) and goes on with the next batch of windows; the keys are compared when the
-// sectors have had that long to arrive.
+// The sector fetch pipeline.  A warp that has 32 candidates requests their 32 sectors -- ONE 256-bit load per
+// lane, one DRAM transaction each -- at the top of a batch iteration, runs the batch's arithmetic and filter
+// loads, and compares the keys at the bottom of the same iteration.
 //
-// ASYNC = true (default): the sectors are copied into the warp's shared memory with cp.async (two slots of
-//   32 x 32 bytes); a batch requested in iteration i is compared in iteration i + 1.  Nothing is held in
-//   registers and, above all, nothing is tracked by the register scoreboard: with the sector in registers
-//   (the first version of this kernel) ptxas made every iteration of the batch loop begin with a wait for
-//   ALL outstanding loads (the loop header carried `wait=01245` in its control code; 19 % of the stall
-//   samples sat on that one instruction), so the fetch never overlapped the next batch's arithmetic.
-// ASYNC = false: the sector travels in registers, requested at the top of a batch iteration and compared
-//   at its bottom, so that no load is in flight across the loop's back edge.
+// Two things were measured on the way here (profiles/README.md, round 2):
+//  * With the consume step at the top of the NEXT iteration (round 1) ptxas made the loop header wait for every
+//    outstanding load (control code `wait=01245` on its first instruction: 19 % of all stall samples), because the
+//    load was in flight across the loop's back edge.  Requesting and comparing inside one iteration avoids that.
+//  * cp.async (LDGSTS) into shared memory instead of registers -- which would let a batch stay in flight across
+//    iterations -- is NOT an option for scattered sectors: per-lane scattered 16-byte cp.async cost ~3.5 LSU cycles
+//    per lane and block the other loads meanwhile; the kernel took 74 ms instead of 47 ms whether the copy was
+//    consumed one iteration later or in the same one, at 2, 3 or 4 CTAs per SM alike.
+// A sector that is full and chained does not make anyone wait either: (k-mer, next sector) goes back onto the
+// candidate stack (overflow sectors live in the same array, same layout) and is fetched with a later batch.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void kmb_cp_async_sector(uint32_t *smem_dst, const uint32_t *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
     asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 16u), "l"(gmem_src + 4) : "memory");
 }
-__device__ __forceinline__ void kmb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void kmb_cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ void kmb_cp_async_wait_all() {
-    kmb_cp_async_commit();
-    kmb_cp_async_wait<0>();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-#define KMB_SECT_SLOT_WORDS (2 * 32 * KMB_LINE_WORDS)  // per warp: two batches of 32 sectors
-template <bool ASYNC>
-struct KmbPipe;
-template <>
-struct KmbPipe<false> {
-    uint32_t r[8];  // the candidate's main sector, in flight between issue and consume
+struct KmbPipe {
+    uint32_t r[8];  // the candidate's sector, in flight between issue and consume
     uint64_t km;
-    unsigned issued;  // candidates of this warp so far (warp-uniform)
+    unsigned issued;  // sector fetches of this warp so far (warp-uniform)
     bool valid;
 };
-template <>
-struct KmbPipe<true> {
-    uint32_t *slots;          // [2][32][8] words of this warp's shared memory
-    uint64_t km_new, km_old;  // the candidate whose sector this lane requested in this / the previous round
-    unsigned issued;
-    int buf;                  // slot the next request goes to (warp-uniform)
-    bool valid_new, valid_old;
-};
-__device__ __forceinline__ void kmb_pipe_init(KmbPipe<false> &pp, uint32_t *) {
+__device__ __forceinline__ void kmb_pipe_init(KmbPipe &pp) {
     pp.valid = false;
     pp.issued = 0;
     pp.km = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) pp.r[i] = 0;
 }
-__device__ __forceinline__ void kmb_pipe_init(KmbPipe<true> &pp, uint32_t *slots) {
-    pp.slots = slots;
-    pp.km_new = pp.km_old = 0;
-    pp.issued = 0;
-    pp.buf = 0;
-    pp.valid_new = pp.valid_old = false;
-}
 // Request the sectors of candidates [base, base + cnt) of the warp's stack, one per lane.  Called by all lanes.
-__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &pol, KmbPipe<false> &pp, const uint64_t *q_kmer,
+__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const uint64_t *q_kmer,
                                                const uint32_t *q_h, int base, int cnt, int lane) {
     pp.issued += (unsigned)cnt;
     if (lane < cnt && !(P.policies & 0x200u)) {
         pp.km = q_kmer[base + lane];
-        KMB_BOUND(1, q_h[base + lane], P.addr.n_main);
+        KMB_BOUND(1, q_h[base + lane], P.n_lines);
         kmb_ld_sector(P.lines + (uint64_t)q_h[base + lane] * KMB_LINE_WORDS, pp.r, pol.line);
         pp.valid = true;
     }
 }
-__device__ __forceinline__ void kmb_pipe_issue(const KmbProbe &P, const KmbPol &, KmbPipe<true> &pp, const uint64_t *q_kmer,
-                                               const uint32_t *q_h, int base, int cnt, int lane) {
-    pp.issued += (unsigned)cnt;
-    if (lane < cnt && !(P.policies & 0x200u)) {
-        pp.km_new = q_kmer[base + lane];
-        KMB_BOUND(1, q_h[base + lane], P.addr.n_main);
-        kmb_cp_async_sector(pp.slots + (pp.buf * 32 + lane) * KMB_LINE_WORDS, P.lines + (uint64_t)q_h[base + lane] * KMB_LINE_WORDS);
-        pp.valid_new = true;
-    }
-    kmb_cp_async_commit();
-}
-// The overflow sectors behind a full main sector (0.8 % of them): walked synchronously, hits straight onto the
-// counts.  Out of line, to keep the rare path out of the hot loop's instruction stream.
-__device__ __forceinline__ unsigned kmb_chain_count(const uint32_t *__restrict__ lines, uint64_t pol_line, uint64_t km, uint32_t hdr,
-                                                 int32_t max_freq, uint32_t *counts) {
-    unsigned counted = 0;
-    while (hdr & KMB_HDR_CHAIN) {
-        uint32_t r[8];
-        kmb_ld_sector(lines + (uint64_t)(hdr & ~KMB_HDR_CHAIN) * KMB_LINE_WORDS, r, pol_line);
-        kmb_match_sector(r, km, [&](uint32_t node, uint32_t freq) {
-            if ((int32_t)freq <= max_freq) {
-                kmb_count_direct(counts, node);
-                counted++;
-            }
-            return false;
-        });
-        hdr = r[0];
-    }
-    return counted;
-}
-// Compare a sector that has arrived with its candidate, stage the hits.  The rare chain behind a full sector is
-// walked synchronously and its hits go straight onto the counts.
-__device__ __forceinline__ void kmb_pipe_match(const KmbProbe &P, const KmbPol &pol, const KmbStage &st, const uint32_t (&r)[8],
-                                               uint64_t km, unsigned &counted) {
+// Compare a sector that has arrived with its candidate, stage the hits.  Returns the next sector of the chain
+// when this one is full and chained (0.8 % of the main sectors, but 3 % of the candidates: a sector that holds
+// the key one is looking for is more likely to be a crowded one), else 0.
+__device__ __forceinline__ uint32_t kmb_pipe_match(const KmbProbe &P, const KmbStage &st, const uint32_t (&r)[8],
+                                                   uint64_t km, unsigned &counted) {
     const int32_t max_freq = P.max_freq;
     const bool no_emit = (P.policies & 0x100u) != 0u;
     kmb_match_sector(r, km, [&](uint32_t node, uint32_t freq) {
@@ -568,59 +601,47 @@ __device__ __forceinline__ void kmb_pipe_match(const KmbProbe &P, const KmbPol &
         }
         return false;
     });
-    if (r[0] & KMB_HDR_CHAIN) counted += kmb_chain_count(P.lines, pol.line, km, r[0], max_freq, P.counts);
+    return (r[0] & KMB_HDR_CHAIN) ? (r[0] & ~KMB_HDR_CHAIN) : 0u;
 }
-// Called by all 32 lanes.  Register version: the batch requested by the last kmb_pipe_issue.
-__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe<false> &pp, const KmbStage &st,
-                                                 unsigned &counted, int lane) {
+// Called by all 32 lanes: compare the batch requested by the last kmb_pipe_issue; chain continuations go back
+// onto the stack.
+__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, KmbPipe &pp, const KmbStage &st, unsigned &counted,
+                                                 uint64_t *q_kmer, uint32_t *q_h, int &qcount, int lane) {
     if (!__any_sync(KMB_FULL_MASK, pp.valid)) return;
+    uint32_t next = 0;
     if (pp.valid) {
         pp.valid = false;
-        kmb_pipe_match(P, pol, st, pp.r, pp.km, counted);
+        next = kmb_pipe_match(P, st, pp.r, pp.km, counted);
+    }
+    const unsigned m = __ballot_sync(KMB_FULL_MASK, next != 0u);
+    if (m) {
+        if (next != 0u) {
+            const int slot = qcount + __popc(m & ((1u << lane) - 1u));
+            q_kmer[slot] = pp.km;
+            q_h[slot] = next;
+        }
+        qcount += __popc(m);
+        __syncwarp();
     }
     kmb_stage_flush(P, st, lane, false);
-}
-// Asynchronous version: wait until at most the newest request group is still on its way, compare the batch
-// before it, and make the newest the next one to be compared.
-__device__ __forceinline__ void kmb_pipe_consume(const KmbProbe &P, const KmbPol &pol, KmbPipe<true> &pp, const KmbStage &st,
-                                                 unsigned &counted, int lane) {
-    kmb_cp_async_wait<1>();
-    if (__any_sync(KMB_FULL_MASK, pp.valid_old)) {
-        if (pp.valid_old) {
-            const uint32_t *sp = pp.slots + ((pp.buf ^ 1) * 32 + lane) * KMB_LINE_WORDS;
-            const uint4 x = *reinterpret_cast<const uint4 *>(sp);
-            const uint4 y = *reinterpret_cast<const uint4 *>(sp + 4);
-            const uint32_t r[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-            kmb_pipe_match(P, pol, st, r, pp.km_old, counted);
-        }
-        kmb_stage_flush(P, st, lane, false);
-    }
-    pp.km_old = pp.km_new;
-    pp.valid_old = pp.valid_new;
-    pp.valid_new = false;
-    pp.buf ^= 1;
 }
 
 // Level 0 for U queries of this lane (all filter loads in flight together).  kf(u) yields query u; bit u of
 // vbits says whether query u exists.  Order of one batch:
 //   0. request the sectors of 32 candidates that earlier batches left on the stack;
 //   1. kmb_locate + the U filter loads of this batch;
-//   2. (ASYNC) compare the sectors requested one batch ago -- between the issue of the filter loads and
-//      their first use;
-//   3. test the filter words; survivors go onto the warp's stack (one inclusive scan of the per-lane
+//   2. test the filter words; survivors go onto the warp's stack (one inclusive scan of the per-lane
 //      survivor counts gives every lane its first slot);
-//   4. (registers) compare the sectors requested in step 0;
-//   5. if two or more batches of candidates are still waiting (thin or no filter), fetch them now.
+//   3. compare the sectors requested in step 0 (they have had steps 1-2 to arrive);
+//   4. if two or more batches of candidates are still waiting (thin or no filter), fetch them now.
 // The stack holds < 64 entries on entry and on exit, so KMB_QUEUE_SLOTS >= 32 * (U + 2).
-template <int U, bool FILT, bool ASYNC, class KF>
-__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe<ASYNC> &pp, const KmbStage &st,
+template <int U, bool FILT, class KF>
+__device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
                                                 unsigned &counted, const KF &kf, uint32_t vbits, uint64_t *q_kmer,
                                                 uint32_t *q_h, int &qcount, int lane) {
     if (qcount >= 32) {
         qcount -= 32;
         kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, 32, lane);
-    } else if (ASYNC) {
-        kmb_cp_async_commit();  // one request group per batch, empty or not: the consume step counts groups
     }
     uint64_t km[U];    // the queries (kept: recomputing them for the push cost more than the registers)
     uint32_t hh[U];    // main sector of the query
@@ -641,7 +662,6 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
             fw[u] = 1u;
         }
     }
-    if (ASYNC) kmb_pipe_consume(P, pol, pp, st, counted, lane);
     uint32_t cmask = 0;
 #pragma unroll
     for (int u = 0; u < U; u++) cmask |= (need[u] != 0u && (fw[u] & need[u]) == need[u]) ? (1u << u) : 0u;
@@ -664,20 +684,20 @@ __device__ __forceinline__ void kmb_probe_batch(const KmbProbe &P, const KmbPol 
         }
     }
     __syncwarp();
-    if (!ASYNC) kmb_pipe_consume(P, pol, pp, st, counted, lane);
+    kmb_pipe_consume(P, pp, st, counted, q_kmer, q_h, qcount, lane);
 #pragma unroll 1
     while (qcount >= 64) {
         qcount -= 32;
         kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, 32, lane);
-        kmb_pipe_consume(P, pol, pp, st, counted, lane);  // ASYNC: the batch before the one just requested
+        kmb_pipe_consume(P, pp, st, counted, q_kmer, q_h, qcount, lane);
     }
     __syncwarp();
 }
 
-// End of kernel: retire the outstanding batches, then what is left on the stack, then the staged hits and the statistics.
-template <bool ASYNC>
-__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe<ASYNC> &pp, const KmbStage &st,
-                                                unsigned &counted, const uint64_t *q_kmer, const uint32_t *q_h, int qcount,
+// End of kernel: what is left on the stack (a consume step may put chain continuations back: go on until it is
+// empty), then the staged hits and the statistics.
+__device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol &pol, KmbPipe &pp, const KmbStage &st,
+                                                unsigned &counted, uint64_t *q_kmer, uint32_t *q_h, int qcount,
                                                 int lane, KmbStatus *status) {
     __syncwarp();
 #pragma unroll 1
@@ -685,13 +705,7 @@ __device__ __forceinline__ void kmb_pipe_finish(const KmbProbe &P, const KmbPol 
         const int n = min(qcount, 32);
         qcount -= n;
         kmb_pipe_issue(P, pol, pp, q_kmer, q_h, qcount, n, lane);
-        kmb_pipe_consume(P, pol, pp, st, counted, lane);
-    }
-    if (ASYNC) {  // the newest request, if any, is still on its way
-        kmb_cp_async_commit();
-        kmb_pipe_consume(P, pol, pp, st, counted, lane);
-        kmb_cp_async_commit();
-        kmb_pipe_consume(P, pol, pp, st, counted, lane);
+        kmb_pipe_consume(P, pp, st, counted, q_kmer, q_h, qcount, lane);
     }
     kmb_stage_flush(P, st, lane, true);
     for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(KMB_FULL_MASK, counted, o);
@@ -778,30 +792,24 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
     return valid;
 }
 
-// Per-warp shared memory of the key-addressed mapping kernels (dynamic: with ASYNC the CTA needs more than the
-// 48 KB a static allocation may have).  ASYNC: 6.8 KB per warp = 54.4 KB per CTA, four CTAs per SM.
-template <int U, bool ASYNC>
+// Per-warp shared memory of the key-addressed mapping kernels: 5.9 KB per warp = 47 KB per CTA, three CTAs per SM.
+template <int U>
 struct alignas(16) KmbWarpShared {
-    static constexpr int kStageSlots = ASYNC ? KMB_STAGE_SLOTS_SMALL : KMB_STAGE_SLOTS;
-    uint32_t sect[ASYNC ? KMB_SECT_SLOT_WORDS : 4];       // sectors on their way (cp.async), 32-byte slots
+    static constexpr int kStageSlots = KMB_STAGE_SLOTS;
     uint64_t qk[KMB_QUEUE_SLOTS(U)];                      // candidate stack: k-mer
     unsigned long long stage_res[KMB_LOG_BINS];
     uint32_t qh[KMB_QUEUE_SLOTS(U)];                      //                  its sector
     uint32_t pack[KMB_WTILE_POS / 16 + 4];                // the tile's packed 2-bit stream: 64 words + halo
+    uint32_t tmask[32];                                   // the tile's 1024 "no window starts here" bits
     uint32_t stage[KMB_LOG_BINS * kStageSlots];           // staged hits per node range
     uint32_t stage_cnt[2 * KMB_LOG_BINS];
 };
-#define KMB_MAP_SMEM_BYTES(U, ASYNC) ((KMB_TILE_THREADS / 32) * sizeof(KmbWarpShared<U, ASYNC>))
-// Resident CTAs per SM.  Registers in flight were what held the first version at three (85 registers: at 64 the
-// sector between issue and consume was spilled); with the sectors in shared memory four CTAs = 32 warps fit.
-#ifndef KMB_MAP_MIN_BLOCKS_ASYNC
-#define KMB_MAP_MIN_BLOCKS_ASYNC 4
-#endif
+#define KMB_MAP_SMEM_BYTES(U) ((KMB_TILE_THREADS / 32) * sizeof(KmbWarpShared<U>))
 
-template <int U, bool FILT, bool REVCOMP, bool ASYNC>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, ASYNC ? KMB_MAP_MIN_BLOCKS_ASYNC : KMB_MAP_MIN_BLOCKS)
+template <int U, bool FILT, bool REVCOMP>
+__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
-                     const uint32_t *__restrict__ mask, int k, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
+                     KmbReads R, int k, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
     const bool n_to_a = (in_mode & KMB_IN_N_TO_A) != 0u;
     // packed transport (host input, kmb_hostpack.cpp): `bases` holds the 2-bit stream already, validated on the host
     const bool packed = (in_mode & KMB_IN_PACKED) != 0u;
@@ -812,16 +820,16 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     extern __shared__ __align__(16) unsigned char kmb_map_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    KmbWarpShared<U, ASYNC> &S = reinterpret_cast<KmbWarpShared<U, ASYNC> *>(kmb_map_smem)[warp];
+    KmbWarpShared<U> &S = reinterpret_cast<KmbWarpShared<U> *>(kmb_map_smem)[warp];
     uint32_t *pack = S.pack;
     uint64_t *q_kmer = S.qk;
     uint32_t *q_h = S.qh;
-    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U, ASYNC>::kStageSlots};
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
-    KmbPipe<ASYNC> pp;
-    kmb_pipe_init(pp, S.sect);
+    KmbPipe pp;
+    kmb_pipe_init(pp);
     const KmbPol pol = kmb_make_policies(P.policies);
     const uint64_t kmask = kmb_kmer_mask(k);
     const uint64_t n_tiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
@@ -848,8 +856,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
         }
         __syncwarp();
         // ---- 2. this lane's 32 positions
-        const uint64_t p0 = t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
-        const uint32_t valid = kmb_valid_starts(mask, p0, n_bases, k);
+        const uint32_t valid = kmb_tile_valid_starts(R, tile, n_bases, k, S.tmask, lane, status);
         mapped += __popc(valid);
         const uint2 a = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
         const uint2 b = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
@@ -859,10 +866,10 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             const uint32_t vb = (valid >> b0) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
             if (!__any_sync(KMB_FULL_MASK, vb != 0u)) continue;
             const KmbWindowFn fw(a.x, a.y, b.x, b.y, b0, kmask);
-            kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, fw, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fw, vb, q_kmer, q_h, qcount, lane);
             if (REVCOMP) {
                 const KmbRcWindowFn rc = {fw, k};
-                kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, rc, vb, q_kmer, q_h, qcount, lane);
+                kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, rc, vb, q_kmer, q_h, qcount, lane);
             }
         }
     }
@@ -1141,7 +1148,7 @@ __device__ __forceinline__ void kmb_mz_late_drain(const KmbProbe &P, const KmbPo
 template <bool FILT>
 __global__ void __launch_bounds__(KMB_MZ_THREADS, 7)
 kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
-                        const uint32_t *__restrict__ mask, uint32_t in_mode, KmbProbe P, KmbProbe Pkey, KmbStatus *status) {
+                        KmbReads R, uint32_t in_mode, KmbProbe P, KmbProbe Pkey, KmbStatus *status) {
     extern __shared__ __align__(16) unsigned char kmb_mz_smem[];
     KmbMzShared &S = reinterpret_cast<KmbMzShared *>(kmb_mz_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -1183,10 +1190,10 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
         if (lane < 2) pack[KMB_WTILE_POS / 16 + 2 + lane] = 0u;  // read (not used) by the window extraction of the last positions
         __syncwarp();
         // ---- 2. this lane's 32 windows: which exist, where their minimizers sit, where runs start
-        const uint64_t p0 = t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
-        const uint32_t valid = kmb_valid_starts(mask, p0, n_bases, k);
+        const uint32_t valid = kmb_tile_valid_starts(R, tile, n_bases, k, S.valid, lane, status);
         mapped += __popc(valid);
         if (!__any_sync(KMB_FULL_MASK, valid != 0u)) continue;
+        __syncwarp();
         S.valid[lane] = valid;
         uint32_t startbits = 0;
         {
@@ -1295,11 +1302,38 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             const unsigned n_have = n_kept;
             const unsigned n_staged = min(n_have, (unsigned)KMB_MZ_SLOTS);
             fetched += n_have;
+#ifdef KMB_MZ_CP_ASYNC
             for (unsigned sl = (unsigned)lane; sl < n_staged; sl += 32u) {
                 KMB_BOUND(1, S.kept_sector[sl], 2ull * P.addr.n_main);
                 kmb_cp_async_sector(S.a.slots[sl], P.lines + (uint64_t)S.kept_sector[sl] * KMB_LINE_WORDS);
             }
             kmb_cp_async_wait_all();
+#else
+            // One 256-bit load per sector into registers, two sectors per lane in flight, then into the staging slots.
+            // (Round 1 used cp.async here; scattered 16-byte cp.async turned out to cost ~3.5 LSU cycles per lane and to
+            // hold up every other load meanwhile -- profiles/README.md, round 2.)
+#pragma unroll 1
+            for (unsigned base = 0; base < n_staged; base += 64u) {
+                const unsigned s0 = base + (unsigned)lane, s1 = s0 + 32u;
+                uint32_t r0[8], r1[8];
+                if (s0 < n_staged) {
+                    KMB_BOUND(1, S.kept_sector[s0], 2ull * P.addr.n_main);
+                    kmb_ld_sector(P.lines + (uint64_t)S.kept_sector[s0] * KMB_LINE_WORDS, r0, pol.line);
+                }
+                if (s1 < n_staged) {
+                    KMB_BOUND(1, S.kept_sector[s1], 2ull * P.addr.n_main);
+                    kmb_ld_sector(P.lines + (uint64_t)S.kept_sector[s1] * KMB_LINE_WORDS, r1, pol.line);
+                }
+                if (s0 < n_staged) {
+                    *reinterpret_cast<uint4 *>(&S.a.slots[s0][0]) = make_uint4(r0[0], r0[1], r0[2], r0[3]);
+                    *reinterpret_cast<uint4 *>(&S.a.slots[s0][4]) = make_uint4(r0[4], r0[5], r0[6], r0[7]);
+                }
+                if (s1 < n_staged) {
+                    *reinterpret_cast<uint4 *>(&S.a.slots[s1][0]) = make_uint4(r1[0], r1[1], r1[2], r1[3]);
+                    *reinterpret_cast<uint4 *>(&S.a.slots[s1][4]) = make_uint4(r1[4], r1[5], r1[6], r1[7]);
+                }
+            }
+#endif
             __syncwarp();
             {
                 unsigned n2 = 0;
@@ -1313,7 +1347,14 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                         if (more) {
                             const unsigned j = n2 + __popc(m & lanemask_lt);
                             if (j < KMB_MZ_SLOTS2) {
+#ifdef KMB_MZ_CP_ASYNC
                                 kmb_cp_async_sector(S.slots2[j], P.lines + (uint64_t)(S.kept_sector[sl] + 1u) * KMB_LINE_WORDS);
+#else
+                                uint32_t r2[8];  // the other half of the 64 bytes the primary's fetch brought into the L2
+                                kmb_ld_sector(P.lines + (uint64_t)(S.kept_sector[sl] + 1u) * KMB_LINE_WORDS, r2, pol.line);
+                                *reinterpret_cast<uint4 *>(&S.slots2[j][0]) = make_uint4(r2[0], r2[1], r2[2], r2[3]);
+                                *reinterpret_cast<uint4 *>(&S.slots2[j][4]) = make_uint4(r2[4], r2[5], r2[6], r2[7]);
+#endif
                                 tag = (uint8_t)j;
                             } else {
                                 tag = KMB_MZ_LATE;
@@ -1323,7 +1364,9 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                     }
                     n2 += __popc(m);
                 }
+#ifdef KMB_MZ_CP_ASYNC
                 if (n2) kmb_cp_async_wait_all();
+#endif
             }
             __syncwarp();
             // ---- 5. 32 kept runs per round, one per lane; per entry of the run's bucket the one window that could match
@@ -1411,22 +1454,22 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
 // K3-4 on ready-made k-mers (drop-in for map_kmers_to_graph_index, mapper.pyx:19-72).
 // Coalesced 8-byte loads, U filter loads in flight per thread, same probe.
 // ================================================================================================
-template <int U, bool FILT, bool REVCOMP, bool ASYNC>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, ASYNC ? KMB_MAP_MIN_BLOCKS_ASYNC : KMB_MAP_MIN_BLOCKS)
+template <int U, bool FILT, bool REVCOMP>
+__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
     extern __shared__ __align__(16) unsigned char kmb_map_smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    KmbWarpShared<U, ASYNC> &S = reinterpret_cast<KmbWarpShared<U, ASYNC> *>(kmb_map_smem)[warp];
+    KmbWarpShared<U> &S = reinterpret_cast<KmbWarpShared<U> *>(kmb_map_smem)[warp];
     uint64_t *q_kmer = S.qk;
     uint32_t *q_h = S.qh;
-    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U, ASYNC>::kStageSlots};
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
-    KmbPipe<ASYNC> pp;
-    kmb_pipe_init(pp, S.sect);
+    KmbPipe pp;
+    kmb_pipe_init(pp);
     const KmbPol pol = kmb_make_policies(P.policies);
     const uint64_t per_block = (uint64_t)KMB_TILE_THREADS * U;
     const uint64_t n_blocks = (n + per_block - 1) / per_block;
@@ -1443,11 +1486,11 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
             vb |= in ? (1u << u) : 0u;
         }
         KmbArrayFn fa = {km};
-        kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
+        kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
         if (REVCOMP) {
 #pragma unroll
             for (int u = 0; u < U; u++) km[u] = kmb_revcomp(km[u], k);
-            kmb_probe_batch<U, FILT, ASYNC>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
+            kmb_probe_batch<U, FILT>(P, pol, pp, st, counted, fa, vb, q_kmer, q_h, qcount, lane);
         }
     }
     kmb_pipe_finish(P, pol, pp, st, counted, q_kmer, q_h, qcount, lane, status);
@@ -1809,6 +1852,38 @@ __device__ __forceinline__ uint64_t kmb_ldg_u64_mode(const uint64_t *p, int mode
     return v;
 }
 
+// The same gather through cp.async: every thread copies UNROLL random 32-byte sectors into its own shared-memory slots
+// (two 16-byte cp.async each, as the mapping kernels would), waits for the group and reads one word of each back.
+// mode 6: plain; mode 7: with the L2::64B prefetch qualifier.  Measures what rate of random fetches LDGSTS sustains.
+template <int UNROLL>
+__global__ void kmb_gather_async_bench_kernel(const uint8_t *__restrict__ table, uint64_t n_sectors, uint64_t n_loads,
+                                              uint64_t seed, uint64_t *sink, int mode) {
+    extern __shared__ __align__(16) unsigned char kmb_ga_smem[];
+    uint32_t *slots = reinterpret_cast<uint32_t *>(kmb_ga_smem) + (size_t)threadIdx.x * UNROLL * 8;
+    uint64_t acc = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_loads; i += stride * UNROLL) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const uint64_t r = kmb_mix64((i + (uint64_t)u * stride) ^ seed);
+            const uint8_t *p = table + kmb_umulhi64(r, n_sectors) * 32;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(slots + u * 8);
+            if (mode == 7) {
+                asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(p) : "memory");
+                asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d + 16u), "l"(p + 16) : "memory");
+            } else {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(p) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u), "l"(p + 16) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) acc ^= slots[u * 8];
+    }
+    if (acc == 0x123456789ABCDEFull) *sink = acc;
+}
+
 template <int W, int UNROLL>
 __global__ void kmb_gather_bench_kernel(const uint8_t *__restrict__ table, uint64_t n_sectors, uint64_t n_loads,
                                         uint64_t seed, uint64_t *sink, int mode) {
@@ -1827,6 +1902,10 @@ __global__ void kmb_gather_bench_kernel(const uint8_t *__restrict__ table, uint6
             } else if (W == 16) {
                 uint4 t = kmb_ldg_v4_nc(p);
                 v[u] = (uint64_t)t.x ^ ((uint64_t)t.y << 32) ^ t.z ^ ((uint64_t)t.w << 32);
+            } else if (mode == 8) {  // one 256-bit load per sector (kmb_ld_sector: what the mapping kernels issue)
+                uint32_t r8[8];
+                kmb_ld_sector(reinterpret_cast<const uint32_t *>(p), r8, kmb_policy_evict_normal());
+                v[u] = (uint64_t)r8[0] ^ ((uint64_t)r8[1] << 32) ^ r8[2] ^ ((uint64_t)r8[3] << 32) ^ r8[4] ^ ((uint64_t)r8[5] << 32) ^ r8[6] ^ r8[7];
             } else {
                 uint4 t0 = kmb_ldg_v4_nc(p), t1 = kmb_ldg_v4_nc(p + 16);
                 v[u] = (uint64_t)t0.x ^ ((uint64_t)t0.y << 32) ^ t0.z ^ ((uint64_t)t0.w << 32) ^ t1.x ^

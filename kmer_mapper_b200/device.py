@@ -203,6 +203,12 @@ class Mapper:
         check(lib().kmb_mapper_lookup_counts(self._h, p, n, out.ctypes.data))
         return out
 
+    def write_counts(self, values):
+        """Replace the counts (``counter._values = ...``, command_line_interface.py:136)."""
+        keep, p, n = as_buffer(values, np.uint32, "values")
+        _order_after_torch(values, same_stream=self._stream)
+        check(lib().kmb_mapper_write_counts(self._h, p, n))
+
     def reset(self):
         check(lib().kmb_mapper_reset(self._h))
 

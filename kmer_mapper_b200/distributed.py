@@ -74,6 +74,45 @@ def chunk_belongs_to_rank(chunk_index: int, rank: int, world_size: int) -> bool:
     return chunk_index % world_size == rank
 
 
+class Comm:
+    """The job's NCCL communicator behind the C ABI (``kmb_comm_*``, include/kmer_mapper_b200.h): what sums the
+    per-GPU count arrays in place of the reference's additive map-reduce (command_line_interface.py:124-130).
+    The 128-byte NCCL id is made by rank 0 and handed to the other ranks through the torch.distributed
+    rendezvous that torchrun already set up (control plane only: the reduction itself is one ncclAllReduce on
+    the mapper's stream, issued by the library)."""
+
+    def __init__(self, device=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        rank, world_size, local_rank = world()
+        self.rank, self.world_size = rank, world_size
+        self.device = local_rank if device is None else int(device)
+        ident = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+        if rank == 0:
+            _lib.check(_lib.lib().kmb_comm_unique_id(ident))
+        if world_size > 1:
+            if not dist.is_initialized():
+                raise RuntimeError("Comm needs the torch.distributed process group (distributed.init_process_group)")
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=0)
+            ident = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(box[0])
+        h = C.c_void_p()
+        _lib.check(_lib.lib().kmb_comm_init_rank(self.device, world_size, rank, ident, C.byref(h)))
+        self._h = h
+        import weakref
+        self._finalizer = weakref.finalize(self, _lib.lib().kmb_comm_destroy, h)
+
+    def all_reduce(self, mapper):
+        """Queue hit log -> counts and the in-place sum over the ranks on the mapper's stream (no host wait)."""
+        from . import _lib
+        _lib.check(_lib.lib().kmb_mapper_allreduce(mapper._h, self._h))
+
+    def close(self):
+        self._finalizer()
+
+
 def all_reduce_counts(counts):
     """In-place sum over ranks of a uint32 count array: a torch tensor (CUDA -> NCCL, CPU -> gloo) or
     a numpy array (gloo).  Returns the reduced array (same object for tensors)."""

@@ -44,6 +44,25 @@ class ACTGTwoBitEncoding:
     letters = ["A", "C", "T", "G"]
     bitcodes = ["00", "01", "10", "11"]
     reverse = np.array([1, 3, 20, 7], dtype=np.uint8)
+    # The helper tables and classmethods of encodings.py:30-42 (API surface only: from_bytes above does the same
+    # work in one kernel and does not go through them).  Built with an int64 index: the reference's own
+    # ``256*reverse[...]`` overflows uint8 under numpy >= 2 (encodings.py:31).
+    _lookup_2bytes_to_4bits = np.zeros(256 * 256, dtype=np.uint8)
+    _lookup_2bytes_to_4bits[256 * reverse.astype(np.int64)[np.arange(4)[:, None]] + reverse[np.arange(4)]] = \
+        np.arange(4)[:, None] * 4 + np.arange(4)
+    _shift_4bits = (4 * np.arange(2, dtype=np.uint8))
+    _shift_2bits = 2 * np.arange(4, dtype=np.uint8)
+
+    @classmethod
+    def convert_2bytes_to_4bits(cls, two_bytes):
+        """encodings.py:36-38: an aligned pair of (``& 31``-masked) bases as one uint16 -> its 4-bit code."""
+        assert two_bytes.dtype == np.uint16, two_bytes.dtype
+        return cls._lookup_2bytes_to_4bits[two_bytes]
+
+    @classmethod
+    def join_4bits_to_byte(cls, four_bits):
+        """encodings.py:40-42: rows of two 4-bit codes -> one byte each, first code in the low nibble."""
+        return np.bitwise_or.reduce(four_bits << cls._shift_4bits, axis=1)
 
     @classmethod
     def complement(cls, char):
@@ -88,6 +107,25 @@ class ACTGTwoBitEncoding:
 
 
 class SimpleEncoding(ACTGTwoBitEncoding):
+    # helper table and classmethods of encodings.py:79-93 (API surface; from_bytes is one kernel)
+    _lookup_byte_to_2bits = np.zeros(256, dtype=np.uint8)
+    _lookup_byte_to_2bits[[97, 65]] = 0
+    _lookup_byte_to_2bits[[99, 67]] = 1
+    _lookup_byte_to_2bits[[116, 84]] = 2
+    _lookup_byte_to_2bits[[103, 71]] = 3
+    _shift_2bits = 2 * np.arange(4, dtype=np.uint8)
+
+    @classmethod
+    def convert_byte_to_2bits(cls, one_byte):
+        """encodings.py:85-88."""
+        assert one_byte.dtype == np.uint8, one_byte.dtype
+        return cls._lookup_byte_to_2bits[one_byte]
+
+    @classmethod
+    def join_2bits_to_byte(cls, two_bits_vector):
+        """encodings.py:90-92: rows of four 2-bit codes -> one byte each, first code in the low bits."""
+        return np.bitwise_or.reduce(two_bits_vector << cls._shift_2bits, axis=-1)
+
     @classmethod
     def from_bytes(cls, sequence):
         """encodings.py:96-102: per-byte table a/A,c/C,t/T,g/G -> 0,1,2,3, anything else -> 0."""

@@ -38,11 +38,32 @@ class _KeyCounter:
         # every key has frequency 1, so no cut-off ever applies: the counter counts all occurrences
         self._mapper = Mapper(self._index, n_counts=max(n, 1), max_index_lookup_frequency=65535)
 
+        self._n_keys = n
+
+    @property
+    def n_keys(self) -> int:
+        return self._n_keys
+
     def count(self, kmers, count_revcomps=False, k=31):
         self._mapper.map_kmers(kmers, revcomp=bool(count_revcomps), k=k)
 
+    def count_reads(self, bases, offsets, k, count_revcomps=False):
+        """The same from raw reads (N -> A, 2-bit, rolling k-mers fused into the counting kernel): no hash array."""
+        self._mapper.map_reads(bases, offsets, k, revcomp=bool(count_revcomps), n_to_a=True)
+
     def __getitem__(self, keys):
         return self._mapper.lookup_counts(np.ascontiguousarray(keys, dtype=np.uint64))
+
+    # ``counter._values``: the per-unique-key counts, in key order (command_line_interface.py:48,119,136)
+    @property
+    def _values(self):
+        return self._mapper.counts()[:self._n_keys]
+
+    @_values.setter
+    def _values(self, values):
+        v = np.zeros(self._mapper.n_counts, dtype=np.uint32)
+        v[:self._n_keys] = np.asarray(values, dtype=np.uint32)
+        self._mapper.write_counts(v)
 
 
 class GpuCounter:

@@ -91,7 +91,10 @@ class KmerIndex:
         path = file_name
         if not os.path.exists(path) and os.path.exists(str(file_name) + ".npz"):
             path = str(file_name) + ".npz"
-        data = np.load(path, allow_pickle=True)
+        # allow_pickle stays off: an archive is user input (-i), and unpickling runs arbitrary code.  The only
+        # pickled members graph_kmer_index writes are None-valued optional entries (ref_offsets, allele_frequencies
+        # saved as object arrays): those fail to load without pickle and are treated as absent.
+        data = np.load(path, allow_pickle=False)
         missing = [k for k in REQUIRED_KEYS if k not in data.files]
         if missing:
             raise KeyError("%s is not a KmerIndex archive: missing key(s) %s (has %s)" % (path, missing, data.files))
@@ -99,8 +102,10 @@ class KmerIndex:
         def opt(key):
             if key not in data.files:
                 return None
-            v = data[key]
-            return None if v.dtype == object and v.shape == () and v.item() is None else v
+            try:
+                return data[key]
+            except ValueError:      # an object array (a pickled None): absent
+                return None
 
         idx = cls(data["hashes_to_index"], data["n_kmers"], data["nodes"], opt("ref_offsets"), data["kmers"],
                   int(data["modulo"]), opt("frequencies"), opt("allele_frequencies"))

@@ -109,11 +109,17 @@ class ParallelGzip:
     """
 
     HEADROOM = 1 << 20   # free bytes in front of every block: the consumer puts its carried-over partial record there
+    # Capacity of one inflate call.  The blocks handed out end where the next member no longer fits, so their
+    # boundaries are a function of this number and the file alone -- NOT of the thread count: the ranks of a
+    # multi-GPU job take every world_size-th block, and ranks with different CPU shares must cut the stream at
+    # the same places (a capacity that grew with n_threads made two ranks with 2 and 12 threads drop or double reads).
+    BATCH_BYTES = 256 << 20
+    MAX_MEMBER_BYTES = 64 << 20   # a member that inflates to more than this is a plain single-member .gz: stream it
 
-    def __init__(self, path, n_threads, max_member_bytes=64 << 20):
+    def __init__(self, path, n_threads, max_member_bytes=None):
         self.path = path
         self.n_threads = max(1, int(n_threads))
-        self.max_member_bytes = int(max_member_bytes)
+        self.max_member_bytes = int(self.MAX_MEMBER_BYTES if max_member_bytes is None else max_member_bytes)
 
     def arrays(self, block_bytes, n_buffers=4):
         """Yields (buffer, n): the next n bytes of text are buffer[HEADROOM : HEADROOM + n], at least block_bytes of
@@ -122,8 +128,7 @@ class ParallelGzip:
         if size == 0:
             return
         lib = _lib.lib()
-        # room for one batch of members per worker thread, so that a call keeps all of them busy
-        cap = max(int(block_bytes) + self.max_member_bytes, self.n_threads * (16 << 20))
+        cap = max(int(block_bytes) + self.max_member_bytes, self.BATCH_BYTES)   # rank-independent, see BATCH_BYTES
         bufs = [None] * n_buffers
         turn = 0
 

@@ -25,11 +25,17 @@ def _looks_like_index(obj) -> bool:
     return all(hasattr(obj, a) for a in ("_hashes_to_index", "_n_kmers", "_nodes", "_kmers", "_modulo"))
 
 
+def _looks_like_counter_index(obj) -> bool:
+    return all(hasattr(obj, a) for a in ("counter", "get_node_counts", "kmers", "nodes"))
+
+
 def _get_kmer_index_from_args(args):
     """util.py:38-68: ``args.kmer_index`` may be a loaded index object or a path (-i); -b bundles,
     MinimalKmerIndex and CounterKmerIndex files belong to graph_kmer_index / shared_memory_wrapper,
     which are outside the mapped path -- they fail loudly here."""
     kmer_index = getattr(args, "kmer_index", None)
+    if kmer_index is not None and not isinstance(kmer_index, (str, bytes)) and _looks_like_counter_index(kmer_index):
+        return kmer_index
     if kmer_index is not None and not isinstance(kmer_index, (str, bytes)) and _looks_like_index(kmer_index):
         if hasattr(kmer_index, "convert_to_int32"):
             kmer_index.convert_to_int32()
@@ -44,9 +50,15 @@ def _get_kmer_index_from_args(args):
                                   ".npz files (-i) are supported on this path")
     if "minimal" in str(kmer_index):
         raise NotImplementedError("MinimalKmerIndex files are not supported; pass a plain KmerIndex .npz")
-    index = KmerIndex.from_file(kmer_index)
-    index.convert_to_int32()
-    index.remove_ref_offsets()  # not needed, will save us some memory
+    try:
+        index = KmerIndex.from_file(kmer_index)
+        index.convert_to_int32()
+        index.remove_ref_offsets()  # not needed, will save us some memory
+    except KeyError:
+        # util.py:63-66: anything that is not a KmerIndex archive is tried as a CounterKmerIndex
+        from .counter_index import CounterKmerIndex
+        index = CounterKmerIndex.from_file(kmer_index)
+        logging.info("Kmer index is counter index")
     return index
 
 

@@ -129,6 +129,12 @@ def main():
     for nm, s in (("any", seq), ("acgt", acgt)):
         e["actg_from_bytes_" + nm] = enc.ACTGTwoBitEncoding.from_bytes(s)
         e["simple_from_bytes_" + nm] = enc.SimpleEncoding.from_bytes(s)
+    # the helper classmethods (encodings.py:36-42, 85-93)
+    masked = (seq & 31)
+    e["helper_2bytes_to_4bits"] = enc.ACTGTwoBitEncoding.convert_2bytes_to_4bits(masked.view(np.uint16))
+    e["helper_join_4bits"] = enc.ACTGTwoBitEncoding.join_4bits_to_byte(e["helper_2bytes_to_4bits"].reshape(-1, 2))
+    e["helper_byte_to_2bits"] = enc.SimpleEncoding.convert_byte_to_2bits(seq)
+    e["helper_join_2bits"] = enc.SimpleEncoding.join_2bits_to_byte(e["helper_byte_to_2bits"].reshape(-1, 4))
     e["actg_to_bytes"] = enc.ACTGTwoBitEncoding.to_bytes(e["actg_from_bytes_acgt"])
     e["simple_to_bytes"] = enc.SimpleEncoding.to_bytes(e["simple_from_bytes_acgt"])
     e["complement64"] = enc.ACTGTwoBitEncoding.complement(words)

@@ -86,3 +86,40 @@ def test_map_gpu_signature_and_invalid_reads(world, tmp_path):
     bad.write_bytes(b">r1\nACGTACGTACGTACGTACGTACGTACGTACGTACGTRACGT\n")
     with pytest.raises(InvalidBaseError):
         map_gpu(world["idx"], open_reads(str(bad)).read_chunks(1000), world["k"], 0, False)
+
+
+def test_counter_kmer_index_route_vs_oracle(world, tmp_path):
+    """The CounterKmerIndex route (command_line_interface.py:46-49, 118-119, 133-138): per-chunk value arrays from
+    map_cpu, their sum, and the final get_node_counts -- through map_cpu directly, through map_bnp with a loaded
+    object, and through the CLI with a counter-index file (util.py:63-66 fallback)."""
+    from oracle import oracle
+    from kmer_mapper_b200.command_line_interface import map_bnp, map_cpu, run_argument_parser
+    from kmer_mapper_b200.counter_index import CounterKmerIndex
+    idx, k = world["idx"], world["k"]
+    bases, offsets = world["bases"], world["offsets"]
+    n = len(offsets) - 1
+    cuts = [0, n // 3, n // 3, n]                      # three chunks, one of them empty
+    chunks = [(np.ascontiguousarray(bases[offsets[a]:offsets[b]]), np.ascontiguousarray(offsets[a:b + 1] - offsets[a]))
+              for a, b in zip(cuts[:-1], cuts[1:])]
+    hashes = [c_oracle.kmer_hashes(b, o, k) for b, o in chunks]
+    want_values, want_nodes = oracle.counter_index_route(idx._kmers, idx._nodes, hashes)
+    cki = CounterKmerIndex.from_kmer_index(idx)
+    total = np.zeros(cki.counter.n_keys, dtype=np.uint32)
+    for chunk in chunks:
+        got = map_cpu({"kmer_size": k}, cki, chunk)
+        assert got.dtype == np.uint32 and got.shape == total.shape
+        total += got
+    assert np.array_equal(total, want_values)
+    cki.counter._values = total                        # command_line_interface.py:136
+    assert np.array_equal(cki.get_node_counts(), want_nodes)
+    # programmatic run with the object, and the CLI with a file that is not a KmerIndex archive
+    d = world["dir"]
+    args = argparse.Namespace(kmer_index=CounterKmerIndex.from_kmer_index(idx), index_bundle=None, reads=str(d / "reads.fq.gz"),
+                              kmer_size=k, n_threads=1, chunk_size=200_000, output_file=None, debug=None,
+                              max_hits_per_kmer=1000, gpu=False, gpu_hash_map_size=0, map_reverse_complements=False, func=map_bnp)
+    assert np.array_equal(map_bnp(args), want_nodes)
+    cki.to_file(str(tmp_path / "counter_index.npz"))
+    out = str(tmp_path / "counter_out")
+    run_argument_parser(["map", "-i", str(tmp_path / "counter_index.npz"), "-f", str(d / "reads.fa"), "-o", out, "-k", str(k),
+                         "-c", "100000"])
+    assert np.array_equal(np.load(out + ".npy"), want_nodes)

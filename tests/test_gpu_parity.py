@@ -19,20 +19,19 @@ def kmb():
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_l2_budget_bytes", 60 << 20),
-                    ("async_sectors", 1), ("apply_window_log2", 24),
+                    ("apply_window_log2", 23),
                     ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0), ("read_table", -1)):
         _lib.set_option(name, v)
 
 
-# async_sectors: sector fetches by cp.async into shared memory (default) / in registers; apply_window_log2: a tiny apply
-# window forces several windows per node range (the large-count-array path) on small inputs
-VARIANTS = [dict(probe_variant=1, use_filter=1, async_sectors=1),
-            dict(probe_variant=1, use_filter=0, async_sectors=1),
-            dict(probe_variant=1, use_filter=1, async_sectors=0, gathers_in_flight=4),
-            dict(probe_variant=1, use_filter=0, async_sectors=0, gathers_in_flight=2),
-            dict(probe_variant=1, use_filter=1, async_sectors=1, filter_l2_budget_bytes=512),
-            dict(probe_variant=1, use_filter=1, async_sectors=1, log_max_entries=4096),
-            dict(probe_variant=1, use_filter=1, async_sectors=1, apply_window_log2=10),
+# apply_window_log2: a tiny apply window forces several windows per node range (the large-count-array path) on small inputs
+VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=4),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=2),
+            dict(probe_variant=1, use_filter=0, gathers_in_flight=2),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, filter_l2_budget_bytes=512),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, log_max_entries=4096),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, apply_window_log2=10),
             dict(probe_variant=0, use_filter=1),
             dict(probe_variant=0, use_filter=0)]
 # the fused reads kernel over the minimizer-bucketed read-path table (k = 31 only; opt-in)
@@ -52,9 +51,8 @@ def _set(kmb, variant):
     kmb.set_option("filter_l2_budget_bytes", 60 << 20)
     kmb.set_option("log_max_entries", 2048 << 20)
     kmb.set_option("read_table", 0)
-    kmb.set_option("async_sectors", 1)
     kmb.set_option("gathers_in_flight", 4)
-    kmb.set_option("apply_window_log2", 24)
+    kmb.set_option("apply_window_log2", 23)
     for k, v in variant.items():
         kmb.set_option(k, v)
 

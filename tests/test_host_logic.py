@@ -155,6 +155,34 @@ def test_reader_parallel_pieces_resynchronise_on_hostile_text(tmp_path, fmt):
             assert got == want, (chunk_size, n_threads)
 
 
+def test_gz_shards_of_ranks_with_different_thread_counts_partition_the_reads(tmp_path, monkeypatch):
+    """The ranks of a multi-GPU job take every world_size-th block of a .gz.  The block boundaries must not depend
+    on a rank's CPU share: with a capacity that grew with n_threads, ranks with 2 and 12 threads cut the stream at
+    different places and reads were dropped or counted twice (round-1 advisor finding)."""
+    from kmer_mapper_b200.reader import ParallelGzip
+    g = synthetic.make_genome(50_000, 31)
+    bases, offsets = synthetic.make_reads(g, 24_000, 100, seed=32)
+    want = [bytes(bases[offsets[r]:offsets[r + 1]]) for r in range(24_000)]
+    path = str(tmp_path / "many_members.fq.gz")
+    synthetic.write_fastq(path, bases, offsets, members=60)      # ~90 KB of text per member
+    monkeypatch.setattr(ParallelGzip, "BATCH_BYTES", 300_000)    # a few members per block: ~20 blocks
+    monkeypatch.setattr(ParallelGzip, "MAX_MEMBER_BYTES", 200_000)
+    for threads in ([4, 4], [2, 12], [1, 16, 3]):
+        world = len(threads)
+        got, n_chunks = [], 0
+        per_rank = []
+        for rank, nt in enumerate(threads):
+            mine = []
+            for chunk in open_reads(path, pinned=False, n_threads=nt).read_chunks(min_chunk_size=50_000, rank=rank, world_size=world):
+                s = chunk.sequence
+                mine += [bytes(s[i]) for i in range(len(s))]
+                n_chunks += 1
+            per_rank.append(mine)
+        assert n_chunks >= 6
+        assert sum(len(m) for m in per_rank) == len(want), threads          # nothing dropped, nothing doubled
+        assert sorted(x for m in per_rank for x in m) == sorted(want), threads
+
+
 def test_parallel_gzip_members_fallback_and_hostile_payload(tmp_path):
     import zlib
     from kmer_mapper_b200.reader import ParallelGzip

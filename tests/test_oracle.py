@@ -149,3 +149,20 @@ def test_legacy_codec_restatement_matches_reference_vectors(golden_encodings):
     assert np.array_equal(oracle.twobit_swap(e["words64"]), e["twobit_swap64"])
     assert np.array_equal(oracle.twobit_swap(e["words32"]), e["twobit_swap32"])
     assert np.array_equal(oracle.actg_from_bytes(np.frombuffer(b"ACTGACTG", np.uint8)), e["from_string_ACTGACTG"])
+
+
+def test_counter_index_route_restatement_equals_bruteforce():
+    """CounterKmerIndex route (command_line_interface.py:46-49,118-119,133-138): values per unique key summed over
+    chunks, then scattered onto nodes -- against a dictionary count."""
+    rng = np.random.default_rng(5)
+    kmers = rng.integers(0, 50, size=40).astype(np.uint64)        # duplicates: several entries share a key
+    nodes = rng.integers(0, 12, size=40)
+    chunks = [rng.integers(0, 60, size=n).astype(np.uint64) for n in (0, 17, 300)]
+    values, node_counts = oracle.counter_index_route(kmers, nodes, chunks, min_nodes=15)
+    allq = np.concatenate(chunks)
+    unique = np.unique(kmers)
+    assert np.array_equal(values, [int((allq == u).sum()) for u in unique])
+    want = np.zeros(15)
+    for km, nd in zip(kmers, nodes):
+        want[nd] += int((allq == km).sum())
+    assert np.array_equal(node_counts, want) and node_counts.dtype == np.float64
