@@ -24,7 +24,7 @@ logging.basicConfig(stream=sys.stdout, level=logging.INFO, format='%(asctime)s %
 
 from . import distributed  # noqa: E402
 from .counter_index import CounterKmerIndex  # noqa: E402
-from .device import DEFAULT_MAX_FREQUENCY, DeviceIndex, Mapper  # noqa: E402
+from .device import DEFAULT_MAX_FREQUENCY, DeviceIndex, Mapper, borrowed_mapper  # noqa: E402
 from .reader import open_reads  # noqa: E402
 from .sequences import as_ragged  # noqa: E402
 from .util import _get_kmer_index_from_args, log_memory_usage_now  # noqa: E402,F401
@@ -53,12 +53,9 @@ def map_cpu(args, kmer_index, chunk_sequence):
         logging.debug("Mapped with counter. Got values of length %d" % len(mapped))
         return mapped
     di = DeviceIndex.from_index(kmer_index)
-    m = Mapper(di, kmer_index.max_node_id() + 1, DEFAULT_MAX_FREQUENCY)
-    try:
+    with borrowed_mapper(di, kmer_index.max_node_id() + 1, DEFAULT_MAX_FREQUENCY) as m:
         m.map_reads(seq.bases, seq.offsets, kmer_size, revcomp=False, n_to_a=True)
         mapped = m.counts()
-    finally:
-        m.close()
     logging.debug("Chunk of %d reads took %.2f sec" % (len(seq), time.perf_counter() - t))
     return mapped
 

@@ -550,7 +550,8 @@ struct kmb_mapper {
     int32_t max_freq = 1000;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     KmbStatus *d_status = nullptr;
-    KmbStatus *h_status = nullptr;  // pinned
+    KmbStatus *h_status = nullptr;  // pinned: [0] what fetch_status reads back, [1] the constant initial state
+    bool log_clean = true;          // nothing has been logged since the log was last emptied: no need to empty it again
     StageSlot slot[KMB_SLOTS];
     uint64_t host_bad = ~0ull;  // first invalid byte met by the host-side encoder since the last reset
     uint32_t *dtiles = nullptr;  // tile -> read table for in-place device input
@@ -599,24 +600,23 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
     return KMB_OK;
 }
 
+// Asynchronous: the source is a pinned block that never changes after mapper creation, so no host wait is needed
+// (a reset per chunk is the reference's calling pattern, command_line_interface.py:51: keep it off the host's clock).
 static int status_reset(kmb_mapper *m) {
-    KmbStatus hs;
-    memset(&hs, 0, sizeof(hs));
-    hs.first_bad_offset = ~0ull;
-    hs.max_node = -1;
     m->host_bad = ~0ull;
-    *m->h_status = hs;
-    KMB_CUDA(cudaMemcpyAsync(m->d_status, m->h_status, sizeof(hs), cudaMemcpyHostToDevice, m->stream));
-    KMB_CUDA(cudaStreamSynchronize(m->stream));
+    KMB_CUDA(cudaMemcpyAsync(m->d_status, &m->h_status[1], sizeof(KmbStatus), cudaMemcpyHostToDevice, m->stream));
     return KMB_OK;
 }
 
 static int launch_log_reset(kmb_mapper *m) {
-    if (!m->log.entries) return KMB_OK;
-    kmb_log_reset_kernel<<<m->index->info.sms * 4, 256, 0, m->stream>>>(m->log);
+    if (!m->log.entries || m->log_clean) return KMB_OK;
+    const uint64_t groups = m->log.cap >> 5;
+    const int grid = (int)std::min<uint64_t>((groups + 255) / 256, (uint64_t)m->index->info.sms * 4);
+    kmb_log_reset_kernel<<<std::max(grid, 1), 256, 0, m->stream>>>(m->log);
     kmb_log_rewind_kernel<<<1, 1, 0, m->stream>>>(m->log);
     g_launches += 2;
     KMB_CUDA(cudaGetLastError());
+    m->log_clean = true;
     return KMB_OK;
 }
 
@@ -746,7 +746,10 @@ extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *
         KMB_CUDA(cudaMemsetAsync(m->counts, 0, n_counts * 4, m->stream));
     }
     KMB_CUDA(cudaMalloc(&m->d_status, sizeof(KmbStatus)));
-    KMB_CUDA(cudaMallocHost(&m->h_status, sizeof(KmbStatus)));
+    KMB_CUDA(cudaMallocHost(&m->h_status, 2 * sizeof(KmbStatus)));
+    memset(m->h_status, 0, 2 * sizeof(KmbStatus));
+    m->h_status[0].first_bad_offset = m->h_status[1].first_bad_offset = ~0ull;
+    m->h_status[0].max_node = m->h_status[1].max_node = -1;
     KMB_TRY(status_reset(m));
     for (int i = 0; i < KMB_SLOTS; i++) {
         KMB_CUDA(cudaEventCreateWithFlags(&m->slot[i].copied, cudaEventDisableTiming));
@@ -962,6 +965,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
         const uint64_t n_cta_tiles = (n_bases + (uint64_t)KMB_WTILE_POS * (KMB_MZ_THREADS / 32) - 1) / ((uint64_t)KMB_WTILE_POS * (KMB_MZ_THREADS / 32));
         int grid = (int)std::min<uint64_t>(n_cta_tiles, (uint64_t)ix->info.sms * per_sm);
         m->dirty = true;
+        m->log_clean = false;
         KMB_TRY(timed_begin(m));
         fn<<<grid, KMB_MZ_THREADS, KMB_MZ_SMEM_BYTES, m->stream>>>(d_bases, n_bases, base0, R, in_mode, P, Pkey, m->d_status);
         g_launches++;
@@ -975,6 +979,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     KMB_TRY(resident_blocks(mk, g_opt.map_reads_blocks_per_sm, &per_sm));
     int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
     m->dirty = true;
+    m->log_clean = false;
     KMB_TRY(timed_begin(m));
     ((MapReadsFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_bases, n_bases, base0, R, k, in_mode, P, m->d_status);
     g_launches++;
@@ -990,6 +995,7 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
     KMB_TRY(ensure_log(m, (rc ? 2 : 1) * n));
     KmbProbe P = make_probe(m);
     m->dirty = true;
+    m->log_clean = false;
     KMB_TRY(timed_begin(m));
     if (g_opt.probe_variant == 0) {
         int grid = grid_for(n, 256, ix->info.sms, 16);

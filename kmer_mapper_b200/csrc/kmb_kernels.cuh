@@ -1302,16 +1302,16 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
             const unsigned n_have = n_kept;
             const unsigned n_staged = min(n_have, (unsigned)KMB_MZ_SLOTS);
             fetched += n_have;
-#ifdef KMB_MZ_CP_ASYNC
+#ifndef KMB_MZ_LDG_STAGING
             for (unsigned sl = (unsigned)lane; sl < n_staged; sl += 32u) {
                 KMB_BOUND(1, S.kept_sector[sl], 2ull * P.addr.n_main);
                 kmb_cp_async_sector(S.a.slots[sl], P.lines + (uint64_t)S.kept_sector[sl] * KMB_LINE_WORDS);
             }
             kmb_cp_async_wait_all();
 #else
-            // One 256-bit load per sector into registers, two sectors per lane in flight, then into the staging slots.
-            // (Round 1 used cp.async here; scattered 16-byte cp.async turned out to cost ~3.5 LSU cycles per lane and to
-            // hold up every other load meanwhile -- profiles/README.md, round 2.)
+            // Alternative (-DKMB_MZ_LDG_STAGING): one 256-bit load per sector into registers, two sectors per lane in
+            // flight, then into the staging slots.  Measured on config 3 (24 G k-mers): 336 ms against 317 ms for the
+            // cp.async burst above, which keeps ~52 fetches per warp in flight without holding registers.
 #pragma unroll 1
             for (unsigned base = 0; base < n_staged; base += 64u) {
                 const unsigned s0 = base + (unsigned)lane, s1 = s0 + 32u;
@@ -1347,7 +1347,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                         if (more) {
                             const unsigned j = n2 + __popc(m & lanemask_lt);
                             if (j < KMB_MZ_SLOTS2) {
-#ifdef KMB_MZ_CP_ASYNC
+#ifndef KMB_MZ_LDG_STAGING
                                 kmb_cp_async_sector(S.slots2[j], P.lines + (uint64_t)(S.kept_sector[sl] + 1u) * KMB_LINE_WORDS);
 #else
                                 uint32_t r2[8];  // the other half of the 64 bytes the primary's fetch brought into the L2
@@ -1364,7 +1364,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
                     }
                     n2 += __popc(m);
                 }
-#ifdef KMB_MZ_CP_ASYNC
+#ifndef KMB_MZ_LDG_STAGING
                 if (n2) kmb_cp_async_wait_all();
 #endif
             }

@@ -96,15 +96,28 @@ class DeviceIndex:
         device = current_device() if device is None else int(device)
         cache = getattr(index, "_kmb_device_index", None)
         arrays = tuple(_index_attr(index, a) for a in ("_hashes_to_index", "_n_kmers", "_nodes", "_kmers", "_frequencies"))
-        key = (device, int(_index_attr(index, "_modulo"))) + tuple(id(a) for a in arrays)
-        if cache is not None and cache[0] == key:
-            return cache[1]
-        di = cls(*arrays, modulo=_index_attr(index, "_modulo"), device=device)
+        modulo = int(_index_attr(index, "_modulo"))
+        # The cache entry keeps references to the arrays it was built from and is valid only while the index still
+        # holds those very objects (`is`): an id() alone could be reused by a new array after the old one was freed.
+        # In-place edits of an array cannot be seen this way: call DeviceIndex.invalidate(index) after such an edit.
+        if cache is not None and cache[0] == (device, modulo) and len(cache[1]) == len(arrays) and \
+                all(a is b for a, b in zip(cache[1], arrays)):
+            return cache[2]
+        di = cls(*arrays, modulo=modulo, device=device)
         try:
-            index._kmb_device_index = (key, di)
+            index._kmb_device_index = ((device, modulo), arrays, di)
         except Exception:
             pass
         return di
+
+    @staticmethod
+    def invalidate(index) -> None:
+        """Drop the device copy cached on an index object (after editing its arrays in place)."""
+        if hasattr(index, "_kmb_device_index"):
+            try:
+                del index._kmb_device_index
+            except Exception:
+                pass
 
     def max_node_id(self) -> int:
         """KmerIndex.max_node_id() = nodes.max() (command_line_interface.py:51,79,117)."""
@@ -239,4 +252,51 @@ class Mapper:
         self._finalizer()
 
 
-__all__ = ["DeviceIndex", "Mapper", "KmbError", "InvalidBaseError", "DEFAULT_MAX_FREQUENCY"]
+class _BorrowedMapper:
+    """Context manager behind ``borrowed_mapper``."""
+
+    def __init__(self, di, n_counts, cutoff):
+        self.di, self.key = di, (int(n_counts), int(cutoff))
+        self.entry = None
+        self.mapper = None
+
+    def __enter__(self) -> Mapper:
+        import threading
+        cache = self.di.__dict__.setdefault("_mapper_cache", {})
+        entry = cache.get(self.key)
+        if entry is None:
+            entry = cache[self.key] = [threading.Lock(), None]
+        if entry[0].acquire(blocking=False):
+            self.entry = entry
+            if entry[1] is None:
+                entry[1] = Mapper(self.di, self.key[0], self.key[1])
+            else:
+                entry[1].reset()
+            self.mapper = entry[1]
+        else:                      # another thread is using the cached one: a private mapper for this call
+            self.mapper = Mapper(self.di, self.key[0], self.key[1])
+        return self.mapper
+
+    def __exit__(self, exc_type, exc, tb):
+        if self.entry is not None:
+            if exc_type is not None:        # do not keep a mapper whose state is unknown
+                try:
+                    self.entry[1].close()
+                finally:
+                    self.entry[1] = None
+            self.entry[0].release()
+        else:
+            self.mapper.close()
+        return False
+
+
+def borrowed_mapper(di: DeviceIndex, n_counts: int, max_index_lookup_frequency: int = DEFAULT_MAX_FREQUENCY):
+    """A zeroed Mapper for one drop-in call (``map_kmers_to_graph_index``, ``map_cpu``).  The reference calls these
+    once per 2.5 MB chunk (command_line_interface.py:51) and gets a fresh count array each time; creating and
+    destroying a device mapper per call would cost a cudaMalloc + memset of the whole count array (320 MB at human
+    scale), two streams and a pinned block each time.  One mapper per (index, n_counts, cut-off) is kept on the
+    DeviceIndex and reset -- asynchronously -- instead."""
+    return _BorrowedMapper(di, n_counts, max_index_lookup_frequency)
+
+
+__all__ = ["DeviceIndex", "Mapper", "KmbError", "InvalidBaseError", "DEFAULT_MAX_FREQUENCY", "borrowed_mapper"]

@@ -8,7 +8,7 @@ import time
 import numpy as np
 
 from . import _lib
-from .device import DEFAULT_MAX_FREQUENCY, DeviceIndex, Mapper
+from .device import DEFAULT_MAX_FREQUENCY, DeviceIndex, borrowed_mapper
 
 
 def _check_kmers(kmers):
@@ -39,12 +39,9 @@ def map_kmers_to_graph_index(index, max_node_id, kmers, max_index_lookup_frequen
     t = time.perf_counter()
     kmers = _check_kmers(kmers)
     di = DeviceIndex.from_index(index)
-    m = Mapper(di, int(max_node_id) + 1, int(max_index_lookup_frequency))
-    try:
+    with borrowed_mapper(di, int(max_node_id) + 1, int(max_index_lookup_frequency)) as m:
         m.map_kmers(kmers)
-        out = m.counts()
-    finally:
-        m.close()
+        out = m.counts()           # a fresh host array per call (mapper.pyx:37)
     logging.debug("Time spent looking up hashes: %.3f", time.perf_counter() - t)  # mapper.pyx:71
     return out
 

@@ -32,7 +32,12 @@ FASTQ_SUFFIXES = (".fq", ".fastq")
 
 
 class ReadChunk:
-    """What the mapping loop consumes: ``chunk.sequence`` (command_line_interface.py:71,110)."""
+    """What the mapping loop consumes: ``chunk.sequence`` (command_line_interface.py:71,110).
+
+    LIFETIME: ``sequence`` is a view into one of the reader's rotating pinned buffers (N_CHUNK_BUFFERS of them): it
+    stays valid while the next N_CHUNK_BUFFERS - 1 chunks are produced and is overwritten after that.  The mapping
+    loop consumes a chunk before asking for the next, so it never notices; anything that keeps chunks around
+    (``list(read_chunks(...))``, a prefetch queue) must take ``chunk.copy()``."""
 
     def __init__(self, sequence: RaggedSequence):
         self.sequence = sequence
@@ -40,20 +45,27 @@ class ReadChunk:
     def __len__(self):
         return len(self.sequence)
 
+    def copy(self) -> "ReadChunk":
+        """An independent chunk in ordinary (pageable) memory."""
+        return ReadChunk(RaggedSequence(np.array(self.sequence.bases, copy=True), np.array(self.sequence.offsets, copy=True)))
+
+
+N_CHUNK_BUFFERS = 4
+
 
 class _PinnedPool:
-    """Two alternating pinned host buffers (grow on demand); pageable numpy memory when no GPU
+    """N_CHUNK_BUFFERS rotating pinned host buffers (grow on demand); pageable numpy memory when no GPU
     runtime is available (parsing itself never needs a GPU)."""
 
-    def __init__(self, pinned=True):
-        self._bufs = [None, None]
-        self._ptrs = [None, None]
+    def __init__(self, pinned=True, n=N_CHUNK_BUFFERS):
+        self._bufs = [None] * n
+        self._ptrs = [None] * n
         self._i = 0
         self._pinned = bool(pinned) and _lib.device_count() > 0
 
     def take(self, n_bytes: int) -> np.ndarray:
         i = self._i
-        self._i ^= 1
+        self._i = (self._i + 1) % len(self._bufs)
         buf = self._bufs[i]
         if buf is None or buf.shape[0] < n_bytes:
             cap = (max(int(n_bytes * 1.25) + 4096, 1 << 16) + 63) & ~63
@@ -70,7 +82,7 @@ class _PinnedPool:
 
     def untake(self):
         """Give back the buffer of the last take() (nothing was handed to a consumer)."""
-        self._i ^= 1
+        self._i = (self._i - 1) % len(self._bufs)
 
     def _release(self, i):
         self._bufs[i] = None
@@ -79,8 +91,8 @@ class _PinnedPool:
             self._ptrs[i] = None
 
     def close(self):
-        self._release(0)
-        self._release(1)
+        for i in range(len(self._bufs)):
+            self._release(i)
 
     def __del__(self):
         try:

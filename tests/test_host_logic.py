@@ -496,3 +496,45 @@ def test_gzstream_decoder_rejects_corrupt_and_truncated_streams():
             _gzstream(bytes(b2))
     with pytest.raises(OSError):
         _gzstream(b"this is not gzip at all, not even close....")
+
+
+def test_encodings_helper_classmethods_match_the_reference(golden_encodings):
+    """encodings.py:36-42, 85-93: the table/bit-join helpers, against vectors generated by the reference module."""
+    from kmer_mapper_b200.encodings import ACTGTwoBitEncoding, SimpleEncoding
+    e = golden_encodings
+    masked = e["seq_any"] & 31
+    four = ACTGTwoBitEncoding.convert_2bytes_to_4bits(masked.view(np.uint16))
+    assert np.array_equal(four, e["helper_2bytes_to_4bits"])
+    assert np.array_equal(ACTGTwoBitEncoding.join_4bits_to_byte(four.reshape(-1, 2)), e["helper_join_4bits"])
+    assert np.array_equal(e["helper_join_4bits"], e["actg_from_bytes_any"])          # the helpers compose to from_bytes
+    two = SimpleEncoding.convert_byte_to_2bits(e["seq_any"])
+    assert np.array_equal(two, e["helper_byte_to_2bits"])
+    assert np.array_equal(SimpleEncoding.join_2bits_to_byte(two.reshape(-1, 4)), e["helper_join_2bits"])
+    assert np.array_equal(e["helper_join_2bits"], e["simple_from_bytes_any"])
+    with pytest.raises(AssertionError):
+        ACTGTwoBitEncoding.convert_2bytes_to_4bits(masked)                           # dtype check (:37)
+
+
+def test_chunks_stay_valid_for_a_few_chunks_and_copy_makes_them_independent(tmp_path):
+    """A chunk is a view into one of N_CHUNK_BUFFERS rotating buffers (reader.ReadChunk): valid while the next
+    N_CHUNK_BUFFERS - 1 chunks are made; chunk.copy() is what a consumer that keeps chunks must take."""
+    from kmer_mapper_b200.reader import N_CHUNK_BUFFERS
+    g = synthetic.make_genome(20_000, 41)
+    bases, offsets = synthetic.make_reads(g, 4_000, 80, seed=42)
+    want = [bytes(bases[offsets[r]:offsets[r + 1]]) for r in range(4_000)]
+    path = str(tmp_path / "many_chunks.fa")
+    synthetic.write_fasta(path, bases, offsets)
+    kept = [c.copy() for c in open_reads(path, pinned=False, n_threads=2).read_chunks(min_chunk_size=20_000)]
+    assert len(kept) > 2 * N_CHUNK_BUFFERS
+    got = [bytes(c.sequence[i]) for c in kept for i in range(len(c))]
+    assert got == want
+    # without copy(): a window of N_CHUNK_BUFFERS - 1 chunks behind the newest is still intact
+    window, got = [], []
+    for c in open_reads(path, pinned=False, n_threads=2).read_chunks(min_chunk_size=20_000):
+        window.append(c)
+        if len(window) == N_CHUNK_BUFFERS:
+            old = window.pop(0)
+            got += [bytes(old.sequence[i]) for i in range(len(old))]
+    for old in window:
+        got += [bytes(old.sequence[i]) for i in range(len(old))]
+    assert got == want
