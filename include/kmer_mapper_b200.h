@@ -90,6 +90,23 @@ int kmb_mapper_set_stream(kmb_mapper *mapper, void *cuda_stream);
 
 /* mapper.pyx:19 map_kmers_to_graph_index(index, max_node_id, kmers): add the counts of n uint64
  * k-mers (host or device buffer) to the mapper's node counts. */
+/* One chunk of raw FASTA (format 0) or FASTQ (format 1) TEXT -- whole records: it begins at a record start and ends
+ * at a record end (the last line may lack its newline) -- parsed ON THE DEVICE and mapped: replaces
+ * bnp.open(f).read_chunks(...) -> chunk.sequence -> map (command_line_interface.py:102-111 + :32-56) for the GPU
+ * route.  The text crosses PCIe once (host text is staged through pinned memory; pageable text is first copied into
+ * it by every core); newline scan, line classification, offsets and the compaction of the bases are kernels
+ * (csrc/kmb_textparse.cuh); then the fused kernel runs as for device-resident input.  Record rules as
+ * kmb_parse_reads.  The previous call's kernels overlap this call's copy and parse.  At most 4 GiB per call. */
+int kmb_mapper_map_text(kmb_mapper *mapper, const uint8_t *text, uint64_t n_text, int format, int k, uint32_t flags);
+/* The device parser on its own (the counterpart of kmb_parse_reads below, run by GPU kernels): bases of the reads back
+ * to back and offsets[0..n_reads], into host or device buffers.  KMB_ERR_NOMEM (with the sizes in n_reads / n_bases)
+ * when a capacity is too small, KMB_ERR_BAD_ARG for malformed records. */
+int kmb_parse_text_device(int device, const uint8_t *text, uint64_t n_text, int format, uint8_t *bases,
+                          uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity, uint64_t *n_reads,
+                          uint64_t *n_bases);
+/* Reads and bases parsed by kmb_mapper_map_text in this process so far. */
+int kmb_text_parsed(uint64_t *n_reads, uint64_t *n_bases);
+
 int kmb_mapper_map_kmers(kmb_mapper *mapper, const uint64_t *kmers, uint64_t n, uint32_t flags, int k);
 
 /* command_line_interface.py:32-56 map_cpu body, fused: N->A (:41), 2-bit encode + every in-read

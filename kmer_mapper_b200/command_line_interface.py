@@ -133,8 +133,16 @@ def map_bnp(args):
     reads = open_reads(args.reads, n_threads=distributed.host_threads_per_rank() if world_size > 1 else None)
     t_map = time.perf_counter()
     try:
-        chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size, rank=rank, world_size=world_size)
-        if isinstance(index, CounterKmerIndex):
+        if not isinstance(index, CounterKmerIndex) and os.environ.get(PARSE_ENV, "device") != "host":
+            # default route: the raw text goes to the GPU and the records are parsed there (kmb_mapper_map_text)
+            node_counts = _map_text(index, reads, kmer_size, want_revcomp, rank, world_size, _frequency_cutoff(args),
+                                    args.chunk_size if args.chunk_size != REFERENCE_CHUNK_SIZE else DEVICE_TEXT_CHUNK)
+            chunk_iter = None
+        else:
+            chunk_iter = reads.read_chunks(min_chunk_size=args.chunk_size, rank=rank, world_size=world_size)
+        if chunk_iter is None:
+            pass
+        elif isinstance(index, CounterKmerIndex):
             node_counts = _map_counter_index(index, chunk_iter, kmer_size, want_revcomp, rank, world_size)
         elif world_size == 1:
             node_counts = map_gpu(index, chunk_iter, kmer_size, _flag(args, "gpu_hash_map_size", 0), want_revcomp,
@@ -154,6 +162,33 @@ def map_bnp(args):
         logging.info("Saved node counts to %s.npy" % args.output_file)
     logging.info("Spent %.3f sec in total mapping kmers using %d threads" % (time.perf_counter() - t_start,
                                                                              _flag(args, "n_threads", 1)))
+
+
+PARSE_ENV = "KMER_MAPPER_B200_PARSE"   # "device" (default): records are parsed by GPU kernels; "host": by the native host parser
+REFERENCE_CHUNK_SIZE = 2500000          # the reference's -c default (command_line_interface.py:169), a CPU-worker setting
+DEVICE_TEXT_CHUNK = 64 << 20            # what the device route reads per chunk when -c is left at that default
+
+
+def _map_text(kmer_index, reads, k, map_reverse_complements, rank, world_size, max_index_lookup_frequency, chunk_bytes):
+    """File text -> pinned staging -> GPU: newline scan, record parsing, 2-bit encoding, k-mers, index probe and counts
+    all on the device (``kmb_mapper_map_text``); the host only cuts the file into whole-record windows.  Under torchrun
+    every rank takes its share of the file and the count arrays are summed by one all-reduce."""
+    di = DeviceIndex.from_index(kmer_index)
+    mapper = Mapper(di, di.max_node_id() + 1, max_index_lookup_frequency)
+    comm = distributed.Comm(device=di.device) if world_size > 1 else None
+    n_chunks = 0
+    for chunk in reads.text_chunks(min_chunk_size=chunk_bytes, rank=rank, world_size=world_size):
+        mapper.map_text(chunk, reads.format, k, revcomp=bool(map_reverse_complements), n_to_a=True)
+        n_chunks += 1
+    mapper.sync()
+    logging.debug("Device-side parsing: %d chunk(s) of text" % n_chunks)
+    if comm is not None:
+        comm.all_reduce(mapper)
+    out = mapper.counts()
+    mapper.close()
+    if comm is not None:
+        comm.close()
+    return out
 
 
 def _map_counter_index(kmer_index, chunks, k, map_reverse_complements, rank, world_size):

@@ -21,6 +21,7 @@
 #include "../../include/kmer_mapper_b200.h"
 #include "kmb_host.h"
 #include "kmb_kernels.cuh"
+#include "kmb_textparse.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -535,6 +536,18 @@ struct StageSlot {
     size_t h_words_cap = 0, h_off_cap = 0;
     cudaEvent_t copied = nullptr, consumed = nullptr;
     bool used = false;
+    // device-side text parsing (kmb_mapper_map_text): the chunk's raw text and what the parse kernels make of it
+    uint8_t *h_text = nullptr;          // pinned staging for text that arrives in pageable memory
+    size_t h_text_cap = 0;
+    uint8_t *text = nullptr;            // the text on the device
+    uint8_t *tbases = nullptr;          // bases of the reads, back to back
+    int64_t *toffsets = nullptr;        // read offsets
+    uint32_t *nl_pos = nullptr;         // position of every newline
+    KmbTextCopy *copies = nullptr;      // one per line
+    uint32_t *blk_nl = nullptr, *blk_reads = nullptr;
+    unsigned long long *blk_bases = nullptr, *scalars = nullptr;  // scalars: [0] newlines, [1] bases, [2] reads
+    KmbTextResult *d_result = nullptr, *h_result = nullptr;       // h_result pinned
+    size_t text_cap = 0, line_cap = 0;
 };
 #define KMB_SLOTS 3  // one chunk being encoded, one on the bus, one under the kernel
 
@@ -564,7 +577,30 @@ struct kmb_mapper {
 static int timed_begin(kmb_mapper *m, int klass = 0);
 static int timed_end(kmb_mapper *m, int klass = 0);
 
+static void slot_free_text(StageSlot &s) {
+    cudaFree(s.text);
+    cudaFree(s.tbases);
+    cudaFree(s.toffsets);
+    cudaFree(s.nl_pos);
+    cudaFree(s.copies);
+    cudaFree(s.blk_nl);
+    cudaFree(s.blk_reads);
+    cudaFree(s.blk_bases);
+    cudaFree(s.scalars);
+    cudaFree(s.d_result);
+    if (s.h_result) cudaFreeHost(s.h_result);
+    s.text = s.tbases = nullptr;
+    s.toffsets = nullptr;
+    s.nl_pos = s.blk_nl = s.blk_reads = nullptr;
+    s.copies = nullptr;
+    s.blk_bases = s.scalars = nullptr;
+    s.d_result = s.h_result = nullptr;
+    s.text_cap = s.line_cap = 0;
+}
+
 static void slot_free(StageSlot &s) {
+    slot_free_text(s);
+    if (s.h_text) cudaFreeHost(s.h_text);
     cudaFree(s.data);
     cudaFree(s.offsets);
     cudaFree(s.tiles);
@@ -1142,6 +1178,184 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
     }
     // the caller may reuse its host buffers as soon as we return
     KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+    return KMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw FASTA / FASTQ text in, counts out: record parsing on the device (kmb_textparse.cuh)
+// ------------------------------------------------------------------------------------------------
+static std::atomic<unsigned long long> g_text_reads{0}, g_text_bases{0};
+
+static int slot_reserve_text(StageSlot &s, size_t n_text, size_t n_lines_cap) {
+    if (n_text > s.text_cap || n_lines_cap > s.line_cap) {
+        slot_free_text(s);
+        const size_t tcap = ((std::max(n_text, s.text_cap) + (n_text >> 3)) + 4095) & ~(size_t)4095;
+        const size_t lcap = std::max(n_lines_cap, s.line_cap) + 1024;
+        KMB_CUDA(cudaMalloc(&s.text, tcap + 16));
+        KMB_CUDA(cudaMalloc(&s.tbases, tcap + 32));
+        KMB_CUDA(cudaMalloc(&s.toffsets, (lcap + 2) * sizeof(int64_t)));
+        KMB_CUDA(cudaMalloc(&s.nl_pos, (lcap + 2) * sizeof(uint32_t)));
+        KMB_CUDA(cudaMalloc(&s.copies, (lcap + 2) * sizeof(KmbTextCopy)));
+        KMB_CUDA(cudaMalloc(&s.blk_nl, (tcap / KMB_TP_BLOCK_BYTES + 2) * sizeof(uint32_t)));
+        KMB_CUDA(cudaMalloc(&s.blk_reads, (lcap / KMB_TP_LINES_PER_BLOCK + 2) * sizeof(uint32_t)));
+        KMB_CUDA(cudaMalloc(&s.blk_bases, (lcap / KMB_TP_LINES_PER_BLOCK + 2) * sizeof(unsigned long long)));
+        KMB_CUDA(cudaMalloc(&s.scalars, 4 * sizeof(unsigned long long)));
+        KMB_CUDA(cudaMalloc(&s.d_result, sizeof(KmbTextResult)));
+        KMB_CUDA(cudaMallocHost(&s.h_result, sizeof(KmbTextResult)));
+        s.text_cap = tcap;
+        s.line_cap = lcap;
+    }
+    return KMB_OK;
+}
+
+// the six parse kernels over s.text[0, n_text) on `st`; result copied to s.h_result (asynchronously)
+static int launch_text_parse(int sms, StageSlot &s, uint64_t n_text, int format, cudaStream_t st) {
+    const unsigned n_blocks = (unsigned)((n_text + KMB_TP_BLOCK_BYTES - 1) / KMB_TP_BLOCK_BYTES);
+    const uint64_t line_cap = s.line_cap;
+    const unsigned n_line_blocks = (unsigned)((line_cap + 1 + KMB_TP_LINES_PER_BLOCK - 1) / KMB_TP_LINES_PER_BLOCK);
+    KMB_CUDA(cudaMemsetAsync(s.d_result, 0, sizeof(KmbTextResult), st));
+    kmb_tp_count_newlines<<<n_blocks, 256, 0, st>>>(s.text, n_text, s.blk_nl);
+    kmb_tp_scan<<<1, 1024, 0, st>>>(s.blk_nl, n_blocks, s.scalars + 0);
+    kmb_tp_line_ends<<<n_blocks, 256, 0, st>>>(s.text, n_text, s.blk_nl, s.nl_pos, line_cap, s.d_result);
+    kmb_tp_classify<<<n_line_blocks, 256, 0, st>>>(s.text, n_text, format, s.nl_pos, s.scalars + 0, line_cap, s.blk_bases, s.blk_reads, s.d_result);
+    kmb_tp_scan64<<<1, 1024, 0, st>>>(s.blk_bases, n_line_blocks, s.scalars + 1);
+    kmb_tp_scan<<<1, 1024, 0, st>>>(s.blk_reads, n_line_blocks, s.scalars + 2);
+    kmb_tp_emit<<<n_line_blocks, 256, 0, st>>>(s.text, n_text, format, s.nl_pos, s.scalars + 0, line_cap, s.blk_bases, s.blk_reads,
+                                               s.scalars + 1, s.scalars + 2, s.toffsets, line_cap + 2, s.copies, s.d_result);
+    kmb_tp_copy<<<std::max(1, std::min<int>((int)n_line_blocks * 4, sms * 8)), 256, 0, st>>>(s.text, s.copies, s.d_result, s.tbases);
+    g_launches += 8;
+    KMB_CUDA(cudaGetLastError());
+    KMB_CUDA(cudaMemcpyAsync(s.h_result, s.d_result, sizeof(KmbTextResult), cudaMemcpyDeviceToHost, st));
+    return KMB_OK;
+}
+
+struct TextCopyJob {
+    const uint8_t *src;
+    uint8_t *dst;
+    uint64_t n;
+    int parts;
+};
+static void text_copy_part(void *ctx, int part) {
+    const TextCopyJob *j = (const TextCopyJob *)ctx;
+    const uint64_t per = (j->n + j->parts - 1) / j->parts;
+    const uint64_t lo = std::min<uint64_t>(j->n, per * part), hi = std::min<uint64_t>(j->n, lo + per);
+    if (hi > lo) memcpy(j->dst + lo, j->src + lo, (size_t)(hi - lo));
+}
+
+extern "C" int kmb_mapper_map_text(kmb_mapper *m, const uint8_t *text, uint64_t n_text, int format, int k, uint32_t flags) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null mapper");
+    KMB_TRY(check_k(k));
+    if (format != 0 && format != 1) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: format must be 0 (FASTA) or 1 (FASTQ)");
+    if (n_text == 0) return KMB_OK;
+    if (!text) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null text");
+    if (n_text >= (1ull << 32) - 64) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: at most 4 GiB of text per call");
+    KMB_ON_DEVICE(m->index->device);
+    bool dev, pinned;
+    KMB_TRY(ptr_on_device(text, m->index->device, &dev, &pinned));
+    StageSlot &s = m->slot[m->next_slot];
+    m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
+    if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
+    // one line per 8 bytes of text is the first guess (FASTQ of 150-base reads has one per 85); a text with more
+    // lines than that is parsed again with room for the worst case
+    uint64_t line_cap = n_text / 8 + 1024;
+    for (int attempt = 0;; attempt++) {
+        KMB_TRY(slot_reserve_text(s, (size_t)n_text, (size_t)line_cap));
+        if (attempt == 0) {
+            const uint8_t *src = text;
+            if (!dev && !pinned) {
+                // pageable source (a mapping of the page cache): every core copies its share into pinned staging, which
+                // the DMA engine then reads at full PCIe speed (a pageable cudaMemcpy goes through a ~10 GB/s bounce buffer)
+                if (n_text > s.h_text_cap) {
+                    if (s.h_text) cudaFreeHost(s.h_text);
+                    s.h_text = nullptr;
+                    s.h_text_cap = 0;
+                    const size_t cap = (size_t)n_text + (size_t)(n_text >> 3) + 4096;
+                    KMB_CUDA(cudaMallocHost(&s.h_text, cap));
+                    s.h_text_cap = cap;
+                }
+                const int threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
+                TextCopyJob job = {text, s.h_text, n_text, std::max(1, std::min(threads, (int)(n_text >> 20) + 1))};
+                kmb_host_parallel(threads, job.parts, text_copy_part, &job);
+                src = s.h_text;
+            }
+            KMB_CUDA(cudaMemcpyAsync(s.text, src, n_text, cudaMemcpyDefault, m->copy_stream));
+            if (!dev) g_h2d_bytes += n_text;
+        }
+        KMB_TRY(launch_text_parse(m->index->info.sms, s, n_text, format, m->copy_stream));
+        // the previous chunk's mapping kernel is running on the compute stream meanwhile
+        KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+        if ((s.h_result->error & KMB_TP_ERR_TOO_MANY_LINES) && attempt == 0) {
+            line_cap = n_text + 16;
+            continue;
+        }
+        break;
+    }
+    if (s.h_result->error)
+        return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: malformed %s text (a FASTQ record must be '@' line, bases, '+' line, "
+                        "qualities; FASTA data must begin with a '>' line; the text must hold whole records)", format ? "FASTQ" : "FASTA");
+    const uint64_t n_reads = s.h_result->n_reads, n_bases = s.h_result->n_bases;
+    g_text_reads += n_reads;
+    g_text_bases += n_bases;
+    if (n_reads && n_bases) {
+        KMB_TRY(slot_reserve(s, 0, 0, (size_t)(n_bases / KMB_WTILE_POS + 1)));
+        KMB_TRY(launch_map_reads(m, s.tbases, n_bases, 0, s.toffsets, n_reads, s.tiles, k, flags, false));
+    }
+    KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
+    s.used = true;
+    return KMB_OK;
+}
+
+// The device parser on its own: text in (host or device), bases + offsets out (host or device buffers).  The device-side
+// counterpart of kmb_parse_reads; what the tests compare with the host parser record by record.
+extern "C" int kmb_parse_text_device(int device, const uint8_t *text, uint64_t n_text, int format, uint8_t *bases,
+                                     uint64_t bases_capacity, int64_t *offsets, uint64_t offsets_capacity, uint64_t *n_reads,
+                                     uint64_t *n_bases) {
+    if (!n_reads || !n_bases) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_parse_text_device: null output");
+    *n_reads = *n_bases = 0;
+    if (format != 0 && format != 1) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_parse_text_device: format must be 0 (FASTA) or 1 (FASTQ)");
+    if (n_text == 0) {
+        if (offsets && offsets_capacity) {
+            const int64_t zero = 0;
+            KMB_CUDA(cudaMemcpy(offsets, &zero, 8, cudaMemcpyDefault));
+        }
+        return KMB_OK;
+    }
+    if (!text || n_text >= (1ull << 32) - 64) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_parse_text_device: bad text");
+    KMB_ON_DEVICE(device);
+    DevInfo info;
+    KMB_TRY(dev_info(device, &info));
+    StageSlot s;
+    struct Cleanup {
+        StageSlot &s;
+        ~Cleanup() { slot_free_text(s); }
+    } cleanup{s};
+    uint64_t line_cap = n_text / 8 + 1024;
+    for (int attempt = 0;; attempt++) {
+        KMB_TRY(slot_reserve_text(s, (size_t)n_text, (size_t)line_cap));
+        KMB_CUDA(cudaMemcpy(s.text, text, n_text, cudaMemcpyDefault));
+        KMB_TRY(launch_text_parse(info.sms, s, n_text, format, 0));
+        KMB_CUDA(cudaStreamSynchronize(0));
+        if ((s.h_result->error & KMB_TP_ERR_TOO_MANY_LINES) && attempt == 0) {
+            line_cap = n_text + 16;
+            continue;
+        }
+        break;
+    }
+    if (s.h_result->error) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_parse_text_device: malformed %s text", format ? "FASTQ" : "FASTA");
+    *n_reads = s.h_result->n_reads;
+    *n_bases = s.h_result->n_bases;
+    if ((bases && *n_bases > bases_capacity) || (offsets && *n_reads + 1 > offsets_capacity))
+        return kmb_fail(KMB_ERR_NOMEM, "kmb_parse_text_device: output capacity too small (%llu bases, %llu reads)",
+                        (unsigned long long)*n_bases, (unsigned long long)*n_reads);
+    if (bases && *n_bases) KMB_CUDA(cudaMemcpy(bases, s.tbases, *n_bases, cudaMemcpyDefault));
+    if (offsets) KMB_CUDA(cudaMemcpy(offsets, s.toffsets, (*n_reads + 1) * 8, cudaMemcpyDefault));
+    return KMB_OK;
+}
+
+// reads and bases that kmb_mapper_map_text has parsed in this process so far
+extern "C" int kmb_text_parsed(uint64_t *n_reads, uint64_t *n_bases) {
+    if (n_reads) *n_reads = g_text_reads.load();
+    if (n_bases) *n_bases = g_text_bases.load();
     return KMB_OK;
 }
 

@@ -181,6 +181,21 @@ class Mapper:
         _order_after_torch(bases, offsets, same_stream=self._stream)
         check(lib().kmb_mapper_map_reads(self._h, pb, nb, po, no - 1, int(k), flags))
 
+    def map_text(self, text, fmt, k, revcomp=False, n_to_a=True):
+        """One chunk of raw FASTA (``fmt`` 0 / "fasta") or FASTQ (1 / "fastq") text holding whole records: parsed on
+        the device and mapped (``kmb_mapper_map_text``).  ``text``: a uint8 numpy array (any host memory), a torch
+        uint8 CUDA tensor, bytes, or a reader.TextChunk."""
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            text = np.frombuffer(text, dtype=np.uint8)
+        if hasattr(text, "ptr") and hasattr(text, "n"):      # reader.TextChunk
+            kt, pt, nt = text, text.ptr, text.n
+        else:
+            kt, pt, nt = as_buffer(text, np.uint8, "text")
+        fmt = {"fasta": 0, "fastq": 1}.get(fmt, fmt)
+        flags = (FLAG_REVCOMP if revcomp else 0) | (0 if n_to_a else FLAG_NO_N_TO_A)
+        _order_after_torch(text, same_stream=self._stream)
+        check(lib().kmb_mapper_map_text(self._h, pt, nt, int(fmt), int(k), flags))
+
     def flush(self):
         """Queue the slot-counter -> node-count pass on the mapper's stream (no host wait)."""
         check(lib().kmb_mapper_flush(self._h))

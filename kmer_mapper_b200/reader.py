@@ -53,6 +53,20 @@ class ReadChunk:
 N_CHUNK_BUFFERS = 4
 
 
+class TextChunk:
+    """A whole-record window of a reads file's raw text: address + length (valid until the next chunk is asked for).
+    No numpy view of the file mapping is handed out, so the mapping can be closed even while a chunk object is alive."""
+
+    def __init__(self, ptr: int, n: int, keep=None):
+        self.ptr, self.n, self._keep = int(ptr), int(n), keep
+
+    def __len__(self):
+        return self.n
+
+    def tobytes(self) -> bytes:
+        return C.string_at(self.ptr, self.n)
+
+
 class _PinnedPool:
     """N_CHUNK_BUFFERS rotating pinned host buffers (grow on demand); pageable numpy memory when no GPU
     runtime is available (parsing itself never needs a GPU)."""
@@ -335,6 +349,82 @@ class ReadFile:
                     yield seq
             finally:
                 del whole
+
+    # ---- raw text for the device-side parser (kmb_mapper_map_text) ------------------------------------------------
+    def _next_record_start(self, ptr, n, at):
+        """First record start in text[ptr, ptr+n) at or after byte ``at`` (n when there is none)."""
+        if at <= 0:
+            return 0
+        if at >= n:
+            return n
+        off = C.c_uint64()
+        fmt = 1 if self.format == "fastq" else 0
+        _lib.check(_lib.lib().kmb_find_record_start(ptr + at - 1, n - (at - 1), fmt, C.byref(off)))
+        return at - 1 + off.value
+
+    def _last_record_start(self, ptr, n):
+        """Last record start in text[ptr, ptr+n) (0 when the only one is the beginning): where a block of inflated text
+        is cut so that what is handed on holds whole records; the rest is carried over to the next block."""
+        window = 1 << 16
+        while True:
+            lo = max(0, n - window)
+            best, p = None, lo
+            while True:
+                q = self._next_record_start(ptr, n, p + 1) if p or lo else self._next_record_start(ptr, n, 1)
+                if q >= n:
+                    break
+                best, p = q, q
+            if best is not None or lo == 0:
+                return best or 0
+            window *= 8
+
+    def text_chunks(self, min_chunk_size=64 << 20, rank=0, world_size=1):
+        """Whole-record windows of the file's TEXT (TextChunk: address + length, valid until the next one is asked for),
+        for the device-side parser.  Sharding as in read_chunks: a contiguous byte range of a plain file per rank, every
+        world_size-th block of a .gz."""
+        if not self.path.lower().endswith(".gz"):
+            file_size = os.path.getsize(self.path)
+            if file_size == 0:
+                return
+            with open(self.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+                if hasattr(mm, "madvise"):
+                    mm.madvise(mmap.MADV_SEQUENTIAL)
+                whole = np.frombuffer(mm, dtype=np.uint8)
+                base_ptr = whole.ctypes.data
+                try:
+                    pos = self._shard_start(base_ptr, file_size, file_size * rank // world_size)
+                    size = self._shard_start(base_ptr, file_size, file_size * (rank + 1) // world_size)
+                    while pos < size:
+                        end = min(size, pos + int(min_chunk_size))
+                        if end < size:
+                            end = min(size, self._next_record_start(base_ptr, file_size, end))
+                            if hasattr(mm, "madvise"):
+                                a = end - end % mmap.PAGESIZE
+                                mm.madvise(mmap.MADV_WILLNEED, a, min(int(min_chunk_size), size - a))
+                        yield TextChunk(base_ptr + pos, end - pos)
+                        pos = end
+                finally:
+                    del whole
+            return
+        head = ParallelGzip.HEADROOM
+        carry = np.zeros(0, dtype=np.uint8)
+        for i, item in enumerate(self._gz_arrays(int(min_chunk_size))):
+            final = item is None
+            if final:
+                if carry.shape[0] and i % world_size == rank:
+                    yield TextChunk(carry.ctypes.data, carry.shape[0], carry)
+                break
+            buf, n = item
+            if carry.shape[0] <= head:
+                start = head - carry.shape[0]
+                buf[start:head] = carry
+                text = buf[start:head + n]
+            else:
+                text = np.concatenate([carry, buf[head:head + n]])
+            cut = self._last_record_start(text.ctypes.data, int(text.shape[0]))
+            carry = text[cut:].copy()
+            if cut and i % world_size == rank:
+                yield TextChunk(text.ctypes.data, cut, text)
 
     def read_chunks(self, min_chunk_size=5_000_000, rank=0, world_size=1):
         """Chunks of at least ``min_chunk_size`` bytes of the file, cut at record boundaries.  ``rank`` /

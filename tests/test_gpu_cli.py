@@ -28,11 +28,14 @@ def world(tmp_path_factory):
     return dict(dir=d, idx=idx, want=want, k=k, bases=bases, offsets=offsets)
 
 
+@pytest.mark.parametrize("parse", ["device", "host"])
 @pytest.mark.parametrize("reads,chunk", [("reads.fa", 2_500_000), ("reads.fa", 20_000), ("reads.fq.gz", 50_000)])
-def test_cli_map_writes_reference_shaped_output(world, reads, chunk):
-    from kmer_mapper_b200.command_line_interface import run_argument_parser
+def test_cli_map_writes_reference_shaped_output(world, reads, chunk, parse, monkeypatch):
+    """Both routes of the CLI: records parsed by GPU kernels from the raw text (default), or by the native host parser."""
+    from kmer_mapper_b200.command_line_interface import PARSE_ENV, run_argument_parser
+    monkeypatch.setenv(PARSE_ENV, parse)
     d = world["dir"]
-    out = str(d / ("out_%s_%d" % (reads.replace(".", "_"), chunk)))
+    out = str(d / ("out_%s_%d_%s" % (reads.replace(".", "_"), chunk, parse)))
     run_argument_parser(["map", "-i", str(d / "index.npz"), "-f", str(d / reads), "-o", out, "-k", str(world["k"]),
                          "-c", str(chunk), "-t", "3"])
     got = np.load(out + ".npy")                    # np.save appends .npy (command_line_interface.py:149)
