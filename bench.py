@@ -74,6 +74,8 @@ def parse_args(argv=None):
     p.add_argument("--scale", type=float, default=1.0, help="shrink genome/index/reads (smoke runs only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-files", action="store_true", help="skip the reads/s leg (FASTQ / FASTQ.gz files -> counts)")
+    p.add_argument("--file-reads", type=int, default=8_000_000, help="reads in the files of the reads/s leg")
     p.add_argument("--no-oracle", action="store_true", help="skip the oracle parity checks (tuning runs only)")
     p.add_argument("--full-oracle", action="store_true", help="N=1: also run EVERY read of the step through the oracle")
     p.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
@@ -294,6 +296,76 @@ def generate(w, rank, device):
     del genome
     return S.TensorIndex(idx), bases, offsets
 
+
+
+# ---------------------------------------------------------------------------------------------
+# reads/s: files in, counts on the host out (the metric's third leg)
+# ---------------------------------------------------------------------------------------------
+def _gz_member(args):
+    import zlib
+    path, lo, hi = args
+    with open(path, "rb") as f:
+        f.seek(lo)
+        blob = f.read(hi - lo)
+    c = zlib.compressobj(1, zlib.DEFLATED, 31)
+    return c.compress(blob) + c.flush()
+
+
+def write_fastq_files(dirname, bases, n_reads, read_len):
+    """<dir>/reads.fq (4-line records, constant quality) from the first n_reads device-resident reads -- assembled on the
+    GPU as one [n, record_len] byte matrix -- and <dir>/reads.fq.gz, the same text as concatenated gzip members of ~4 MB
+    (what bgzip / `cat a.gz b.gz` produce; BASELINE configs[1] names FASTQ.gz)."""
+    import multiprocessing as mp
+    import torch
+    dev = bases.device
+    digits = 9
+    rec = 1 + digits + 1 + read_len + 3 + read_len + 1
+    m = torch.empty((n_reads, rec), dtype=torch.uint8, device=dev)
+    m[:, 0] = ord("@")
+    ids = torch.arange(n_reads, device=dev)
+    for d in range(digits):
+        m[:, 1 + d] = ((ids // (10 ** (digits - 1 - d))) % 10 + ord("0")).to(torch.uint8)
+    m[:, 1 + digits] = 10
+    s0 = 2 + digits
+    m[:, s0:s0 + read_len] = bases[:n_reads * read_len].view(n_reads, read_len)
+    m[:, s0 + read_len] = 10
+    m[:, s0 + read_len + 1] = ord("+")
+    m[:, s0 + read_len + 2] = 10
+    m[:, s0 + read_len + 3:s0 + 2 * read_len + 3] = ord("I")
+    m[:, rec - 1] = 10
+    fq = os.path.join(dirname, "reads.fq")
+    m.cpu().numpy().tofile(fq)
+    del m
+    size = os.path.getsize(fq)
+    per = max(rec, (4 << 20) // rec * rec)
+    cuts = [(fq, lo, min(lo + per, size)) for lo in range(0, size, per)]
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool, open(fq + ".gz", "wb") as out:
+        for blob in pool.imap(_gz_member, cuts, chunksize=4):
+            out.write(blob)
+    return fq, fq + ".gz"
+
+
+def time_file_to_counts(path, di, n_counts, k):
+    """Wall clock from opening the reads file to the count array on the host, through the library's own route: text
+    windows -> pinned staging -> H2D -> device-side record parsing -> fused kernel -> counts D2H.  Second of two passes."""
+    from kmer_mapper_b200.device import Mapper
+    from kmer_mapper_b200.reader import open_reads
+    from kmer_mapper_b200 import _lib
+    best, counts = None, None
+    for _ in range(2):
+        r0 = _lib.get_option("text_reads")
+        t0 = time.perf_counter()
+        reads = open_reads(path)
+        m = Mapper(di, n_counts)
+        for tc in reads.text_chunks(min_chunk_size=64 << 20):
+            m.map_text(tc, reads.format, k)
+        counts = m.counts()
+        dt = time.perf_counter() - t0
+        n = _lib.get_option("text_reads") - r0
+        m.close()
+        reads.close()
+        best = dt
+    return n / best, n, best, counts
 
 # ---------------------------------------------------------------------------------------------
 # main arms
@@ -533,6 +605,9 @@ def main_ours(args):
         ho.copy_(offsets)
         torch.cuda.synchronize()
         hb_np, ho_np, hc_np = hb.numpy(), ho.numpy(), hc.numpy().view(np.uint32)
+        # the same transport at every N: bases cross PCIe as 2 bits each, encoded inside the timed region by this
+        # rank's share of the host cores (distributed.init_process_group set host_threads = cores / ranks)
+        _lib.set_option("host_pack", 1)
 
         def step_e2e():
             mapper.reset()
@@ -562,7 +637,35 @@ def main_ours(args):
                "ms_per_step": dt * 1e3 / args.steps, "timing": "host wall clock between device synchronisations",
                "bytes_are": "per rank"}
         checks["e2e_counts_equal_resident_counts"] = bool(np.array_equal(hc_np, full_counts.cpu().numpy().view(np.uint32)))
+        _lib.set_option("host_pack", -1)
         del hb, ho, hc
+
+    # ---- reads/s from files (N == 1): FASTQ and multi-member FASTQ.gz of the batch's first reads, file open -> counts on
+    # the host, records parsed on the device; the counts must equal those of the same reads mapped device-resident
+    reads_per_s = None
+    if world == 1 and not args.no_files and L * n_reads >= 1000:
+        n_file_reads = min(n_reads, args.file_reads)
+        fdir = tempfile.mkdtemp(prefix="kmb_files_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            fq, fqgz = write_fastq_files(fdir, bases, n_file_reads, L)
+            with torch.cuda.stream(stream):
+                mapper.reset()
+                mapper.map_reads(bases[:n_file_reads * L], offsets[:n_file_reads + 1], k)
+                mapper.flush()
+                torch.cuda.synchronize()
+            want_counts = counts.cpu().numpy().view(np.uint32)
+            reads_per_s = {"n_reads": int(n_file_reads), "route": "file text -> pinned staging -> H2D -> record parsing on the "
+                           "device (kmb_mapper_map_text) -> fused kernel -> counts D2H; wall clock from opening the file, "
+                           "index already on the device, file in the page cache (tmpfs)",
+                           "host_cores": cores}
+            for name, path in (("fastq", fq), ("fastq_gz_multi_member", fqgz)):
+                rate, n_seen, secs, got_counts = time_file_to_counts(path, di, n_counts, k)
+                reads_per_s[name] = rate
+                reads_per_s[name + "_file_bytes"] = os.path.getsize(path)
+                reads_per_s[name + "_seconds"] = secs
+                checks["file_%s_counts_equal_resident_counts" % name] = bool(n_seen == n_file_reads and np.array_equal(got_counts, want_counts))
+        finally:
+            shutil.rmtree(fdir, ignore_errors=True)
 
     # ---- roofline.  SURVEY.md 8(d): A = L/(L-k+1) + 32 + 8h bytes per k-mer.  The fused kernel streams the bases
     # and gathers the sectors (L/(L-k+1) + 32); the 8h counter bytes belong to the apply pass, which is what
@@ -641,7 +744,7 @@ def main_ours(args):
                                                  filter_bytes=di.filter_bytes),
                                options={n: _lib.get_option(n) for n in ("gathers_in_flight", "use_filter", "apply_window_log2",
                                                                         "map_reads_blocks_per_sm")}),
-                "clocks": clock_rec, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "clocks": clock_rec, "e2e": e2e, "reads_per_s": reads_per_s, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_rec, "checks": checks}
         print(json.dumps(line))
     bad = [k_ for k_, v in checks.items() if v is False]

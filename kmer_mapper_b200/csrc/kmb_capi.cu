@@ -105,6 +105,7 @@ struct KmbOptions {
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<unsigned long long> g_h2d_bytes{0};  // bytes the mapping calls sent host -> device (bench.py's e2e)
+static std::atomic<unsigned long long> g_text_reads{0}, g_text_bases{0};  // parsed by kmb_mapper_map_text
 static std::atomic<int> g_last_reads_kernel{0};  // 0 = key-addressed fused kernel, 1 = read-path table kernel
 
 extern "C" int kmb_set_option(const char *name, int64_t value) {
@@ -182,6 +183,10 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
 #undef OPT
     if (!strcmp(name, "last_reads_kernel")) {  // read-only: which fused kernel the last map_reads launch used
         *value = g_last_reads_kernel.load();
+        return KMB_OK;
+    }
+    if (!strcmp(name, "text_reads")) {  // read-only: reads parsed by kmb_mapper_map_text so far
+        *value = (int64_t)g_text_reads.load();
         return KMB_OK;
     }
     if (!strcmp(name, "h2d_bytes")) {  // read-only
@@ -1184,7 +1189,6 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
 // ------------------------------------------------------------------------------------------------
 // raw FASTA / FASTQ text in, counts out: record parsing on the device (kmb_textparse.cuh)
 // ------------------------------------------------------------------------------------------------
-static std::atomic<unsigned long long> g_text_reads{0}, g_text_bases{0};
 
 static int slot_reserve_text(StageSlot &s, size_t n_text, size_t n_lines_cap) {
     if (n_text > s.text_cap || n_lines_cap > s.line_cap) {
