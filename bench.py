@@ -350,6 +350,7 @@ def time_file_to_counts(path, di, n_counts, k):
     windows -> pinned staging -> H2D -> device-side record parsing -> fused kernel -> counts D2H.  Second of two passes."""
     from kmer_mapper_b200.device import Mapper
     from kmer_mapper_b200.reader import open_reads
+    from kmer_mapper_b200.command_line_interface import map_file_text
     import torch
     from kmer_mapper_b200 import _lib
     out = torch.empty(n_counts, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)   # where the counts land
@@ -360,8 +361,7 @@ def time_file_to_counts(path, di, n_counts, k):
         r0 = _lib.get_option("text_reads")
         t0 = time.perf_counter()
         reads = open_reads(path)
-        for tc in reads.text_chunks(min_chunk_size=64 << 20):
-            m.map_text(tc, reads.format, k)
+        map_file_text(m, reads, k)
         m.counts(out=out)
         dt = time.perf_counter() - t0
         n = _lib.get_option("text_reads") - r0

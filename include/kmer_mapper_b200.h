@@ -101,6 +101,23 @@ int kmb_mapper_map_text(kmb_mapper *mapper, const uint8_t *text, uint64_t n_text
 /* The same with the text taken from bytes [offset, offset + n_text) of an open file descriptor: the cores pread their
  * shares straight into the pinned staging buffer. */
 int kmb_mapper_map_text_fd(kmb_mapper *mapper, int fd, uint64_t offset, uint64_t n_text, int format, int k, uint32_t flags);
+/* A multi-member .gz of FASTA / FASTQ (bgzip / BGZF, concatenated .gz files) -- gz[0, n_gz) begins at a member --
+ * inflated, parsed and mapped ON THE DEVICE: the compressed bytes cross PCIe, every member is decoded by one warp
+ * (csrc/kmb_gzdev.cuh), checked against the length and CRC-32 of its trailer, and the text goes straight into the
+ * device parser.  The members are taken in batches (gz_device_batch_bytes of text); of these the call processes every
+ * shard_count-th one, starting with shard_index (the ranks of a multi-GPU job), and a record that straddles two
+ * batches is mapped by the batch it begins in (each batch inflates up to 1 MB of the next one's text to complete it).
+ * A batch the device decoder gets wrong is inflated again by the host decoder (kmb_gunzip_members); data neither can
+ * decode is KMB_ERR_BAD_ARG.  *resume_offset = n_gz when everything was done here; otherwise the offset of the member
+ * from which the host decoders (kmb_gunzip_members / kmb_gzstream_*) have to continue because a member further on is
+ * too large to give to one warp (a plain single-member .gz: *resume_offset = 0) -- a function of the data alone, so all
+ * ranks get the same answer -- skipping, unless that offset is 0, the text up to the first record start after the
+ * first newline (kmb_find_record_start), which this call has already mapped.
+ * Replaces the .gz side of bnp.open(path) (command_line_interface.py:102-103, Readme.md:11). */
+int kmb_mapper_map_gz(kmb_mapper *mapper, const uint8_t *gz, uint64_t n_gz, int format, int k, uint32_t flags,
+                      int shard_index, int shard_count, uint64_t *resume_offset);
+/* gzip members and text bytes inflated by the device so far in this process; batches the host decoder had to redo. */
+int kmb_gz_device_stats(uint64_t *n_members, uint64_t *text_bytes, uint64_t *host_batches);
 /* The device parser on its own (the counterpart of kmb_parse_reads below, run by GPU kernels): bases of the reads back
  * to back and offsets[0..n_reads], into host or device buffers.  KMB_ERR_NOMEM (with the sizes in n_reads / n_bases)
  * when a capacity is too small, KMB_ERR_BAD_ARG for malformed records. */
@@ -282,6 +299,7 @@ int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kern
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
  *  "apply_window_log2" (nodes per apply window, default 23 = 32 MB of counters),
+ *  "gz_device_max_member_bytes", "gz_device_batch_bytes", "gz_device_crc" (kmb_mapper_map_gz),
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
  *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
  *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),

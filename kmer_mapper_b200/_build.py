@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("KMB_LIB_PATH") or os.path.join(PKG, "libkmer_mapper_b
 SOURCES = [os.path.join(CSRC, "kmb_capi.cu"), os.path.join(CSRC, "kmb_reader.cpp"), os.path.join(CSRC, "kmb_hostpack.cpp"),
            os.path.join(CSRC, "kmb_gunzip.cpp"), os.path.join(CSRC, "kmb_inflate.cpp")]
 HEADERS = [os.path.join(CSRC, "kmb_kernels.cuh"), os.path.join(CSRC, "kmb_core.cuh"), os.path.join(CSRC, "kmb_host.h"),
-           os.path.join(CSRC, "kmb_textparse.cuh"),
+           os.path.join(CSRC, "kmb_textparse.cuh"), os.path.join(CSRC, "kmb_gzdev.cuh"),
            os.path.join(os.path.dirname(PKG), "include", "kmer_mapper_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]

@@ -61,6 +61,8 @@ SIGNATURES = {
     "kmb_mapper_map_text": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_uint32]),
     "kmb_mapper_map_text_fd": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32]),
     "kmb_text_parsed": (C.c_int, [_u64p, _u64p]),
+    "kmb_mapper_map_gz": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, _u64p]),
+    "kmb_gz_device_stats": (C.c_int, [_u64p, _u64p, _u64p]),
     "kmb_parse_text_device": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_int, _vp, C.c_uint64, _vp, C.c_uint64, _u64p, _u64p]),
     "kmb_mapper_flush": (C.c_int, [_vp]),
     "kmb_mapper_sync": (C.c_int, [_vp]),

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import argparse
 import logging
+import mmap
 import os
 import sys
 import time
@@ -164,24 +165,46 @@ def map_bnp(args):
                                                                              _flag(args, "n_threads", 1)))
 
 
+GZ_ENV = "KMER_MAPPER_B200_GZ"         # "device" (default): multi-member .gz inflated by GPU warps; "host": by the host decoders
 PARSE_ENV = "KMER_MAPPER_B200_PARSE"   # "device" (default): records are parsed by GPU kernels; "host": by the native host parser
 REFERENCE_CHUNK_SIZE = 2500000          # the reference's -c default (command_line_interface.py:169), a CPU-worker setting
 DEVICE_TEXT_CHUNK = 64 << 20            # what the device route reads per chunk when -c is left at that default
 
 
+def map_file_text(mapper, reads, k, map_reverse_complements=False, rank=0, world_size=1, chunk_bytes=DEVICE_TEXT_CHUNK):
+    """This rank's share of an open reads file (reader.ReadFile) through ``mapper``, records parsed on the device.  Plain
+    files: whole-record windows of text, pread into pinned staging (``kmb_mapper_map_text_fd``).  Multi-member .gz
+    (bgzip, concatenated members): the COMPRESSED bytes go to the GPU and are inflated there, one member per warp
+    (``kmb_mapper_map_gz``); what the device cannot take (a plain single-member .gz) is inflated by the host decoders
+    from where it stopped.  Returns (text chunks mapped, offset the host decoders took over at or None)."""
+    n_chunks, gz_start, done = 0, 0, False
+    if reads.path.lower().endswith(".gz") and os.environ.get(GZ_ENV, "device") != "host" and os.path.getsize(reads.path):
+        with open(reads.path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            whole = np.frombuffer(mm, dtype=np.uint8)
+            try:
+                gz_start = mapper.map_gz(whole, reads.format, k, revcomp=bool(map_reverse_complements), n_to_a=True,
+                                         shard_index=rank, shard_count=world_size)
+                done = gz_start >= whole.shape[0]
+            finally:
+                del whole
+    if not done:
+        for chunk in reads.text_chunks(min_chunk_size=chunk_bytes, rank=rank, world_size=world_size, gz_start=gz_start):
+            mapper.map_text(chunk, reads.format, k, revcomp=bool(map_reverse_complements), n_to_a=True)
+            n_chunks += 1
+    return n_chunks, (None if done else gz_start)
+
+
 def _map_text(kmer_index, reads, k, map_reverse_complements, rank, world_size, max_index_lookup_frequency, chunk_bytes):
-    """File text -> pinned staging -> GPU: newline scan, record parsing, 2-bit encoding, k-mers, index probe and counts
-    all on the device (``kmb_mapper_map_text``); the host only cuts the file into whole-record windows.  Under torchrun
+    """File -> pinned staging -> GPU: (inflate,) newline scan, record parsing, 2-bit encoding, k-mers, index probe and
+    counts all on the device; the host only cuts the file into whole-record windows or gzip members.  Under torchrun
     every rank takes its share of the file and the count arrays are summed by one all-reduce."""
     di = DeviceIndex.from_index(kmer_index)
     mapper = Mapper(di, di.max_node_id() + 1, max_index_lookup_frequency)
     comm = distributed.Comm(device=di.device) if world_size > 1 else None
-    n_chunks = 0
-    for chunk in reads.text_chunks(min_chunk_size=chunk_bytes, rank=rank, world_size=world_size):
-        mapper.map_text(chunk, reads.format, k, revcomp=bool(map_reverse_complements), n_to_a=True)
-        n_chunks += 1
+    n_chunks, host_from = map_file_text(mapper, reads, k, map_reverse_complements, rank, world_size, chunk_bytes)
     mapper.sync()
-    logging.debug("Device-side parsing: %d chunk(s) of text" % n_chunks)
+    logging.debug("Device-side parsing: %d chunk(s) of text%s" % (n_chunks, "" if not reads.path.lower().endswith(".gz") else
+                  "; gzip members inflated on the device" + ("" if host_from is None else " up to byte %d, by the host from there" % host_from)))
     if comm is not None:
         comm.all_reduce(mapper)
     out = mapper.counts()

@@ -24,6 +24,7 @@
 #include "kmb_host.h"
 #include "kmb_kernels.cuh"
 #include "kmb_textparse.cuh"
+#include "kmb_gzdev.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -103,6 +104,12 @@ struct KmbOptions {
     // windows of one launch overlap where one ends and the next begins, so two must fit the L2 together: measured on
     // config 2 (516 M reductions): 9.4 ms at 2^24, 5.3 ms at 2^23, 6.2 ms at 2^22 (more passes over the log).
     int64_t apply_window_log2 = 23;
+    // gzip members inflated on the device (kmb_mapper_map_gz): a member that announces more text than this is left to
+    // the host decoders (one warp decodes one member: a plain single-member .gz has no parallelism to offer); text per
+    // batch; whether every member's CRC-32 is recomputed on the device and compared with its trailer
+    int64_t gz_device_max_member_bytes = 16ll << 20;
+    int64_t gz_device_batch_bytes = 256ll << 20;
+    int64_t gz_device_crc = 1;
 };
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
@@ -144,6 +151,9 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(apply_window_log2)
+    OPT(gz_device_max_member_bytes)
+    OPT(gz_device_batch_bytes)
+    OPT(gz_device_crc)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
         if (value < (1 << 16)) return kmb_fail(KMB_ERR_BAD_ARG, "chunk_bytes must be >= 65536");
@@ -184,6 +194,9 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(apply_window_log2)
+    OPT(gz_device_max_member_bytes)
+    OPT(gz_device_batch_bytes)
+    OPT(gz_device_crc)
     OPT(chunk_bytes)
 #undef OPT
     if (!strcmp(name, "last_reads_kernel")) {  // read-only: which fused kernel the last map_reads launch used
@@ -562,6 +575,15 @@ struct StageSlot {
     unsigned long long *blk_bases = nullptr, *scalars = nullptr;  // scalars: [0] newlines, [1] bases, [2] reads
     KmbTextResult *d_result = nullptr, *h_result = nullptr;       // h_result pinned
     size_t text_cap = 0, line_cap = 0;
+    // gzip members inflated on the device (kmb_mapper_map_gz): compressed bytes, member table, results
+    uint8_t *h_gz = nullptr, *d_gz = nullptr;      // h_gz pinned
+    size_t h_gz_cap = 0, d_gz_cap = 0;
+    KmbGzMember *h_members = nullptr, *d_members = nullptr;   // h_members pinned
+    KmbGzResult *h_results = nullptr, *d_results = nullptr;   // h_results pinned
+    uint32_t *h_crc = nullptr, *d_crc = nullptr;              // h_crc pinned
+    uint8_t *h_windows = nullptr;                             // pinned: the first bytes of the batch's text and of its extra member
+    size_t members_cap = 0;
+    const uint8_t *text_ptr = nullptr;  // the text the parse kernels read: s.text, or a window of it (gz route)
     uint64_t text_n = 0;                // the chunk in flight: its size, format and the mapping arguments
     int text_format = 0, text_k = 0;
     uint32_t text_flags = 0;
@@ -617,8 +639,26 @@ static void slot_free_text(StageSlot &s) {
     s.text_cap = s.line_cap = 0;
 }
 
+static void slot_free_gz(StageSlot &s) {
+    if (s.h_gz) cudaFreeHost(s.h_gz);
+    cudaFree(s.d_gz);
+    if (s.h_members) cudaFreeHost(s.h_members);
+    cudaFree(s.d_members);
+    if (s.h_results) cudaFreeHost(s.h_results);
+    cudaFree(s.d_results);
+    if (s.h_crc) cudaFreeHost(s.h_crc);
+    cudaFree(s.d_crc);
+    if (s.h_windows) cudaFreeHost(s.h_windows);
+    s.h_gz = s.d_gz = s.h_windows = nullptr;
+    s.h_members = s.d_members = nullptr;
+    s.h_results = s.d_results = nullptr;
+    s.h_crc = s.d_crc = nullptr;
+    s.h_gz_cap = s.d_gz_cap = s.members_cap = 0;
+}
+
 static void slot_free(StageSlot &s) {
     slot_free_text(s);
+    slot_free_gz(s);
     if (s.h_text) cudaFreeHost(s.h_text);
     cudaFree(s.data);
     cudaFree(s.offsets);
@@ -1229,20 +1269,21 @@ static int slot_reserve_text(StageSlot &s, size_t n_text, size_t n_lines_cap) {
 }
 
 // the six parse kernels over s.text[0, n_text) on `st`; result copied to s.h_result (asynchronously)
-static int launch_text_parse(int sms, StageSlot &s, uint64_t n_text, int format, cudaStream_t st) {
+static int launch_text_parse(int sms, StageSlot &s, uint64_t n_text, int format, cudaStream_t st, const uint8_t *text = nullptr) {
+    if (!text) text = s.text;
     const unsigned n_blocks = (unsigned)((n_text + KMB_TP_BLOCK_BYTES - 1) / KMB_TP_BLOCK_BYTES);
     const uint64_t line_cap = s.line_cap;
     const unsigned n_line_blocks = (unsigned)((line_cap + 1 + KMB_TP_LINES_PER_BLOCK - 1) / KMB_TP_LINES_PER_BLOCK);
     KMB_CUDA(cudaMemsetAsync(s.d_result, 0, sizeof(KmbTextResult), st));
-    kmb_tp_count_newlines<<<n_blocks, 256, 0, st>>>(s.text, n_text, s.blk_nl);
+    kmb_tp_count_newlines<<<n_blocks, 256, 0, st>>>(text, n_text, s.blk_nl);
     kmb_tp_scan<<<1, 1024, 0, st>>>(s.blk_nl, n_blocks, s.scalars + 0);
-    kmb_tp_line_ends<<<n_blocks, 256, 0, st>>>(s.text, n_text, s.blk_nl, s.nl_pos, line_cap, s.d_result);
-    kmb_tp_classify<<<n_line_blocks, 256, 0, st>>>(s.text, n_text, format, s.nl_pos, s.scalars + 0, line_cap, s.blk_bases, s.blk_reads, s.d_result);
+    kmb_tp_line_ends<<<n_blocks, 256, 0, st>>>(text, n_text, s.blk_nl, s.nl_pos, line_cap, s.d_result);
+    kmb_tp_classify<<<n_line_blocks, 256, 0, st>>>(text, n_text, format, s.nl_pos, s.scalars + 0, line_cap, s.blk_bases, s.blk_reads, s.d_result);
     kmb_tp_scan64<<<1, 1024, 0, st>>>(s.blk_bases, n_line_blocks, s.scalars + 1);
     kmb_tp_scan<<<1, 1024, 0, st>>>(s.blk_reads, n_line_blocks, s.scalars + 2);
-    kmb_tp_emit<<<n_line_blocks, 256, 0, st>>>(s.text, n_text, format, s.nl_pos, s.scalars + 0, line_cap, s.blk_bases, s.blk_reads,
+    kmb_tp_emit<<<n_line_blocks, 256, 0, st>>>(text, n_text, format, s.nl_pos, s.scalars + 0, line_cap, s.blk_bases, s.blk_reads,
                                                s.scalars + 1, s.scalars + 2, s.toffsets, line_cap + 2, s.copies, s.d_result);
-    kmb_tp_copy<<<std::max(1, std::min<int>((int)n_line_blocks * 4, sms * 8)), 256, 0, st>>>(s.text, s.copies, s.d_result, s.tbases);
+    kmb_tp_copy<<<std::max(1, std::min<int>((int)n_line_blocks * 4, sms * 8)), 256, 0, st>>>(text, s.copies, s.d_result, s.tbases);
     g_launches += 8;
     KMB_CUDA(cudaGetLastError());
     KMB_CUDA(cudaMemcpyAsync(s.h_result, s.d_result, sizeof(KmbTextResult), cudaMemcpyDeviceToHost, st));
@@ -1297,10 +1338,11 @@ static int text_finish_pending(kmb_mapper *m) {
         // more lines than one per 8 bytes: parse again (the text is still on the device) with room for the worst case
         DevBuf<uint8_t> keep;
         KMB_TRY(keep.alloc((size_t)s.text_n + 16));
-        KMB_CUDA(cudaMemcpyAsync(keep.p, s.text, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
+        KMB_CUDA(cudaMemcpyAsync(keep.p, s.text_ptr, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
         KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
         KMB_TRY(slot_reserve_text(s, (size_t)s.text_n, (size_t)s.text_n + 16));
         KMB_CUDA(cudaMemcpyAsync(s.text, keep.p, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
+        s.text_ptr = s.text;
         KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, s.text_format, m->copy_stream));
         KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
     }
@@ -1380,6 +1422,7 @@ static int map_text_impl(kmb_mapper *m, const uint8_t *text, int fd, uint64_t fd
         KMB_CUDA(cudaEventCreateWithFlags(&caller_buffer_read, cudaEventDisableTiming));
         KMB_CUDA(cudaEventRecord(caller_buffer_read, m->copy_stream));
     }
+    s.text_ptr = s.text;
     s.text_n = n_text;
     s.text_format = format;
     s.text_k = k;
@@ -1395,6 +1438,292 @@ static int map_text_impl(kmb_mapper *m, const uint8_t *text, int fd, uint64_t fd
     } else if (dev) {
         KMB_CUDA(cudaStreamSynchronize(m->copy_stream));  // a device buffer of the caller: read before we return
     }
+    return KMB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// multi-member .gz in, counts out: members inflated by the device (kmb_gzdev.cuh), then parsed and mapped there
+// ------------------------------------------------------------------------------------------------
+static std::atomic<unsigned long long> g_gz_members{0}, g_gz_text_bytes{0}, g_gz_host_batches{0};
+#define KMB_GZ_WINDOW (1u << 20)   // text looked at for a record start on either side of a batch boundary
+
+struct GzScanJob {
+    const uint8_t *gz;
+    uint64_t n, per;
+    std::vector<std::vector<uint64_t>> *found;
+};
+// A gzip member header (RFC 1952): ID1 ID2 CM=8, no reserved flag bits, XFL 0/2/4, a known OS byte.  The last two make a
+// chance match inside compressed data 1500x rarer than the three magic bytes alone (~3 per GB -> ~0.002 per GB).
+static inline bool gz_header_at(const uint8_t *p) {
+    return p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 0xE0) == 0 && (p[8] == 0 || p[8] == 2 || p[8] == 4) &&
+           (p[9] <= 13 || p[9] == 255);
+}
+static void gz_scan_part(void *ctx, int part) {
+    GzScanJob *j = (GzScanJob *)ctx;
+    const uint64_t lo = j->per * (uint64_t)part, hi = std::min<uint64_t>(j->n, lo + j->per);
+    std::vector<uint64_t> &out = (*j->found)[(size_t)part];
+    uint64_t p = lo;
+    while (p < hi && p + 18 <= j->n) {
+        const uint8_t *q = (const uint8_t *)memchr(j->gz + p, 0x1f, (size_t)(hi - p));
+        if (!q) break;
+        p = (uint64_t)(q - j->gz);
+        if (p + 18 <= j->n && gz_header_at(q)) out.push_back(p);
+        p++;
+    }
+}
+
+static int slot_reserve_gz(StageSlot &s, size_t gz_bytes, size_t n_members) {
+    if (gz_bytes + 64 > s.h_gz_cap) {
+        if (s.h_gz) cudaFreeHost(s.h_gz);
+        cudaFree(s.d_gz);
+        s.h_gz = s.d_gz = nullptr;
+        s.h_gz_cap = s.d_gz_cap = 0;
+        const size_t cap = gz_bytes + (gz_bytes >> 2) + 4096;
+        KMB_CUDA(cudaMallocHost(&s.h_gz, cap));
+        KMB_CUDA(cudaMalloc(&s.d_gz, cap));
+        s.h_gz_cap = s.d_gz_cap = cap;
+    }
+    if (n_members > s.members_cap) {
+        if (s.h_members) cudaFreeHost(s.h_members);
+        if (s.h_results) cudaFreeHost(s.h_results);
+        if (s.h_crc) cudaFreeHost(s.h_crc);
+        cudaFree(s.d_members);
+        cudaFree(s.d_results);
+        cudaFree(s.d_crc);
+        s.h_members = s.d_members = nullptr;
+        s.h_results = s.d_results = nullptr;
+        s.h_crc = s.d_crc = nullptr;
+        s.members_cap = 0;
+        const size_t cap = n_members + n_members / 4 + 64;
+        KMB_CUDA(cudaMallocHost(&s.h_members, cap * sizeof(KmbGzMember)));
+        KMB_CUDA(cudaMalloc(&s.d_members, cap * sizeof(KmbGzMember)));
+        KMB_CUDA(cudaMallocHost(&s.h_results, cap * sizeof(KmbGzResult)));
+        KMB_CUDA(cudaMalloc(&s.d_results, cap * sizeof(KmbGzResult)));
+        KMB_CUDA(cudaMallocHost(&s.h_crc, cap * sizeof(uint32_t)));
+        KMB_CUDA(cudaMalloc(&s.d_crc, cap * sizeof(uint32_t)));
+        s.members_cap = cap;
+    }
+    if (!s.h_windows) KMB_CUDA(cudaMallocHost(&s.h_windows, 2 * KMB_GZ_WINDOW));
+    return KMB_OK;
+}
+
+struct GzBatch {      // what a slot is working on
+    size_t m0 = 0, m1 = 0, x1 = 0;   // members [m0, m1) are the batch; [m1, x1) complete its last record ("overlap")
+    bool first = false, overlap_is_tail = false;   // overlap_is_tail: the overlap runs to the end of the data
+    uint64_t text_len = 0, extra_len = 0;   // text of [m0, m1) / of [m1, x1)
+    uint64_t gz_offset = 0, gz_len = 0;     // compressed bytes of [m0, x1)
+    int slot = -1;
+};
+
+// Verify the inflated members of a batch (a batch the device got wrong is inflated again by the host decoders, so a
+// decoder fault costs time, not correctness; data that neither can decode is an error), cut its text at record
+// starts, parse and map it.
+static int gz_finish_batch(kmb_mapper *m, const GzBatch &b, int format, int k, uint32_t flags, bool check_crc, int threads) {
+    StageSlot &s = m->slot[b.slot];
+    KMB_CUDA(cudaEventSynchronize(s.copied));
+    const size_t n_mem = b.x1 - b.m0;
+    const uint64_t total = b.text_len + b.extra_len;
+    bool verified = true;
+    for (size_t i = 0; i < n_mem && verified; i++) {
+        const KmbGzResult &r = s.h_results[i];
+        const KmbGzMember &mem = s.h_members[i];
+        if (r.status != KMB_GZ_OK || r.out_len != mem.out_len || r.in_used != mem.in_len) verified = false;
+        if (check_crc && s.h_crc[i] != r.crc) verified = false;
+    }
+    if (!verified) {
+        std::vector<uint8_t> text((size_t)total + 64);
+        uint64_t consumed = 0, produced = 0;
+        int flag = 0;
+        const int rc = kmb_gunzip_members(s.h_gz, b.gz_len, threads, text.data(), total, 0, &consumed, &produced, &flag);
+        if (rc != KMB_OK || consumed != b.gz_len || produced != total)
+            return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: corrupt gzip data in the members at bytes [%llu, %llu) (or a false member "
+                            "start: map the file through the host decoders instead)", (unsigned long long)b.gz_offset,
+                            (unsigned long long)(b.gz_offset + b.gz_len));
+        KMB_CUDA(cudaMemcpyAsync(s.text, text.data(), (size_t)total, cudaMemcpyHostToDevice, m->copy_stream));
+        KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+        memcpy(s.h_windows, text.data(), (size_t)std::min<uint64_t>(KMB_GZ_WINDOW, total));
+        if (b.extra_len) memcpy(s.h_windows + KMB_GZ_WINDOW, text.data() + b.text_len, (size_t)std::min<uint64_t>(KMB_GZ_WINDOW, b.extra_len));
+        g_gz_host_batches++;
+        g_h2d_bytes += total;
+    }
+    // Where the batch's records begin and end in its text.  Both neighbours apply the same rule to the same bytes
+    // (kmb_find_record_start from the first byte of member m's text): the record that straddles a batch boundary
+    // belongs to the batch it begins in.
+    uint64_t start = 0, end = b.text_len;
+    if (!b.first) {
+        uint64_t off = 0;
+        const uint64_t w = std::min<uint64_t>(KMB_GZ_WINDOW, total);
+        KMB_TRY(kmb_find_record_start(s.h_windows, w, format, &off));
+        if (off >= w && w < total) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: a record longer than %u bytes: map the file through the host decoders", KMB_GZ_WINDOW);
+        start = std::min<uint64_t>(off, b.text_len);
+    }
+    if (b.x1 > b.m1) {
+        uint64_t off = 0;
+        const uint64_t w = std::min<uint64_t>(KMB_GZ_WINDOW, b.extra_len);
+        KMB_TRY(kmb_find_record_start(s.h_windows + KMB_GZ_WINDOW, w, format, &off));
+        if (off >= w) {
+            // no record start in the overlap: fine if the data ends with it (the rest IS the last record) ...
+            if (!b.overlap_is_tail)
+                return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: a record longer than %u bytes: map the file through the host decoders", KMB_GZ_WINDOW);
+            off = b.extra_len;
+        }
+        end = b.text_len + off;
+    }
+    g_gz_members += b.m1 - b.m0;
+    g_gz_text_bytes += b.text_len;
+    if (end <= start) {
+        KMB_CUDA(cudaEventRecord(s.consumed, m->stream));
+        s.used = true;
+        return KMB_OK;
+    }
+    s.text_ptr = s.text + start;
+    s.text_n = end - start;
+    s.text_format = format;
+    s.text_k = k;
+    s.text_flags = flags;
+    KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, format, m->copy_stream, s.text_ptr));
+    KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
+    m->text_pending = b.slot;
+    return text_finish_pending(m);   // waits for the parse result, launches the mapping kernel, records `consumed`
+}
+
+extern "C" int kmb_mapper_map_gz(kmb_mapper *m, const uint8_t *gz, uint64_t n_gz, int format, int k, uint32_t flags,
+                                 int shard_index, int shard_count, uint64_t *resume_offset) {
+    if (!m || !resume_offset) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: null argument");
+    *resume_offset = 0;
+    KMB_TRY(check_k(k));
+    if (format != 0 && format != 1) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: format must be 0 (FASTA) or 1 (FASTQ)");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: bad shard");
+    if (n_gz == 0) return KMB_OK;
+    if (!gz) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: null data");
+    if (n_gz < 18 || !gz_header_at(gz)) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_gz: the data does not begin with a gzip member");
+    KMB_ON_DEVICE(m->index->device);
+    KMB_TRY(text_finish_pending(m));
+    const int threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
+    // ---- 1. member starts (host, all cores) and the text length each trailer announces
+    std::vector<uint64_t> starts;
+    {
+        const int parts = std::max(1, std::min(threads * 4, (int)(n_gz >> 20) + 1));
+        std::vector<std::vector<uint64_t>> found((size_t)parts);
+        GzScanJob job = {gz, n_gz, (n_gz + parts - 1) / parts, &found};
+        kmb_host_parallel(threads, parts, gz_scan_part, &job);
+        for (auto &v : found) starts.insert(starts.end(), v.begin(), v.end());
+    }
+    const size_t n_members = starts.size();
+    starts.push_back(n_gz);   // starts[i + 1] = end of member i
+    const uint64_t max_member = (uint64_t)std::max<int64_t>(g_opt.gz_device_max_member_bytes, 1 << 16);
+    std::vector<uint32_t> isize(n_members);
+    size_t n_ok = 0;          // members [0, n_ok) can be given to a warp each
+    for (; n_ok < n_members; n_ok++) {
+        const uint64_t len = starts[n_ok + 1] - starts[n_ok];
+        const uint8_t *t = gz + starts[n_ok + 1] - 4;
+        isize[n_ok] = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (len < 18 || len >= (1ull << 32) || isize[n_ok] > max_member) break;   // a plain single-member .gz, or a false start
+    }
+    // The device takes members [0, n_dev).  When something further on is not for it (a function of the file alone, so
+    // all ranks agree), the last members before it -- KMB_GZ_WINDOW of text -- serve only as the overlap that completes
+    // the last record, and the host decoders resume AT the first of them, skipping its first partial record by the same
+    // rule: every record is mapped exactly once.
+    size_t n_dev = n_members;
+    if (n_ok < n_members) {
+        uint64_t text = 0;
+        n_dev = n_ok;
+        while (n_dev > 0 && text < KMB_GZ_WINDOW) text += isize[--n_dev];
+    }
+    if (n_dev == 0) return KMB_OK;   // *resume_offset == 0: everything through the host decoders
+    const uint64_t batch_cap = (uint64_t)std::max<int64_t>(g_opt.gz_device_batch_bytes, 1 << 20);
+    const bool check_crc = g_opt.gz_device_crc != 0;
+    // ---- 2. batches of whole members, each followed by its overlap
+    std::vector<GzBatch> batches;
+    for (size_t i = 0; i < n_dev;) {
+        GzBatch b;
+        b.m0 = i;
+        uint64_t text = 0;
+        while (i < n_dev && (i == b.m0 || (text + isize[i] <= batch_cap && i - b.m0 < 60000))) text += isize[i++];
+        b.m1 = i;
+        b.text_len = text;
+        size_t x = i;
+        uint64_t extra = 0;
+        while (x < n_ok && extra < KMB_GZ_WINDOW) extra += isize[x++];
+        b.x1 = x;
+        b.extra_len = extra;
+        b.overlap_is_tail = x == n_members;
+        b.first = b.m0 == 0;
+        b.gz_offset = starts[b.m0];
+        b.gz_len = starts[b.x1] - starts[b.m0];
+        batches.push_back(b);
+    }
+    // ---- 3. pipeline: while batch b is on the bus and being inflated, batch b-1 is verified, parsed and mapped
+    GzBatch pending;
+    bool have_pending = false;
+    size_t bi = 0;
+    for (GzBatch &b : batches) {
+        if ((int)(bi++ % (size_t)shard_count) != shard_index) continue;
+        b.slot = m->next_slot;
+        m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
+        StageSlot &s = m->slot[b.slot];
+        if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
+        const size_t n_mem = b.x1 - b.m0;
+        const uint64_t total_text = b.text_len + b.extra_len;
+        KMB_TRY(slot_reserve_gz(s, (size_t)b.gz_len, n_mem));
+        KMB_TRY(slot_reserve_text(s, (size_t)total_text + 64, (size_t)(total_text / 8 + 1024)));
+        {
+            TextCopyJob job;
+            job.src = gz + b.gz_offset;
+            job.fd = -1;
+            job.offset = 0;
+            job.dst = s.h_gz;
+            job.n = b.gz_len;
+            job.parts = std::max(1, std::min(threads, (int)(b.gz_len >> 20) + 1));
+            job.failed = 0;
+            kmb_host_parallel(threads, job.parts, text_copy_part, &job);
+            memset(s.h_gz + b.gz_len, 0, 48);
+        }
+        uint64_t out = 0;
+        for (size_t i = 0; i < n_mem; i++) {
+            KmbGzMember &mem = s.h_members[i];
+            mem.in_off = starts[b.m0 + i] - b.gz_offset;
+            mem.in_len = (uint32_t)(starts[b.m0 + i + 1] - starts[b.m0 + i]);
+            mem.out_off = out;
+            mem.out_len = isize[b.m0 + i];
+            out += mem.out_len;
+        }
+        cudaStream_t st = m->copy_stream;
+        KMB_CUDA(cudaMemcpyAsync(s.d_gz, s.h_gz, (size_t)b.gz_len + 48, cudaMemcpyHostToDevice, st));
+        KMB_CUDA(cudaMemcpyAsync(s.d_members, s.h_members, n_mem * sizeof(KmbGzMember), cudaMemcpyHostToDevice, st));
+        g_h2d_bytes += b.gz_len + n_mem * sizeof(KmbGzMember);
+        const size_t smem = KMB_GZ_WARPS * sizeof(KmbGzShared);
+        KMB_CUDA(cudaFuncSetAttribute((const void *)kmb_gz_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>((n_mem + KMB_GZ_WARPS - 1) / KMB_GZ_WARPS, (size_t)m->index->info.sms * 8);
+        kmb_gz_inflate_kernel<<<grid, KMB_GZ_WARPS * 32, smem, st>>>(s.d_gz, s.d_members, (uint32_t)n_mem, s.text, s.d_results);
+        g_launches++;
+        if (check_crc) {
+            kmb_gz_crc_kernel<<<(unsigned)((n_mem + 3) / 4), 128, 0, st>>>(s.text, s.d_members, (uint32_t)n_mem, s.d_crc);
+            g_launches++;
+            KMB_CUDA(cudaMemcpyAsync(s.h_crc, s.d_crc, n_mem * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        KMB_CUDA(cudaGetLastError());
+        KMB_CUDA(cudaMemcpyAsync(s.h_results, s.d_results, n_mem * sizeof(KmbGzResult), cudaMemcpyDeviceToHost, st));
+        KMB_CUDA(cudaMemcpyAsync(s.h_windows, s.text, (size_t)std::min<uint64_t>(KMB_GZ_WINDOW, total_text), cudaMemcpyDeviceToHost, st));
+        if (b.extra_len)
+            KMB_CUDA(cudaMemcpyAsync(s.h_windows + KMB_GZ_WINDOW, s.text + b.text_len, (size_t)std::min<uint64_t>(KMB_GZ_WINDOW, b.extra_len),
+                                     cudaMemcpyDeviceToHost, st));
+        KMB_CUDA(cudaEventRecord(s.copied, st));
+        if (have_pending) KMB_TRY(gz_finish_batch(m, pending, format, k, flags, check_crc, threads));
+        pending = b;
+        have_pending = true;
+    }
+    if (have_pending) KMB_TRY(gz_finish_batch(m, pending, format, k, flags, check_crc, threads));
+    *resume_offset = n_dev == n_members ? n_gz : starts[n_dev];
+    return KMB_OK;
+}
+
+// members and text bytes inflated by the device so far in this process; batches the host decoders had to redo
+extern "C" int kmb_gz_device_stats(uint64_t *n_members, uint64_t *text_bytes, uint64_t *host_batches) {
+    if (n_members) *n_members = g_gz_members.load();
+    if (text_bytes) *text_bytes = g_gz_text_bytes.load();
+    if (host_batches) *host_batches = g_gz_host_batches.load();
     return KMB_OK;
 }
 

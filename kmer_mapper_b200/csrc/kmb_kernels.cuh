@@ -327,21 +327,27 @@ __global__ void kmb_tile_reads_kernel(KmbReads R, uint64_t n_bases, uint64_t n_t
         tile_read[t] = (uint32_t)(lo ? lo - 1 : 0);
     }
 }
+// Where read r begins and ends (relative to the launch's first base); INT64_MAX beyond the last read.
+__device__ __forceinline__ void kmb_read_span(const KmbReads &R, uint64_t r, int64_t &s, int64_t &e) {
+    s = e = INT64_MAX;
+    if (r < R.n_reads) {
+        s = kmb_read_offset(R, r);
+        e = kmb_read_offset(R, r + 1);
+    }
+}
 // Valid window starts among this lane's 32 positions [t0 + 32 lane, +32) of tile `tile`.  Called by all 32 lanes;
-// tmask = 32 words of the warp's shared memory.
+// tmask = 32 words of the warp's shared memory; r0 = tile_read[tile] and (s, e) = span of read r0 + lane, loaded by
+// the caller ahead of time (kmb_read_span) so that their latency hides behind the tile's base loads.
 __device__ __forceinline__ uint32_t kmb_tile_valid_starts(const KmbReads &R, uint64_t tile, uint64_t n_bases, int k,
-                                                          uint32_t *tmask, int lane, KmbStatus *status) {
+                                                          uint32_t *tmask, int lane, KmbStatus *status, uint64_t r0,
+                                                          int64_t s, int64_t e) {
     const int64_t t0 = (int64_t)(tile * KMB_WTILE_POS), t1 = t0 + KMB_WTILE_POS;
     tmask[lane] = 0u;
     __syncwarp();
-    uint64_t r = R.tile_read[tile];
+    uint64_t r = r0;
 #pragma unroll 1
     for (;;) {
-        const uint64_t mine = r + (uint64_t)lane;
-        int64_t s = INT64_MAX, e = INT64_MAX;
-        if (mine < R.n_reads) {
-            s = kmb_read_offset(R, mine);
-            e = kmb_read_offset(R, mine + 1);
+        if (r + (uint64_t)lane < R.n_reads) {
             if (e < s) atomicOr(&status->index_flags, KMB_FLAG_BAD_OFFSETS);
             // the last k-1 bases of the read (all of it if shorter) cannot start a window: [lo, hi) within the tile
             int64_t lo = e - (int64_t)(k - 1);
@@ -354,7 +360,7 @@ __device__ __forceinline__ uint32_t kmb_tile_valid_starts(const KmbReads &R, uin
                 const uint32_t from_a = ~0u << (a & 31u), upto_b = ~0u >> (31u - (b & 31u));
                 if (wa == wb) {
                     atomicOr(&tmask[wa], from_a & upto_b);
-                } else {  // k - 1 <= 30 bits, but a read shorter than k... no: at most k-1 bits, so at most two words
+                } else {  // at most k-1 <= 30 bits: two words
                     atomicOr(&tmask[wa], from_a);
                     for (uint32_t w = wa + 1; w < wb; w++) atomicOr(&tmask[w], ~0u);
                     atomicOr(&tmask[wb], upto_b);
@@ -363,6 +369,7 @@ __device__ __forceinline__ uint32_t kmb_tile_valid_starts(const KmbReads &R, uin
         }
         if (__shfl_sync(KMB_FULL_MASK, s, 31) >= t1) break;  // the next read starts beyond the tile (or there is none)
         r += 32;
+        kmb_read_span(R, r + (uint64_t)lane, s, e);             // more than 32 reads touch the tile (short reads)
     }
     __syncwarp();
     const uint64_t p0 = (uint64_t)t0 + (uint64_t)lane * KMB_POS_PER_THREAD;
@@ -847,8 +854,14 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     const uint64_t warp_stride = (uint64_t)gridDim.x * (KMB_MAP_THREADS / 32);
     unsigned long long mapped = 0;
 
-    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_MAP_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
+    const uint64_t first_tile = (uint64_t)blockIdx.x * (KMB_MAP_THREADS / 32) + warp;
+    uint32_t r_next = first_tile < n_tiles ? R.tile_read[first_tile] : 0u;  // one tile ahead: its latency is never waited for
+    for (uint64_t tile = first_tile; tile < n_tiles; tile += warp_stride) {
         const uint64_t t0 = tile * KMB_WTILE_POS;
+        const uint64_t r0 = r_next;
+        if (tile + warp_stride < n_tiles) r_next = R.tile_read[tile + warp_stride];
+        int64_t rs, re;  // span of read r0 + lane: in flight while the bases are loaded and encoded
+        kmb_read_span(R, r0 + (uint64_t)lane, rs, re);
         __syncwarp();  // the previous tile's readers are done with pack
         // ---- 1. load + encode: vectors v = t0/16 + i, i in [0, 66)
 #pragma unroll
@@ -866,7 +879,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
         }
         __syncwarp();
         // ---- 2. this lane's 32 positions
-        const uint32_t valid = kmb_tile_valid_starts(R, tile, n_bases, k, S.tmask, lane, status);
+        const uint32_t valid = kmb_tile_valid_starts(R, tile, n_bases, k, S.tmask, lane, status, r0, rs, re);
         mapped += __popc(valid);
         const uint2 a = *reinterpret_cast<const uint2 *>(&pack[2 * lane]);
         const uint2 b = *reinterpret_cast<const uint2 *>(&pack[2 * lane + 2]);
@@ -1181,8 +1194,14 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
     int late_n = 0;  // warp-uniform
     const uint32_t lanemask_lt = (1u << lane) - 1u;
 
-    for (uint64_t tile = (uint64_t)blockIdx.x * (KMB_MZ_THREADS / 32) + warp; tile < n_tiles; tile += warp_stride) {
+    const uint64_t first_tile = (uint64_t)blockIdx.x * (KMB_MZ_THREADS / 32) + warp;
+    uint32_t r_next = first_tile < n_tiles ? R.tile_read[first_tile] : 0u;
+    for (uint64_t tile = first_tile; tile < n_tiles; tile += warp_stride) {
         const uint64_t t0 = tile * KMB_WTILE_POS;
+        const uint64_t r0 = r_next;
+        if (tile + warp_stride < n_tiles) r_next = R.tile_read[tile + warp_stride];
+        int64_t rs, re;
+        kmb_read_span(R, r0 + (uint64_t)lane, rs, re);
         __syncwarp();
         // ---- 1. load + encode
 #pragma unroll 1
@@ -1200,7 +1219,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
         if (lane < 2) pack[KMB_WTILE_POS / 16 + 2 + lane] = 0u;  // read (not used) by the window extraction of the last positions
         __syncwarp();
         // ---- 2. this lane's 32 windows: which exist, where their minimizers sit, where runs start
-        const uint32_t valid = kmb_tile_valid_starts(R, tile, n_bases, k, S.valid, lane, status);
+        const uint32_t valid = kmb_tile_valid_starts(R, tile, n_bases, k, S.valid, lane, status, r0, rs, re);
         mapped += __popc(valid);
         if (!__any_sync(KMB_FULL_MASK, valid != 0u)) continue;
         __syncwarp();

@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) kmb_tp_count_newlines(const uint8_t *__re
     __shared__ uint32_t s_w[8];
     const uint64_t base = (uint64_t)blockIdx.x * KMB_TP_BLOCK_BYTES + (uint64_t)threadIdx.x * 16;
     uint32_t c = 0;
-    if (base + 16 <= n_text) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(text + base);   // text is 16-byte aligned (device allocation)
+    if (base + 16 <= n_text && (reinterpret_cast<uintptr_t>(text + base) & 15u) == 0u) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(text + base);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; i++) {

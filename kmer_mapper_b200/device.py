@@ -199,6 +199,20 @@ class Mapper:
         _order_after_torch(text, same_stream=self._stream)
         check(lib().kmb_mapper_map_text(self._h, pt, nt, int(fmt), int(k), flags))
 
+    def map_gz(self, gz, fmt, k, revcomp=False, n_to_a=True, shard_index=0, shard_count=1) -> int:
+        """A multi-member .gz of FASTA / FASTQ text, from its first byte: inflated, parsed and mapped on the device
+        (``kmb_mapper_map_gz``).  ``gz``: a uint8 numpy array (e.g. over a read-only file mapping) or bytes.  Returns the
+        offset from which the host decoders have to continue (``len(gz)`` when the device did everything, 0 when it
+        did nothing: a plain single-member .gz), skipping the first partial record there unless the offset is 0."""
+        if isinstance(gz, (bytes, bytearray, memoryview)):
+            gz = np.frombuffer(gz, dtype=np.uint8)
+        fmt = {"fasta": 0, "fastq": 1}.get(fmt, fmt)
+        flags = (FLAG_REVCOMP if revcomp else 0) | (0 if n_to_a else FLAG_NO_N_TO_A)
+        kg, pg, ng = as_buffer(gz, np.uint8, "gz")
+        resume = C.c_uint64(0)
+        check(lib().kmb_mapper_map_gz(self._h, pg, ng, int(fmt), int(k), flags, int(shard_index), int(shard_count), C.byref(resume)))
+        return int(resume.value)
+
     def flush(self):
         """Queue the slot-counter -> node-count pass on the mapper's stream (no host wait)."""
         check(lib().kmb_mapper_flush(self._h))

@@ -150,9 +150,10 @@ class ParallelGzip:
         self.n_threads = max(1, int(n_threads))
         self.max_member_bytes = int(self.MAX_MEMBER_BYTES if max_member_bytes is None else max_member_bytes)
 
-    def arrays(self, block_bytes, n_buffers=4):
+    def arrays(self, block_bytes, n_buffers=4, start=0):
         """Yields (buffer, n): the next n bytes of text are buffer[HEADROOM : HEADROOM + n], at least block_bytes of
-        them except at the end of the file.  Buffers rotate: one stays valid while the next n_buffers - 1 are made."""
+        them except at the end of the file.  Buffers rotate: one stays valid while the next n_buffers - 1 are made.
+        ``start``: offset of the member to begin with."""
         size = os.path.getsize(self.path)
         if size == 0:
             return
@@ -174,7 +175,7 @@ class ParallelGzip:
             whole = np.frombuffer(mm, dtype=np.uint8)
             base_ptr = whole.ctypes.data
             try:
-                pos = 0
+                pos = int(start)
                 while pos < size:
                     buf = next_buffer()
                     consumed, produced, flag = C.c_uint64(), C.c_uint64(), C.c_int()
@@ -242,14 +243,14 @@ class ReadFile:
         self._bases_per_byte = 0.0   # densest window seen so far: sizes the next window's output buffers
         self._reads_per_byte = 0.0
 
-    def _gz_arrays(self, block_bytes):
+    def _gz_arrays(self, block_bytes, start=0):
         """Background thread: inflate the next blocks while the current one is parsed and mapped.  Yields
         (buffer, n) like ParallelGzip.arrays, then None."""
         q = queue.Queue(maxsize=1)
 
         def produce():
             try:
-                for item in ParallelGzip(self.path, self.n_threads).arrays(block_bytes, n_buffers=4):
+                for item in ParallelGzip(self.path, self.n_threads).arrays(block_bytes, n_buffers=4, start=start):
                     q.put(item)          # 1 queued + 1 being parsed + 1 being filled < 4 buffers
                 q.put(None)
             except BaseException as e:  # surfaced in the consumer
@@ -381,10 +382,11 @@ class ReadFile:
                 return best or 0
             window *= 8
 
-    def text_chunks(self, min_chunk_size=64 << 20, rank=0, world_size=1):
+    def text_chunks(self, min_chunk_size=64 << 20, rank=0, world_size=1, gz_start=0):
         """Whole-record windows of the file's TEXT (TextChunk: address + length, valid until the next one is asked for),
         for the device-side parser.  Sharding as in read_chunks: a contiguous byte range of a plain file per rank, every
-        world_size-th block of a .gz."""
+        world_size-th block of a .gz.  ``gz_start``: begin at the gzip member at this offset and drop the text in front
+        of the first record start after the first newline (what ``Mapper.map_gz`` left to the host decoders)."""
         if not self.path.lower().endswith(".gz"):
             file_size = os.path.getsize(self.path)
             if file_size == 0:
@@ -419,13 +421,25 @@ class ReadFile:
             return
         head = ParallelGzip.HEADROOM
         carry = np.zeros(0, dtype=np.uint8)
-        for i, item in enumerate(self._gz_arrays(int(min_chunk_size))):
+        skip_partial = gz_start > 0
+        for i, item in enumerate(self._gz_arrays(int(min_chunk_size), start=gz_start)):
             final = item is None
             if final:
                 if carry.shape[0] and i % world_size == rank:
                     yield TextChunk(carry.ctypes.data, carry.shape[0], carry)
                 break
             buf, n = item
+            if skip_partial:
+                # what map_gz's last batch has already mapped: everything in front of the first record start after the
+                # first newline (the same rule on the same bytes: kmb_find_record_start from the member's first byte)
+                skip_partial = False
+                first = self._next_record_start(buf.ctypes.data + head, n, 1)
+                if first >= n and n >= (1 << 20):
+                    raise ValueError("%s: a record longer than 1 MB where the host decoders take over" % self.path)
+                buf = buf[first:]
+                n -= first
+                if n == 0:
+                    continue
             if carry.shape[0] <= head:
                 start = head - carry.shape[0]
                 buf[start:head] = carry

@@ -153,3 +153,181 @@ def test_map_text_route_vs_oracle_in_many_chunks(kmb, tmp_path):
     m.map_text(b">r1\nACGTACGTACGTACGTACGTACGTACGTACGTACGTRACGT\n", "fasta", k)
     with pytest.raises(InvalidBaseError):
         m.sync()
+
+
+# ---- gzip members inflated on the device (csrc/kmb_gzdev.cuh, kmb_mapper_map_gz) ------------------------------------
+def _gz_members(blobs, levels):
+    import zlib
+    out = []
+    for i, blob in enumerate(blobs):
+        c = zlib.compressobj(levels[i % len(levels)], zlib.DEFLATED, 31)
+        out.append(c.compress(blob) + c.flush())
+    return out
+
+
+def _fastq_text(bases, offsets, rng=None, lo=0, hi=None):
+    hi = len(offsets) - 1 if hi is None else hi
+    parts = []
+    for r in range(lo, hi):
+        seq = bytes(bases[offsets[r]:offsets[r + 1]])
+        q = b"I" * len(seq) if rng is None else bytes(rng.integers(33, 74, size=len(seq), dtype=np.uint8))
+        parts.append(b"@read%d some text\n%s\n+\n%s\n" % (r, seq, q))
+    return b"".join(parts)
+
+
+def _cut(text, sizes):
+    """text cut into pieces of the given sizes (cycled), anywhere -- not at record boundaries."""
+    out, p, i = [], 0, 0
+    while p < len(text):
+        n = sizes[i % len(sizes)]
+        out.append(text[p:p + n])
+        p += n
+        i += 1
+    return out
+
+
+@pytest.fixture(scope="module")
+def gz_case():
+    from kmer_mapper_b200 import synthetic
+    from kmer_mapper_b200.device import DeviceIndex
+    k = 31
+    g = synthetic.make_genome(300_000, 21)
+    idx = synthetic.make_index(g, 40_000, k, 30_000, 200_003, 22, n_hot_nodes=1100)
+    bases, offsets = synthetic.make_reads(g, 20_000, 150, seed=23, n_rate=0.01, lower_rate=0.2, ragged=True)
+    want, n_kmers = c_oracle.map_reads(idx, idx.max_node_id(), bases, offsets, k, n_threads=4)
+    return dict(k=k, idx=idx, di=DeviceIndex.from_index(idx), bases=bases, offsets=offsets, want=want, n_kmers=n_kmers)
+
+
+def _gz_stats(kmb):
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    kmb.check(kmb.lib().kmb_gz_device_stats(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+@pytest.mark.parametrize("name,sizes,levels,quality", [
+    ("bgzf_like", [65_280], [6], "random"),                       # dynamic Huffman blocks, few matches
+    ("constant_quality", [200_000], [1, 9], "const"),             # long overlapping matches (distance 1)
+    ("stored_and_fixed", [3_000, 40, 70_000, 1], [0, 1, 6], "const"),   # stored blocks, tiny members (fixed Huffman), 1-byte members
+    ("large_members", [1_500_000], [6], "random"),
+])
+def test_map_gz_on_device_vs_oracle(kmb, gz_case, name, sizes, levels, quality):
+    """Multi-member FASTQ.gz -> counts with every member inflated by a GPU warp == oracle; the device did it all (no
+    batch redone by the host decoder), in one batch and in many small ones (records straddle members and batches)."""
+    from kmer_mapper_b200.device import Mapper
+    rng = np.random.default_rng(5) if quality == "random" else None
+    text = _fastq_text(gz_case["bases"], gz_case["offsets"], rng)
+    gz = b"".join(_gz_members(_cut(text, sizes), levels))
+    for batch in (256 << 20, 1 << 20):
+        kmb.set_option("gz_device_batch_bytes", batch)
+        try:
+            before = _gz_stats(kmb)
+            m = Mapper(gz_case["di"])
+            resume = m.map_gz(gz, "fastq", gz_case["k"])
+            got = m.counts()
+            after = _gz_stats(kmb)
+            assert resume == len(gz)
+            assert np.array_equal(got, gz_case["want"]), (name, batch)
+            assert m.stats()[0] == gz_case["n_kmers"]
+            assert after[1] - before[1] == len(text) and after[2] == before[2], (before, after)
+            m.close()
+        finally:
+            kmb.set_option("gz_device_batch_bytes", 256 << 20)
+
+
+def test_map_gz_fasta_and_shards(kmb, gz_case):
+    """FASTA.gz (multi-line records), and the batches dealt to two shards: the two count arrays add up to the oracle's."""
+    from kmer_mapper_b200.device import Mapper
+    b, o = gz_case["bases"], gz_case["offsets"]
+    text = b"".join(b">r%d\n" % r + b"".join(bytes(b[i:min(i + 61, o[r + 1])]) + b"\n" for i in range(o[r], o[r + 1], 61)) for r in range(len(o) - 1))
+    gz = b"".join(_gz_members(_cut(text, [50_000, 7_000]), [6, 1]))
+    kmb.set_option("gz_device_batch_bytes", 1 << 20)
+    try:
+        total = np.zeros_like(gz_case["want"])
+        n = 0
+        for shard in range(2):
+            m = Mapper(gz_case["di"])
+            assert m.map_gz(gz, "fasta", gz_case["k"], shard_index=shard, shard_count=2) == len(gz)
+            c = m.counts()
+            assert c.any()
+            total += c
+            n += m.stats()[0]
+            m.close()
+        assert np.array_equal(total, gz_case["want"]) and n == gz_case["n_kmers"]
+    finally:
+        kmb.set_option("gz_device_batch_bytes", 256 << 20)
+
+
+def test_map_gz_hands_over_to_the_host_decoders(kmb, gz_case, tmp_path):
+    """A member too large for one warp (gz_device_max_member_bytes) ends the device's part: resume offset = a member
+    start, the host decoders continue there and every record is mapped exactly once (CLI route, 1 and 2 shards).  A plain
+    single-member .gz is left to the host entirely."""
+    from kmer_mapper_b200.command_line_interface import map_file_text
+    from kmer_mapper_b200.device import Mapper
+    from kmer_mapper_b200.reader import open_reads
+    text = _fastq_text(gz_case["bases"], gz_case["offsets"])
+    n = len(text)
+    pieces = _cut(text[:n // 2], [300_000]) + [text[n // 2: n // 2 + 2_500_000]] + _cut(text[n // 2 + 2_500_000:], [200_000])
+    members = _gz_members(pieces, [6])
+    path = str(tmp_path / "mixed.fq.gz")
+    with open(path, "wb") as f:
+        f.write(b"".join(members))
+    from kmer_mapper_b200.reader import ParallelGzip
+    old = ParallelGzip.BATCH_BYTES, ParallelGzip.MAX_MEMBER_BYTES
+    ParallelGzip.BATCH_BYTES, ParallelGzip.MAX_MEMBER_BYTES = 3_000_000, 2_600_000     # several host blocks, too
+    kmb.set_option("gz_device_max_member_bytes", 2_000_000)
+    kmb.set_option("gz_device_batch_bytes", 1 << 20)
+    try:
+        for world in (1, 2):
+            total = np.zeros_like(gz_case["want"])
+            for rank in range(world):
+                m = Mapper(gz_case["di"])
+                reads = open_reads(path, n_threads=3)
+                n_chunks, host_from = map_file_text(m, reads, gz_case["k"], rank=rank, world_size=world, chunk_bytes=400_000)
+                assert host_from is not None and 0 < host_from < os.path.getsize(path)
+                total += m.counts()
+                m.close()
+                reads.close()
+            assert np.array_equal(total, gz_case["want"]), world
+        # single member: nothing for the device
+        single = str(tmp_path / "single.fq.gz")
+        with open(single, "wb") as f:
+            f.write(_gz_members([text], [6])[0])
+        m = Mapper(gz_case["di"])
+        reads = open_reads(single, n_threads=3)
+        n_chunks, host_from = map_file_text(m, reads, gz_case["k"])
+        assert host_from == 0 and n_chunks >= 1
+        assert np.array_equal(m.counts(), gz_case["want"])
+        m.close()
+        reads.close()
+    finally:
+        ParallelGzip.BATCH_BYTES, ParallelGzip.MAX_MEMBER_BYTES = old
+        kmb.set_option("gz_device_max_member_bytes", 16 << 20)
+        kmb.set_option("gz_device_batch_bytes", 256 << 20)
+
+
+def test_map_gz_corrupt_member_is_an_error_and_wrong_crc_is_caught(kmb, gz_case):
+    from kmer_mapper_b200._lib import KmbError
+    from kmer_mapper_b200.device import Mapper
+    text = _fastq_text(gz_case["bases"], gz_case["offsets"], hi=4000)
+    members = _gz_members(_cut(text, [100_000]), [6])
+    # a flipped CRC byte in one trailer: the device decodes fine, the CRC comparison fails, the host decoder fails too
+    bad = bytearray(b"".join(members))
+    pos = len(members[0]) + len(members[1]) - 8
+    bad[pos] ^= 0x55
+    m = Mapper(gz_case["di"])
+    with pytest.raises(KmbError):
+        m.map_gz(bytes(bad), "fastq", gz_case["k"])
+    m.close()
+    # garbage in the middle of a deflate stream
+    bad = bytearray(b"".join(members))
+    mid = len(members[0]) + len(members[1]) // 2
+    bad[mid:mid + 64] = bytes(range(64))
+    m = Mapper(gz_case["di"])
+    with pytest.raises(KmbError):
+        m.map_gz(bytes(bad), "fastq", gz_case["k"])
+    m.close()
+    # not a gzip file at all
+    m = Mapper(gz_case["di"])
+    with pytest.raises(KmbError):
+        m.map_gz(b"@r\nACGT\n+\nIIII\n" * 10, "fastq", gz_case["k"])
+    m.close()
