@@ -76,6 +76,8 @@ def parse_args(argv=None):
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-files", action="store_true", help="skip the reads/s leg (FASTQ / FASTQ.gz files -> counts)")
     p.add_argument("--file-reads", type=int, default=8_000_000, help="reads in the files of the reads/s leg")
+    p.add_argument("--host-pack", type=int, default=-1, help="e2e leg: library option host_pack (-1 default = hybrid for pinned input, "
+                   "1 every chunk 2-bit packed by the CPU, 0 every chunk ASCII)")
     p.add_argument("--no-oracle", action="store_true", help="skip the oracle parity checks (tuning runs only)")
     p.add_argument("--full-oracle", action="store_true", help="N=1: also run EVERY read of the step through the oracle")
     p.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
@@ -313,8 +315,8 @@ def _gz_member(args):
 
 def write_fastq_files(dirname, bases, n_reads, read_len):
     """<dir>/reads.fq (4-line records, constant quality) from the first n_reads device-resident reads -- assembled on the
-    GPU as one [n, record_len] byte matrix -- and <dir>/reads.fq.gz, the same text as concatenated gzip members of ~4 MB
-    (what bgzip / `cat a.gz b.gz` produce; BASELINE configs[1] names FASTQ.gz)."""
+    GPU as one [n, record_len] byte matrix -- and the same text as two multi-member .gz files (BASELINE configs[1] names
+    FASTQ.gz): <dir>/reads.fq.gz and <dir>/reads_bgzf.fq.gz."""
     import multiprocessing as mp
     import torch
     dev = bases.device
@@ -337,12 +339,16 @@ def write_fastq_files(dirname, bases, n_reads, read_len):
     m.cpu().numpy().tofile(fq)
     del m
     size = os.path.getsize(fq)
-    per = max(rec, (4 << 20) // rec * rec)
-    cuts = [(fq, lo, min(lo + per, size)) for lo in range(0, size, per)]
-    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool, open(fq + ".gz", "wb") as out:
-        for blob in pool.imap(_gz_member, cuts, chunksize=4):
-            out.write(blob)
-    return fq, fq + ".gz"
+    out = [fq]
+    # members of ~4 MB of text cut at records (`cat a.gz b.gz ...`), and BGZF-like members of 65280 bytes of text cut
+    # anywhere (what bgzip writes: the usual multi-member FASTQ.gz)
+    for name, per in (("reads.fq.gz", max(rec, (4 << 20) // rec * rec)), ("reads_bgzf.fq.gz", 65280)):
+        cuts = [(fq, lo, min(lo + per, size)) for lo in range(0, size, per)]
+        with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool, open(os.path.join(dirname, name), "wb") as f:
+            for blob in pool.imap(_gz_member, cuts, chunksize=max(4, (1 << 20) // per)):
+                f.write(blob)
+        out.append(os.path.join(dirname, name))
+    return tuple(out)
 
 
 def time_file_to_counts(path, di, n_counts, k):
@@ -356,6 +362,7 @@ def time_file_to_counts(path, di, n_counts, k):
     out = torch.empty(n_counts, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)   # where the counts land
     m = Mapper(di, n_counts)           # the mapper (its staging buffers) outlives a file, like the index
     best = None
+    g0 = _gz_device_members()
     for _ in range(2):
         m.reset()
         r0 = _lib.get_option("text_reads")
@@ -369,7 +376,15 @@ def time_file_to_counts(path, di, n_counts, k):
         best = dt
     counts = out.copy()
     m.close()
-    return n / best, n, best, counts
+    return n / best, n, best, counts, (_gz_device_members() - g0) // 2
+
+
+def _gz_device_members():
+    import ctypes as C
+    from kmer_mapper_b200 import _lib
+    a = C.c_uint64()
+    _lib.check(_lib.lib().kmb_gz_device_stats(C.byref(a), None, None))
+    return int(a.value)
 
 # ---------------------------------------------------------------------------------------------
 # main arms
@@ -609,9 +624,10 @@ def main_ours(args):
         ho.copy_(offsets)
         torch.cuda.synchronize()
         hb_np, ho_np, hc_np = hb.numpy(), ho.numpy(), hc.numpy().view(np.uint32)
-        # the same transport at every N: bases cross PCIe as 2 bits each, encoded inside the timed region by this
-        # rank's share of the host cores (distributed.init_process_group set host_threads = cores / ranks)
-        _lib.set_option("host_pack", 1)
+        # the same transport policy at every N -- the library's default for a pinned source, the hybrid: a chunk goes as
+        # ASCII straight from this buffer when the bus is about to run dry and is packed to 2 bits per base by this
+        # rank's share of the host cores otherwise (distributed.init_process_group set host_threads = cores / ranks)
+        _lib.set_option("host_pack", args.host_pack)
 
         def step_e2e():
             mapper.reset()
@@ -624,6 +640,7 @@ def main_ours(args):
         torch.cuda.synchronize()
         barrier()
         h2d_before = _lib.get_option("h2d_bytes")
+        chunks_before = _lib.get_option("host_chunks_packed"), _lib.get_option("host_chunks_ascii")
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_e2e()
@@ -631,13 +648,17 @@ def main_ours(args):
         barrier()
         dt = float(over_ranks(time.perf_counter() - t0, dist.ReduceOp.MAX))
         h2d_per_step = (_lib.get_option("h2d_bytes") - h2d_before) // args.steps
+        n_packed = _lib.get_option("host_chunks_packed") - chunks_before[0]
+        n_ascii = _lib.get_option("host_chunks_ascii") - chunks_before[1]
+        host_threads = _lib.get_option("host_threads") or len(os.sched_getaffinity(0))
         e2e = {"value": total_kmers * args.steps / dt / 1e9, "unit": UNIT,
                # bytes the library actually put on the bus (counted where it issues the copies): with the packed
                # transport the bases cross as 2 bits each, encoded on the host inside the timed region
                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(4 * n_counts),
                "host_input_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
-               "host_transport": "2-bit packed on %d CPU threads" % (_lib.get_option("host_threads") or len(os.sched_getaffinity(0)))
-               if h2d_per_step < n_bases else "ascii",
+               "host_transport": "%d of %d chunks 2-bit packed on %d CPU threads, the others ASCII over the bus from the caller's "
+               "pinned buffer (host_pack=%d)" % (n_packed, n_packed + n_ascii, host_threads, args.host_pack),
+               "chunks_packed_fraction": n_packed / max(n_packed + n_ascii, 1),
                "ms_per_step": dt * 1e3 / args.steps, "timing": "host wall clock between device synchronisations",
                "bytes_are": "per rank"}
         checks["e2e_counts_equal_resident_counts"] = bool(np.array_equal(hc_np, full_counts.cpu().numpy().view(np.uint32)))
@@ -651,20 +672,25 @@ def main_ours(args):
         n_file_reads = min(n_reads, args.file_reads)
         fdir = tempfile.mkdtemp(prefix="kmb_files_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
-            fq, fqgz = write_fastq_files(fdir, bases, n_file_reads, L)
+            fq, fqgz, fqbgzf = write_fastq_files(fdir, bases, n_file_reads, L)
             with torch.cuda.stream(stream):
                 mapper.reset()
                 mapper.map_reads(bases[:n_file_reads * L], offsets[:n_file_reads + 1], k)
                 mapper.flush()
                 torch.cuda.synchronize()
             want_counts = counts.cpu().numpy().view(np.uint32)
-            reads_per_s = {"n_reads": int(n_file_reads), "route": "file text -> pinned staging -> H2D -> record parsing on the "
-                           "device (kmb_mapper_map_text) -> fused kernel -> counts D2H; wall clock from opening the file, "
-                           "index already on the device, file in the page cache (tmpfs)",
-                           "host_cores": cores}
-            for name, path in (("fastq", fq), ("fastq_gz_multi_member", fqgz)):
-                rate, n_seen, secs, got_counts = time_file_to_counts(path, di, n_counts, k)
+            reads_per_s = {"n_reads": int(n_file_reads), "route": "file -> pinned staging -> H2D -> [gzip members inflated on the "
+                           "device, one per warp: kmb_mapper_map_gz, when they average <= 512 KB of text (BGZF); by the host "
+                           "decoders on all cores otherwise] -> record parsing on the device (kmb_mapper_map_text) -> fused "
+                           "kernel -> counts D2H; wall clock from opening the file, index already on the device, file in "
+                           "the page cache (tmpfs)", "host_cores": cores,
+                           "fastq_gz_bgzf_members": "65280 bytes of text each (what bgzip writes)",
+                           "fastq_gz_multi_member_members": "~4 MB of text each"}
+            for name, path in (("fastq", fq), ("fastq_gz_bgzf", fqbgzf), ("fastq_gz_multi_member", fqgz)):
+                rate, n_seen, secs, got_counts, dev_members = time_file_to_counts(path, di, n_counts, k)
                 reads_per_s[name] = rate
+                if path.endswith(".gz"):
+                    reads_per_s[name + "_members_inflated_on_device"] = dev_members
                 reads_per_s[name + "_file_bytes"] = os.path.getsize(path)
                 reads_per_s[name + "_seconds"] = secs
                 checks["file_%s_counts_equal_resident_counts" % name] = bool(n_seen == n_file_reads and np.array_equal(got_counts, want_counts))

@@ -257,11 +257,12 @@ int kmb_gzstream_close(kmb_gzstream *stream);
 int kmb_find_record_start(const uint8_t *text, uint64_t n_text, int format, uint64_t *offset);
 
 /* ---- packed transport of host-resident reads -----------------------------------------------------
- * kmb_mapper_map_reads on HOST buffers encodes the bases to 2 bits each on the CPU (all cores, AVX2 when the
- * CPU has it), straight into pinned staging, and sends a quarter of the bytes over PCIe (option "host_pack": 1 always, 0 never,
- * default -1 = when the encoder threads outrun the bus: a pinned source with >= 10 threads and the host to itself
- * ("host_ranks" = 1: the encoder is bound by host DRAM bandwidth, which the ranks of a node share), a pageable source
- * with >= 2 threads; "host_threads", default 0 = every CPU of the affinity mask).  Same table as the kernels apply to
+ * kmb_mapper_map_reads on HOST buffers can encode the bases to 2 bits each on the CPU (all cores, AVX2 when the CPU has
+ * it), straight into pinned staging, and send a quarter of the bytes over PCIe.  Option "host_pack": 1 every chunk packed,
+ * 0 every chunk as ASCII, 2 hybrid -- a chunk goes as ASCII straight from the caller's pinned buffer whenever the bus is
+ * about to run dry (costs no CPU time) and is packed by the cores otherwise, so bases arrive at about the sum of the two
+ * rates (config 2, 16 cores: 38.7 GK/s ASCII, 51.2 packed, 66.8 hybrid) --, default -1 = hybrid for a pinned source, packed
+ * for a pageable one with >= 2 threads ("host_threads", default 0 = every CPU of the affinity mask).  Same table as the kernels apply to
  * unpacked input (DNAEncoding as used at util.py:71-75; N -> A of command_line_interface.py:41), same invalid-byte
  * report.  kmb_pack_bases is that encoder on its own: word j of words[] = bases 16j..16j+15, base 16j in the lowest
  * bits, positions past n_bases read as 'A'; words_capacity >= (n_bases + 15) / 16 + 4 (the last 4 are zero padding).
@@ -299,7 +300,10 @@ int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kern
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
  *  "apply_window_log2" (nodes per apply window, default 23 = 32 MB of counters),
- *  "gz_device_max_member_bytes", "gz_device_batch_bytes", "gz_device_crc" (kmb_mapper_map_gz),
+ *  "gz_device_max_member_bytes", "gz_device_batch_bytes", "gz_device_crc", "gz_device_max_mean_member_bytes" (kmb_mapper_map_gz:
+ *  files whose members average more text than the last one are left to the host decoders, *resume_offset = 0),
+ *  "host_pack" (host chunks of kmb_mapper_map_reads: 1 packed to 2 bits per base by the CPU, 0 ASCII, 2 hybrid -- both pipes side
+ *  by side --, -1 default: hybrid for a pinned source, packed for a pageable one), "host_hybrid_backlog_bytes",
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
  *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
  *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),

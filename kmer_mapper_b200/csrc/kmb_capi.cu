@@ -97,7 +97,13 @@ struct KmbOptions {
     // The encoder is bound by the host's DRAM bandwidth, which the ranks of a multi-GPU node share, while every GPU
     // has its own PCIe link: with 2 ranks on one host a pinned source went 46.9 GK/s packed against 74.3 as ASCII
     // (profiles/README.md), so auto packs a pinned source only when this process has the host to itself.
+    // 1 = every chunk packed, 0 = every chunk as ASCII, 2 = hybrid: the bus and the cores work SIDE BY SIDE -- a chunk
+    // goes as ASCII straight from the caller's pinned buffer whenever less than host_hybrid_backlog_bytes are waiting
+    // for the bus (costs no CPU time), and is packed by the cores otherwise (costs a quarter of the bus time), so
+    // bases reach the GPU at about the SUM of the two rates; -1 (default) = hybrid for a pinned source, packed for a
+    // pageable one (which has to be staged by the CPU anyway).
     int64_t host_pack = -1;
+    int64_t host_hybrid_backlog_bytes = 0;   // 0 = one chunk (chunk_bytes)
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
     int64_t host_ranks = 1;               // processes sharing this host's memory system (set by distributed.py)
     // The apply pass reduces into one window of 2^apply_window_log2 nodes at a time (x 4 bytes: 23 = 32 MB).  The
@@ -109,10 +115,16 @@ struct KmbOptions {
     // batch; whether every member's CRC-32 is recomputed on the device and compared with its trailer
     int64_t gz_device_max_member_bytes = 16ll << 20;
     int64_t gz_device_batch_bytes = 256ll << 20;
+    // one warp inflates ~15 MB/s of text, the host decoders ~0.3 GB/s per core: the device wins when a batch holds
+    // hundreds of members (bgzip: 64 KB each -> 4000 per batch, 14.5 GB/s measured against 4.8 on 16 cores), and loses
+    // when it holds a few dozen large ones (4 MB members: 0.9 GB/s), so files whose members average more text than
+    // this are left to the host decoders
+    int64_t gz_device_max_mean_member_bytes = 512ll << 10;
     int64_t gz_device_crc = 1;
 };
 static KmbOptions g_opt;
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_host_chunks_packed{0}, g_host_chunks_ascii{0};
 static std::atomic<unsigned long long> g_h2d_bytes{0};  // bytes the mapping calls sent host -> device (bench.py's e2e)
 static std::atomic<unsigned long long> g_text_reads{0}, g_text_bases{0};  // parsed by kmb_mapper_map_text
 // where the host side of kmb_mapper_map_text spends its time (microseconds, cumulative): waiting for a free slot,
@@ -151,8 +163,10 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(apply_window_log2)
+    OPT(host_hybrid_backlog_bytes)
     OPT(gz_device_max_member_bytes)
     OPT(gz_device_batch_bytes)
+    OPT(gz_device_max_mean_member_bytes)
     OPT(gz_device_crc)
 #undef OPT
     if (!strcmp(name, "chunk_bytes")) {
@@ -194,8 +208,10 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(apply_window_log2)
+    OPT(host_hybrid_backlog_bytes)
     OPT(gz_device_max_member_bytes)
     OPT(gz_device_batch_bytes)
+    OPT(gz_device_max_mean_member_bytes)
     OPT(gz_device_crc)
     OPT(chunk_bytes)
 #undef OPT
@@ -203,6 +219,8 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
         *value = g_last_reads_kernel.load();
         return KMB_OK;
     }
+    if (!strcmp(name, "host_chunks_packed")) { *value = (int64_t)g_host_chunks_packed.load(); return KMB_OK; }   // read-only
+    if (!strcmp(name, "host_chunks_ascii")) { *value = (int64_t)g_host_chunks_ascii.load(); return KMB_OK; }     // read-only
     if (!strcmp(name, "text_us_slot")) { *value = (int64_t)g_text_us_slot.load(); return KMB_OK; }
     if (!strcmp(name, "text_us_stage")) { *value = (int64_t)g_text_us_stage.load(); return KMB_OK; }
     if (!strcmp(name, "text_us_wait")) { *value = (int64_t)g_text_us_wait.load(); return KMB_OK; }
@@ -583,12 +601,14 @@ struct StageSlot {
     uint32_t *h_crc = nullptr, *d_crc = nullptr;              // h_crc pinned
     uint8_t *h_windows = nullptr;                             // pinned: the first bytes of the batch's text and of its extra member
     size_t members_cap = 0;
+    uint64_t bus_bytes = 0;             // host chunks: what this slot put on the bus (0 once seen across), hybrid transport
     const uint8_t *text_ptr = nullptr;  // the text the parse kernels read: s.text, or a window of it (gz route)
     uint64_t text_n = 0;                // the chunk in flight: its size, format and the mapping arguments
     int text_format = 0, text_k = 0;
     uint32_t text_flags = 0;
 };
-#define KMB_SLOTS 3  // one chunk being encoded, one on the bus, one under the kernel
+#define KMB_SLOTS 6       // host chunks: being encoded / queued for the bus (a few, see the hybrid transport) / under the kernel
+#define KMB_TEXT_SLOTS 3  // text and gz batches (large): one being staged, one on the bus + parsed, one under the kernel
 
 struct kmb_mapper {
     kmb_index *index = nullptr;
@@ -1196,8 +1216,12 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_reads: offsets[0] must be 0 and offsets[n_reads] must equal n_bases");
     const uint64_t chunk = (uint64_t)g_opt.chunk_bytes;
     const int pack_threads = g_opt.host_threads > 0 ? (int)g_opt.host_threads : kmb_host_cpus();
-    const bool want_pack = g_opt.host_pack > 0 ||
-                           (g_opt.host_pack < 0 && (pinned_b ? (pack_threads >= 10 && g_opt.host_ranks <= 1) : pack_threads >= 2));
+    // transport of a host chunk (see KmbOptions::host_pack): 0 ASCII, 1 packed, 2 hybrid
+    int mode;
+    if (g_opt.host_pack >= 0) mode = (int)std::min<int64_t>(g_opt.host_pack, 2);
+    else mode = pack_threads >= 2 ? (pinned_b ? 2 : 1) : 0;
+    if (mode == 2 && !pinned_b) mode = 1;
+    const uint64_t backlog_limit = g_opt.host_hybrid_backlog_bytes > 0 ? (uint64_t)g_opt.host_hybrid_backlog_bytes : chunk;
     uint64_t r0 = 0;
     while (r0 < n_reads) {
         // largest r1 with offsets[r1] - offsets[r0] <= chunk (at least one read)
@@ -1211,7 +1235,20 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
             StageSlot &s = m->slot[m->next_slot];
             m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
             if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));  // also makes re-allocation safe
-            const bool packed = want_pack && nb < (1ull << 32);
+            s.bus_bytes = 0;
+            bool packed = mode == 1;
+            if (mode == 2) {
+                // bytes queued for the bus and not yet across: the bus must never run dry, the cores take the rest
+                uint64_t waiting = 0;
+                for (int i = 0; i < KMB_SLOTS; i++)
+                    if (m->slot[i].bus_bytes) {
+                        if (cudaEventQuery(m->slot[i].copied) == cudaErrorNotReady) waiting += m->slot[i].bus_bytes;
+                        else m->slot[i].bus_bytes = 0;
+                    }
+                (void)cudaGetLastError();
+                packed = waiting >= backlog_limit;
+            }
+            packed = packed && nb < (1ull << 32);
             if (packed) {
                 // encode on the CPU into pinned staging while the previous chunks are on the bus / under the kernel
                 const size_t n_words = (size_t)kmb_packed_words(nb);
@@ -1222,13 +1259,16 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
                 kmb_host_rel_offsets(offsets + r0, nr + 1, (int64_t)b0, pack_threads, s.h_off);
                 KMB_CUDA(cudaMemcpyAsync(s.data, s.h_words, n_words * 4, cudaMemcpyHostToDevice, m->copy_stream));
                 KMB_CUDA(cudaMemcpyAsync(s.offsets, s.h_off, (nr + 1) * 4, cudaMemcpyHostToDevice, m->copy_stream));
-                g_h2d_bytes += n_words * 4 + (nr + 1) * 4;
+                s.bus_bytes = n_words * 4 + (nr + 1) * 4;
+                g_host_chunks_packed++;
             } else {
                 KMB_TRY(slot_reserve(s, nb + 16, nr + 1, nb / KMB_WTILE_POS + 1));
                 KMB_CUDA(cudaMemcpyAsync(s.data, bases + b0, nb, cudaMemcpyHostToDevice, m->copy_stream));
                 KMB_CUDA(cudaMemcpyAsync(s.offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, m->copy_stream));
-                g_h2d_bytes += nb + (nr + 1) * 8;
+                s.bus_bytes = nb + (nr + 1) * 8;
+                g_host_chunks_ascii++;
             }
+            g_h2d_bytes += s.bus_bytes;
             KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
             KMB_CUDA(cudaStreamWaitEvent(m->stream, s.copied, 0));
             KMB_TRY(launch_map_reads(m, s.data, nb, b0, s.offsets, nr, s.tiles, k, flags, packed));
@@ -1376,11 +1416,11 @@ static int map_text_impl(kmb_mapper *m, const uint8_t *text, int fd, uint64_t fd
     KMB_ON_DEVICE(m->index->device);
     bool dev = false, pinned = false;
     if (text) KMB_TRY(ptr_on_device(text, m->index->device, &dev, &pinned));
-    const int slot_index = m->next_slot;
+    const int slot_index = m->next_slot % KMB_TEXT_SLOTS;
     if (m->text_pending == slot_index) KMB_TRY(text_finish_pending(m));
     unsigned long long t0 = text_now_us();
     StageSlot &s = m->slot[slot_index];
-    m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
+    m->next_slot = (slot_index + 1) % KMB_TEXT_SLOTS;
     if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
     g_text_us_slot += text_now_us() - t0;
     t0 = text_now_us();
@@ -1632,6 +1672,11 @@ extern "C" int kmb_mapper_map_gz(kmb_mapper *m, const uint8_t *gz, uint64_t n_gz
         while (n_dev > 0 && text < KMB_GZ_WINDOW) text += isize[--n_dev];
     }
     if (n_dev == 0) return KMB_OK;   // *resume_offset == 0: everything through the host decoders
+    {
+        uint64_t text = 0;
+        for (size_t i = 0; i < n_dev; i++) text += isize[i];
+        if (text / n_dev > (uint64_t)std::max<int64_t>(g_opt.gz_device_max_mean_member_bytes, 1)) return KMB_OK;   // too few, too large
+    }
     const uint64_t batch_cap = (uint64_t)std::max<int64_t>(g_opt.gz_device_batch_bytes, 1 << 20);
     const bool check_crc = g_opt.gz_device_crc != 0;
     // ---- 2. batches of whole members, each followed by its overlap
@@ -1660,8 +1705,8 @@ extern "C" int kmb_mapper_map_gz(kmb_mapper *m, const uint8_t *gz, uint64_t n_gz
     size_t bi = 0;
     for (GzBatch &b : batches) {
         if ((int)(bi++ % (size_t)shard_count) != shard_index) continue;
-        b.slot = m->next_slot;
-        m->next_slot = (m->next_slot + 1) % KMB_SLOTS;
+        b.slot = m->next_slot % KMB_TEXT_SLOTS;
+        m->next_slot = (b.slot + 1) % KMB_TEXT_SLOTS;
         StageSlot &s = m->slot[b.slot];
         if (s.used) KMB_CUDA(cudaEventSynchronize(s.consumed));
         const size_t n_mem = b.x1 - b.m0;

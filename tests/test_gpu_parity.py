@@ -323,8 +323,10 @@ def test_read_table_is_chosen_by_itself_only_behind_a_thin_key_filter(kmb):
         kmb.set_option("read_table", -1)
 
 
-@pytest.mark.parametrize("host_pack,host_threads,read_table", [(1, 0, 0), (1, 3, 0), (0, 0, 0), (1, 0, 1), (0, 0, 1)])
+@pytest.mark.parametrize("host_pack,host_threads,read_table", [(1, 0, 0), (1, 3, 0), (0, 0, 0), (1, 0, 1), (0, 0, 1), (2, 0, 0), (-1, 2, 0)])
 def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads, read_table):
+    """host_pack 2 / -1 with a PINNED source: the hybrid transport -- some chunks packed by the cores, the others as
+    ASCII straight from the caller's buffer, whichever pipe is free -- must give the same counts as either alone."""
     from kmer_mapper_b200 import synthetic as S
     from kmer_mapper_b200.device import DeviceIndex, Mapper
     kmb.set_option("host_pack", host_pack)
@@ -336,10 +338,18 @@ def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads,
     mx = idx.max_node_id()
     bases, offsets = S.make_reads(g, 50_000, 150, seed=9, ragged=True, n_rate=0.01)
     want, _ = c_oracle.map_reads(idx, mx, bases, offsets, k, n_threads=4)
+    hybrid = host_pack in (2, -1)
+    if hybrid:
+        import torch
+        pb, po = torch.from_numpy(bases).pin_memory(), torch.from_numpy(offsets).pin_memory()
+        bases, offsets = pb.numpy(), po.numpy()
     kmb.set_option("chunk_bytes", 1 << 16)                  # ~120 chunks: exercises the slot ring
     m = Mapper(di, mx + 1)
+    before = kmb.get_option("host_chunks_packed"), kmb.get_option("host_chunks_ascii")
     m.map_reads(bases, offsets, k)
     assert np.array_equal(m.counts(), want)
+    if hybrid:     # both pipes were used
+        assert kmb.get_option("host_chunks_packed") > before[0] and kmb.get_option("host_chunks_ascii") > before[1]
     # linearity: mapping two halves into the same mapper == mapping the whole (additive map-reduce, cli:124-130)
     m.reset()
     half = 25_000

@@ -219,6 +219,7 @@ def test_map_gz_on_device_vs_oracle(kmb, gz_case, name, sizes, levels, quality):
     gz = b"".join(_gz_members(_cut(text, sizes), levels))
     for batch in (256 << 20, 1 << 20):
         kmb.set_option("gz_device_batch_bytes", batch)
+        kmb.set_option("gz_device_max_mean_member_bytes", 16 << 20)     # also the large members go to the device here
         try:
             before = _gz_stats(kmb)
             m = Mapper(gz_case["di"])
@@ -232,6 +233,11 @@ def test_map_gz_on_device_vs_oracle(kmb, gz_case, name, sizes, levels, quality):
             m.close()
         finally:
             kmb.set_option("gz_device_batch_bytes", 256 << 20)
+            kmb.set_option("gz_device_max_mean_member_bytes", 512 << 10)
+    if name == "large_members":      # by default a file of few large members is left to the host decoders
+        m = Mapper(gz_case["di"])
+        assert m.map_gz(gz, "fastq", gz_case["k"]) == 0 and not m.counts().any()
+        m.close()
 
 
 def test_map_gz_fasta_and_shards(kmb, gz_case):
@@ -266,15 +272,17 @@ def test_map_gz_hands_over_to_the_host_decoders(kmb, gz_case, tmp_path):
     from kmer_mapper_b200.reader import open_reads
     text = _fastq_text(gz_case["bases"], gz_case["offsets"])
     n = len(text)
-    pieces = _cut(text[:n // 2], [300_000]) + [text[n // 2: n // 2 + 2_500_000]] + _cut(text[n // 2 + 2_500_000:], [200_000])
+    a, b = n // 2, n // 2 + 1_300_000
+    assert n > 3_000_000
+    pieces = _cut(text[:a], [150_000]) + [text[a:b]] + _cut(text[b:], [100_000])
     members = _gz_members(pieces, [6])
     path = str(tmp_path / "mixed.fq.gz")
     with open(path, "wb") as f:
         f.write(b"".join(members))
     from kmer_mapper_b200.reader import ParallelGzip
     old = ParallelGzip.BATCH_BYTES, ParallelGzip.MAX_MEMBER_BYTES
-    ParallelGzip.BATCH_BYTES, ParallelGzip.MAX_MEMBER_BYTES = 3_000_000, 2_600_000     # several host blocks, too
-    kmb.set_option("gz_device_max_member_bytes", 2_000_000)
+    ParallelGzip.BATCH_BYTES, ParallelGzip.MAX_MEMBER_BYTES = 1_500_000, 1_400_000     # several host blocks, too
+    kmb.set_option("gz_device_max_member_bytes", 1_000_000)
     kmb.set_option("gz_device_batch_bytes", 1 << 20)
     try:
         for world in (1, 2):

@@ -26,13 +26,9 @@ tindex, bases, offsets = bench.generate(w, 0, torch.device("cuda", 0))
 di = DeviceIndex.from_index(tindex, device=0)
 n_counts = tindex.max_node_id() + 1
 d = tempfile.mkdtemp(prefix="kmb_files_", dir="/dev/shm")
-fq, fqgz = bench.write_fastq_files(d, bases, n_reads, w["read_len"])
+fq, fqgz, bgzf = bench.write_fastq_files(d, bases, n_reads, w["read_len"])
 size = os.path.getsize(fq)
-bgzf = os.path.join(d, "reads_bgzf.fq.gz")
-cuts = [(fq, lo, min(lo + 65280, size)) for lo in range(0, size, 65280)]
-with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool, open(bgzf, "wb") as out:
-    for blob in pool.imap(bench._gz_member, cuts, chunksize=64):
-        out.write(blob)
+_lib.set_option("gz_device_max_mean_member_bytes", 64 << 20)    # the device route also for the large members
 
 mapper = Mapper(di, n_counts)
 mapper.map_reads(bases[:n_reads * w["read_len"]], offsets[:n_reads + 1], w["k"])
