@@ -60,6 +60,7 @@ static int kmb_fail(int code, const char *fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 struct KmbOptions {
     int64_t map_reads_blocks_per_sm = 0;  // 0 = whatever the occupancy calculator allows
+    int64_t map_carveout = -1;            // shared-memory carve-out of the mapping kernels in percent of the maximum, -1 = driver's choice
     int64_t map_kmers_blocks_per_sm = 0;
     int64_t probe_variant = 1;            // map_kmers: 0 = one query per thread, 1 = staged probe with warp stack
     int64_t chunk_bytes = 64ll << 20;     // staging slot size for host input
@@ -140,6 +141,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
         return KMB_OK;            \
     }
     OPT(map_reads_blocks_per_sm)
+    OPT(map_carveout)
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
     OPT(gathers_in_flight)
@@ -185,6 +187,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
         return KMB_OK;            \
     }
     OPT(map_reads_blocks_per_sm)
+    OPT(map_carveout)
     OPT(map_kmers_blocks_per_sm)
     OPT(probe_variant)
     OPT(gathers_in_flight)
@@ -615,7 +618,7 @@ struct kmb_mapper {
     uint64_t n_counts = 0;
     uint32_t *counts = nullptr;
     bool own_counts = false;
-    KmbLog log = {nullptr, nullptr, nullptr, 0, 0, 1, 0};  // hit log (grown on demand), its group tags and cursor
+    KmbLog log = {nullptr, nullptr, nullptr, 0, 0, 1, 0, KMB_LOG_BINS};  // hit log (grown on demand), its group tags and cursor
     int log_windows = 1;           // apply windows: ((n_counts - 1) >> win_shift) + 1
     bool dirty = false;            // the logs may hold hits that are not yet in the node counts
     uint64_t queries_since_flush = 0;
@@ -760,6 +763,7 @@ static int launch_flush(kmb_mapper *m) {
 // Size the log for a launch of n_queries look-ups: room for one hit per four queries (twice the hit rate of
 // the benchmark shapes), between 2^23 and log_max_entries ids.  A log that runs full is not an error: the
 // kernels then reduce directly onto the counts.
+static bool may_use_read_table(const kmb_index *ix);
 static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
     uint64_t want = std::max<uint64_t>(n_queries / 4, 1ull << 23);
     want = std::min<uint64_t>(want, (uint64_t)std::max<int64_t>(g_opt.log_max_entries, 1 << 10));
@@ -767,10 +771,13 @@ static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
     if (!m->log.cursor) {
         KMB_CUDA(cudaMalloc(&m->log.cursor, sizeof(unsigned long long)));
         KMB_CUDA(cudaMemsetAsync(m->log.cursor, 0, sizeof(unsigned long long), m->stream));
+        // 16 node ranges, or 8 where the read-path kernel (whose shared memory has room for 8 stacks) may serve this index
+        const uint32_t n_bins = may_use_read_table(m->index) ? KMB_MZ_LOG_BINS : KMB_LOG_BINS;
         uint32_t shift = 0;
-        while (((m->n_counts ? m->n_counts - 1 : 0) >> shift) >= KMB_LOG_BINS) shift++;
+        while (((m->n_counts ? m->n_counts - 1 : 0) >> shift) >= n_bins) shift++;
         m->log.bin_shift = shift;
         m->log.win_shift = shift;
+        m->log.n_bins = n_bins;
     }
     if (want > m->log.cap) {
         if (m->dirty) KMB_TRY(launch_flush(m));
@@ -941,6 +948,7 @@ static MapKernel pick_map_kernel(bool reads, bool filt, bool rc) {
 static int resident_blocks(const MapKernel &mk, int64_t opt, int *out) {
     int b = 0;
     KMB_CUDA(cudaFuncSetAttribute(mk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk.smem));
+    if (g_opt.map_carveout >= 0) KMB_CUDA(cudaFuncSetAttribute(mk.fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<int64_t>(g_opt.map_carveout, 100)));
     KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mk.fn, KMB_MAP_THREADS, mk.smem));
     if (b < 1) b = 1;
     if (opt > 0) b = (int)std::min<int64_t>(opt, 32);
@@ -1036,11 +1044,16 @@ static int ensure_read_table(kmb_index *ix, int k) {
     return KMB_OK;
 }
 
-static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
-    if (k != KMB_MZ_K || (flags & KMB_FLAG_REVCOMP) || g_opt.read_table == 0 || ix->mz_k < 0) return false;
+// whether some launch on this index could take the read-path kernel (decides the shape of a mapper's hit log)
+static bool may_use_read_table(const kmb_index *ix) {
+    if (g_opt.read_table == 0 || ix->mz_k < 0) return false;
     if (g_opt.read_table > 0) return true;
     const bool thin_filter = !ix->filter_on || ix->addr.n_probes <= 1u;
     return thin_filter && ix->n_live >= (uint64_t)std::max<int64_t>(g_opt.read_table_min_entries, 0);
+}
+static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
+    if (k != KMB_MZ_K || (flags & KMB_FLAG_REVCOMP)) return false;
+    return may_use_read_table(ix);
 }
 
 // launch the tile -> read table + the fused kernel over one device-resident batch.  packed: d_bases is the 2-bit
@@ -1062,8 +1075,10 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases));
     KmbProbe P = make_probe(m);
     const uint32_t in_mode = ((flags & KMB_FLAG_NO_N_TO_A) ? 0u : KMB_IN_N_TO_A) | (packed ? KMB_IN_PACKED : 0u);
-    if (use_read_table(ix, k, flags)) KMB_TRY(ensure_read_table(m->index, k));
-    if (use_read_table(ix, k, flags) && ix->mz_k == k) {
+    // (a log shaped for the key-addressed kernels -- the option was switched on after it was made -- keeps them)
+    const bool want_mz = use_read_table(ix, k, flags) && m->log.n_bins <= KMB_MZ_LOG_BINS;
+    if (want_mz) KMB_TRY(ensure_read_table(m->index, k));
+    if (want_mz && ix->mz_k == k) {
         g_last_reads_kernel = 1;
         const KmbProbe Pkey = P;  // the key-addressed sectors: where the rare tile that overflows the run table goes
         P.lines = ix->mz_lines;

@@ -68,6 +68,7 @@ struct KmbLog {  // hit log of one mapper: `cap` node ids in groups of 32, one n
     uint32_t bin_shift;          // bin = node >> bin_shift
     uint32_t chunk_groups;       // groups reserved per atomic
     uint32_t win_shift;          // apply pass: one window of 2^win_shift nodes at a time (<= bin_shift)
+    uint32_t n_bins;             // node ranges in use: (n_counts - 1) >> bin_shift < n_bins <= KMB_LOG_BINS
 };
 
 struct KmbProbe {  // everything a probe needs, passed by value to the kernels
@@ -454,7 +455,9 @@ __device__ __forceinline__ void kmb_probe_line(const KmbProbe &P, const KmbPol &
 // and let the overflow valve of kmb_emit work).  A stack with >= 32 ids sends its top 32 as one
 // coalesced 128-byte store to the log; the space is reserved with one atomic per 32 hits or more.
 // ------------------------------------------------------------------------------------------------
+#ifndef KMB_STAGE_SLOTS
 #define KMB_STAGE_SLOTS 96
+#endif
 #define KMB_LOG_HOLE 0xFFFFFFFFu
 #define KMB_LOG_NO_BIN 0xFFu
 #define KMB_RES_FULL 0xFFFFFFFFu
@@ -464,6 +467,7 @@ struct KmbStage {
     unsigned long long *res_base;  // [KMB_LOG_BINS] next free position of this warp's reservation for the bin
     uint32_t *res_left;            // [KMB_LOG_BINS] groups left in that reservation, or KMB_RES_FULL
     uint32_t slots;                // capacity of one bin's stack
+    uint32_t bins;                 // stacks there are room for (>= the log's n_bins)
 };
 // `node_counts[node] += 1` (mapper.pyx:68) straight onto the count array: the fallback of every path that cannot
 // use the log (log full, hit found in an overflow chain, staging stack full, apply-table collision).  Warp-
@@ -479,9 +483,9 @@ __device__ __forceinline__ void kmb_count_direct(uint32_t *counts, uint32_t node
     }
 }
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
-    const uint32_t b = kmb_log_bin(node, P.log.bin_shift);
+    const uint32_t b = min(node >> P.log.bin_shift, st.bins - 1u);
     KMB_BOUND(6, node, P.n_counts);
-    KMB_BOUND(3, b, KMB_LOG_BINS);
+    KMB_BOUND(3, b, st.bins);
     const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
     if (pos < st.slots) st.buf[b * st.slots + pos] = node;
     else kmb_count_direct(P.counts, node);  // valve: the stack is full (the flush clamps the count)
@@ -540,13 +544,13 @@ __device__ __forceinline__ void kmb_stage_send(const KmbLog &log, uint32_t *coun
 // Groups that were reserved but never written keep the tag KMB_LOG_NO_BIN and are skipped by the apply pass.
 __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStage &st, int lane, bool all) {
     __syncwarp();
-    const uint32_t c = lane < KMB_LOG_BINS ? min(st.cnt[lane], st.slots) : 0u;  // clamp: the valve of kmb_emit
+    const uint32_t c = (uint32_t)lane < st.bins ? min(st.cnt[lane], st.slots) : 0u;  // clamp: the valve of kmb_emit
     const unsigned ready = __ballot_sync(KMB_FULL_MASK, all ? c > 0u : c >= 32u);
     if (ready) kmb_stage_send(P.log, P.counts, st, ready, c, lane, all);
     __syncwarp();
 }
 __device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane) {
-    if (lane < KMB_LOG_BINS) {
+    if ((uint32_t)lane < st.bins) {
         st.cnt[lane] = 0;
         st.res_left[lane] = 0;
         st.res_base[lane] = 0;
@@ -810,6 +814,7 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
 }
 
 // Per-warp shared memory of the key-addressed mapping kernels: 5.9 KB per warp = 47 KB per CTA, three CTAs per SM.
+#define KMB_TILE_VECS (KMB_WTILE_POS / 16 + 2)  // 16-byte vectors of bases per warp tile, halo included
 template <int U>
 struct alignas(16) KmbWarpShared {
     static constexpr int kStageSlots = KMB_STAGE_SLOTS;
@@ -841,7 +846,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     uint32_t *pack = S.pack;
     uint64_t *q_kmer = S.qk;
     uint32_t *q_h = S.qh;
-    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots};
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots, (uint32_t)KMB_LOG_BINS};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
@@ -944,7 +949,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 // a run of one lane: lane | first window << 5 | last window << 10 | minimizer position (0..47) << 15
 #define KMB_MZ_RUN(lane, s, e, j) ((uint32_t)(lane) | ((uint32_t)(s) << 5) | ((uint32_t)((e) - 1) << 10) | ((uint32_t)(j) << 15))
 struct alignas(16) KmbMzShared {  // per warp
-    unsigned long long stage_res[KMB_LOG_BINS];
+    unsigned long long stage_res[KMB_MZ_LOG_BINS];
     unsigned long long late_lo[KMB_MZ_LATE_CAP], late_hi[KMB_MZ_LATE_CAP];  // the 64 bases of the run's lane
     uint32_t pack[KMB_MZ_PACK_WORDS];
     union {
@@ -958,8 +963,8 @@ struct alignas(16) KmbMzShared {  // per warp
     uint32_t valid[32];                      // per lane: which of its 32 windows exist
     uint8_t slot2_of[KMB_MZ_SLOTS];          // secondary slot of a primary slot, KMB_MZ_NONE, or KMB_MZ_LATE
     uint32_t late_valid[KMB_MZ_LATE_CAP], late_sector[KMB_MZ_LATE_CAP], late_sej[KMB_MZ_LATE_CAP];  // s | e << 8 | jpos << 16
-    uint32_t stage[KMB_LOG_BINS * KMB_MZ_STAGE_SLOTS];
-    uint32_t stage_cnt[2 * KMB_LOG_BINS];
+    uint32_t stage[KMB_MZ_LOG_BINS * KMB_MZ_STAGE_SLOTS];
+    uint32_t stage_cnt[2 * KMB_MZ_LOG_BINS];
 };
 #define KMB_MZ_SMEM_BYTES ((KMB_MZ_THREADS / 32) * sizeof(KmbMzShared))
 static_assert(sizeof(KmbMzShared) % 16 == 0, "per-warp shared block must keep the 16-byte alignment of the staged sectors");
@@ -1180,7 +1185,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
     const bool packed = (in_mode & KMB_IN_PACKED) != 0u;
     const uint32_t *__restrict__ words = reinterpret_cast<const uint32_t *>(bases);
     const uint64_t n_words = (n_bases + 15) / 16 + 4;
-    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, KMB_MZ_STAGE_SLOTS};
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_MZ_LOG_BINS, KMB_MZ_STAGE_SLOTS, KMB_MZ_LOG_BINS};
     kmb_stage_init(st, lane);
     unsigned counted = 0, fetched = 0;
     const KmbPol pol = kmb_make_policies(P.policies);
@@ -1493,7 +1498,7 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
     KmbWarpShared<U> &S = reinterpret_cast<KmbWarpShared<U> *>(kmb_map_smem)[warp];
     uint64_t *q_kmer = S.qk;
     uint32_t *q_h = S.qh;
-    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots};
+    const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots, (uint32_t)KMB_LOG_BINS};
     kmb_stage_init(st, lane);
     unsigned counted = 0;
     int qcount = 0;
@@ -1583,6 +1588,9 @@ __global__ void kmb_map_kmers_simple_kernel(const uint64_t *__restrict__ kmers, 
 // already present switches the table off, so uniformly distributed nodes (config 2) pay almost nothing.
 // ================================================================================================
 #define KMB_APPLY_TABLE 2048
+#ifndef KMB_APPLY_UNROLL
+#define KMB_APPLY_UNROLL 8   // groups of 32 ids a warp has in flight
+#endif
 __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, uint32_t *__restrict__ counts) {
     __shared__ uint32_t s_id[KMB_APPLY_TABLE];
     __shared__ uint32_t s_cnt[KMB_APPLY_TABLE];
@@ -1593,7 +1601,7 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, uint32_t
     __syncthreads();
     const uint32_t window = blockIdx.y;
     const uint32_t sub_shift = log.bin_shift - log.win_shift;
-    const uint32_t bin = min(window >> sub_shift, (uint32_t)(KMB_LOG_BINS - 1));
+    const uint32_t bin = min(window >> sub_shift, log.n_bins - 1u);
     // the last range takes every node beyond it (kmb_log_bin clamps), so only a window that is not the last one of
     // its range has to look at the ids; with one window per range nothing does
     const bool filter_ids = sub_shift != 0u;
@@ -1609,18 +1617,46 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, uint32_t
     const uint32_t *__restrict__ tags4 = reinterpret_cast<const uint32_t *>(log.tags);  // capacity is a multiple of 4096 ids
     bool use_table = true, decided = false;
     uint32_t seen = 0, present = 0;
-    for (uint64_t g0 = g_lo + (uint64_t)warp * 128; g0 < g_hi; g0 += (uint64_t)warps * 128) {
+    const uint64_t g_first = g_lo + (uint64_t)warp * 128, g_step = (uint64_t)warps * 128;
+    // the tags of the NEXT 128 groups are requested before this block's groups are played, and the groups of a block
+    // that belong to the window are fetched KMB_APPLY_UNROLL at a time: their DRAM latencies overlap instead of adding up
+    // (one group per warp in flight made the pass latency-bound at 0.4 TB/s)
+    uint32_t t4_next = (g_first < g_hi && g_first + 4ull * lane < g_hi) ? tags4[(g_first + 4ull * lane) >> 2] : 0xFFFFFFFFu;
+    for (uint64_t g0 = g_first; g0 < g_hi; g0 += g_step) {
         const uint64_t gl = g0 + 4ull * lane;  // this lane's four groups
         if (gl < g_hi) KMB_BOUND(10, gl >> 2, log.cap >> 7);
-        const uint32_t t4 = gl < g_hi ? tags4[gl >> 2] : 0xFFFFFFFFu;
+        const uint32_t t4 = t4_next;
+        {
+            const uint64_t gn = g0 + g_step + 4ull * lane;
+            t4_next = gn < g_hi ? tags4[gn >> 2] : 0xFFFFFFFFu;
+        }
+        // bit p of (hi:lo) <=> group g0 + 4 (p % 32) + p / 32 belongs to this window's range
+        unsigned long long lo = (unsigned long long)__ballot_sync(KMB_FULL_MASK, gl + 0 < g_hi && ((t4 >> 0) & 0xFFu) == bin) |
+                                ((unsigned long long)__ballot_sync(KMB_FULL_MASK, gl + 1 < g_hi && ((t4 >> 8) & 0xFFu) == bin) << 32);
+        unsigned long long hi = (unsigned long long)__ballot_sync(KMB_FULL_MASK, gl + 2 < g_hi && ((t4 >> 16) & 0xFFu) == bin) |
+                                ((unsigned long long)__ballot_sync(KMB_FULL_MASK, gl + 3 < g_hi && ((t4 >> 24) & 0xFFu) == bin) << 32);
+        while (lo | hi) {
+            uint32_t ids[KMB_APPLY_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            unsigned mine = __ballot_sync(KMB_FULL_MASK, gl + k < g_hi && ((t4 >> (8 * k)) & 0xFFu) == bin);
-            while (mine) {
-                const int j = __ffs(mine) - 1;
-                mine &= mine - 1u;
-                KMB_BOUND(11, ((g0 + 4ull * j + k) << 5) + lane, log.cap);
-                uint32_t id = log.entries[((g0 + 4ull * j + k) << 5) + lane];
+            for (int q = 0; q < KMB_APPLY_UNROLL; q++) {
+                int p = -1;
+                if (lo) {
+                    p = __ffsll((long long)lo) - 1;
+                    lo &= lo - 1ull;
+                } else if (hi) {
+                    p = 64 + __ffsll((long long)hi) - 1;
+                    hi &= hi - 1ull;
+                }
+                ids[q] = KMB_LOG_HOLE;
+                if (p >= 0) {
+                    const uint64_t g = g0 + 4ull * (uint64_t)(p & 31) + (uint64_t)(p >> 5);
+                    KMB_BOUND(11, (g << 5) + lane, log.cap);
+                    ids[q] = log.entries[(g << 5) + lane];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < KMB_APPLY_UNROLL; q++) {
+                uint32_t id = ids[q];
                 if (filter_ids && id != KMB_LOG_HOLE) {
                     const uint32_t w = id >> log.win_shift;
                     if (!(w == window || (last_window && w > window))) id = KMB_LOG_HOLE;
@@ -1638,12 +1674,12 @@ __global__ void __launch_bounds__(256) kmb_log_apply_kernel(KmbLog log, uint32_t
                     }
                 }
                 if (use_table && !decided && __any_sync(KMB_FULL_MASK, seen >= 8u)) {  // ~256 ids per warp looked at: decide once
-                    uint32_t p = present, t = seen;
+                    uint32_t pp = present, t = seen;
                     for (int o = 16; o > 0; o >>= 1) {
-                        p += __shfl_xor_sync(KMB_FULL_MASK, p, o);
+                        pp += __shfl_xor_sync(KMB_FULL_MASK, pp, o);
                         t += __shfl_xor_sync(KMB_FULL_MASK, t, o);
                     }
-                    if (p * 16u < t) use_table = false;
+                    if (pp * 16u < t) use_table = false;
                     decided = true;
                 }
             }

@@ -1,0 +1,6 @@
+set -x
+run() { KMB_LIB_PATH=$PWD/kmer_mapper_b200/libkmer_mapper_b200$1.so timeout 400 python tools/sweep.py --grid $2 --steps 3 > gpurun_out/r2_sweep_l1$1_$2.jsonl 2>gpurun_out/r2_sweep_l1$1_$2.err; echo "variant '$1' grid $2"; cut -c1-330 gpurun_out/r2_sweep_l1$1_$2.jsonl; }
+run _bins8 carve
+run _bins8s64 carve
+run _bins8s48 r2
+run "" cta2
