@@ -663,6 +663,30 @@ def main_ours(args):
                "bytes_are": "per rank"}
         checks["e2e_counts_equal_resident_counts"] = bool(np.array_equal(hc_np, full_counts.cpu().numpy().view(np.uint32)))
         _lib.set_option("host_pack", -1)
+        # what bounds it: the host's memory system (every base is read from host DRAM at least once -- by the cores that
+        # pack it or by the GPU's DMA engine -- and all ranks of the node share it) and this GPU's PCIe link
+        import ctypes as C
+        gbs = C.c_double()
+        probe = min(n_bases, 4 << 30)
+        _lib.check(_lib.lib().kmb_host_read_bandwidth(hb_np.ctypes.data, probe, 0, C.byref(gbs)))      # page in / warm up
+        barrier()                                                                                        # all ranks at once
+        _lib.check(_lib.lib().kmb_host_read_bandwidth(hb_np.ctypes.data, probe, 0, C.byref(gbs)))
+        e2e["host_read_GBps_per_rank_all_ranks_at_once"] = round(gbs.value, 1)
+        dst = torch.empty(min(n_bases, 1 << 30), dtype=torch.uint8, device=device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(hb[:dst.shape[0]], non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        ev0.record()
+        for i in range(6):
+            lo = (i * dst.shape[0]) % max(n_bases - dst.shape[0], 1)
+            dst.copy_(hb[lo:lo + dst.shape[0]], non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        e2e["pcie_h2d_GBps_per_rank_all_ranks_at_once"] = round(6 * dst.shape[0] / (ev0.elapsed_time(ev1) / 1e3) / 1e9, 1)
+        e2e["bound"] = ("host memory bandwidth and PCIe: every base is read from host DRAM once (1 byte: DMA of an ASCII chunk) or "
+                        "~1.5 times (read by the cores, written packed, read by the DMA engine), and an ASCII chunk needs 4x the bus time")
+        del dst
         del hb, ho, hc
 
     # ---- reads/s from files (N == 1): FASTQ and multi-member FASTQ.gz of the batch's first reads, file open -> counts on

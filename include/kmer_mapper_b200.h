@@ -275,7 +275,11 @@ int kmb_pack_bases(const uint8_t *bases, uint64_t n_bases, uint32_t flags, int n
 int kmb_host_alloc(void **ptr, size_t bytes);
 int kmb_host_free(void *ptr);
 
-/* ---- measurement helpers (bench.py): the random-gather micro-roofline of SURVEY.md 8(d) -------
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------
+ * Host memory read bandwidth in GB/s: n_threads (0 = all) workers sum buf[0, n_bytes) once.  What the packed transport
+ * and the DMA engines of all GPUs of a host share: the bound of the end-to-end numbers. */
+int kmb_host_read_bandwidth(const void *buf, uint64_t n_bytes, int n_threads, double *gb_per_s);
+/* The random-gather micro-roofline of SURVEY.md 8(d).
  * Issues n_loads uniform random loads of load_bytes (8, 16 or 32) from a table of table_bytes,
  * `unroll` independent loads in flight per thread; returns the CUDA-event time in ms. */
 int kmb_bench_gather(int device, uint64_t table_bytes, uint64_t n_loads, int load_bytes, int unroll,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "kmb_gzstream_error": (C.c_char_p, [_vp]),
     "kmb_gzstream_close": (C.c_int, [_vp]),
     "kmb_find_record_start": (C.c_int, [_vp, C.c_uint64, C.c_int, _u64p]),
+    "kmb_host_read_bandwidth": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "kmb_pack_bases": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_int64)]),
     "kmb_parse_reads": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp, C.c_uint64,
                                   _u64p, _u64p, _u64p]),

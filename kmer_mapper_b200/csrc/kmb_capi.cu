@@ -2192,6 +2192,44 @@ extern "C" int kmb_pack_bases(const uint8_t *bases, uint64_t n_bases, uint32_t f
     return KMB_OK;
 }
 
+// Host memory read bandwidth: n_threads workers of the library's pool sum buf[0, n_bytes) once (64-bit loads);
+// what the packed transport and the DMA engines of every GPU on the host have to share (bench.py reports it next to
+// the end-to-end number it bounds).
+struct HostReadJob {
+    const uint64_t *p;
+    uint64_t n_words, per;
+    std::atomic<uint64_t> sum;
+};
+static void host_read_part(void *ctx, int part) {
+    HostReadJob *j = (HostReadJob *)ctx;
+    const uint64_t lo = std::min(j->n_words, j->per * (uint64_t)part), hi = std::min(j->n_words, lo + j->per);
+    uint64_t a = 0, b = 0, c = 0, d = 0;
+    uint64_t i = lo;
+    for (; i + 4 <= hi; i += 4) {
+        a += j->p[i];
+        b += j->p[i + 1];
+        c += j->p[i + 2];
+        d += j->p[i + 3];
+    }
+    for (; i < hi; i++) a += j->p[i];
+    j->sum += a + b + c + d;
+}
+extern "C" int kmb_host_read_bandwidth(const void *buf, uint64_t n_bytes, int n_threads, double *gb_per_s) {
+    if (!buf || !gb_per_s || n_bytes < 8) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_host_read_bandwidth: bad argument");
+    const int threads = n_threads > 0 ? n_threads : kmb_host_cpus();
+    HostReadJob job;
+    job.p = (const uint64_t *)(((uintptr_t)buf + 7) & ~(uintptr_t)7);
+    job.n_words = (n_bytes - 8) / 8;
+    const int parts = threads * 8;
+    job.per = (job.n_words + parts - 1) / parts;
+    job.sum = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    kmb_host_parallel(threads, parts, host_read_part, &job);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *gb_per_s = (double)job.n_words * 8.0 / dt / 1e9 + (job.sum.load() == 0x123456789ull ? 1e-30 : 0.0);
+    return KMB_OK;
+}
+
 extern "C" int kmb_in_graph_index(kmb_index *ix, const uint64_t *kmers, uint64_t n, uint8_t *out) {
     if (!ix) return kmb_fail(KMB_ERR_BAD_ARG, "kmb_in_graph_index: null index");
     KMB_ON_DEVICE(ix->device);
