@@ -261,8 +261,10 @@ int kmb_find_record_start(const uint8_t *text, uint64_t n_text, int format, uint
  * it), straight into pinned staging, and send a quarter of the bytes over PCIe.  Option "host_pack": 1 every chunk packed,
  * 0 every chunk as ASCII, 2 hybrid -- a chunk goes as ASCII straight from the caller's pinned buffer whenever the bus is
  * about to run dry (costs no CPU time) and is packed by the cores otherwise, so bases arrive at about the sum of the two
- * rates (config 2, 16 cores: 38.7 GK/s ASCII, 51.2 packed, 66.8 hybrid) --, default -1 = hybrid for a pinned source, packed
- * for a pageable one with >= 2 threads ("host_threads", default 0 = every CPU of the affinity mask).  Same table as the kernels apply to
+ * rates (config 2, 16 cores: 38.7 GK/s ASCII, 51.2 packed, 66.8 hybrid) --, default -1 = packed for a pageable source with
+ * >= 2 threads ("host_threads", default 0 = every CPU of the affinity mask); for a pinned one hybrid when the process has the
+ * host to itself ("host_ranks" = 1, set by distributed.init_process_group) and ASCII when several ranks share the host's memory
+ * system (the cores' streaming reads slow every rank's DMA down: 8 ranks, 557 ms per step hybrid, 380 ASCII).  Same table as the kernels apply to
  * unpacked input (DNAEncoding as used at util.py:71-75; N -> A of command_line_interface.py:41), same invalid-byte
  * report.  kmb_pack_bases is that encoder on its own: word j of words[] = bases 16j..16j+15, base 16j in the lowest
  * bits, positions past n_bases read as 'A'; words_capacity >= (n_bases + 15) / 16 + 4 (the last 4 are zero padding).

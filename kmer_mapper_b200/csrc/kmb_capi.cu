@@ -101,8 +101,9 @@ struct KmbOptions {
     // 1 = every chunk packed, 0 = every chunk as ASCII, 2 = hybrid: the bus and the cores work SIDE BY SIDE -- a chunk
     // goes as ASCII straight from the caller's pinned buffer whenever less than host_hybrid_backlog_bytes are waiting
     // for the bus (costs no CPU time), and is packed by the cores otherwise (costs a quarter of the bus time), so
-    // bases reach the GPU at about the SUM of the two rates; -1 (default) = hybrid for a pinned source, packed for a
-    // pageable one (which has to be staged by the CPU anyway).
+    // bases reach the GPU at about the SUM of the two rates; -1 (default) = packed for a pageable source (which has to
+    // be staged by the CPU anyway); for a pinned one hybrid when the process has the host to itself (host_ranks = 1),
+    // ASCII when it shares it.
     int64_t host_pack = -1;
     int64_t host_hybrid_backlog_bytes = 0;   // 0 = one chunk (chunk_bytes)
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
@@ -1234,7 +1235,11 @@ extern "C" int kmb_mapper_map_reads(kmb_mapper *m, const uint8_t *bases, uint64_
     // transport of a host chunk (see KmbOptions::host_pack): 0 ASCII, 1 packed, 2 hybrid
     int mode;
     if (g_opt.host_pack >= 0) mode = (int)std::min<int64_t>(g_opt.host_pack, 2);
-    else mode = pack_threads >= 2 ? (pinned_b ? 2 : 1) : 0;
+    else if (!pinned_b) mode = pack_threads >= 2 ? 1 : 0;
+    // a pinned source: hybrid when this process has the host to itself.  When several ranks share the host's memory
+    // system the cores' streaming reads slow every rank's DMA down (measured, 8 ranks x 4 threads: 557 ms per step
+    // hybrid against 380 ms ASCII; 4 ranks: 300 / 300; 2 ranks: 162 / 156), so there the bases go as they are.
+    else mode = (pack_threads >= 4 && g_opt.host_ranks <= 1) ? 2 : 0;
     if (mode == 2 && !pinned_b) mode = 1;
     const uint64_t backlog_limit = g_opt.host_hybrid_backlog_bytes > 0 ? (uint64_t)g_opt.host_hybrid_backlog_bytes : chunk;
     uint64_t r0 = 0;
