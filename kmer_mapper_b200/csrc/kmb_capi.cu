@@ -108,10 +108,12 @@ struct KmbOptions {
     int64_t host_hybrid_backlog_bytes = 0;   // 0 = one chunk (chunk_bytes)
     int64_t host_threads = 0;             // CPU threads of the host-side encoder: 0 = every CPU of the affinity mask
     int64_t host_ranks = 1;               // processes sharing this host's memory system (set by distributed.py)
-    // The apply pass reduces into one window of 2^apply_window_log2 nodes at a time (x 4 bytes: 23 = 32 MB).  The
-    // windows of one launch overlap where one ends and the next begins, so two must fit the L2 together: measured on
-    // config 2 (516 M reductions): 9.4 ms at 2^24, 5.3 ms at 2^23, 6.2 ms at 2^22 (more passes over the log).
-    int64_t apply_window_log2 = 23;
+    // The apply pass reduces into one window of 2^apply_window_log2 nodes at a time (x 4 bytes: 23 = 32 MB), reading the
+    // groups of the window's node range once per window of the range.  0 = auto: 2^23 when that means at most two
+    // passes over a range's groups, else 2^24.  Measured per 0.51 G reductions with the stream evict-first and the
+    // counters evict-last: 80 M nodes (ranges of 2^24): 3.3 ms at 2^23, 4.0 at 2^24; 400 M nodes (ranges of 2^26):
+    // 12.1 ms at 2^23 (eight passes), 6.6 at 2^24, 10.8 at 2^25, 16.0 at 2^26 (one pass, window far larger than the L2).
+    int64_t apply_window_log2 = 0;
     // gzip members inflated on the device (kmb_mapper_map_gz): a member that announces more text than this is left to
     // the host decoders (one warp decodes one member: a plain single-member .gz has no parallelism to offer); text per
     // batch; whether every member's CRC-32 is recomputed on the device and compared with its trailer
@@ -746,7 +748,8 @@ static int launch_flush(kmb_mapper *m) {
     if (m->log.entries) {
         // one launch, blockIdx.y = node window: the windows are worked off in dispatch order
         const uint64_t last = m->n_counts ? m->n_counts - 1 : 0;
-        const uint32_t want = (uint32_t)std::min<int64_t>(std::max<int64_t>(g_opt.apply_window_log2, 10), 31);
+        const uint32_t want = g_opt.apply_window_log2 > 0 ? (uint32_t)std::min<int64_t>(std::max<int64_t>(g_opt.apply_window_log2, 10), 31)
+                                                         : (m->log.bin_shift <= 24u ? 23u : 24u);
         m->log.win_shift = std::min(m->log.bin_shift, want);
         m->log_windows = (int)((last >> m->log.win_shift) + 1);
         KMB_TRY(timed_begin(m, 1));

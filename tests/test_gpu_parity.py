@@ -323,7 +323,7 @@ def test_read_table_is_chosen_by_itself_only_behind_a_thin_key_filter(kmb):
         kmb.set_option("read_table", -1)
 
 
-@pytest.mark.parametrize("host_pack,host_threads,read_table", [(1, 0, 0), (1, 3, 0), (0, 0, 0), (1, 0, 1), (0, 0, 1), (2, 0, 0), (-1, 2, 0)])
+@pytest.mark.parametrize("host_pack,host_threads,read_table", [(1, 0, 0), (1, 3, 0), (0, 0, 0), (1, 0, 1), (0, 0, 1), (2, 0, 0), (-1, 4, 0)])
 def test_map_reads_chunked_host_path_and_linearity(kmb, host_pack, host_threads, read_table):
     """host_pack 2 / -1 with a PINNED source: the hybrid transport -- some chunks packed by the cores, the others as
     ASCII straight from the caller's buffer, whichever pipe is free -- must give the same counts as either alone."""

@@ -36,10 +36,11 @@ def main():
         "filter": dict(gathers_in_flight=[2], filter_l2_budget_bytes=[40 << 20, 48 << 20, 52 << 20, 56 << 20, 60 << 20], use_filter=[1]),
         "size": dict(gathers_in_flight=[2], filter_l2_budget_bytes=[54 << 20, 57 << 20], sectors_per_100_entries=[200, 226, 250, 300], use_filter=[1]),
         "persist": dict(use_filter=[1], gathers_in_flight=[8], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
-        "r2": dict(apply_window_log2=[23]),
+        "r2": dict(apply_window_log2=[0]),
         "carve": dict(map_carveout=[-1, 100, 72, 58]),
         "cta2": dict(map_reads_blocks_per_sm=[0, 2]),
         "u": dict(gathers_in_flight=[4, 8]),
+        "window3": dict(apply_window_log2=[26, 25, 24, 23]),
         "window": dict(apply_window_log2=[26, 25, 24, 23, 22, 21]),
     }[a.grid]
     names = list(grids)
