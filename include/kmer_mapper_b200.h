@@ -305,6 +305,7 @@ int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kern
  *  "use_filter", "filter_l2_budget_bytes", "sectors_per_100_entries", "l2_persist", "ablate", "policy_filter", "policy_line", "log_max_entries",
  *  "time_kernels",
  *  "l2_fetch_granularity", "bench_grid_blocks", "bench_load_mode", "chunk_bytes", "host_pack", "host_threads", "host_ranks", "filter_probes" (filter bits per key, 0 = by density),
+ *  "direct_counts_max_nodes" (count arrays up to this size -- default 4 Mi nodes -- are reduced onto directly: no hit log, no apply pass),
  *  "apply_window_log2" (nodes per apply window; default 0 = auto: 2^23 = 32 MB of counters, 2^24 for count arrays beyond 128 M nodes),
  *  "gz_device_max_member_bytes", "gz_device_batch_bytes", "gz_device_crc", "gz_device_max_mean_member_bytes" (kmb_mapper_map_gz:
  *  files whose members average more text than the last one are left to the host decoders, *resume_offset = 0),

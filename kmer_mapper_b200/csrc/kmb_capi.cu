@@ -114,6 +114,10 @@ struct KmbOptions {
     // counters evict-last: 80 M nodes (ranges of 2^24): 3.3 ms at 2^23, 4.0 at 2^24; 400 M nodes (ranges of 2^26):
     // 12.1 ms at 2^23 (eight passes), 6.6 at 2^24, 10.8 at 2^25, 16.0 at 2^26 (one pass, window far larger than the L2).
     int64_t apply_window_log2 = 0;
+    // Count arrays of at most this many nodes (4 Mi = 16 MB: L2-resident whatever else is going on) are reduced onto
+    // directly by the mapping kernels (warp-aggregated RED, kmb_count_direct): no hit log, no apply pass, no log reset --
+    // three launches less per step, which is what a small job consists of (config 1: 100 k reads, 0.18 ms per step).
+    int64_t direct_counts_max_nodes = 4ll << 20;
     // gzip members inflated on the device (kmb_mapper_map_gz): a member that announces more text than this is left to
     // the host decoders (one warp decodes one member: a plain single-member .gz has no parallelism to offer); text per
     // batch; whether every member's CRC-32 is recomputed on the device and compared with its trailer
@@ -168,6 +172,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(apply_window_log2)
+    OPT(direct_counts_max_nodes)
     OPT(host_hybrid_backlog_bytes)
     OPT(gz_device_max_member_bytes)
     OPT(gz_device_batch_bytes)
@@ -214,6 +219,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(read_table_buckets_per_100_entries)
     OPT(filter_probes)
     OPT(apply_window_log2)
+    OPT(direct_counts_max_nodes)
     OPT(host_hybrid_backlog_bytes)
     OPT(gz_device_max_member_bytes)
     OPT(gz_device_batch_bytes)
@@ -769,6 +775,10 @@ static int launch_flush(kmb_mapper *m) {
 // kernels then reduce directly onto the counts.
 static bool may_use_read_table(const kmb_index *ix);
 static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
+    if (!m->log.entries && m->n_counts <= (uint64_t)std::max<int64_t>(g_opt.direct_counts_max_nodes, 0)) {
+        m->log.cap = 0;   // small count array: the kernels reduce onto it directly (kmb_emit)
+        return KMB_OK;
+    }
     uint64_t want = std::max<uint64_t>(n_queries / 4, 1ull << 23);
     want = std::min<uint64_t>(want, (uint64_t)std::max<int64_t>(g_opt.log_max_entries, 1 << 10));
     want = (want + 4095) & ~4095ull;  // whole 128-group blocks: the apply pass reads four tags per 4-byte load

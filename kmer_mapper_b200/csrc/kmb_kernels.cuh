@@ -553,10 +553,13 @@ __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStag
     if (ready) kmb_stage_send(P.log, P.counts, st, ready, c, lane, all);
     __syncwarp();
 }
-__device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane) {
+// no_log: the mapper has no hit log (small, L2-resident count array: KmbOptions::direct_counts_max_nodes) -- every
+// group then leaves through the "log is full" exit of kmb_log_write, straight onto the counts, warp-aggregated.  (A
+// test inside kmb_emit instead made the read-path kernel 10 % slower: 355 ms against 321 on config 3.)
+__device__ __forceinline__ void kmb_stage_init(const KmbStage &st, int lane, bool no_log) {
     if ((uint32_t)lane < st.bins) {
         st.cnt[lane] = 0;
-        st.res_left[lane] = 0;
+        st.res_left[lane] = no_log ? KMB_RES_FULL : 0u;
         st.res_base[lane] = 0;
     }
     __syncwarp();
@@ -851,7 +854,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
     uint64_t *q_kmer = S.qk;
     uint32_t *q_h = S.qh;
     const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots, (uint32_t)KMB_LOG_BINS};
-    kmb_stage_init(st, lane);
+    kmb_stage_init(st, lane, P.log.cap == 0);
     unsigned counted = 0;
     int qcount = 0;
     KmbPipe pp;
@@ -1190,7 +1193,7 @@ kmb_map_reads_mz_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uin
     const uint32_t *__restrict__ words = reinterpret_cast<const uint32_t *>(bases);
     const uint64_t n_words = (n_bases + 15) / 16 + 4;
     const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_MZ_LOG_BINS, KMB_MZ_STAGE_SLOTS, KMB_MZ_LOG_BINS};
-    kmb_stage_init(st, lane);
+    kmb_stage_init(st, lane, P.log.cap == 0);
     unsigned counted = 0, fetched = 0;
     const KmbPol pol = kmb_make_policies(P.policies);
     const int k = KMB_MZ_K;
@@ -1503,7 +1506,7 @@ kmb_map_kmers_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, KmbP
     uint64_t *q_kmer = S.qk;
     uint32_t *q_h = S.qh;
     const KmbStage st = {S.stage_cnt, S.stage, S.stage_res, S.stage_cnt + KMB_LOG_BINS, (uint32_t)KmbWarpShared<U>::kStageSlots, (uint32_t)KMB_LOG_BINS};
-    kmb_stage_init(st, lane);
+    kmb_stage_init(st, lane, P.log.cap == 0);
     unsigned counted = 0;
     int qcount = 0;
     KmbPipe pp;

@@ -17,9 +17,12 @@ LOOKUP_CASES = ["gpucounter", "test_mapping", "long_buckets", "long_buckets_cut5
 def kmb():
     from kmer_mapper_b200 import _lib
     _lib.require_device()  # fail loudly: these tests are meaningless without the CUDA library + a GPU
+    # the count arrays of these tests are small enough for the direct-reduction route (no hit log); the hit log and its
+    # apply pass are what the full-size runs use, so that is what this module exercises unless a variant says otherwise
+    _lib.set_option("direct_counts_max_nodes", 0)
     yield _lib
     for name, v in (("probe_variant", 1), ("use_filter", -1), ("gathers_in_flight", 4), ("filter_l2_budget_bytes", 60 << 20),
-                    ("apply_window_log2", 23),
+                    ("apply_window_log2", 0), ("direct_counts_max_nodes", 4 << 20),
                     ("log_max_entries", 2048 << 20), ("chunk_bytes", 64 << 20), ("host_pack", -1), ("host_threads", 0), ("read_table", -1)):
         _lib.set_option(name, v)
 
@@ -32,12 +35,14 @@ VARIANTS = [dict(probe_variant=1, use_filter=1, gathers_in_flight=4),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4, filter_l2_budget_bytes=512),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4, log_max_entries=4096),
             dict(probe_variant=1, use_filter=1, gathers_in_flight=4, apply_window_log2=10),
+            dict(probe_variant=1, use_filter=1, gathers_in_flight=4, direct_counts_max_nodes=4 << 20),   # no hit log: direct reductions
             dict(probe_variant=0, use_filter=1),
             dict(probe_variant=0, use_filter=0)]
 # the fused reads kernel over the minimizer-bucketed read-path table (k = 31 only; opt-in)
 READ_TABLE_VARIANTS = [dict(read_table=1, use_filter=1), dict(read_table=1, use_filter=0),
                        dict(read_table=1, use_filter=1, filter_l2_budget_bytes=512),
-                       dict(read_table=1, use_filter=1, log_max_entries=4096)]
+                       dict(read_table=1, use_filter=1, log_max_entries=4096),
+                       dict(read_table=1, use_filter=1, direct_counts_max_nodes=4 << 20)]
 
 
 def _fresh(index):
@@ -53,6 +58,7 @@ def _set(kmb, variant):
     kmb.set_option("read_table", 0)
     kmb.set_option("gathers_in_flight", 4)
     kmb.set_option("apply_window_log2", 23)
+    kmb.set_option("direct_counts_max_nodes", 0)
     for k, v in variant.items():
         kmb.set_option(k, v)
 
@@ -110,7 +116,7 @@ def test_gpu_counter_matches_restated_semantics(kmb):
         assert got.shape == want.shape and np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", VARIANTS[:7], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
+@pytest.mark.parametrize("variant", VARIANTS[:8], ids=lambda v: "-".join("%s%d" % (k[0], x) for k, x in v.items()))
 def test_lookup_random_indexes_vs_oracle(kmb, variant):
     from kmer_mapper_b200.mapper import in_graph_index, map_kmers_to_graph_index
     _set(kmb, variant)
@@ -261,7 +267,7 @@ def _small_world(k, seed, n_entries=60_000, modulo=262_147, zipf=False, hot=1200
     return g, idx
 
 
-@pytest.mark.parametrize("k,variant", [(k, v) for k in (31, 21, 15, 5) for v in VARIANTS[:7]] +
+@pytest.mark.parametrize("k,variant", [(k, v) for k in (31, 21, 15, 5) for v in VARIANTS[:8]] +
                          [(31, v) for v in READ_TABLE_VARIANTS],
                          ids=lambda x: str(x) if isinstance(x, int) else "-".join("%s%d" % (k[0], v) for k, v in x.items()))
 def test_map_reads_vs_oracle(kmb, k, variant):
