@@ -633,6 +633,8 @@ struct kmb_mapper {
     uint64_t queries_since_flush = 0;
     int32_t max_freq = 1000;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaStream_t parse_stream = nullptr;   // record parsing of chunk i runs beside the H2D copy / inflate of chunk i + 1
+    cudaEvent_t text_on_device = nullptr;
     KmbStatus *d_status = nullptr;
     KmbStatus *h_status = nullptr;  // pinned: [0] what fetch_status reads back, [1] the constant initial state
     bool log_clean = true;          // nothing has been logged since the log was last emptied: no need to empty it again
@@ -707,6 +709,7 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
     DeviceGuard g(m->index->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+    if (m->parse_stream) cudaStreamSynchronize(m->parse_stream);
     for (int i = 0; i < KMB_SLOTS; i++) slot_free(m->slot[i]);
     for (auto &v : m->timed)
         for (auto &pr : v) {
@@ -722,6 +725,8 @@ extern "C" int kmb_mapper_destroy(kmb_mapper *m) {
     if (m->h_status) cudaFreeHost(m->h_status);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->parse_stream) cudaStreamDestroy(m->parse_stream);
+    if (m->text_on_device) cudaEventDestroy(m->text_on_device);
     cudaGetLastError();
     delete m;
     return KMB_OK;
@@ -870,6 +875,8 @@ extern "C" int kmb_mapper_create(kmb_index *index, uint64_t n_counts, uint32_t *
     m->max_freq = max_index_lookup_frequency;  // a C int like the reference's (mapper.pyx:19,64)
     KMB_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
     KMB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    KMB_CUDA(cudaStreamCreateWithFlags(&m->parse_stream, cudaStreamNonBlocking));
+    KMB_CUDA(cudaEventCreateWithFlags(&m->text_on_device, cudaEventDisableTiming));
     m->stream = m->own_stream;
     if (counts_device) {
         bool dev;
@@ -1411,13 +1418,13 @@ static int text_finish_pending(kmb_mapper *m) {
         // more lines than one per 8 bytes: parse again (the text is still on the device) with room for the worst case
         DevBuf<uint8_t> keep;
         KMB_TRY(keep.alloc((size_t)s.text_n + 16));
-        KMB_CUDA(cudaMemcpyAsync(keep.p, s.text_ptr, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
-        KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+        KMB_CUDA(cudaMemcpyAsync(keep.p, s.text_ptr, s.text_n, cudaMemcpyDeviceToDevice, m->parse_stream));
+        KMB_CUDA(cudaStreamSynchronize(m->parse_stream));
         KMB_TRY(slot_reserve_text(s, (size_t)s.text_n, (size_t)s.text_n + 16));
-        KMB_CUDA(cudaMemcpyAsync(s.text, keep.p, s.text_n, cudaMemcpyDeviceToDevice, m->copy_stream));
+        KMB_CUDA(cudaMemcpyAsync(s.text, keep.p, s.text_n, cudaMemcpyDeviceToDevice, m->parse_stream));
         s.text_ptr = s.text;
-        KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, s.text_format, m->copy_stream));
-        KMB_CUDA(cudaStreamSynchronize(m->copy_stream));
+        KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, s.text_format, m->parse_stream));
+        KMB_CUDA(cudaStreamSynchronize(m->parse_stream));
     }
     if (s.h_result->error)
         return kmb_fail(KMB_ERR_BAD_ARG, "kmb_mapper_map_text: malformed %s text (a FASTQ record must be '@' line, bases, '+' line, "
@@ -1500,8 +1507,11 @@ static int map_text_impl(kmb_mapper *m, const uint8_t *text, int fd, uint64_t fd
     s.text_format = format;
     s.text_k = k;
     s.text_flags = flags;
-    KMB_TRY(launch_text_parse(m->index->info.sms, s, n_text, format, m->copy_stream));
-    KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
+    // the parse kernels run on their own stream, so that the next chunk's copy does not queue up behind them
+    KMB_CUDA(cudaEventRecord(m->text_on_device, m->copy_stream));
+    KMB_CUDA(cudaStreamWaitEvent(m->parse_stream, m->text_on_device, 0));
+    KMB_TRY(launch_text_parse(m->index->info.sms, s, n_text, format, m->parse_stream));
+    KMB_CUDA(cudaEventRecord(s.copied, m->parse_stream));
     // now that this chunk is on its way, finish the previous one: its mapping kernel goes onto the compute stream
     KMB_TRY(text_finish_pending(m));
     m->text_pending = slot_index;
@@ -1655,8 +1665,9 @@ static int gz_finish_batch(kmb_mapper *m, const GzBatch &b, int format, int k, u
     s.text_format = format;
     s.text_k = k;
     s.text_flags = flags;
-    KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, format, m->copy_stream, s.text_ptr));
-    KMB_CUDA(cudaEventRecord(s.copied, m->copy_stream));
+    // (the batch's text is complete: s.copied was waited for above) -- beside the next batch's copy and inflate
+    KMB_TRY(launch_text_parse(m->index->info.sms, s, s.text_n, format, m->parse_stream, s.text_ptr));
+    KMB_CUDA(cudaEventRecord(s.copied, m->parse_stream));
     m->text_pending = b.slot;
     return text_finish_pending(m);   // waits for the parse result, launches the mapping kernel, records `consumed`
 }

@@ -24,7 +24,7 @@ tindex, bases, offsets = bench.generate(w, 0, torch.device("cuda", 0))
 di = DeviceIndex.from_index(tindex, device=0)
 n_counts = tindex.max_node_id() + 1
 d = tempfile.mkdtemp(prefix="kmb_files_", dir="/dev/shm")
-fq, fqgz = bench.write_fastq_files(d, bases, n_reads, w["read_len"])
+fq, fqgz, _bgzf = bench.write_fastq_files(d, bases, n_reads, w["read_len"])
 names = ("text_us_slot", "text_us_stage", "text_us_wait", "text_us_alloc")
 for path in (fq, fqgz):
     out = torch.empty(n_counts, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
