@@ -225,7 +225,7 @@ KMB_HD uint64_t kmb_revcomp(uint64_t x, int k) {
 // only): entries are filed under the MINIMIZER of their key instead of the key itself.
 //
 // Consecutive windows of a read overlap in k-1 bases, and the minimizer of a k-mer -- the smallest
-// hash among its k-m+1 m-mers (m = 15) -- is shared by ~(k-m+2)/2 consecutive windows on average (9
+// hash among its k-m+1 m-mers (m = 16) -- is shared by ~(k-m+2)/2 consecutive windows on average (8.5
 // at k = 31).  Filing the index entries under hash(minimizer) therefore sends a whole RUN of windows
 // to the same bucket: one filter word and one sector fetch per run instead of one per window, after
 // which every window of the run is compared, in registers, with the full keys the bucket holds.
@@ -237,8 +237,14 @@ KMB_HD uint64_t kmb_revcomp(uint64_t x, int k) {
 // the primary holds entries 0-1, the secondary entries 2-3 and, beyond that, the link into a pool of
 // ordinary chained sectors.
 // ---------------------------------------------------------------------------------------------
-#define KMB_MZ_M 15
-#define KMB_MZ_MASK ((1u << (2 * KMB_MZ_M)) - 1u)
+// m = 16: the longest m-mer that is still one 32-bit word.  The table was first built with m = 15; on a 5 Gbp genome
+// (config 3) every 15-mer occurs 4.7 times and the m-mers that win are the ~1/9 with the smallest ordering keys, so
+// a popular minimizer collected the entries of several places of the genome: half of the entries sat in buckets of
+// more than four, 23 % of the buckets ended in a pool chain, and walking those chains was 17 % of the kernel's
+// instructions and its largest source of memory stalls (profiles/r02_v11_config3_*).  One base more divides the
+// occurrences per m-mer by four (16 % of the entries / 6 % of the buckets beyond four in the same simulation).
+#define KMB_MZ_M 16
+#define KMB_MZ_MASK (KMB_MZ_M >= 16 ? 0xFFFFFFFFu : ((1u << (2 * (KMB_MZ_M & 15))) - 1u))
 // Ordering key of an m-mer: 26 hash bits above 6 bits that the caller fills with the m-mer's position, so that one
 // 32-bit minimum yields the minimizer AND where it sits (leftmost among equal hashes).  The bucket is addressed by
 // the m-mer itself, not by this hash, so the 26 bits only decide which m-mer wins.

@@ -921,8 +921,8 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 // bucket fetch, and one key comparison per entry of the bucket (the entry's minimizer offset says
 // which window of the run it could equal).  Tile-synchronous, per warp:
 //   1. load + encode the tile (as in kmb_map_reads_kernel);
-//   2. per lane: 48 m-mer ordering keys (26 hash bits | position) and a log-step sliding minimum
-//      (window 17 = k - 15 + 1) give minimizer and position for its 32 windows; a bit mask marks
+//   2. per lane: 47 m-mer ordering keys (26 hash bits | position) and a log-step sliding minimum
+//      (window 16 = k - 16 + 1) give minimizer and position for its 32 windows; a bit mask marks
 //      where runs start;
 //   then, in two passes of 16 lanes' runs each (so that everything below is sized for half a tile):
 //   2b. the pass's run list (lanes append the runs that hold an existing window);
@@ -1064,7 +1064,7 @@ __device__ __forceinline__ void kmb_mz_half(const uint32_t (&w4)[4], int h, uint
         // m-mer starting at base 16 h + t: bits [2t, 2t + 30) of the 96-bit stream w
         a[t] = kmb_mmer_order(__funnelshift_r(w[t >> 4], w[(t >> 4) + 1], (2 * t) & 31) & KMB_MZ_MASK) | (jbase + (uint32_t)t);
     }
-    // sliding minimum over 17 = 16 + 1 by doubling: after the four rounds a[t] = min of m-mers t .. t+15
+    // sliding minimum over the k - m + 1 m-mers of a window by doubling: after the four rounds a[t] = min of m-mers t .. t+15
 #pragma unroll
     for (int t = 0; t < 31; t++) a[t] = min(a[t], a[t + 1]);
 #pragma unroll
@@ -1073,10 +1073,11 @@ __device__ __forceinline__ void kmb_mz_half(const uint32_t (&w4)[4], int h, uint
     for (int t = 0; t < 25; t++) a[t] = min(a[t], a[t + 4]);
 #pragma unroll
     for (int t = 0; t < 17; t++) a[t] = min(a[t], a[t + 8]);
+    static_assert(KMB_MZ_K - KMB_MZ_M + 1 == 16 || KMB_MZ_K - KMB_MZ_M + 1 == 17, "window of 16 or 17 m-mers");
     uint32_t sb = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const uint32_t v = min(a[i], a[i + 1]);
+        const uint32_t v = (KMB_MZ_K - KMB_MZ_M + 1 == 17) ? min(a[i], a[i + 1]) : a[i];
         pos_col[(jbase + i) * 32] = (uint8_t)(v & 63u);
         sb |= (v != prev ? 1u : 0u) << i;
         prev = v;
