@@ -17,6 +17,8 @@ void kmb_host_parallel(int n_threads, int n_parts, void (*fn)(void *ctx, int par
 #define KMB_PACK_PAD_WORDS 4
 static inline uint64_t kmb_packed_words(uint64_t n_bases) { return (n_bases + 15) / 16 + KMB_PACK_PAD_WORDS; }
 uint64_t kmb_host_pack(const uint8_t *bases, uint64_t n_bases, bool n_to_a, int n_threads, uint32_t *words);
+// Streaming (non-temporal) stores for the packed words from now on (option "host_pack_streaming").
+void kmb_host_pack_streaming(bool on);
 
 // out[i] = offsets[i] - base for i in [0, n): the chunk-relative 32-bit read offsets that travel with a packed chunk.
 void kmb_host_rel_offsets(const int64_t *offsets, uint64_t n, int64_t base, int n_threads, uint32_t *out);

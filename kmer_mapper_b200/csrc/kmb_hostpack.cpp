@@ -157,6 +157,8 @@ namespace {
 const uint64_t NO_BAD = ~0ull;
 
 // words [w_lo, w_hi) from whole 16-base groups; portable SWAR (the device routine, compiled for the host)
+std::atomic<bool> g_pack_streaming{true};
+
 uint64_t pack_words_swar(const uint8_t *bases, uint64_t w_lo, uint64_t w_hi, bool n_to_a, uint32_t *words) {
     uint64_t bad = NO_BAD;
     for (uint64_t j = w_lo; j < w_hi; j++) {
@@ -189,6 +191,10 @@ __attribute__((target("avx2"))) uint64_t pack_words_avx2(const uint8_t *bases, u
     const __m256i mul2 = _mm256_set1_epi32(0x00100001);  // w0 + 16 w1
     const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
                                             -1, -1, -1, -1, 0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1);
+    // Streaming stores (kmb_host_pack_streaming): the packed words are written once and read next by the DMA engine, so
+    // they need not pass through the caches -- and a write-allocating store first READS the line it is about to
+    // overwrite, a quarter of a byte of host DRAM traffic per base on top of the byte read and the quarter written.
+    const bool nt = g_pack_streaming.load(std::memory_order_relaxed) && (reinterpret_cast<uintptr_t>(words) & 15u) == 0;
     uint64_t j = w_lo;
     while (j < w_hi && (j & 3)) {  // leading words up to a multiple of four
         uint64_t b = pack_words_swar(bases, j, j + 1, n_to_a, words);
@@ -217,7 +223,8 @@ __attribute__((target("avx2"))) uint64_t pack_words_avx2(const uint8_t *bases, u
             // [a0 . . . . a1 . .] and [b0 . . . . b1 . .] -> a0 a1 b0 b1
             const __m256i both = _mm256_or_si256(packed[0], _mm256_slli_si256(packed[1], 8));
             const __m256i q = _mm256_permutevar8x32_epi32(both, _mm256_setr_epi32(0, 5, 2, 7, 0, 0, 0, 0));
-            _mm_storeu_si128(reinterpret_cast<__m128i *>(words + j), _mm256_castsi256_si128(q));
+            if (nt) _mm_stream_si128(reinterpret_cast<__m128i *>(words + j), _mm256_castsi256_si128(q));
+            else _mm_storeu_si128(reinterpret_cast<__m128i *>(words + j), _mm256_castsi256_si128(q));
         }
         if ((uint32_t)_mm256_movemask_epi8(all_ok) != 0xFFFFFFFFu && bad == NO_BAD) {
             uint32_t scratch[BLOCK];
@@ -229,6 +236,7 @@ __attribute__((target("avx2"))) uint64_t pack_words_avx2(const uint8_t *bases, u
         uint64_t b = pack_words_swar(bases, j, w_hi, n_to_a, words);
         if (b < bad) bad = b;
     }
+    if (nt) _mm_sfence();  // streaming stores are weakly ordered: make them visible before this part reports done
     return bad;
 }
 #endif
@@ -265,6 +273,8 @@ void pack_part(void *p, int part) {
 }
 
 }  // namespace
+
+void kmb_host_pack_streaming(bool on) { g_pack_streaming.store(on, std::memory_order_relaxed); }
 
 uint64_t kmb_host_pack(const uint8_t *bases, uint64_t n_bases, bool n_to_a, int n_threads, uint32_t *words) {
     const uint64_t n_full = n_bases / 16;

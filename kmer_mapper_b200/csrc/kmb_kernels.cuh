@@ -553,6 +553,9 @@ __device__ __forceinline__ void kmb_stage_flush(const KmbProbe &P, const KmbStag
     if (ready) kmb_stage_send(P.log, P.counts, st, ready, c, lane, all);
     __syncwarp();
 }
+// (Measured and rejected for the read-path kernel, whose 96 KB of SASS are half this send path inlined at four sites
+// and whose stall samples were 20 % `no_instruction`: the send path and the valve of kmb_emit as __noinline__
+// functions shrink the kernel by 42 % and make it 1.2 % SLOWER -- 29.25 ms against 28.88 per 3 G k-mers of config 3.)
 // no_log: the mapper has no hit log (small, L2-resident count array: KmbOptions::direct_counts_max_nodes) -- every
 // group then leaves through the "log is full" exit of kmb_log_write, straight onto the counts, warp-aggregated.  (A
 // test inside kmb_emit instead made the read-path kernel 10 % slower: 355 ms against 321 on config 3.)
@@ -934,6 +937,8 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 //      is extracted and compared; buckets that continue in the pool go onto a per-warp list that is
 //      retired 32 runs at a time.
 // No cross-tile state except the staged hits and that list.
+// Also measured and rejected (config 3, 3 G k-mers, same box): an L2 prefetch of the warp's next tile of bases 29.3 ms
+// against 28.9 without; the filter words of three rounds requested before the first is tested 30.4 ms.
 // ================================================================================================
 #define KMB_MZ_K 31
 #define KMB_MZ_THREADS 128  // 4 warps per CTA, seven CTAs per SM

@@ -328,8 +328,17 @@ def _oracle_words(bases, n_to_a=True):
     return (padded.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
 
 
+@pytest.fixture
+def streaming(request):
+    from kmer_mapper_b200 import _lib
+    _lib.set_option("host_pack_streaming", request.param)
+    yield request.param
+    _lib.set_option("host_pack_streaming", 1)
+
+
+@pytest.mark.parametrize("streaming", [0, 1], indirect=True)   # 1: non-temporal stores where the destination is 16-byte aligned
 @pytest.mark.parametrize("threads", [1, 0, 3])
-def test_host_pack_matches_oracle_encoding(threads):
+def test_host_pack_matches_oracle_encoding(threads, streaming):
     rng = np.random.default_rng(5)
     alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
     for n in (0, 1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 1000, 4097, 65_536 * 16 + 7, (1 << 22) + 5):
