@@ -312,6 +312,7 @@ int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kern
  *  "host_pack" (host chunks of kmb_mapper_map_reads: 1 packed to 2 bits per base by the CPU, 0 ASCII, 2 hybrid -- both pipes side
  *  by side --, -1 default: hybrid for a pinned source, packed for a pageable one), "host_hybrid_backlog_bytes",
  *  "host_pack_streaming" (default 1: the host encoder writes its 2-bit words with non-temporal stores),
+ *  "apply_slabs_per_sm" (8: CTAs of the apply pass per SM and node window; 16 and 32 measured slower),
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
  *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
  *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),

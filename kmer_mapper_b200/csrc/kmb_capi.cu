@@ -106,6 +106,7 @@ struct KmbOptions {
     // ASCII when it shares it.
     int64_t host_pack = -1;
     int64_t host_hybrid_backlog_bytes = 0;   // 0 = one chunk (chunk_bytes)
+    int64_t apply_slabs_per_sm = 8;          // apply pass: CTAs per SM and node window (each walks one slab of the log)
     // 1 = the encoder writes the packed words with streaming (non-temporal) stores: written once, read next by the DMA
     // engine, and a write-allocating store would first read the line it overwrites (config 2 end to end, 16 cores:
     // packed 51.7 -> 55.2 GK/s, hybrid 68.3 -> 70.3)
@@ -178,6 +179,7 @@ extern "C" int kmb_set_option(const char *name, int64_t value) {
     OPT(apply_window_log2)
     OPT(direct_counts_max_nodes)
     OPT(host_hybrid_backlog_bytes)
+    OPT(apply_slabs_per_sm)
     OPT(host_pack_streaming)
     OPT(gz_device_max_member_bytes)
     OPT(gz_device_batch_bytes)
@@ -226,6 +228,7 @@ extern "C" int kmb_get_option(const char *name, int64_t *value) {
     OPT(apply_window_log2)
     OPT(direct_counts_max_nodes)
     OPT(host_hybrid_backlog_bytes)
+    OPT(apply_slabs_per_sm)
     OPT(host_pack_streaming)
     OPT(gz_device_max_member_bytes)
     OPT(gz_device_batch_bytes)
@@ -770,7 +773,7 @@ static int launch_flush(kmb_mapper *m) {
         m->log.win_shift = std::min(m->log.bin_shift, want);
         m->log_windows = (int)((last >> m->log.win_shift) + 1);
         KMB_TRY(timed_begin(m, 1));
-        kmb_log_apply_kernel<<<dim3((unsigned)ix->info.sms * 8u, (unsigned)m->log_windows), 256, 0, m->stream>>>(m->log, m->counts);
+        kmb_log_apply_kernel<<<dim3((unsigned)ix->info.sms * (unsigned)std::min<int64_t>(std::max<int64_t>(g_opt.apply_slabs_per_sm, 1), 256), (unsigned)m->log_windows), 256, 0, m->stream>>>(m->log, m->counts);
         g_launches++;
         KMB_CUDA(cudaGetLastError());
         KMB_TRY(timed_end(m, 1));

@@ -38,6 +38,7 @@ def main():
         "persist": dict(use_filter=[1], gathers_in_flight=[8], map_reads_blocks_per_sm=[0], l2_persist=[0, 1]),
         "r2": dict(apply_window_log2=[0]),
         "filt": dict(use_filter=[1, 0]),
+        "slabs": dict(apply_slabs_per_sm=[8, 16, 32]),
         "carve": dict(map_carveout=[-1, 100, 72, 58]),
         "cta2": dict(map_reads_blocks_per_sm=[0, 2]),
         "u": dict(gathers_in_flight=[4, 8]),
