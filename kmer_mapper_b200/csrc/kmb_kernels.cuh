@@ -823,11 +823,40 @@ __device__ __forceinline__ uint32_t kmb_valid_starts(const uint32_t *__restrict_
     return valid;
 }
 
+// Bulk-async copy (TMA, 1-D): `bytes` (a multiple of 16) from global to shared memory, completion counted in bytes on
+// an mbarrier.  One instruction of one lane moves a whole tile of bases without passing through the LSU / L1TEX, the
+// unit this kernel keeps busiest, and without holding registers while the bytes are under way.
+__device__ __forceinline__ void kmb_mbar_init(unsigned long long *mbar, uint32_t arrivals) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void kmb_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, unsigned long long *mbar, uint64_t pol) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), a = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(a), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void kmb_mbar_wait(unsigned long long *mbar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+
 // Per-warp shared memory of the key-addressed mapping kernels: 5.9 KB per warp = 47 KB per CTA, three CTAs per SM.
 #define KMB_TILE_VECS (KMB_WTILE_POS / 16 + 2)  // 16-byte vectors of bases per warp tile, halo included
 template <int U>
 struct alignas(16) KmbWarpShared {
     static constexpr int kStageSlots = KMB_STAGE_SLOTS;
+#ifdef KMB_MAP_BULK_BASES
+    uint4 raw[KMB_TILE_VECS];                             // the NEXT tile's ASCII bases, landed by a bulk-async copy
+    unsigned long long raw_mbar;                          // its mbarrier (complete_tx)
+    unsigned long long raw_pad;
+#endif
     uint64_t qk[KMB_QUEUE_SLOTS(U)];                      // candidate stack: k-mer
     unsigned long long stage_res[KMB_LOG_BINS];
     uint32_t qh[KMB_QUEUE_SLOTS(U)];                      //                  its sector
@@ -871,6 +900,25 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 
     const uint64_t first_tile = (uint64_t)blockIdx.x * (KMB_MAP_THREADS / 32) + warp;
     uint32_t r_next = first_tile < n_tiles ? R.tile_read[first_tile] : 0u;  // one tile ahead: its latency is never waited for
+#ifdef KMB_MAP_BULK_BASES
+    // Opt-in (-DKMB_MAP_BULK_BASES), measured and NOT the default: the ASCII bases of a tile (1056 bytes, halo
+    // included) fetched ONE TILE AHEAD by a bulk-async copy (UBLKCP) into S.raw -- requested by lane 0 as soon as the
+    // previous tile has been encoded, waited for on the warp's mbarrier; tiles that are not wholly inside the buffer,
+    // unaligned buffers and packed input take the loads below.  Waiting for the bases is 14 % of this kernel's stall
+    // samples, and the copy does remove it, but the kernel gets SLOWER: config 2 50.0 ms against 46.9, config 5 52.9 / 47.0,
+    // config 4 k=21 54.3 / 51.0 (same box, parity green on both).  The 8.6 KB per CTA come out of the L1 (3 CTAs: 167 KB
+    // of shared memory instead of 141), which this kernel needs for the sectors of its loads in flight.
+    const bool bulk_ok = !packed && (reinterpret_cast<uintptr_t>(bases) & 15u) == 0;
+    auto bulk_tile = [&](uint64_t t) { return bulk_ok && t < n_tiles && t * KMB_WTILE_POS + 16ull * KMB_TILE_VECS <= n_bases; };
+    uint32_t raw_parity = 0;
+    bool raw_pending = false;  // warp-uniform
+    if (lane == 0) kmb_mbar_init(&S.raw_mbar, 1);
+    __syncwarp();
+    if (bulk_tile(first_tile)) {
+        if (lane == 0) kmb_bulk_load(S.raw, bases + first_tile * KMB_WTILE_POS, 16u * KMB_TILE_VECS, &S.raw_mbar, pol.first);
+        raw_pending = true;
+    }
+#endif
     for (uint64_t tile = first_tile; tile < n_tiles; tile += warp_stride) {
         const uint64_t t0 = tile * KMB_WTILE_POS;
         const uint64_t r0 = r_next;
@@ -879,6 +927,26 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
         kmb_read_span(R, r0 + (uint64_t)lane, rs, re);
         __syncwarp();  // the previous tile's readers are done with pack
         // ---- 1. load + encode: vectors v = t0/16 + i, i in [0, 66)
+#ifdef KMB_MAP_BULK_BASES
+        const bool from_raw = raw_pending;
+        if (from_raw) {
+            kmb_mbar_wait(&S.raw_mbar, raw_parity);
+            raw_parity ^= 1u;
+#pragma unroll
+            for (int i = lane; i < KMB_TILE_VECS; i += 32) {
+                const uint4 w = S.raw[i];
+                uint32_t inv;
+                pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
+                if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + t0 + 16ull * (uint64_t)i + (uint64_t)(__ffs(inv) - 1)));
+            }
+            __syncwarp();  // every lane has read its share of raw: the next tile may land there
+        }
+        raw_pending = bulk_tile(tile + warp_stride);
+        if (raw_pending && lane == 0)
+            kmb_bulk_load(S.raw, bases + (tile + warp_stride) * KMB_WTILE_POS, 16u * KMB_TILE_VECS, &S.raw_mbar, pol.first);
+        if (!from_raw)
+#endif
+        {
 #pragma unroll
         for (int i = lane; i < KMB_WTILE_POS / 16 + 2; i += 32) {
             uint64_t v = t0 / 16 + (uint64_t)i;
@@ -891,6 +959,7 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
             uint32_t inv;
             pack[i] = kmb_encode16(w.x, w.y, w.z, w.w, n_to_a, inv);
             if (inv) atomicMin(&status->first_bad_offset, (unsigned long long)(base0 + v * 16 + (uint64_t)(__ffs(inv) - 1)));
+        }
         }
         __syncwarp();
         // ---- 2. this lane's 32 positions
