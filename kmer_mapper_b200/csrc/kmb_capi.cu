@@ -1792,12 +1792,10 @@ extern "C" int kmb_mapper_map_gz(kmb_mapper *m, const uint8_t *gz, uint64_t n_gz
         KMB_CUDA(cudaMemcpyAsync(s.d_gz, s.h_gz, (size_t)b.gz_len + 48, cudaMemcpyHostToDevice, st));
         KMB_CUDA(cudaMemcpyAsync(s.d_members, s.h_members, n_mem * sizeof(KmbGzMember), cudaMemcpyHostToDevice, st));
         g_h2d_bytes += b.gz_len + n_mem * sizeof(KmbGzMember);
-        const size_t smem = sizeof(KmbGzShared);
+        const size_t smem = KMB_GZ_WARPS * sizeof(KmbGzShared);
         KMB_CUDA(cudaFuncSetAttribute((const void *)kmb_gz_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        KMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kmb_gz_inflate_kernel, 32, smem));
-        const unsigned grid = (unsigned)std::min<size_t>(n_mem, (size_t)m->index->info.sms * (size_t)std::max(per_sm, 1));
-        kmb_gz_inflate_kernel<<<grid, 32, smem, st>>>(s.d_gz, s.d_members, (uint32_t)n_mem, s.text, s.d_results);
+        const unsigned grid = (unsigned)std::min<size_t>((n_mem + KMB_GZ_WARPS - 1) / KMB_GZ_WARPS, (size_t)m->index->info.sms * 8);
+        kmb_gz_inflate_kernel<<<grid, KMB_GZ_WARPS * 32, smem, st>>>(s.d_gz, s.d_members, (uint32_t)n_mem, s.text, s.d_results);
         g_launches++;
         if (check_crc) {
             kmb_gz_crc_kernel<<<(unsigned)((n_mem + 3) / 4), 128, 0, st>>>(s.text, s.d_members, (uint32_t)n_mem, s.d_crc);

@@ -8,16 +8,21 @@
 //
 //   * lane 0 walks the bit stream (RFC 1951): 64-bit bit buffer refilled with two aligned loads, two-level decode
 //     tables (10-bit primary for literals/lengths, 8-bit for distances) in the warp's shared memory, built per
-//     block by the same lane;
-//   * the last 32 KB of the member's text -- everything a match can refer to -- live in a ring in shared memory:
-//     literals are stored there, matches are copied ring -> ring (a first version kept the text in global memory
-//     only: every match then waited for an L2 round trip and a warp inflated 15 MB/s);
-//   * whenever 16 KB are waiting the whole warp writes them to global memory in 16-byte vectors (the ring is
-//     indexed by the low bits of the output ADDRESS, so ring and output are aligned alike).
+//     block by the same lane; literals are stored as they come;
+//   * a match (length, distance) is broadcast and copied by all 32 lanes -- byte i of the match is
+//     out[pos - distance + i % distance], so overlapping matches (distance < length: the runs of equal quality
+//     characters FASTQ is full of) need no serial copy;
+//   * stored blocks are copied by the whole warp.
 // Every member is then checked on the host: decoded length == the ISIZE of its trailer, the stream ended exactly
 // where the next member begins, and (option gz_device_crc) its CRC-32.  Anything else -- a member too large for a
 // warp's patience, a corrupt stream, a false member start -- makes the caller fall back to the host decoders from
 // that member on.
+//
+// Measured and rejected: the last 32 KB of a member's text in a shared-memory ring (matches copied ring -> ring, the
+// ring written out 16 KB at a time) with the stream words read two ahead.  A single warp gets faster (a file of 4 MB
+// members: 0.93 -> 1.02 GB/s of text), but 44 KB of shared memory per warp leave 5 warps per SM instead of 16, and BGZF
+// -- the files this route is for: tens of thousands of 64 KB members, all latency hidden by the other warps -- falls
+// from 46 to 30 M reads/s (14.5 -> 9.3 GB/s of text).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +31,7 @@
 #define KMB_GZ_DIST_BITS 8
 #define KMB_GZ_LIT_MAX 2048   // primary + sub-tables (zlib's bound for 286 symbols, 10 root bits, 15-bit codes is 1332)
 #define KMB_GZ_DIST_MAX 768   //                                  (30 symbols, 8 root bits: 400)
+#define KMB_GZ_WARPS 4        // members per CTA
 
 #define KMB_GZ_OK 0u
 #define KMB_GZ_ERR_HEADER 1u
@@ -150,48 +156,22 @@ __device__ bool kmb_gz_build_table(const uint8_t *lens, int n_syms, int alphabet
     return true;
 }
 
-// Lane 0's view of the compressed stream.  The stream is read in aligned 8-byte words, two words AHEAD of the bits being
-// decoded (`next`, partly moved into the bit buffer, and `after`, untouched), so that topping the bit buffer up never
-// waits for memory: the load issued when the reader crosses into a new word is needed one word -- several symbols --
-// later.  (With the two loads inside every refill a warp inflated 15 MB/s: the decode loop is one dependent chain and
-// each refill put an L1 round trip on it.)
-struct KmbGzBits {
-    const uint64_t *words;   // 8-byte aligned address at or below the member's first byte
-    uint64_t end;            // end of the member's bytes, relative to words
-    uint64_t buf;            // bit buffer: the low `cnt` bits are unread stream bits (bits above them are stream bits too)
-    uint64_t next, after;    // words[wi], words[wi + 1]
-    uint32_t wi;             // index of `next`
-    uint32_t c;              // bytes of `next` already moved into buf
+struct KmbGzBits {   // lane 0's view of the compressed stream
+    const uint8_t *base;   // 8-byte aligned address at or below the member's first byte
+    uint64_t pos;          // next unread byte, relative to base
+    uint64_t end;          // end of the member's bytes, relative to base
+    uint64_t buf;
     int cnt;
 };
-__device__ __forceinline__ void kmb_gz_bits_init(KmbGzBits &b, uint64_t byte_pos) {   // start reading at this byte
-    b.wi = (uint32_t)(byte_pos >> 3);
-    b.c = (uint32_t)(byte_pos & 7ull);
-    b.next = b.words[b.wi];
-    b.after = b.words[b.wi + 1];
-    b.buf = 0;
-    b.cnt = 0;
-}
-// byte position (relative to words) of the first byte none of whose bits has been handed out
-__device__ __forceinline__ uint64_t kmb_gz_bits_pos(const KmbGzBits &b) {
-    return ((uint64_t)b.wi << 3) + b.c - (uint64_t)(b.cnt >> 3);
-}
-// at least 56 bits in the buffer (zeros / foreign bytes beyond the member's end: the caller checks the position)
+// at least 56 bits in the buffer (zeros beyond the end: the caller checks pos against end when a block ends)
 __device__ __forceinline__ void kmb_gz_refill(KmbGzBits &b) {
-    uint32_t k = (uint32_t)(63 - b.cnt) >> 3;   // whole bytes that fit
-    const uint32_t avail = 8u - b.c;
-    if (k >= avail) {                            // everything left of `next`, then on into `after`
-        b.buf |= (b.next >> (8u * b.c)) << b.cnt;
-        b.cnt += (int)(8u * avail);
-        k -= avail;
-        b.next = b.after;
-        b.wi++;
-        b.after = b.words[b.wi + 1];
-        b.c = 0;
-    }
-    b.buf |= (b.next >> (8u * b.c)) << b.cnt;    // (shift count < 64: c <= 7, cnt <= 63)
-    b.cnt += (int)(8u * k);
-    b.c += k;
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(b.base + (b.pos & ~7ull));
+    const uint32_t sh = (uint32_t)(b.pos & 7ull) * 8u;
+    uint64_t v = w[0] >> sh;
+    if (sh) v |= w[1] << (64u - sh);
+    b.buf |= v << b.cnt;
+    b.pos += (uint64_t)((63 - b.cnt) >> 3);
+    b.cnt |= 56;
 }
 __device__ __forceinline__ uint32_t kmb_gz_take(KmbGzBits &b, int n) {
     const uint32_t v = (uint32_t)(b.buf & ((1ull << n) - 1ull));
@@ -199,234 +179,46 @@ __device__ __forceinline__ uint32_t kmb_gz_take(KmbGzBits &b, int n) {
     b.cnt -= n;
     return v;
 }
-// drop to the next byte boundary and return its position; the reader has to be re-initialised before it is used again
-__device__ __forceinline__ uint64_t kmb_gz_align(KmbGzBits &b) {
-    b.cnt -= b.cnt & 7;
-    return kmb_gz_bits_pos(b);
+__device__ __forceinline__ void kmb_gz_align(KmbGzBits &b) {  // drop to the next byte boundary, give whole bytes back
+    const int drop = b.cnt & 7;
+    b.buf >>= drop;
+    b.cnt -= drop;
+    b.pos -= (uint64_t)(b.cnt >> 3);
+    b.buf = 0;
+    b.cnt = 0;
 }
 
-#define KMB_GZ_RING 32768u    // DEFLATE looks back at most 32768 bytes
-#define KMB_GZ_FLUSH 16384u   // the warp writes the ring out when this much is waiting (+ 258 for a match in progress < the ring)
 struct alignas(16) KmbGzShared {
-    uint8_t ring[KMB_GZ_RING];   // the last 32 KB of the member's text; byte p lives at (address of p in `out`) mod 32768
     uint32_t lit[KMB_GZ_LIT_MAX];
     uint32_t dist[KMB_GZ_DIST_MAX];
     uint32_t pre[128];
     uint8_t lens[288 + 32 + 32];
 };
 
-// why lane 0 came back from kmb_gz_run
-#define KMB_GZ_R_FLUSH 0u   // KMB_GZ_FLUSH bytes are waiting in the ring
-#define KMB_GZ_R_DONE 1u    // the member's last block has ended
-#define KMB_GZ_R_ERROR 2u
-
-struct KmbGzState {   // lane 0's registers across calls of kmb_gz_run
-    KmbGzBits B;
-    uint32_t pos;        // bytes of text produced
-    uint32_t flushed;    // bytes of text written to global memory
-    uint32_t stored;     // bytes left of a stored block
-    uint64_t stored_at;  // and where they are in the input
-    uint32_t status;
-    bool in_block, last_block, coded;
-};
-
-// Lane 0: decode until the ring has to be written out, the member ends or the stream is bad.
-__device__ __forceinline__ uint32_t kmb_gz_run(KmbGzState &T, KmbGzShared &S, const uint32_t ring0, const uint32_t out_len) {
-    KmbGzBits &B = T.B;
-    uint8_t *ring = S.ring;
-    for (;;) {
-        if (!T.in_block) {
-            if (T.last_block) return KMB_GZ_R_DONE;
-            // ---- block header
-            kmb_gz_refill(B);
-            T.last_block = kmb_gz_take(B, 1) != 0;
-            const uint32_t type = kmb_gz_take(B, 2);
-            if (type == 0) {
-                const uint64_t at0 = kmb_gz_align(B);
-                const uint8_t *p = reinterpret_cast<const uint8_t *>(B.words) + at0;
-                const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8), nlen = (uint32_t)p[2] | ((uint32_t)p[3] << 8);
-                if (at0 + 4 > B.end || (len ^ 0xFFFFu) != nlen) return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-                if (at0 + 4 + len > B.end) return T.status = KMB_GZ_ERR_INPUT, KMB_GZ_R_ERROR;
-                if (T.pos + len > out_len) return T.status = KMB_GZ_ERR_OUTPUT, KMB_GZ_R_ERROR;
-                T.stored = len;
-                T.stored_at = at0 + 4;
-                T.coded = false;
-            } else if (type == 3) {
-                return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-            } else {
-                int n_lit = 288, n_dist = 32;
-                uint8_t *lens = S.lens;
-                if (type == 1) {
-                    for (int i = 0; i < 144; i++) lens[i] = 8;
-                    for (int i = 144; i < 256; i++) lens[i] = 9;
-                    for (int i = 256; i < 280; i++) lens[i] = 7;
-                    for (int i = 280; i < 288; i++) lens[i] = 8;
-                    for (int i = 0; i < 32; i++) lens[288 + i] = 5;
-                } else {
-                    n_lit = (int)kmb_gz_take(B, 5) + 257;
-                    n_dist = (int)kmb_gz_take(B, 5) + 1;
-                    const int n_pre = (int)kmb_gz_take(B, 4) + 4;
-                    if (n_lit > 286 || n_dist > 30) return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-                    uint8_t *pre_lens = S.lens + 320;
-                    for (int i = 0; i < 19; i++) pre_lens[i] = 0;
-                    for (int i = 0; i < n_pre; i++) {
-                        if (B.cnt < 3) kmb_gz_refill(B);
-                        pre_lens[c_kmb_gz_order[i]] = (uint8_t)kmb_gz_take(B, 3);
-                    }
-                    if (!kmb_gz_build_table(pre_lens, 19, 2, 7, S.pre, 128)) return T.status = KMB_GZ_ERR_TABLE, KMB_GZ_R_ERROR;
-                    int i = 0;
-                    while (i < n_lit + n_dist) {
-                        if (B.cnt < 14) kmb_gz_refill(B);
-                        const uint32_t e = S.pre[B.buf & 127u];
-                        if (((e >> 10) & 7u) != KMB_GZ_K_LITERAL) return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-                        kmb_gz_take(B, (int)(e & 31u));
-                        const uint32_t sym = e >> 16;
-                        if (sym < 16) {
-                            lens[i++] = (uint8_t)sym;
-                            continue;
-                        }
-                        int rep;
-                        uint8_t v = 0;
-                        if (sym == 16) {
-                            if (i == 0) return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-                            v = lens[i - 1];
-                            rep = 3 + (int)kmb_gz_take(B, 2);
-                        } else if (sym == 17) {
-                            rep = 3 + (int)kmb_gz_take(B, 3);
-                        } else {
-                            rep = 11 + (int)kmb_gz_take(B, 7);
-                        }
-                        if (i + rep > n_lit + n_dist) return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-                        while (rep--) lens[i++] = v;
-                    }
-                    if (lens[256] == 0) return T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-                    // distance lengths follow the literal/length ones: to their own place
-                    for (int j = n_dist - 1; j >= 0; j--) lens[288 + j] = lens[n_lit + j];
-                    for (int j = n_lit; j < 288; j++) lens[j] = 0;
-                    for (int j = n_dist; j < 32; j++) lens[288 + j] = 0;
-                }
-                if (!kmb_gz_build_table(lens, type == 1 ? 288 : n_lit, 0, KMB_GZ_LIT_BITS, S.lit, KMB_GZ_LIT_MAX) ||
-                    !kmb_gz_build_table(lens + 288, type == 1 ? 32 : n_dist, 1, KMB_GZ_DIST_BITS, S.dist, KMB_GZ_DIST_MAX))
-                    return T.status = KMB_GZ_ERR_TABLE, KMB_GZ_R_ERROR;
-                T.coded = true;
-            }
-            T.in_block = true;
-        }
-        if (!T.coded) {
-            // ---- stored block: bytes from the input to the ring, as many as the ring has room for
-            while (T.stored) {
-                if (T.pos - T.flushed >= KMB_GZ_FLUSH) return KMB_GZ_R_FLUSH;
-                const uint32_t n = min(T.stored, KMB_GZ_FLUSH - (T.pos - T.flushed));
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(B.words) + T.stored_at;
-                for (uint32_t i = 0; i < n; i++) ring[(ring0 + T.pos + i) & (KMB_GZ_RING - 1u)] = src[i];
-                T.pos += n;
-                T.stored_at += n;
-                T.stored -= n;
-            }
-            kmb_gz_bits_init(B, T.stored_at);   // the bit stream goes on after the stored bytes
-            T.in_block = false;
-            continue;
-        }
-        // ---- coded block: everything stays in the ring (literals stored, matches copied ring -> ring)
-        uint32_t at = T.pos;
-        for (;;) {
-            if (at - T.flushed >= KMB_GZ_FLUSH) {
-                T.pos = at;
-                return KMB_GZ_R_FLUSH;
-            }
-            if (B.cnt < 48) kmb_gz_refill(B);
-            uint32_t e = S.lit[B.buf & ((1u << KMB_GZ_LIT_BITS) - 1u)];
-            if (((e >> 10) & 7u) == KMB_GZ_K_SUB) {
-                B.buf >>= KMB_GZ_LIT_BITS;
-                B.cnt -= KMB_GZ_LIT_BITS;
-                e = S.lit[(e >> 16) + (uint32_t)(B.buf & ((1ull << ((e >> 5) & 31u)) - 1ull))];
-            }
-            const uint32_t kind = (e >> 10) & 7u;
-            B.buf >>= (e & 31u);
-            B.cnt -= (int)(e & 31u);
-            if (kind == KMB_GZ_K_LITERAL) {
-                if (at >= out_len) return T.pos = at, T.status = KMB_GZ_ERR_OUTPUT, KMB_GZ_R_ERROR;
-                ring[(ring0 + at) & (KMB_GZ_RING - 1u)] = (uint8_t)(e >> 16);
-                at++;
-                continue;
-            }
-            if (kind == KMB_GZ_K_END) {
-                T.in_block = false;
-                break;
-            }
-            if (kind != KMB_GZ_K_BASE) return T.pos = at, T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-            const uint32_t xl = (e >> 5) & 31u;
-            const uint32_t mlen = (e >> 16) + (uint32_t)(B.buf & ((1ull << xl) - 1ull));
-            B.buf >>= xl;
-            B.cnt -= (int)xl;
-            uint32_t d = S.dist[B.buf & ((1u << KMB_GZ_DIST_BITS) - 1u)];
-            if (((d >> 10) & 7u) == KMB_GZ_K_SUB) {
-                B.buf >>= KMB_GZ_DIST_BITS;
-                B.cnt -= KMB_GZ_DIST_BITS;
-                d = S.dist[(d >> 16) + (uint32_t)(B.buf & ((1ull << ((d >> 5) & 31u)) - 1ull))];
-            }
-            if (((d >> 10) & 7u) != KMB_GZ_K_BASE) return T.pos = at, T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-            B.buf >>= (d & 31u);
-            B.cnt -= (int)(d & 31u);
-            const uint32_t xd = (d >> 5) & 31u;
-            if (B.cnt < (int)xd) kmb_gz_refill(B);
-            const uint32_t mdist = (d >> 16) + (uint32_t)(B.buf & ((1ull << xd) - 1ull));
-            B.buf >>= xd;
-            B.cnt -= (int)xd;
-            if (mdist > at) return T.pos = at, T.status = KMB_GZ_ERR_STREAM, KMB_GZ_R_ERROR;
-            if (at + mlen > out_len) return T.pos = at, T.status = KMB_GZ_ERR_OUTPUT, KMB_GZ_R_ERROR;
-            // byte i of the match = byte (at - mdist + i): in order, so an overlapping match (mdist < mlen) reads what
-            // it has just written; ring indices wrap
-            uint32_t w = (ring0 + at) & (KMB_GZ_RING - 1u), r = (w - mdist) & (KMB_GZ_RING - 1u);
-            if (mdist >= 4u && w + mlen <= KMB_GZ_RING && r + mlen <= KMB_GZ_RING) {
-                uint32_t i = 0;
-                for (; i + 4u <= mlen; i += 4u) {   // four independent loads, then four stores (mdist >= 4: no overlap inside a quad)
-                    const uint8_t b0 = ring[r + i], b1 = ring[r + i + 1], b2 = ring[r + i + 2], b3 = ring[r + i + 3];
-                    ring[w + i] = b0;
-                    ring[w + i + 1] = b1;
-                    ring[w + i + 2] = b2;
-                    ring[w + i + 3] = b3;
-                }
-                for (; i < mlen; i++) ring[w + i] = ring[r + i];
-            } else {
-                for (uint32_t i = 0; i < mlen; i++) ring[(w + i) & (KMB_GZ_RING - 1u)] = ring[(r + i) & (KMB_GZ_RING - 1u)];
-            }
-            at += mlen;
-        }
-        T.pos = at;
-        if (kmb_gz_bits_pos(B) > B.end) return T.status = KMB_GZ_ERR_INPUT, KMB_GZ_R_ERROR;
-    }
-}
-
-// One warp per member (one-warp CTAs: 45 KB of shared memory each, five per SM).  Lane 0 walks the bit stream and keeps
-// the member's text in a 32 KB ring in shared memory (kmb_gz_run); whenever 16 KB are waiting the whole warp writes them
-// to global memory in 16-byte vectors.  `gz` must be readable 16 bytes past the last member (the host pads its buffer).
-__global__ void __launch_bounds__(32) kmb_gz_inflate_kernel(const uint8_t *__restrict__ gz, const KmbGzMember *__restrict__ members,
-                                                            uint32_t n_members, uint8_t *__restrict__ out, KmbGzResult *__restrict__ results) {
+// One warp per member.  `gz` must be readable 16 bytes past the last member (the host pads its buffer).
+__global__ void __launch_bounds__(KMB_GZ_WARPS * 32) kmb_gz_inflate_kernel(const uint8_t *__restrict__ gz, const KmbGzMember *__restrict__ members,
+                                                                            uint32_t n_members, uint8_t *__restrict__ out, KmbGzResult *__restrict__ results) {
     extern __shared__ __align__(16) unsigned char kmb_gz_smem[];
-    KmbGzShared &S = *reinterpret_cast<KmbGzShared *>(kmb_gz_smem);
+    KmbGzShared &S = reinterpret_cast<KmbGzShared *>(kmb_gz_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    for (uint32_t mi = blockIdx.x; mi < n_members; mi += gridDim.x) {
+    const uint32_t warps = gridDim.x * KMB_GZ_WARPS;
+    for (uint32_t mi = blockIdx.x * KMB_GZ_WARPS + (threadIdx.x >> 5); mi < n_members; mi += warps) {
         const KmbGzMember M = members[mi];
         uint8_t *dst = out + M.out_off;
-        const uint32_t ring0 = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & (KMB_GZ_RING - 1u));
-        KmbGzState T;
-        T.B.words = reinterpret_cast<const uint64_t *>(gz + (M.in_off & ~7ull));
-        T.B.end = (M.in_off & 7ull) + M.in_len;
-        T.B.buf = T.B.next = T.B.after = 0;
-        T.B.wi = T.B.c = 0;
-        T.B.cnt = 0;
-        T.pos = T.flushed = T.stored = 0;
-        T.stored_at = 0;
-        T.status = KMB_GZ_OK;
-        T.in_block = T.last_block = T.coded = false;
+        uint32_t produced = 0;
+        uint32_t status = KMB_GZ_OK;
+        KmbGzBits B;
+        B.base = gz + (M.in_off & ~7ull);
+        B.pos = M.in_off & 7ull;
+        B.end = B.pos + M.in_len;
+        B.buf = 0;
+        B.cnt = 0;
         // ---- gzip header (RFC 1952), lane 0
         if (lane == 0) {
-            const uint8_t *p0 = reinterpret_cast<const uint8_t *>(T.B.words);
-            const uint8_t *p = p0 + (M.in_off & 7ull);
-            const uint8_t *e = p0 + T.B.end;
+            const uint8_t *p = B.base + B.pos;
+            const uint8_t *e = B.base + B.end;
             if (M.in_len < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xE0)) {
-                T.status = KMB_GZ_ERR_HEADER;
+                status = KMB_GZ_ERR_HEADER;
             } else {
                 const int flags = p[3];
                 p += 10;
@@ -440,56 +232,218 @@ __global__ void __launch_bounds__(32) kmb_gz_inflate_kernel(const uint8_t *__res
                     p++;
                 }
                 if (flags & 2) p += 2;
-                if (p + 8 > e) T.status = KMB_GZ_ERR_HEADER;
-                else kmb_gz_bits_init(T.B, (uint64_t)(p - p0));
+                if (p + 8 > e) status = KMB_GZ_ERR_HEADER;
+                B.pos = (uint64_t)(p - B.base);
             }
         }
-        uint32_t reason = KMB_GZ_R_ERROR;
-        for (;;) {
-            if (lane == 0) reason = T.status != KMB_GZ_OK ? KMB_GZ_R_ERROR : kmb_gz_run(T, S, ring0, M.out_len);
-            __syncwarp();   // lane 0's writes to the ring are visible to the warp
-            reason = __shfl_sync(0xFFFFFFFFu, reason, 0);
-            const uint32_t pos = __shfl_sync(0xFFFFFFFFu, T.pos, 0);
-            uint32_t flushed = __shfl_sync(0xFFFFFFFFu, T.flushed, 0);
-            // ---- write [flushed, upto) out: single bytes up to a 16-byte boundary of the output, then whole vectors; the
-            // rest waits for the next round unless this is the last one
-            const bool final_round = reason != KMB_GZ_R_FLUSH;
-            uintptr_t a = reinterpret_cast<uintptr_t>(dst) + flushed;
-            const uint32_t head = min((uint32_t)((16u - (a & 15u)) & 15u), pos - flushed);
-            if ((uint32_t)lane < head) dst[flushed + lane] = S.ring[(ring0 + flushed + lane) & (KMB_GZ_RING - 1u)];
-            flushed += head;
-            const uint32_t n_vec = (pos - flushed) >> 4;
-            for (uint32_t v = (uint32_t)lane; v < n_vec; v += 32u) {
-                const uint32_t p = flushed + (v << 4);
-                *reinterpret_cast<uint4 *>(dst + p) = *reinterpret_cast<const uint4 *>(&S.ring[(ring0 + p) & (KMB_GZ_RING - 1u)]);
+        status = __shfl_sync(0xFFFFFFFFu, status, 0);
+        bool last_block = false;
+        // ---- deflate blocks
+        while (status == KMB_GZ_OK && !last_block) {
+            uint32_t type = 0, stored = 0;
+            if (lane == 0) {
+                kmb_gz_refill(B);
+                last_block = kmb_gz_take(B, 1) != 0;
+                type = kmb_gz_take(B, 2);
+                if (type == 0) {
+                    kmb_gz_align(B);
+                    const uint8_t *p = B.base + B.pos;
+                    const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8), nlen = (uint32_t)p[2] | ((uint32_t)p[3] << 8);
+                    if (B.pos + 4 > B.end || (len ^ 0xFFFFu) != nlen) status = KMB_GZ_ERR_STREAM;
+                    B.pos += 4;
+                    stored = len;
+                    if (B.pos + len > B.end) status = KMB_GZ_ERR_INPUT;
+                } else if (type == 3) {
+                    status = KMB_GZ_ERR_STREAM;
+                } else {
+                    int n_lit = 288, n_dist = 32;
+                    uint8_t *lens = S.lens;
+                    if (type == 1) {
+                        for (int i = 0; i < 144; i++) lens[i] = 8;
+                        for (int i = 144; i < 256; i++) lens[i] = 9;
+                        for (int i = 256; i < 280; i++) lens[i] = 7;
+                        for (int i = 280; i < 288; i++) lens[i] = 8;
+                        for (int i = 0; i < 32; i++) lens[288 + i] = 5;
+                    } else {
+                        n_lit = (int)kmb_gz_take(B, 5) + 257;
+                        n_dist = (int)kmb_gz_take(B, 5) + 1;
+                        const int n_pre = (int)kmb_gz_take(B, 4) + 4;
+                        if (n_lit > 286 || n_dist > 30) status = KMB_GZ_ERR_STREAM;
+                        uint8_t *pre_lens = S.lens + 320;
+                        for (int i = 0; i < 19; i++) pre_lens[i] = 0;
+                        for (int i = 0; i < n_pre && status == KMB_GZ_OK; i++) {
+                            if (B.cnt < 3) kmb_gz_refill(B);
+                            pre_lens[c_kmb_gz_order[i]] = (uint8_t)kmb_gz_take(B, 3);
+                        }
+                        if (status == KMB_GZ_OK && !kmb_gz_build_table(pre_lens, 19, 2, 7, S.pre, 128)) status = KMB_GZ_ERR_TABLE;
+                        int i = 0;
+                        while (status == KMB_GZ_OK && i < n_lit + n_dist) {
+                            if (B.cnt < 14) kmb_gz_refill(B);
+                            const uint32_t e = S.pre[B.buf & 127u];
+                            if (((e >> 10) & 7u) != KMB_GZ_K_LITERAL) {
+                                status = KMB_GZ_ERR_STREAM;
+                                break;
+                            }
+                            kmb_gz_take(B, (int)(e & 31u));
+                            const uint32_t sym = e >> 16;
+                            if (sym < 16) {
+                                lens[i++] = (uint8_t)sym;
+                                continue;
+                            }
+                            int rep;
+                            uint8_t v = 0;
+                            if (sym == 16) {
+                                if (i == 0) {
+                                    status = KMB_GZ_ERR_STREAM;
+                                    break;
+                                }
+                                v = lens[i - 1];
+                                rep = 3 + (int)kmb_gz_take(B, 2);
+                            } else if (sym == 17) {
+                                rep = 3 + (int)kmb_gz_take(B, 3);
+                            } else {
+                                rep = 11 + (int)kmb_gz_take(B, 7);
+                            }
+                            if (i + rep > n_lit + n_dist) {
+                                status = KMB_GZ_ERR_STREAM;
+                                break;
+                            }
+                            while (rep--) lens[i++] = v;
+                        }
+                        if (status == KMB_GZ_OK && lens[256] == 0) status = KMB_GZ_ERR_STREAM;
+                        if (status == KMB_GZ_OK) {  // distance lengths follow the literal/length ones: to their own place
+                            for (int j = n_dist - 1; j >= 0; j--) lens[288 + j] = lens[n_lit + j];
+                            for (int j = n_lit; j < 288; j++) lens[j] = 0;
+                            for (int j = n_dist; j < 32; j++) lens[288 + j] = 0;
+                        }
+                    }
+                    if (status == KMB_GZ_OK && !kmb_gz_build_table(lens, type == 1 ? 288 : n_lit, 0, KMB_GZ_LIT_BITS, S.lit, KMB_GZ_LIT_MAX))
+                        status = KMB_GZ_ERR_TABLE;
+                    if (status == KMB_GZ_OK && !kmb_gz_build_table(lens + 288, type == 1 ? 32 : n_dist, 1, KMB_GZ_DIST_BITS, S.dist, KMB_GZ_DIST_MAX))
+                        status = KMB_GZ_ERR_TABLE;
+                }
             }
-            flushed += n_vec << 4;
-            if (final_round) {
-                if ((uint32_t)lane < pos - flushed) dst[flushed + lane] = S.ring[(ring0 + flushed + lane) & (KMB_GZ_RING - 1u)];
-                flushed = pos;
+            status = __shfl_sync(0xFFFFFFFFu, status, 0);
+            type = __shfl_sync(0xFFFFFFFFu, type, 0);
+            last_block = __shfl_sync(0xFFFFFFFFu, (int)last_block, 0) != 0;
+            if (status != KMB_GZ_OK) break;
+            if (type == 0) {  // stored block: the whole warp copies
+                stored = __shfl_sync(0xFFFFFFFFu, stored, 0);
+                const uint64_t src = __shfl_sync(0xFFFFFFFFu, B.pos, 0);
+                if (produced + stored > M.out_len) {
+                    status = KMB_GZ_ERR_OUTPUT;
+                    break;
+                }
+                for (uint32_t i = (uint32_t)lane; i < stored; i += 32u) dst[produced + i] = B.base[src + i];
+                produced += stored;
+                if (lane == 0) B.pos += stored;
+                __syncwarp();
+                continue;
             }
-            T.flushed = flushed;   // (every lane keeps a copy; lane 0's is the one kmb_gz_run reads)
-            __syncwarp();          // the ring may be overwritten from here on
-            if (final_round) break;
+            // ---- coded block: lane 0 decodes, literals stored as they come; matches copied by the warp
+            for (;;) {
+                uint32_t mlen = 0, mdist = 0, lits = 0;   // what lane 0 found: `lits` literals written, then a match or the end
+                uint32_t st = KMB_GZ_OK;
+                bool end_of_block = false;
+                if (lane == 0) {
+                    uint32_t at = produced;
+                    for (;;) {
+                        if (B.cnt < 48) kmb_gz_refill(B);
+                        uint32_t e = S.lit[B.buf & ((1u << KMB_GZ_LIT_BITS) - 1u)];
+                        if (((e >> 10) & 7u) == KMB_GZ_K_SUB) {
+                            B.buf >>= KMB_GZ_LIT_BITS;
+                            B.cnt -= KMB_GZ_LIT_BITS;
+                            e = S.lit[(e >> 16) + (uint32_t)(B.buf & ((1ull << ((e >> 5) & 31u)) - 1ull))];
+                        }
+                        const uint32_t kind = (e >> 10) & 7u;
+                        B.buf >>= (e & 31u);
+                        B.cnt -= (int)(e & 31u);
+                        if (kind == KMB_GZ_K_LITERAL) {
+                            if (at >= M.out_len) {
+                                st = KMB_GZ_ERR_OUTPUT;
+                                break;
+                            }
+                            dst[at++] = (uint8_t)(e >> 16);
+                            continue;
+                        }
+                        if (kind == KMB_GZ_K_END) {
+                            end_of_block = true;
+                            break;
+                        }
+                        if (kind != KMB_GZ_K_BASE) {
+                            st = KMB_GZ_ERR_STREAM;
+                            break;
+                        }
+                        const uint32_t xl = (e >> 5) & 31u;
+                        mlen = (e >> 16) + (uint32_t)(B.buf & ((1ull << xl) - 1ull));
+                        B.buf >>= xl;
+                        B.cnt -= (int)xl;
+                        uint32_t d = S.dist[B.buf & ((1u << KMB_GZ_DIST_BITS) - 1u)];
+                        if (((d >> 10) & 7u) == KMB_GZ_K_SUB) {
+                            B.buf >>= KMB_GZ_DIST_BITS;
+                            B.cnt -= KMB_GZ_DIST_BITS;
+                            d = S.dist[(d >> 16) + (uint32_t)(B.buf & ((1ull << ((d >> 5) & 31u)) - 1ull))];
+                        }
+                        if (((d >> 10) & 7u) != KMB_GZ_K_BASE) {
+                            st = KMB_GZ_ERR_STREAM;
+                            break;
+                        }
+                        B.buf >>= (d & 31u);
+                        B.cnt -= (int)(d & 31u);
+                        const uint32_t xd = (d >> 5) & 31u;
+                        if (B.cnt < (int)xd) kmb_gz_refill(B);
+                        mdist = (d >> 16) + (uint32_t)(B.buf & ((1ull << xd) - 1ull));
+                        B.buf >>= xd;
+                        B.cnt -= (int)xd;
+                        if (mdist > at || at + mlen > M.out_len) st = mdist > at ? KMB_GZ_ERR_STREAM : KMB_GZ_ERR_OUTPUT;
+                        break;
+                    }
+                    lits = at - produced;
+                    if (B.pos - (uint64_t)(B.cnt >> 3) > B.end) st = KMB_GZ_ERR_INPUT;
+                }
+                st = __shfl_sync(0xFFFFFFFFu, st, 0);
+                lits = __shfl_sync(0xFFFFFFFFu, lits, 0);
+                mlen = __shfl_sync(0xFFFFFFFFu, mlen, 0);
+                mdist = __shfl_sync(0xFFFFFFFFu, mdist, 0);
+                end_of_block = __shfl_sync(0xFFFFFFFFu, (int)end_of_block, 0) != 0;
+                produced += lits;
+                if (st != KMB_GZ_OK) {
+                    status = st;
+                    break;
+                }
+                if (end_of_block) break;
+                // the match: byte i = out[produced - mdist + i % mdist]  (everything before `produced` is written and,
+                // after the shuffles above, visible to the whole warp)
+                __syncwarp();
+                const uint8_t *src = dst + produced - mdist;
+                if (mdist >= mlen) {
+                    for (uint32_t i = (uint32_t)lane; i < mlen; i += 32u) dst[produced + i] = src[i];
+                } else {
+                    for (uint32_t i = (uint32_t)lane; i < mlen; i += 32u) dst[produced + i] = src[i % mdist];
+                }
+                produced += mlen;
+                __syncwarp();
+            }
         }
         // ---- trailer
+        uint32_t in_used = 0, crc = 0;
         if (lane == 0) {
-            uint32_t status = T.status, in_used = 0, crc = 0;
             if (status == KMB_GZ_OK) {
-                const uint64_t at0 = kmb_gz_align(T.B);
-                if (at0 + 8 > T.B.end) {
+                kmb_gz_align(B);
+                if (B.pos + 8 > B.end) {
                     status = KMB_GZ_ERR_INPUT;
                 } else {
-                    const uint8_t *p = reinterpret_cast<const uint8_t *>(T.B.words) + at0;
+                    const uint8_t *p = B.base + B.pos;
                     crc = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
                     const uint32_t isize = (uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
-                    if (isize != T.pos) status = KMB_GZ_ERR_STREAM;
-                    in_used = (uint32_t)(at0 + 8 - (M.in_off & 7ull));
+                    if (isize != produced) status = KMB_GZ_ERR_STREAM;
+                    B.pos += 8;
+                    in_used = (uint32_t)(B.pos - (M.in_off & 7ull));
                 }
             }
             KmbGzResult r;
             r.status = status;
-            r.out_len = T.pos;
+            r.out_len = produced;
             r.in_used = in_used;
             r.crc = crc;
             results[mi] = r;
