@@ -788,7 +788,7 @@ static int launch_flush(kmb_mapper *m) {
 // the benchmark shapes), between 2^23 and log_max_entries ids.  A log that runs full is not an error: the
 // kernels then reduce directly onto the counts.
 static bool may_use_read_table(const kmb_index *ix);
-static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
+static int ensure_log(kmb_mapper *m, uint64_t n_queries, bool for_read_table) {
     if (!m->log.entries && m->n_counts <= (uint64_t)std::max<int64_t>(g_opt.direct_counts_max_nodes, 0)) {
         m->log.cap = 0;   // small count array: the kernels reduce onto it directly (kmb_emit)
         return KMB_OK;
@@ -799,8 +799,12 @@ static int ensure_log(kmb_mapper *m, uint64_t n_queries) {
     if (!m->log.cursor) {
         KMB_CUDA(cudaMalloc(&m->log.cursor, sizeof(unsigned long long)));
         KMB_CUDA(cudaMemsetAsync(m->log.cursor, 0, sizeof(unsigned long long), m->stream));
-        // 16 node ranges, or 8 where the read-path kernel (whose shared memory has room for 8 stacks) may serve this index
-        const uint32_t n_bins = may_use_read_table(m->index) ? KMB_MZ_LOG_BINS : KMB_LOG_BINS;
+        // The log is laid out for the kernel that asks for it first: KMB_MZ_LOG_BINS node ranges for the read-path
+        // kernel (12 stacks of 35 ids fit its shared memory: at 400 M nodes a range is then two apply windows wide
+        // instead of four and the apply pass reads the log twice instead of four times, 6.66 -> 4.67 ms per 6 G k-mers
+        // of config 3), KMB_LOG_BINS for the key-addressed kernels.  A kernel that meets a log with more ranges than
+        // it has stacks reduces the ids of the ranges beyond them directly (kmb_emit).
+        const uint32_t n_bins = for_read_table ? KMB_MZ_LOG_BINS : KMB_LOG_BINS;
         uint32_t shift = 0;
         while (((m->n_counts ? m->n_counts - 1 : 0) >> shift) >= n_bins) shift++;
         m->log.bin_shift = shift;
@@ -1102,7 +1106,7 @@ static int launch_map_reads(kmb_mapper *m, const uint8_t *d_bases, uint64_t n_ba
     kmb_tile_reads_kernel<<<grid_for(n_wtiles, 256, ix->info.sms), 256, 0, m->stream>>>(R, n_bases, n_wtiles, d_tiles, m->d_status);
     g_launches++;
     // every window, both strands when asked: the number of look-ups this launch can make
-    KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases));
+    KMB_TRY(ensure_log(m, ((flags & KMB_FLAG_REVCOMP) ? 2 : 1) * n_bases, use_read_table(ix, k, flags)));
     KmbProbe P = make_probe(m);
     const uint32_t in_mode = ((flags & KMB_FLAG_NO_N_TO_A) ? 0u : KMB_IN_N_TO_A) | (packed ? KMB_IN_PACKED : 0u);
     // (a log shaped for the key-addressed kernels -- the option was switched on after it was made -- keeps them)
@@ -1153,7 +1157,7 @@ static int launch_map_kmers(kmb_mapper *m, const uint64_t *d_kmers, uint64_t n, 
     if (n == 0) return KMB_OK;
     const kmb_index *ix = m->index;
     bool rc = (flags & KMB_FLAG_REVCOMP) != 0;
-    KMB_TRY(ensure_log(m, (rc ? 2 : 1) * n));
+    KMB_TRY(ensure_log(m, (rc ? 2 : 1) * n, false));
     KmbProbe P = make_probe(m);
     m->dirty = true;
     m->log_clean = false;

@@ -107,7 +107,9 @@ KMB_HD uint32_t kmb_header_count(uint32_t hdr) { return (hdr & KMB_HDR_CHAIN) ? 
 #ifndef KMB_LOG_BINS
 #define KMB_LOG_BINS 8
 #endif
-#define KMB_MZ_LOG_BINS 8
+#ifndef KMB_MZ_LOG_BINS
+#define KMB_MZ_LOG_BINS 12  // the read-path kernel's stacks are shallower (KMB_MZ_STAGE_SLOTS), so it has room for more ranges
+#endif
 KMB_HD uint32_t kmb_log_bin(uint32_t node, uint32_t bin_shift) {
     uint32_t b = node >> bin_shift;
     return b < KMB_LOG_BINS ? b : (uint32_t)(KMB_LOG_BINS - 1);

@@ -487,10 +487,11 @@ __device__ __forceinline__ void kmb_count_direct(uint32_t *counts, uint32_t node
     }
 }
 __device__ __forceinline__ void kmb_emit(const KmbProbe &P, const KmbStage &st, uint32_t node) {
-    const uint32_t b = min(node >> P.log.bin_shift, st.bins - 1u);
+    const uint32_t b = node >> P.log.bin_shift;
     KMB_BOUND(6, node, P.n_counts);
-    KMB_BOUND(3, b, st.bins);
-    const uint32_t pos = atomicAdd(&st.cnt[b], 1u);
+    // (a log may have more ranges than this kernel has stacks: a mapper whose log was laid out for the read-path
+    // kernel's KMB_MZ_LOG_BINS and that is then used with another k or with reverse complements; those ids go direct)
+    const uint32_t pos = b < st.bins ? atomicAdd(&st.cnt[b], 1u) : 0xFFFFFFFFu;
     if (pos < st.slots) st.buf[b * st.slots + pos] = node;
     else kmb_count_direct(P.counts, node);  // valve: the stack is full (the flush clamps the count)
 }
@@ -1019,14 +1020,18 @@ kmb_map_reads_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, uint64
 // A tile is worked off in two passes of 16 lanes' runs each, so that everything below is sized for half a tile:
 // 7.7 KB of shared memory per warp = 28 warps per SM instead of 20.
 #define KMB_MZ_SLOTS 64     // primary sectors staged per pass (half a tile has ~73 runs, ~52 pass the filter)
+#ifndef KMB_MZ_SLOTS2
 #define KMB_MZ_SLOTS2 24    // secondary sectors staged per pass (buckets with more than two entries)
+#endif
 #define KMB_MZ_RUNS_KEPT 96  // passing runs remembered per pass; beyond KMB_MZ_SLOTS they load their bucket late
 #endif
 #define KMB_MZ_NONE 0xFFu   // secondary table: the bucket has no secondary sector to look at
 #define KMB_MZ_LATE 0xFEu   // secondary table: no staging slot left, load from global memory instead
 #define KMB_MZ_PACK_WORDS (KMB_WTILE_POS / 16 + 4)
 #define KMB_MZ_LATE_CAP 40  // <= 8 left over + at most 32 new per round
-#define KMB_MZ_STAGE_SLOTS 48
+#ifndef KMB_MZ_STAGE_SLOTS
+#define KMB_MZ_STAGE_SLOTS 35  // 12 ranges x 35 ids (was 8 x 48): a full group of 32 + what one round can add before the flush
+#endif
 // a run of one lane: lane | first window << 5 | last window << 10 | minimizer position (0..47) << 15
 #define KMB_MZ_RUN(lane, s, e, j) ((uint32_t)(lane) | ((uint32_t)(s) << 5) | ((uint32_t)((e) - 1) << 10) | ((uint32_t)(j) << 15))
 struct alignas(16) KmbMzShared {  // per warp
