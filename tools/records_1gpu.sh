@@ -4,9 +4,9 @@ V=$1
 (timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_${V}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_${V}_pytest_gpu.log); tail -2 gpurun_out/r2_${V}_pytest_gpu.log
 (timeout 300 python __graft_entry__.py smoke > gpurun_out/r2_${V}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2_${V}_smoke.log); tail -2 gpurun_out/r2_${V}_smoke.log
 timeout 900 python bench.py --impl reference > gpurun_out/r2_${V}_bench_config2_reference_arm.log 2> gpurun_out/r2_${V}_bench_config2_reference_arm.err; tail -1 gpurun_out/r2_${V}_bench_config2_reference_arm.log | cut -c1-200
-/usr/bin/time -v timeout 1200 python bench.py --full-oracle > gpurun_out/r2_${V}_bench_config2.log 2> gpurun_out/r2_${V}_bench_config2.err; echo "bench rc=$?"; tail -1 gpurun_out/r2_${V}_bench_config2.log | python -c "
+timeout 1200 python bench.py --full-oracle > gpurun_out/r2_${V}_bench_config2.log 2> gpurun_out/r2_${V}_bench_config2.err; echo "bench rc=$?"; tail -1 gpurun_out/r2_${V}_bench_config2.log | python -c "
 import sys,json
-d=json.loads(sys.stdin.read()); r=d['roofline']; print('config2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'frac', r['frac'], r['frac_step'], 'reads/s', {k:v for k,v in d['reads_per_s'].items() if isinstance(v,float)}, d['checks'])"; grep -i "elapsed (wall" gpurun_out/r2_${V}_bench_config2.err
+d=json.loads(sys.stdin.read()); r=d['roofline']; print('config2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'frac', r['frac'], r['frac_step'], 'reads/s', {k:v for k,v in d['reads_per_s'].items() if isinstance(v,float)}, d['checks'])"
 for w in config1 config3 config4_k21 config4_k15 config5; do
 timeout 1500 python bench.py --workload $w --no-files --no-cpu-baseline --full-oracle --steps 4 --warmup 3 > gpurun_out/r2_${V}_bench_$w.log 2> gpurun_out/r2_${V}_bench_$w.err; echo "$w rc=$?"; tail -1 gpurun_out/r2_${V}_bench_$w.log | python -c "
 import sys,json

@@ -1,4 +1,4 @@
-# usage: bash tools/_finalN.sh N V   -- multi-GPU records (torchrun, one rank per GPU)
+# usage: bash tools/records_ngpu.sh N V   -- multi-GPU records (torchrun, one rank per GPU)
 N=$1
 V=$2
 P=29711
