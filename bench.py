@@ -108,17 +108,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def known_traffic(name):
-    """DRAM bytes per launch of the fused kernel from the committed ncu --set full capture, if any, and where
-    the figure comes from (it is evidence of that capture, not of this run: ncu cannot run inside a timed bench)."""
+def known_traffic(name, kernel):
+    """DRAM bytes per launch of the fused kernel from the committed ncu --set full capture of THAT kernel on this
+    workload, if any, and where the figure comes from (it is evidence of that capture, not of this run: ncu cannot
+    run inside a timed bench)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         rec = json.load(open(path)).get(name)
     except Exception:
         return None, None
+    if isinstance(rec, dict) and "bytes" not in rec:
+        rec = rec.get(kernel)
     if isinstance(rec, dict):
         return rec.get("bytes"), "static ncu capture: " + str(rec.get("source"))
-    return rec, ("static ncu capture (profiles/traffic.json)" if rec is not None else None)
+    return None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -734,12 +737,13 @@ def main_ours(args):
     step_ms_rank = ms / args.steps
     achieved_step = bytes_per_kmer * n_kmers_step / (step_ms_rank / 1e3) / 1e9
     apply_avg_ms = apply_ms / max(apply_n, 1)
-    traffic, traffic_src = known_traffic(args.workload)
+    kernel_name = "kmb_map_reads_mz_kernel (read-path table)" if _lib.get_option("last_reads_kernel") else "kmb_map_reads_kernel"
+    traffic, traffic_src = known_traffic(args.workload, kernel_name.split(" ")[0])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
                 "achieved_step": achieved_step, "frac_step": achieved_step / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "kmb_map_reads_mz_kernel (read-path table)" if _lib.get_option("last_reads_kernel") else "kmb_map_reads_kernel",
+                "kernel": kernel_name,
                 "kernel_ms": kernel_avg_ms, "kernel_share_of_step": kernel_ms / ms if ms else None,
                 "kernel_bytes_per_kmer": kernel_bytes_per_kmer, "bytes_per_kmer": bytes_per_kmer, "counted_entries_per_kmer": h,
                 "apply": {"kernel": "kmb_log_apply_kernel", "ms": apply_avg_ms, "share_of_step": apply_ms / ms if ms else None,

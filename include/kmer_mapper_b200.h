@@ -314,7 +314,7 @@ int kmb_mapper_apply_time(kmb_mapper *mapper, double *ms_total, uint64_t *n_kern
  *  "host_pack_streaming" (default 1: the host encoder writes its 2-bit words with non-temporal stores),
  *  "apply_slabs_per_sm" (8: CTAs of the apply pass per SM and node window; 16 and 32 measured slower),
  *  "read_table" (k = 31 reads through the minimizer-bucketed second table, see csrc/kmb_core.cuh: 1 always, 0 never,
- *  default -1 = when the key filter has less than 2.5 bits per key, i.e. for indexes of several hundred million entries),
+ *  default -1 = for every index of at least "read_table_min_entries" live entries when there is room for the second table),
  *  "read_table_min_entries" (8 Mi: auto never builds the table for smaller indexes),
  *  "read_table_buckets_per_100_entries" (150)};
  * read-only: "h2d_bytes" (bytes the mapping calls have copied host -> device so far), "last_reads_kernel" (0 = the

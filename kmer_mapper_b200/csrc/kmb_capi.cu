@@ -1082,8 +1082,11 @@ static int ensure_read_table(kmb_index *ix, int k) {
 static bool may_use_read_table(const kmb_index *ix) {
     if (g_opt.read_table == 0 || ix->mz_k < 0) return false;
     if (g_opt.read_table > 0) return true;
-    const bool thin_filter = !ix->filter_on || ix->addr.n_probes <= 1u;
-    return thin_filter && ix->n_live >= (uint64_t)std::max<int64_t>(g_opt.read_table_min_entries, 0);
+    // Automatic: every index that is not small.  Until the end of round 2 the table was only chosen behind a thin key
+    // filter (< 2.5 bits per key: config 3); with 16-base minimizers, the one-multiplication order and the cheaper
+    // encode the read-path kernel also wins where the filter is good: config 2 48.7 ms per step against 50.3 (123.3 /
+    // 119.3 GK/s), config 5 39.4 against 48.6 (190 / 154).  Small indexes (config 1) fit the L2 and stay key-addressed.
+    return ix->n_live >= (uint64_t)std::max<int64_t>(g_opt.read_table_min_entries, 0);
 }
 static bool use_read_table(const kmb_index *ix, int k, uint32_t flags) {
     if (k != KMB_MZ_K || (flags & KMB_FLAG_REVCOMP)) return false;

@@ -301,9 +301,9 @@ def test_map_reads_vs_oracle(kmb, k, variant):
         m.close()
 
 
-def test_read_table_is_chosen_by_itself_only_behind_a_thin_key_filter(kmb):
-    """read_table = -1: the minimizer-bucketed table serves k = 31 reads when the key filter has less than 2.5 bits
-    per key (here: a 512-byte filter budget) and the index is not small (threshold lowered for the test)."""
+def test_read_table_is_chosen_by_itself_for_indexes_that_are_not_small(kmb):
+    """read_table = -1: the minimizer-bucketed table serves k = 31 reads without reverse complements when the index has
+    at least read_table_min_entries live entries (threshold lowered for the test), whatever its key filter looks like."""
     from kmer_mapper_b200 import synthetic as S
     from kmer_mapper_b200.device import DeviceIndex, Mapper
     k = 31
@@ -312,8 +312,8 @@ def test_read_table_is_chosen_by_itself_only_behind_a_thin_key_filter(kmb):
     bases, offsets = S.make_reads(g, 4_000, 150, seed=5, ragged=True)
     want, _ = c_oracle.map_reads(idx, mx, bases, offsets, k, n_threads=4)
     try:
-        for budget, min_entries, rc, expect in ((512, 1, False, 1), (60 << 20, 1, False, 0), (512, 1 << 40, False, 0),
-                                                (512, 1, True, 0)):
+        for budget, min_entries, rc, expect in ((512, 1, False, 1), (60 << 20, 1, False, 1), (512, 1 << 40, False, 0),
+                                                (60 << 20, 1 << 40, False, 0), (512, 1, True, 0)):
             _set(kmb, dict(filter_l2_budget_bytes=budget, read_table=-1))
             kmb.set_option("read_table_min_entries", min_entries)
             m = Mapper(DeviceIndex.from_index(_fresh(idx)), mx + 1)
