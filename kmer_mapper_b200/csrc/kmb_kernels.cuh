@@ -1,10 +1,11 @@
 // kmb_kernels.cuh -- hand-written sm_100a kernels of the k-mer mapping path.
 //
 //   K5  kmb_build_check_buckets / _count / _plan / _scatter   index re-layout into 32-byte sectors (once per index)
-//   K0  kmb_mark_read_ends        read-boundary bitmask (one bit per base = "no window starts here")
-//   K1-4 kmb_map_reads_kernel     fused encode + window + filter + sector probe + hit log  (production path)
-//   K1-4 kmb_map_reads_mz_kernel  the same over the minimizer-bucketed read-path table (k = 31; indexes whose key
-//                                 filter is too thin to screen), kmb_mz_build_* build that table
+//   K0  kmb_tile_reads_kernel     first read of every 1024-base tile (the fused kernels derive "which windows exist"
+//                                 from it); kmb_mark_read_ends: the one-bit-per-base mask the hashing kernels use
+//   K1-4 kmb_map_reads_kernel     fused encode + window + filter + sector probe + hit log  (any k; small indexes)
+//   K1-4 kmb_map_reads_mz_kernel  the same over the minimizer-bucketed read-path table (k = 31, indexes of >= 8 M
+//                                 entries: the default there), kmb_mz_build_* build that table
 //   K3-4 kmb_map_kmers_kernel     probe + hit log on ready-made uint64 k-mers (mapper.pyx:19 drop-in)
 //   K4b kmb_log_apply_kernel      hit log -> per-node counts, one L2-sized window of nodes at a time, hot nodes
 //                                 aggregated in shared memory first
